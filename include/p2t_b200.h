@@ -1,0 +1,170 @@
+/* p2t_b200.h — C ABI of the B200-native Stage-1 contrastive hot path of Prot2Text-V2.
+ *
+ * The reference (RockingMat/Prot2Text-V2-esm3) is pure Python and has NO plugin/FFI layer for this
+ * path: its boundary is a set of Python call signatures.  Each entry point below
+ * names the reference interface it stands behind (paths relative to the reference root); the
+ * Python host layer in `prot2text-v2-esm3_b200/` binds them with ctypes and mirrors those
+ * signatures one-for-one (see INTEGRATION.md for the reference-side stub).
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, a stream handle.  No C++/torch types.
+ *   - every data pointer is a DEVICE pointer owned by the caller (the host layer allocates with
+ *     torch's caching allocator); nothing is allocated, freed or retained by the library.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises.
+ *   - return value: 0 = ok, < 0 = argument/setup error, > 0 = cudaError_t.  p2t_last_error()
+ *     returns the message of the last failure on the calling thread.
+ *   - bf16 tensors are row-major with 16-byte aligned rows (row length multiple of 8).
+ *   - "packed rows": the valid residue rows of all sequences back to back, [n_rows][D];
+ *     seq_off[b] (int32, B+1 entries) is the first packed row of sequence b.  n_rows lives in
+ *     device memory (`n_rows_dev`) so ragged batches never force a host sync; `rows_cap` is the
+ *     allocated row count (>= n_rows rounded up to 256).
+ *   - there is no CPU fallback anywhere: without a CUDA device every compute entry returns > 0.
+ */
+#ifndef P2T_B200_H_
+#define P2T_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P2T_ABI_VERSION 1
+
+/* readout modes — scripts/train_contrast.py:198-248 readout_fn */
+#define P2T_READOUT_MEAN 1
+#define P2T_READOUT_STD 2
+#define P2T_READOUT_MIX 3
+
+int p2t_abi_version(void);
+const char* p2t_last_error(void);
+/* kernels launched by this library since the last reset (bench.py reports it as gpu_launches) */
+unsigned long long p2t_launch_count(void);
+void p2t_reset_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * tcgen05 GEMM  D[m][n] = alpha * sum_k A[m][k] * B[n][k]      (bf16 in, fp32 accumulate in TMEM)
+ * Replaces: torch.mm / nn.Linear / their autograd GEMMs (cuBLAS in the reference):
+ *   scripts/train_contrast.py:87,108 (similarity), models/modeling_esm2llama_instruct.py:62,65.
+ * a_mn_major = 0: A stored [m][lda] (K contiguous); 1: A stored [k][lda] (M contiguous). Same for B.
+ * d_is_f32 selects fp32 or bf16 output.  dyn_m / dyn_k: optional device int32 overriding m / k
+ * (must be <= the static value).  cta_group: 1 = one SM per tile (128x256), 2 = CTA pair (256x256).
+ * ------------------------------------------------------------------------------------------- */
+int p2t_gemm_bf16(const void* a, long long lda, int a_mn_major, const void* b, long long ldb, int b_mn_major,
+                  void* d, long long ldd, int d_is_f32, int m, int n, int k, float alpha, const int* dyn_m,
+                  const int* dyn_k, int cta_group, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Ragged row plan from a {0,1} attention mask [B][L] (mask_bytes = 1, 4 or 8 per element; the
+ * reference passes int64, scripts/train_contrast.py:270-275 / dataset collaters).  Any mask
+ * pattern is accepted (right padded, left padded, holes).
+ *   counts[B], seq_off[B+1], chunk_off[B+1] (pooling chunks of `chunk_rows` rows), n_rows_dev[1],
+ *   row_src[>= sum(mask)] = flat source row b*L + r of each packed row (may be NULL).
+ * ------------------------------------------------------------------------------------------- */
+int p2t_rows_plan(const void* mask, int mask_bytes, int B, int L, int chunk_rows, int* counts, int* seq_off,
+                  int* chunk_off, int* n_rows_dev, int* row_src, void* stream);
+
+/* out[i] = src[row_src[i]] (bf16 rows of D elements), zero rows from n_rows up to the next multiple
+ * of 256 (<= rows_cap).  Packs the padded (B, L, D_in) residue states that
+ * models/esmc_qwen_arc.py:84-86 hands to the adapter. */
+int p2t_gather_rows(const void* src, long long ld_src, const int* row_src, const int* n_rows_dev, int rows_cap,
+                    int D, void* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ModalityAdapter.forward on packed rows — models/modeling_esm2llama_instruct.py:60-68.
+ *   h1 = drop(GELU(x W1^T + b1))            [rows_cap][d_mid] bf16   (fc1 epilogue)
+ *   g1 = keep * GELU'(x W1^T + b1)          [rows_cap][d_mid] bf16   (NULL when no backward)
+ *   a  = drop(GELU(h1 W2^T + b2))           [rows_cap][d_out] bf16   (fc2 epilogue)
+ *   g2 = keep * GELU'(h1 W2^T + b2)         [rows_cap][d_out] bf16   (NULL when no backward)
+ *   rowsq[row][nblk] = partial sums of a^2, nblk = ceil(d_out/256) — the per-residue L2 norm (:67)
+ * x has x_rows rows allocated (TMA zero-fills beyond); outputs have rows_cap rows.
+ * Weights in nn.Linear layout (out, in), bf16.  dropout_p = 0 is eval mode; otherwise a Philox
+ * mask keyed by (seed, layer, row, column) with multiplier 1/(1-p) (nn.Dropout, :63,:66).
+ * ------------------------------------------------------------------------------------------- */
+int p2t_adapter_fwd(const void* x, int x_rows, const void* w1, const void* b1, const void* w2, const void* b2, int d_in,
+                    int d_mid, int d_out, int rows_cap, const int* n_rows_dev, void* h1, void* g1, void* a,
+                    void* g2, float* rowsq, float dropout_p, unsigned long long seed, int cta_group, void* stream);
+
+/* y[row] = a[row] / max(|a[row]|, 1e-12) for the first n rows: the (B, L, d_out) tensor that
+ * ModalityAdapter.forward returns (:67-68).  inv_norm[row] is saved for backward (may be NULL). */
+int p2t_adapter_scale_rows(const void* a, const float* rowsq, int nblk, int n, int d_out, void* y, float* inv_norm,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * readout_embeddings(..., "mean"|"std"|"mix") — scripts/train_contrast.py:217-248 — over the rows
+ * listed by a plan.  `src` is bf16 [*][ld_src]; row_src == NULL means rows are already packed.
+ * With rowsq != NULL every row is first scaled by its inverse L2 norm (adapter output fused in).
+ * partial_ws: float2 [max_chunks][D]; out: fp32 [B][ld_out] (mean | std for mix).
+ * ------------------------------------------------------------------------------------------- */
+int p2t_pool_fwd(const void* src, long long ld_src, const int* row_src, const float* rowsq, int nblk,
+                 const int* seq_off, const int* chunk_off, int B, int D, int chunk_rows, int max_chunks, int mode,
+                 void* partial_ws, float* inv_norm_out, float* out, long long ld_out, void* stream);
+
+/* readout_embeddings(..., "last") — :207-215 — out fp32 [B][D] from padded x [B][S][D] */
+int p2t_readout_last(const void* x, const int* counts, int B, int S, int D, float* out, void* stream);
+
+/* F.normalize(p=2, dim=-1) on pooled embeddings — scripts/train_contrast.py:354,365.
+ * e fp32 [B][E] -> p (bf16 and/or fp32, either may be NULL), norm[B] (unclamped). */
+int p2t_l2norm_fwd(const float* e, int B, int E, void* p_bf16, float* p_f32, float* norm, void* stream);
+int p2t_l2norm_bwd(const float* dp, const float* p_f32, const float* norm, int B, int E, float* de, void* stream);
+
+/* backward of the readout: coefficient vectors with dy_r = c1[b] + c2[b] * y_r (fp32 [B][D]) */
+int p2t_pool_bwd_coef(const float* de, long long ld_de, const float* stats, long long ld_stats, const int* seq_off,
+                      int B, int D, int mode, float* c1, float* c2, void* stream);
+/* dx[b,r] = mask[b,r] * (c1[b] + c2[b] * x[b,r]) on a padded bf16 (B, S, D) tensor */
+int p2t_readout_bwd(const void* x, const void* mask, int mask_bytes, int B, int S, int D, const float* c1,
+                    const float* c2, void* dx, void* stream);
+
+/* backward through normalise -> GELU(fc2) on packed rows (autograd of :65-67):
+ *   dz2 = ((dy - y (y.dy)) / |a|) * g2,  dy = c1[b] + c2[b]*y   (pooled)   or given per row (_dy) */
+int p2t_adapter_tail_bwd(const void* a, const void* g2, const float* inv_norm, const int* seq_off, int B,
+                         const float* c1, const float* c2, const int* n_rows_dev, int rows_cap, int d_out, void* dz2,
+                         void* stream);
+int p2t_adapter_tail_bwd_dy(const void* a, const void* g2, const float* inv_norm, const void* dy, int n,
+                            int rows_cap, int d_out, void* dz2, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * backward GEMMs of the adapter (autograd of :62-65; scripts/train_contrast.py:448):
+ *   dz1 = (dz2 W2) * g1;  dW2 = dz2^T h1;  db2 = colsum dz2;  dW1 = dz1^T x;  db1 = colsum dz1
+ *   dx  = dz1 W1 (only when dx != NULL; the encoder is frozen in Stage 1, :186)
+ * Gradients are written (not accumulated) in bf16, nn.Linear layout.  colsum_ws: fp32
+ * [64][max(d_mid, d_out)] scratch.
+ * ------------------------------------------------------------------------------------------- */
+int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, const void* h1, const void* g1, const void* dz2,
+                    int d_in, int d_mid, int d_out, int rows_cap, const int* n_rows_dev, void* dz1, void* dw1,
+                    void* db1, void* dw2, void* db2, void* dx, float* colsum_ws, int cta_group, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * InfoNCE — scripts/train_contrast.py:86-91 (BatchInfoNCELoss), :100-114 (Segmented...).
+ * p2t_similarity : S[R][C] = (p . t^T) / tau   (fp32; bf16 unit-norm inputs [R][E], [C][E])
+ * p2t_infonce_col_stats : per-column online (max, sum exp, argmax row) — the text->protein term
+ * p2t_infonce_ce : one pass per row: loss_i, row lse, argmax, and dS written over S
+ *      loss_i = w_row (lse_j S_ij - S_i,lab) + w_col (lse_col[lab] - S_i,lab);  dS scaled by inv_rn
+ * p2t_infonce_grad : dp = dS t / tau (fp32 [R][E]) and optionally dt = dS^T p / tau (fp32 [C][E])
+ * p2t_loss_mean : loss[0] (+)= scale * sum_i row_loss[i], fixed-order reduction
+ * ------------------------------------------------------------------------------------------- */
+int p2t_similarity(const void* p, const void* t, int R, int C, int E, float tau, float* S, int cta_group,
+                   void* stream);
+int p2t_infonce_col_stats(const float* S, int R, int C, float* col_max, float* col_sum, int* col_argmax,
+                          int row_index_base, void* stream);
+int p2t_infonce_ce(float* S, const int* labels, int R, int C, float w_row, float w_col, float inv_rn,
+                   const float* col_max, const float* col_sum, unsigned char* col_labelled_ws, float* row_loss,
+                   float* row_lse, int* argmax_row, void* dS_bf16, int write_ds, void* stream);
+int p2t_infonce_grad(const float* dS, const void* dS_bf16, const void* p, const void* t, int R, int C, int E,
+                     float tau, float* dp, float* dt, void* bf16_ws, int cta_group, void* stream);
+int p2t_loss_mean(const float* row_loss, int R, float scale, float* loss, int accumulate, void* stream);
+
+/* dtype helpers used by the host layer around the fp32 <-> bf16 boundaries */
+int p2t_f32_to_bf16(const float* in, long long n, void* out, void* stream);
+int p2t_bf16_to_f32(const void* in, long long n, float* out, void* stream);
+/* deterministic column sums of a packed bf16 matrix (bias gradients) */
+int p2t_colsum(const void* x, const int* n_rows_dev, int n_static, int D, float* ws, void* out_bf16, float* out_f32,
+               void* stream);
+/* debug/test aid: the dropout keep-multipliers the kernels use, as fp32 [rows][cols] */
+int p2t_dropout_mask(int rows, int cols, float dropout_p, unsigned long long seed, int layer, float* out,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P2T_B200_H_ */

@@ -1,0 +1,22 @@
+"""B200-native Stage-1 contrastive hot path of Prot2Text-V2 (imported as `p2t_b200`).
+
+Public surface = the reference's own call signatures for this path:
+    ModalityAdapterConfig, ModalityAdapter           models/modeling_esm2llama_instruct.py:45-68
+    readout_embeddings                               scripts/train_contrast.py:198-248
+    BatchInfoNCELoss, SegmentedBatchInfoNCELoss      scripts/train_contrast.py:72-114
+plus the fused entry `contrastive_step` (scripts/train_contrast.py:313-379 from trunk outputs on)
+and its multi-GPU form in `dist`.  All compute goes through the C-ABI CUDA library
+(include/p2t_b200.h); there is no CPU fallback.
+"""
+from . import _lib
+from ._lib import P2TError
+from .adapter import ModalityAdapter, ModalityAdapterConfig
+from .losses import BatchInfoNCELoss, SegmentedBatchInfoNCELoss, SymmetricInfoNCELoss
+from .readout import readout_embeddings
+from .step import StepAux, contrastive_step, text_embeddings
+
+__all__ = [
+    "ModalityAdapter", "ModalityAdapterConfig", "readout_embeddings", "BatchInfoNCELoss",
+    "SegmentedBatchInfoNCELoss", "SymmetricInfoNCELoss", "contrastive_step", "text_embeddings", "StepAux",
+    "P2TError",
+]

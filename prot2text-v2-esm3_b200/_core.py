@@ -1,0 +1,295 @@
+"""Raw-buffer host functions: allocate workspaces with torch, enqueue kernels through the C ABI.
+
+Nothing here knows about autograd; `adapter.py`, `readout.py`, `losses.py` and `step.py` wrap
+these in `torch.autograd.Function`s that mirror the reference's call signatures.
+All functions enqueue on the CURRENT torch CUDA stream and never synchronise.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+CHUNK_ROWS = 64          # pooling chunk (rows per partial-moment block)
+ROW_ALIGN = 256          # packed buffers are allocated in multiples of this many rows
+READOUT_MODES = {"mean": 1, "std": 2, "mix": 3}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _round_up(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+def require_cuda_bf16(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise _lib.P2TError(f"{name} must be a CUDA tensor: this package has no CPU path")
+    if t.dtype != torch.bfloat16:
+        raise _lib.P2TError(f"{name} must be bfloat16 (got {t.dtype}); the sm_100a kernels compute in bf16 "
+                            "with fp32 accumulation, as the reference's default --torch_dtype bfloat16")
+
+
+def default_cta_group() -> int:
+    import os
+    return int(os.environ.get("P2T_CTA_GROUP", "2"))
+
+
+# --------------------------------------------------------------------------------------------------
+# ragged plan
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class RowPlan:
+    B: int
+    L: int
+    counts: torch.Tensor      # int32 [B]
+    seq_off: torch.Tensor     # int32 [B+1]
+    chunk_off: torch.Tensor   # int32 [B+1]
+    n_rows: torch.Tensor      # int32 [1] (device)
+    row_src: Optional[torch.Tensor]  # int32 [B*L]
+    rows_cap: int             # allocation size for packed buffers
+    max_chunks: int           # upper bound on pooling chunks
+
+
+def plan_rows(mask: torch.Tensor, want_row_src: bool = True) -> RowPlan:
+    """Device-side plan of the valid rows of a {0,1} mask (B, L); no host synchronisation."""
+    if mask.dim() != 2 or not mask.is_cuda:
+        raise _lib.P2TError("attention mask must be a 2-D CUDA tensor")
+    mask = mask.contiguous()
+    if mask.dtype == torch.bool:
+        mask = mask.view(torch.uint8)
+    nbytes = mask.element_size()
+    if mask.dtype.is_floating_point or nbytes not in (1, 4, 8):
+        mask = mask.to(torch.int32)
+        nbytes = 4
+    B, L = mask.shape
+    dev = mask.device
+    ints = torch.empty(3 * (B + 1) + 1, dtype=torch.int32, device=dev)
+    counts, seq_off, chunk_off, n_rows = ints[:B], ints[B + 1:2 * B + 2], ints[2 * B + 2:3 * B + 3], ints[3 * B + 3:]
+    row_src = torch.empty(B * L, dtype=torch.int32, device=dev) if want_row_src else None
+    _lib.call("p2t_rows_plan", _ptr(mask), nbytes, B, L, CHUNK_ROWS, _ptr(counts), _ptr(seq_off), _ptr(chunk_off),
+              _ptr(n_rows), _ptr(row_src), _stream())
+    return RowPlan(B=B, L=L, counts=counts, seq_off=seq_off, chunk_off=chunk_off, n_rows=n_rows, row_src=row_src,
+                   rows_cap=_round_up(B * L, ROW_ALIGN), max_chunks=(B * L + CHUNK_ROWS - 1) // CHUNK_ROWS + B)
+
+
+def dense_plan(B: int, L: int, device) -> RowPlan:
+    """Plan for an all-ones mask (every row valid) without reading a mask."""
+    ones = torch.ones(B, L, dtype=torch.uint8, device=device)
+    return plan_rows(ones, want_row_src=False)
+
+
+def gather_rows(x2d: torch.Tensor, plan: RowPlan) -> torch.Tensor:
+    """Pack the valid rows of x2d (B*L, D) into [rows_cap, D]; pad rows up to the next 256 are zeroed."""
+    D = x2d.shape[1]
+    out = torch.empty(plan.rows_cap, D, dtype=torch.bfloat16, device=x2d.device)
+    _lib.call("p2t_gather_rows", _ptr(x2d), x2d.stride(0), _ptr(plan.row_src), _ptr(plan.n_rows), plan.rows_cap, D,
+              _ptr(out), _stream())
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# GEMM
+# --------------------------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, b: torch.Tensor, m: int, n: int, k: int, *, a_mn: bool = False, b_mn: bool = False,
+         out_dtype=torch.bfloat16, alpha: float = 1.0, cta_group: Optional[int] = None,
+         dyn_m: Optional[torch.Tensor] = None, dyn_k: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """D[m][n] = alpha * sum_k A[m][k] B[n][k] on the tcgen05 kernel.
+
+    a is stored [m][k] (a_mn=False) or [k][m] (a_mn=True); b likewise with n.
+    """
+    require_cuda_bf16(a, "a")
+    require_cuda_bf16(b, "b")
+    out = torch.empty(m, n, dtype=out_dtype, device=a.device)
+    _lib.call("p2t_gemm_bf16", _ptr(a), a.stride(0), int(a_mn), _ptr(b), b.stride(0), int(b_mn), _ptr(out),
+              out.stride(0), int(out_dtype == torch.float32), m, n, k, float(alpha), _ptr(dyn_m), _ptr(dyn_k),
+              cta_group or default_cta_group(), _stream())
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# adapter on packed rows
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class AdapterActs:
+    x: torch.Tensor           # packed input rows [x_rows, d_in]
+    x_rows: int
+    h1: torch.Tensor          # [rows_cap, d_mid]
+    g1: Optional[torch.Tensor]
+    a: torch.Tensor           # [rows_cap, d_out]
+    g2: Optional[torch.Tensor]
+    rowsq: torch.Tensor       # fp32 [rows_cap, nblk]
+    nblk: int
+    rows_cap: int
+    n_rows: torch.Tensor      # int32 [1] device
+
+
+def adapter_forward(x: torch.Tensor, x_rows: int, rows_cap: int, n_rows: torch.Tensor, w1, b1, w2, b2,
+                    dropout_p: float, seed: int, need_grad: bool, cta_group: Optional[int] = None) -> AdapterActs:
+    d_mid, d_in = w1.shape
+    d_out = w2.shape[0]
+    dev = x.device
+    bf = torch.bfloat16
+    h1 = torch.empty(rows_cap, d_mid, dtype=bf, device=dev)
+    a = torch.empty(rows_cap, d_out, dtype=bf, device=dev)
+    g1 = torch.empty(rows_cap, d_mid, dtype=bf, device=dev) if need_grad else None
+    g2 = torch.empty(rows_cap, d_out, dtype=bf, device=dev) if need_grad else None
+    nblk = (d_out + 255) // 256
+    rowsq = torch.empty(rows_cap, nblk, dtype=torch.float32, device=dev)
+    _lib.call("p2t_adapter_fwd", _ptr(x), x_rows, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), d_in, d_mid, d_out,
+              rows_cap, _ptr(n_rows), _ptr(h1), _ptr(g1), _ptr(a), _ptr(g2), _ptr(rowsq), float(dropout_p),
+              int(seed) & 0xFFFFFFFFFFFFFFFF, cta_group or default_cta_group(), _stream())
+    return AdapterActs(x=x, x_rows=x_rows, h1=h1, g1=g1, a=a, g2=g2, rowsq=rowsq, nblk=nblk, rows_cap=rows_cap,
+                       n_rows=n_rows)
+
+
+def adapter_backward(acts: AdapterActs, dz2: torch.Tensor, w1, w2, need_dx: bool = False,
+                     cta_group: Optional[int] = None):
+    """Returns (dw1, db1, dw2, db2, dx_or_None) in bf16, nn.Linear layout."""
+    d_mid, d_in = w1.shape
+    d_out = w2.shape[0]
+    dev = dz2.device
+    bf = torch.bfloat16
+    dz1 = torch.empty(acts.rows_cap, d_mid, dtype=bf, device=dev)
+    dw1 = torch.empty(d_mid, d_in, dtype=bf, device=dev)
+    db1 = torch.empty(d_mid, dtype=bf, device=dev)
+    dw2 = torch.empty(d_out, d_mid, dtype=bf, device=dev)
+    db2 = torch.empty(d_out, dtype=bf, device=dev)
+    dx = torch.empty(acts.rows_cap, d_in, dtype=bf, device=dev) if need_dx else None
+    ws = torch.empty(64, max(d_mid, d_out), dtype=torch.float32, device=dev)
+    _lib.call("p2t_adapter_bwd", _ptr(acts.x), acts.x_rows, _ptr(w1), _ptr(w2), _ptr(acts.h1), _ptr(acts.g1),
+              _ptr(dz2), d_in, d_mid, d_out, acts.rows_cap, _ptr(acts.n_rows), _ptr(dz1), _ptr(dw1), _ptr(db1),
+              _ptr(dw2), _ptr(db2), _ptr(dx), _ptr(ws), cta_group or default_cta_group(), _stream())
+    return dw1, db1, dw2, db2, dx
+
+
+# --------------------------------------------------------------------------------------------------
+# pooling / normalisation
+# --------------------------------------------------------------------------------------------------
+def pool_forward(src: torch.Tensor, plan: RowPlan, D: int, *, row_src: Optional[torch.Tensor],
+                 rowsq: Optional[torch.Tensor] = None, nblk: int = 0, want_inv_norm: bool = False):
+    """(mean | std) statistics fp32 [B, 2D] of the plan's rows of `src` (bf16, row stride src.stride(0))."""
+    dev = src.device
+    partial = torch.empty(plan.max_chunks, D, 2, dtype=torch.float32, device=dev)
+    stats = torch.empty(plan.B, 2 * D, dtype=torch.float32, device=dev)
+    inv_norm = torch.empty(plan.rows_cap, dtype=torch.float32, device=dev) if want_inv_norm else None
+    _lib.call("p2t_pool_fwd", _ptr(src), src.stride(0), _ptr(row_src), _ptr(rowsq), nblk, _ptr(plan.seq_off),
+              _ptr(plan.chunk_off), plan.B, D, CHUNK_ROWS, plan.max_chunks, READOUT_MODES["mix"], _ptr(partial),
+              _ptr(inv_norm), _ptr(stats), 2 * D, _stream())
+    return stats, inv_norm
+
+
+def l2norm_forward(e: torch.Tensor, want_f32: bool = True):
+    B, E = e.shape
+    p_bf = torch.empty(B, E, dtype=torch.bfloat16, device=e.device)
+    p_f32 = torch.empty(B, E, dtype=torch.float32, device=e.device) if want_f32 else None
+    norm = torch.empty(B, dtype=torch.float32, device=e.device)
+    _lib.call("p2t_l2norm_fwd", _ptr(e), B, E, _ptr(p_bf), _ptr(p_f32), _ptr(norm), _stream())
+    return p_bf, p_f32, norm
+
+
+def l2norm_backward(dp: torch.Tensor, p_f32: torch.Tensor, norm: torch.Tensor) -> torch.Tensor:
+    de = torch.empty_like(dp)
+    B, E = dp.shape
+    _lib.call("p2t_l2norm_bwd", _ptr(dp), _ptr(p_f32), _ptr(norm), B, E, _ptr(de), _stream())
+    return de
+
+
+def pool_backward_coef(de: torch.Tensor, stats: torch.Tensor, plan: RowPlan, D: int, mode: str):
+    c1 = torch.empty(plan.B, D, dtype=torch.float32, device=de.device)
+    c2 = torch.empty(plan.B, D, dtype=torch.float32, device=de.device)
+    _lib.call("p2t_pool_bwd_coef", _ptr(de), de.stride(0), _ptr(stats), stats.stride(0), _ptr(plan.seq_off), plan.B, D,
+              READOUT_MODES[mode], _ptr(c1), _ptr(c2), _stream())
+    return c1, c2
+
+
+def adapter_tail_backward(acts: AdapterActs, inv_norm: torch.Tensor, plan: RowPlan, c1, c2) -> torch.Tensor:
+    d_out = acts.a.shape[1]
+    dz2 = torch.empty(acts.rows_cap, d_out, dtype=torch.bfloat16, device=acts.a.device)
+    _lib.call("p2t_adapter_tail_bwd", _ptr(acts.a), _ptr(acts.g2), _ptr(inv_norm), _ptr(plan.seq_off), plan.B,
+              _ptr(c1), _ptr(c2), _ptr(acts.n_rows), acts.rows_cap, d_out, _ptr(dz2), _stream())
+    return dz2
+
+
+# --------------------------------------------------------------------------------------------------
+# InfoNCE
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class InfoNCEResult:
+    loss: torch.Tensor                 # fp32 0-dim
+    dS: Optional[torch.Tensor]         # fp32 [R, C] (gradient of loss w.r.t. scaled logits), None if no grad
+    dS_bf16: Optional[torch.Tensor]
+    row_lse: torch.Tensor
+    argmax_row: torch.Tensor           # int32 [R]
+    argmax_col: Optional[torch.Tensor]  # int32 [C] (only when column statistics were computed)
+    col_max: Optional[torch.Tensor]
+    col_sum: Optional[torch.Tensor]
+
+
+def infonce_forward(p_bf: torch.Tensor, t_bf: torch.Tensor, labels: torch.Tensor, tau: float, *, w_row: float = 1.0,
+                    w_col: float = 0.0, need_grad: bool = True, want_col_argmax: bool = False,
+                    col_stats_hook=None, loss_scale: Optional[float] = None,
+                    cta_group: Optional[int] = None) -> InfoNCEResult:
+    """loss = mean_i [ w_row (lse_j S_ij - S_i,lab) + w_col (lse_col[lab] - S_i,lab) ], S = p t^T / tau.
+
+    `col_stats_hook(col_max, col_sum) -> (col_max, col_sum)` lets the multi-GPU layer merge column
+    statistics across ranks before the gradient pass.  `loss_scale` overrides 1/R.
+    """
+    require_cuda_bf16(p_bf, "p")
+    require_cuda_bf16(t_bf, "t")
+    R, E = p_bf.shape
+    C = t_bf.shape[0]
+    dev = p_bf.device
+    cg = cta_group or default_cta_group()
+    labels32 = labels.to(device=dev, dtype=torch.int32).contiguous()
+    S = torch.empty(R, C, dtype=torch.float32, device=dev)
+    _lib.call("p2t_similarity", _ptr(p_bf), _ptr(t_bf), R, C, E, float(tau), _ptr(S), cg, _stream())
+    col_max = col_sum = argmax_col = marks = None
+    if w_col != 0.0 or want_col_argmax:
+        col_max = torch.empty(C, dtype=torch.float32, device=dev)
+        col_sum = torch.empty(C, dtype=torch.float32, device=dev)
+        argmax_col = torch.empty(C, dtype=torch.int32, device=dev)
+        _lib.call("p2t_infonce_col_stats", _ptr(S), R, C, _ptr(col_max), _ptr(col_sum), _ptr(argmax_col), 0, _stream())
+        if col_stats_hook is not None:
+            col_max, col_sum = col_stats_hook(col_max, col_sum)
+        marks = torch.empty(C, dtype=torch.uint8, device=dev)
+    row_loss = torch.empty(R, dtype=torch.float32, device=dev)
+    row_lse = torch.empty(R, dtype=torch.float32, device=dev)
+    argmax_row = torch.empty(R, dtype=torch.int32, device=dev)
+    big = (R * C * E > (1 << 26)) and C % 8 == 0
+    dS_bf16 = torch.empty(R, C, dtype=torch.bfloat16, device=dev) if (need_grad and big) else None
+    scale = (1.0 / R) if loss_scale is None else float(loss_scale)
+    _lib.call("p2t_infonce_ce", _ptr(S), _ptr(labels32), R, C, float(w_row), float(w_col), scale, _ptr(col_max),
+              _ptr(col_sum), _ptr(marks), _ptr(row_loss), _ptr(row_lse), _ptr(argmax_row), _ptr(dS_bf16),
+              int(need_grad), _stream())
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    _lib.call("p2t_loss_mean", _ptr(row_loss), R, scale, _ptr(loss), 0, _stream())
+    return InfoNCEResult(loss=loss, dS=S if need_grad else None, dS_bf16=dS_bf16, row_lse=row_lse,
+                         argmax_row=argmax_row, argmax_col=argmax_col, col_max=col_max, col_sum=col_sum)
+
+
+def infonce_backward(res: InfoNCEResult, p_bf, t_bf, tau: float, need_dp: bool = True, need_dt: bool = False,
+                     cta_group: Optional[int] = None):
+    R, E = p_bf.shape
+    C = t_bf.shape[0]
+    dev = p_bf.device
+    dp = torch.empty(R, E, dtype=torch.float32, device=dev) if need_dp else None
+    dt = torch.empty(C, E, dtype=torch.float32, device=dev) if need_dt else None
+    _lib.call("p2t_infonce_grad", _ptr(res.dS), _ptr(res.dS_bf16), _ptr(p_bf), _ptr(t_bf), R, C, E, float(tau),
+              _ptr(dp), _ptr(dt), None, cta_group or default_cta_group(), _stream())
+    return dp, dt
+
+
+def dropout_mask(rows: int, cols: int, p: float, seed: int, layer: int, device) -> torch.Tensor:
+    """The keep multipliers (0 or 1/(1-p)) the kernels apply for (seed, layer) — test aid."""
+    out = torch.empty(rows, cols, dtype=torch.float32, device=device)
+    _lib.call("p2t_dropout_mask", rows, cols, float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, layer, _ptr(out), _stream())
+    return out

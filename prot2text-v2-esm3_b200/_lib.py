@@ -1,0 +1,88 @@
+"""ctypes binding of the C-ABI CUDA library (include/p2t_b200.h).
+
+There is no CPU fallback: if the shared library is missing the import of any compute entry fails
+loudly (build it with `python prot2text-v2-esm3_b200/build.py` or `__graft_entry__.build()`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libp2t_b200.so")
+
+_vp, _i, _ll, _f, _ull = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulonglong
+
+# name -> argument ctypes, in header order (include/p2t_b200.h)
+SIGNATURES = {
+    "p2t_gemm_bf16": [_vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp],
+    "p2t_rows_plan": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "p2t_gather_rows": [_vp, _ll, _vp, _vp, _i, _i, _vp, _vp],
+    "p2t_adapter_fwd": [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _ull, _i, _vp],
+    "p2t_adapter_scale_rows": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp],
+    "p2t_pool_fwd": [_vp, _ll, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _ll, _vp],
+    "p2t_readout_last": [_vp, _vp, _i, _i, _i, _vp, _vp],
+    "p2t_l2norm_fwd": [_vp, _i, _i, _vp, _vp, _vp, _vp],
+    "p2t_l2norm_bwd": [_vp, _vp, _vp, _i, _i, _vp, _vp],
+    "p2t_pool_bwd_coef": [_vp, _ll, _vp, _ll, _vp, _i, _i, _i, _vp, _vp, _vp],
+    "p2t_readout_bwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "p2t_adapter_tail_bwd": [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp],
+    "p2t_adapter_tail_bwd_dy": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp],
+    "p2t_adapter_bwd": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+    "p2t_similarity": [_vp, _vp, _i, _i, _i, _f, _vp, _i, _vp],
+    "p2t_infonce_col_stats": [_vp, _i, _i, _vp, _vp, _vp, _i, _vp],
+    "p2t_infonce_ce": [_vp, _vp, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+    "p2t_infonce_grad": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _i, _vp],
+    "p2t_loss_mean": [_vp, _i, _f, _vp, _i, _vp],
+    "p2t_f32_to_bf16": [_vp, _ll, _vp, _vp],
+    "p2t_bf16_to_f32": [_vp, _ll, _vp, _vp],
+    "p2t_colsum": [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp],
+    "p2t_dropout_mask": [_i, _i, _f, _ull, _i, _vp, _vp],
+}
+NON_STATUS = {"p2t_abi_version": (_i, []), "p2t_last_error": (C.c_char_p, []),
+              "p2t_launch_count": (_ull, []), "p2t_reset_launch_count": (None, [])}
+
+_lib = None
+
+
+class P2TError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen the library once; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise P2TError(
+            f"{LIB_PATH} not found: the CUDA extension is not built and there is no CPU fallback. "
+            "Run `python prot2text-v2-esm3_b200/build.py`.")
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = _i
+    for name, (res, argtypes) in NON_STATUS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = res
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args) -> None:
+    """Invoke a status-returning entry point; raise P2TError with the library's message on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.p2t_last_error()
+        raise P2TError(f"{name} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def launch_count() -> int:
+    return int(load().p2t_launch_count())
+
+
+def reset_launch_count() -> None:
+    load().p2t_reset_launch_count()

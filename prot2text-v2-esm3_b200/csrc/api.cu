@@ -1,0 +1,290 @@
+// C ABI (include/p2t_b200.h): argument checking and composition of the kernels.
+#include "../../include/p2t_b200.h"
+
+#include "common.h"
+#include "gemm_sm100.cuh"
+#include "rows.h"
+
+using namespace p2t;
+
+namespace {
+
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+DropoutParams make_dropout(float p, unsigned long long seed, int layer) {
+  DropoutParams d{};
+  d.seed = seed;
+  d.layer = (uint32_t)layer;
+  if (p > 0.f) {
+    long t = lroundf(p * 65536.f);
+    if (t < 1) t = 1;
+    if (t > 65535) t = 65535;
+    d.threshold = (uint32_t)t;
+    d.scale = 1.f / (1.f - p);
+  } else {
+    d.threshold = 0;
+    d.scale = 1.f;
+  }
+  return d;
+}
+
+GemmParams base_params(int m, int n, int k) {
+  GemmParams p{};
+  p.m = m; p.n = n; p.k = k;
+  p.alpha = 1.f;
+  p.rows_cap = m;
+  p.drop = make_dropout(0.f, 0, 0);
+  return p;
+}
+
+__global__ void dropout_mask_kernel(int rows, int cols, DropoutParams d, float* out) {
+  const long long groups = (long long)rows * ((cols + 7) / 8);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < groups; i += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(i / ((cols + 7) / 8)), g = (int)(i % ((cols + 7) / 8));
+    float k[8];
+    dropout_keep8(d, (uint32_t)row, (uint32_t)g, k);
+    for (int j = 0; j < 8; ++j)
+      if (g * 8 + j < cols) out[(long long)row * cols + g * 8 + j] = k[j];
+  }
+}
+
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int p2t_abi_version(void) { return P2T_ABI_VERSION; }
+const char* p2t_last_error(void) { return last_error(); }
+unsigned long long p2t_launch_count(void) { return launches(); }
+void p2t_reset_launch_count(void) { reset_launches(); }
+
+int p2t_gemm_bf16(const void* a, long long lda, int a_mn_major, const void* b, long long ldb, int b_mn_major,
+                  void* d, long long ldd, int d_is_f32, int m, int n, int k, float alpha, const int* dyn_m,
+                  const int* dyn_k, int cta_group, void* stream) {
+  if (!a || !b || !d) return set_error(-1, "p2t_gemm_bf16: null pointer");
+  GemmParams p = base_params(m, n, k);
+  p.dyn_m = dyn_m; p.dyn_k = dyn_k;
+  p.d0 = d; p.ldd0 = ldd; p.alpha = alpha;
+  return launch_gemm(a, lda, a_mn_major != 0, b, ldb, b_mn_major != 0, d_is_f32 ? EPI_STORE_F32 : EPI_STORE_BF16, p,
+                     cta_group, S(stream));
+}
+
+int p2t_rows_plan(const void* mask, int mask_bytes, int B, int L, int chunk_rows, int* counts, int* seq_off,
+                  int* chunk_off, int* n_rows_dev, int* row_src, void* stream) {
+  if (!mask || !counts || !seq_off || !chunk_off || !n_rows_dev) return set_error(-1, "p2t_rows_plan: null pointer");
+  if (mask_bytes != 1 && mask_bytes != 4 && mask_bytes != 8) return set_error(-1, "p2t_rows_plan: mask_bytes must be 1, 4 or 8");
+  if (chunk_rows <= 0) return set_error(-1, "p2t_rows_plan: chunk_rows must be positive");
+  return rows_plan(mask, mask_bytes, B, L, chunk_rows, counts, seq_off, chunk_off, n_rows_dev, row_src, S(stream));
+}
+
+int p2t_gather_rows(const void* src, long long ld_src, const int* row_src, const int* n_rows_dev, int rows_cap,
+                    int D, void* out, void* stream) {
+  if (!src || !row_src || !n_rows_dev || !out) return set_error(-1, "p2t_gather_rows: null pointer");
+  return gather_rows(src, ld_src, row_src, n_rows_dev, rows_cap, D, out, S(stream));
+}
+
+int p2t_adapter_fwd(const void* x, int x_rows, const void* w1, const void* b1, const void* w2, const void* b2, int d_in,
+                    int d_mid, int d_out, int rows_cap, const int* n_rows_dev, void* h1, void* g1, void* a,
+                    void* g2, float* rowsq, float dropout_p, unsigned long long seed, int cta_group, void* stream) {
+  if (!x || !w1 || !w2 || !h1 || !a || !rowsq) return set_error(-1, "p2t_adapter_fwd: null pointer");
+  if (d_in % 8 || d_mid % 8 || d_out % 8) return set_error(-1, "p2t_adapter_fwd: dims must be multiples of 8");
+  if (dropout_p < 0.f || dropout_p >= 1.f) return set_error(-1, "p2t_adapter_fwd: dropout_p must be in [0, 1)");
+  GemmParams p = base_params(rows_cap, d_mid, d_in);
+  p.dyn_m = n_rows_dev;
+  p.d0 = h1; p.ldd0 = d_mid; p.d1 = g1; p.ldd1 = d_mid;
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(b1);
+  p.drop = make_dropout(dropout_p, seed, 1);
+  p.a_extent = x_rows;
+  if (int rc = launch_gemm(x, d_in, false, w1, d_in, false, EPI_FC1, p, cta_group, S(stream))) return rc;
+  GemmParams q = base_params(rows_cap, d_out, d_mid);
+  q.dyn_m = n_rows_dev;
+  q.d0 = a; q.ldd0 = d_out; q.d1 = g2; q.ldd1 = d_out;
+  q.bias = reinterpret_cast<const __nv_bfloat16*>(b2);
+  q.rowsq = rowsq; q.ld_rowsq = (d_out + GEMM_BLOCK_N - 1) / GEMM_BLOCK_N;
+  q.drop = make_dropout(dropout_p, seed, 2);
+  return launch_gemm(h1, d_mid, false, w2, d_mid, false, EPI_FC2, q, cta_group, S(stream));
+}
+
+int p2t_adapter_scale_rows(const void* a, const float* rowsq, int nblk, int n, int d_out, void* y, float* inv_norm,
+                           void* stream) {
+  if (!a || !rowsq || !y) return set_error(-1, "p2t_adapter_scale_rows: null pointer");
+  if (d_out % 8) return set_error(-1, "p2t_adapter_scale_rows: d_out must be a multiple of 8");
+  return scale_rows(a, rowsq, nblk, n, d_out, y, inv_norm, S(stream));
+}
+
+int p2t_pool_fwd(const void* src, long long ld_src, const int* row_src, const float* rowsq, int nblk,
+                 const int* seq_off, const int* chunk_off, int B, int D, int chunk_rows, int max_chunks, int mode,
+                 void* partial_ws, float* inv_norm_out, float* out, long long ld_out, void* stream) {
+  if (!src || !seq_off || !chunk_off || !partial_ws || !out) return set_error(-1, "p2t_pool_fwd: null pointer");
+  if (mode < 1 || mode > 3) return set_error(-1, "p2t_pool_fwd: mode must be MEAN, STD or MIX");
+  if (max_chunks <= 0) return 0;
+  return pool_forward(src, ld_src, row_src, rowsq, nblk, seq_off, chunk_off, B, D, chunk_rows, max_chunks, mode,
+                      reinterpret_cast<float2*>(partial_ws), inv_norm_out, out, ld_out, S(stream));
+}
+
+int p2t_readout_last(const void* x, const int* counts, int B, int S_, int D, float* out, void* stream) {
+  if (!x || !counts || !out) return set_error(-1, "p2t_readout_last: null pointer");
+  return readout_last(x, counts, B, S_, D, out, S(stream));
+}
+
+int p2t_l2norm_fwd(const float* e, int B, int E, void* p_bf16, float* p_f32, float* norm, void* stream) {
+  if (!e) return set_error(-1, "p2t_l2norm_fwd: null pointer");
+  return l2norm_forward(e, B, E, p_bf16, p_f32, norm, S(stream));
+}
+int p2t_l2norm_bwd(const float* dp, const float* p_f32, const float* norm, int B, int E, float* de, void* stream) {
+  if (!dp || !p_f32 || !norm || !de) return set_error(-1, "p2t_l2norm_bwd: null pointer");
+  return l2norm_backward(dp, p_f32, norm, B, E, de, S(stream));
+}
+
+int p2t_pool_bwd_coef(const float* de, long long ld_de, const float* stats, long long ld_stats, const int* seq_off,
+                      int B, int D, int mode, float* c1, float* c2, void* stream) {
+  if (!de || !seq_off || !c1 || !c2) return set_error(-1, "p2t_pool_bwd_coef: null pointer");
+  if (mode != P2T_READOUT_MEAN && !stats) return set_error(-1, "p2t_pool_bwd_coef: stats required for std/mix");
+  return pool_bwd_coef(de, ld_de, stats, ld_stats, seq_off, B, D, mode, c1, c2, S(stream));
+}
+int p2t_readout_bwd(const void* x, const void* mask, int mask_bytes, int B, int S_, int D, const float* c1,
+                    const float* c2, void* dx, void* stream) {
+  if (!x || !mask || !c1 || !c2 || !dx) return set_error(-1, "p2t_readout_bwd: null pointer");
+  if (D % 8) return set_error(-1, "p2t_readout_bwd: D must be a multiple of 8");
+  return readout_backward(x, mask, mask_bytes, B, S_, D, c1, c2, dx, S(stream));
+}
+
+int p2t_adapter_tail_bwd(const void* a, const void* g2, const float* inv_norm, const int* seq_off, int B,
+                         const float* c1, const float* c2, const int* n_rows_dev, int rows_cap, int d_out, void* dz2,
+                         void* stream) {
+  if (!a || !g2 || !inv_norm || !seq_off || !c1 || !c2 || !n_rows_dev || !dz2)
+    return set_error(-1, "p2t_adapter_tail_bwd: null pointer");
+  return adapter_tail_backward(a, g2, inv_norm, seq_off, B, c1, c2, n_rows_dev, rows_cap, d_out, dz2, S(stream));
+}
+int p2t_adapter_tail_bwd_dy(const void* a, const void* g2, const float* inv_norm, const void* dy, int n,
+                            int rows_cap, int d_out, void* dz2, void* stream) {
+  if (!a || !g2 || !inv_norm || !dy || !dz2) return set_error(-1, "p2t_adapter_tail_bwd_dy: null pointer");
+  return adapter_tail_backward_dy(a, g2, inv_norm, dy, n, rows_cap, d_out, dz2, S(stream));
+}
+
+int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, const void* h1, const void* g1, const void* dz2,
+                    int d_in, int d_mid, int d_out, int rows_cap, const int* n_rows_dev, void* dz1, void* dw1,
+                    void* db1, void* dw2, void* db2, void* dx, float* colsum_ws, int cta_group, void* stream) {
+  if (!x || !w2 || !h1 || !g1 || !dz2 || !dz1 || !dw1 || !dw2 || !colsum_ws)
+    return set_error(-1, "p2t_adapter_bwd: null pointer");
+  cudaStream_t st = S(stream);
+  // dz1 = (dz2 W2) * g1      A = dz2 [rows][d_out] (K-major), B[n][k] = W2[k][n] (MN-major, ld d_mid)
+  {
+    GemmParams p = base_params(rows_cap, d_mid, d_out);
+    p.dyn_m = n_rows_dev;
+    p.d0 = dz1; p.ldd0 = d_mid;
+    p.aux = reinterpret_cast<const __nv_bfloat16*>(g1); p.ldaux = d_mid;
+    if (int rc = launch_gemm(dz2, d_out, false, w2, d_mid, true, EPI_MUL_AUX, p, cta_group, st)) return rc;
+  }
+  // dW2 = dz2^T h1           both operands MN-major, K = residue rows
+  {
+    GemmParams p = base_params(d_out, d_mid, rows_cap);
+    p.dyn_k = n_rows_dev;
+    p.d0 = dw2; p.ldd0 = d_mid;
+    if (int rc = launch_gemm(dz2, d_out, true, h1, d_mid, true, EPI_STORE_BF16, p, cta_group, st)) return rc;
+  }
+  // dW1 = dz1^T x
+  {
+    GemmParams p = base_params(d_mid, d_in, rows_cap);
+    p.dyn_k = n_rows_dev;
+    p.d0 = dw1; p.ldd0 = d_in;
+    p.b_extent = x_rows;
+    if (int rc = launch_gemm(dz1, d_mid, true, x, d_in, true, EPI_STORE_BF16, p, cta_group, st)) return rc;
+  }
+  if (db2) if (int rc = colsum(dz2, n_rows_dev, rows_cap, d_out, colsum_ws, 64, db2, nullptr, st)) return rc;
+  if (db1) if (int rc = colsum(dz1, n_rows_dev, rows_cap, d_mid, colsum_ws, 64, db1, nullptr, st)) return rc;
+  if (dx) {
+    if (!w1) return set_error(-1, "p2t_adapter_bwd: w1 required for dx");
+    GemmParams p = base_params(rows_cap, d_in, d_mid);
+    p.dyn_m = n_rows_dev;
+    p.d0 = dx; p.ldd0 = d_in;
+    if (int rc = launch_gemm(dz1, d_mid, false, w1, d_in, true, EPI_STORE_BF16, p, cta_group, st)) return rc;
+  }
+  return 0;
+}
+
+static bool small_problem(int R, int C, int E) { return (long long)R * C * E <= (1LL << 26); }
+
+int p2t_similarity(const void* p, const void* t, int R, int C, int E, float tau, float* Sm, int cta_group,
+                   void* stream) {
+  if (!p || !t || !Sm) return set_error(-1, "p2t_similarity: null pointer");
+  if (tau <= 0.f) return set_error(-1, "p2t_similarity: temperature must be positive");
+  if (small_problem(R, C, E)) return sim_small(p, t, R, C, E, 1.f / tau, Sm, S(stream));
+  GemmParams q = base_params(R, C, E);
+  q.d0 = Sm; q.ldd0 = C; q.alpha = 1.f / tau;
+  return launch_gemm(p, E, false, t, E, false, EPI_STORE_F32, q, cta_group, S(stream));
+}
+
+int p2t_infonce_col_stats(const float* Sm, int R, int C, float* col_max, float* col_sum, int* col_argmax,
+                          int row_index_base, void* stream) {
+  if (!Sm || !col_max || !col_sum) return set_error(-1, "p2t_infonce_col_stats: null pointer");
+  return col_stats(Sm, R, C, col_max, col_sum, col_argmax, row_index_base, S(stream));
+}
+
+int p2t_infonce_ce(float* Sm, const int* labels, int R, int C, float w_row, float w_col, float inv_rn,
+                   const float* col_max, const float* col_sum, unsigned char* col_labelled_ws, float* row_loss,
+                   float* row_lse, int* argmax_row, void* dS_bf16, int write_ds, void* stream) {
+  if (!Sm || !labels || !row_loss) return set_error(-1, "p2t_infonce_ce: null pointer");
+  if (w_col != 0.f) {
+    if (!col_max || !col_sum || !col_labelled_ws) return set_error(-1, "p2t_infonce_ce: column statistics required");
+    if (int rc = mark_labelled(labels, R, C, col_labelled_ws, S(stream))) return rc;
+  }
+  return ce_rows(Sm, labels, R, C, w_row, w_col, inv_rn, col_max, col_sum, col_labelled_ws, row_loss, row_lse,
+                 argmax_row, dS_bf16, write_ds, S(stream));
+}
+
+int p2t_infonce_grad(const float* dS, const void* dS_bf16, const void* p, const void* t, int R, int C, int E,
+                     float tau, float* dp, float* dt, void* bf16_ws, int cta_group, void* stream) {
+  if (!dS || !t) return set_error(-1, "p2t_infonce_grad: null pointer");
+  cudaStream_t st = S(stream);
+  (void)bf16_ws;
+  if (small_problem(R, C, E) || (C % 8) || !dS_bf16) {
+    if (dp) if (int rc = contract_small(dS, C, false, t, R, C, E, 1.f / tau, dp, st)) return rc;
+    if (dt) {
+      if (!p) return set_error(-1, "p2t_infonce_grad: p required for dt");
+      if (int rc = contract_small(dS, C, true, p, C, R, E, 1.f / tau, dt, st)) return rc;
+    }
+    return 0;
+  }
+  if (dp) {  // dp[i][e] = sum_j dS[i][j] t[j][e]: A = dS (K-major), B[n=e][k=j] = t[j][e] (MN-major)
+    GemmParams q = base_params(R, E, C);
+    q.d0 = dp; q.ldd0 = E; q.alpha = 1.f / tau;
+    if (int rc = launch_gemm(dS_bf16, C, false, t, E, true, EPI_STORE_F32, q, cta_group, st)) return rc;
+  }
+  if (dt) {  // dt[j][e] = sum_i dS[i][j] p[i][e]: A[m=j][k=i] (MN-major), B[n=e][k=i] (MN-major)
+    if (!p) return set_error(-1, "p2t_infonce_grad: p required for dt");
+    GemmParams q = base_params(C, E, R);
+    q.d0 = dt; q.ldd0 = E; q.alpha = 1.f / tau;
+    if (int rc = launch_gemm(dS_bf16, C, true, p, E, true, EPI_STORE_F32, q, cta_group, st)) return rc;
+  }
+  return 0;
+}
+
+int p2t_loss_mean(const float* row_loss, int R, float scale, float* loss, int accumulate, void* stream) {
+  if (!row_loss || !loss) return set_error(-1, "p2t_loss_mean: null pointer");
+  return loss_mean(row_loss, R, scale, loss, accumulate, S(stream));
+}
+
+int p2t_f32_to_bf16(const float* in, long long n, void* out, void* stream) {
+  if (!in || !out) return set_error(-1, "p2t_f32_to_bf16: null pointer");
+  return convert_f32_to_bf16(in, n, out, S(stream));
+}
+int p2t_bf16_to_f32(const void* in, long long n, float* out, void* stream) {
+  if (!in || !out) return set_error(-1, "p2t_bf16_to_f32: null pointer");
+  return convert_bf16_to_f32(in, n, out, S(stream));
+}
+int p2t_colsum(const void* x, const int* n_rows_dev, int n_static, int D, float* ws, void* out_bf16, float* out_f32,
+               void* stream) {
+  if (!x || !ws) return set_error(-1, "p2t_colsum: null pointer");
+  return colsum(x, n_rows_dev, n_static, D, ws, 64, out_bf16, out_f32, S(stream));
+}
+int p2t_dropout_mask(int rows, int cols, float dropout_p, unsigned long long seed, int layer, float* out,
+                     void* stream) {
+  if (!out) return set_error(-1, "p2t_dropout_mask: null pointer");
+  DropoutParams d = make_dropout(dropout_p, seed, layer);
+  dropout_mask_kernel<<<256, 256, 0, S(stream)>>>(rows, cols, d, out);
+  return check_launch("dropout_mask_kernel");
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,17 @@
+// Library-internal helpers: error reporting and launch accounting behind the C ABI (include/p2t_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace p2t {
+
+// Records a message retrievable through p2t_last_error(); returns `code` so callers can `return set_error(...)`.
+int set_error(int code, const char* fmt, ...);
+// Every kernel launch made by the library bumps this counter (bench.py reports it as gpu_launches).
+void count_launch();
+// cudaGetLastError() after a <<<>>> launch -> 0 or a recorded error
+int check_launch(const char* what);
+
+int sm_count();
+
+}  // namespace p2t

@@ -1,0 +1,132 @@
+// Host side of the tcgen05 GEMM: TMA tensor-map construction (driver entry point resolved at run
+// time, so the library links without libcuda) and template dispatch.
+#include "common.h"
+#include "gemm_sm100.cuh"
+
+namespace p2t {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !sym) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// bf16 row-major matrix [outer][inner] with leading dimension `ld` elements; box = {64 inner, box_outer}
+static int make_tmap_bf16(CUtensorMap* map, const void* ptr, long long inner, long long outer, long long ld,
+                          int box_outer) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return set_error(-10, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * 2) % 16)
+    return set_error(-11, "GEMM operand must be 16-byte aligned with a leading dimension multiple of 8");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_outer)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(-12, "cuTensorMapEncodeTiled failed (code %d)", (int)r);
+  return 0;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <int CTA_GROUP, bool A_MN, bool B_MN, int EPI>
+static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  using S = GemmSmem<CTA_GROUP>;
+  auto kern = gemm_bf16_tcgen05_kernel<CTA_GROUP, A_MN, B_MN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(smem=%d): %s", S::TOTAL, cudaGetErrorString(e));
+    configured = true;
+  }
+  const int tile_m = GEMM_BLOCK_M * CTA_GROUP;
+  const long long tiles = (long long)((p.m + tile_m - 1) / tile_m) * ((p.n + GEMM_BLOCK_N - 1) / GEMM_BLOCK_N);
+  if (tiles == 0) return 0;
+  int workers = sm_count() / CTA_GROUP;
+  if (tiles < workers) workers = (int)tiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(workers * CTA_GROUP);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = S::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTA_GROUP;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+  if (e != cudaSuccess) return set_error((int)e, "GEMM launch failed: %s", cudaGetErrorString(e));
+  count_launch();
+  return 0;
+}
+
+template <int CTA_GROUP, bool A_MN, bool B_MN>
+static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
+  switch (epi) {
+    case EPI_STORE_BF16: return launch_inst<CTA_GROUP, A_MN, B_MN, EPI_STORE_BF16>(ta, tb, p, s);
+    case EPI_STORE_F32: return launch_inst<CTA_GROUP, A_MN, B_MN, EPI_STORE_F32>(ta, tb, p, s);
+    default: break;
+  }
+  if constexpr (!A_MN && !B_MN) {
+    if (epi == EPI_FC1) return launch_inst<CTA_GROUP, false, false, EPI_FC1>(ta, tb, p, s);
+    if (epi == EPI_FC2) return launch_inst<CTA_GROUP, false, false, EPI_FC2>(ta, tb, p, s);
+  }
+  if constexpr (!A_MN) {
+    if (epi == EPI_MUL_AUX) return launch_inst<CTA_GROUP, false, B_MN, EPI_MUL_AUX>(ta, tb, p, s);
+  }
+  return set_error(-13, "unsupported GEMM epilogue/layout combination (epi=%d)", epi);
+}
+
+// A: logical [M][K]; memory [M][lda] (K-major) or [K][lda] (MN-major).  Same for B with N.
+// `a_rows_cap`/`b_rows_cap`: extent of the operand along its row (M/N resp. K for MN-major) axis that is
+// physically present, used for TMA bounds (zero fill beyond).
+int launch_gemm(const void* a, long long lda, bool a_mn, const void* b, long long ldb, bool b_mn, int epi,
+                GemmParams p, int cta_group, cudaStream_t stream) {
+  if (p.m <= 0 || p.n <= 0 || p.k <= 0) return 0;
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a_mn) rc = make_tmap_bf16(&ta, a, p.k, p.a_extent > 0 ? p.a_extent : p.m, lda, GEMM_BLOCK_M);
+  else rc = make_tmap_bf16(&ta, a, p.m, p.a_extent > 0 ? p.a_extent : p.k, lda, GEMM_BLOCK_K);
+  if (rc) return rc;
+  const int b_rows = GEMM_BLOCK_N / cta_group;
+  if (!b_mn) rc = make_tmap_bf16(&tb, b, p.k, p.b_extent > 0 ? p.b_extent : p.n, ldb, b_rows);
+  else rc = make_tmap_bf16(&tb, b, p.n, p.b_extent > 0 ? p.b_extent : p.k, ldb, GEMM_BLOCK_K);
+  if (rc) return rc;
+  if (p.rows_cap <= 0) p.rows_cap = p.m;
+  if (cta_group == 2) {
+    if (a_mn && b_mn) return launch_epi<2, true, true>(epi, ta, tb, p, stream);
+    if (a_mn) return launch_epi<2, true, false>(epi, ta, tb, p, stream);
+    if (b_mn) return launch_epi<2, false, true>(epi, ta, tb, p, stream);
+    return launch_epi<2, false, false>(epi, ta, tb, p, stream);
+  } else if (cta_group == 1) {
+    if (a_mn && b_mn) return launch_epi<1, true, true>(epi, ta, tb, p, stream);
+    if (a_mn) return launch_epi<1, true, false>(epi, ta, tb, p, stream);
+    if (b_mn) return launch_epi<1, false, true>(epi, ta, tb, p, stream);
+    return launch_epi<1, false, false>(epi, ta, tb, p, stream);
+  }
+  return set_error(-14, "cta_group must be 1 or 2");
+}
+
+}  // namespace p2t

@@ -1,0 +1,296 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a with fused epilogues.
+//
+//   D[M,N] = epilogue( sum_k A[m,k] * B[n,k] )      bf16 operands, fp32 accumulation in TMEM
+//
+// * operands arrive by TMA (128-byte swizzle) into a multi-stage shared-memory ring; either
+//   operand may be K-major (memory [rows][K]) or MN-major (memory [K][rows]) — the latter is what
+//   the weight-gradient GEMMs need (dW = dZ^T H with the long residue axis as K)
+// * one elected thread issues tcgen05.mma (UMMA 128x256x16, or 256x256x16 across a CTA pair with
+//   cta_group::2, each CTA loading half of B)
+// * two 256-column fp32 accumulators live in TMEM so the epilogue of tile i overlaps the MMAs of
+//   tile i+1; 4 epilogue warps read TMEM with tcgen05.ld (one row per thread)
+// * M and/or K may be read from device memory (ragged batches: the residue-row count is produced
+//   on the device by the packing kernel, no host sync)
+//
+// Epilogues (reference sites in models/modeling_esm2llama_instruct.py:60-68 and its autograd):
+//   EPI_STORE_BF16 / EPI_STORE_F32 : D = alpha * acc
+//   EPI_FC1    : z1 = acc + b1;  D0 = h1 = keep*GELU(z1) (bf16);  D1 = g1 = keep*GELU'(z1) (bf16)   (:62-63)
+//   EPI_FC2    : z2 = acc + b2;  D0 = a  = keep*GELU(z2) (bf16);  D1 = g2 = keep*GELU'(z2) (bf16);
+//                rowsq[row][n_blk] = sum_cols a^2 (of the bf16-rounded a)                        (:65-67)
+//   EPI_MUL_AUX: D0 = alpha * acc * aux   (fc2 dgrad chained into GELU'(z1): aux = g1)
+// Storing (value, derivative) pairs instead of the pre-activation keeps every later HBM-bound pass
+// free of erf/exp and of Philox re-generation: the dropout multiplier is folded into both.
+#pragma once
+#include <cuda.h>
+#include "ptx.cuh"
+#include "mathfn.cuh"
+
+namespace p2t {
+
+enum GemmEpilogue : int { EPI_STORE_BF16 = 0, EPI_STORE_F32 = 1, EPI_FC1 = 2, EPI_FC2 = 3, EPI_MUL_AUX = 4 };
+
+constexpr int GEMM_BLOCK_M = 128;  // rows per CTA
+constexpr int GEMM_BLOCK_N = 256;  // UMMA N
+constexpr int GEMM_BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle row
+constexpr int GEMM_UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA + TMEM alloc, warps 2..5 epilogue
+constexpr int GEMM_TMEM_COLS = 512;
+
+struct GemmParams {
+  int m, n, k;          // problem size (upper bounds when dyn_* are set)
+  const int* dyn_m;     // optional device scalar: actual M (<= m)
+  const int* dyn_k;     // optional device scalar: actual K (<= k)
+  int rows_cap;         // rows physically present in D0/D1/aux (>= m rounded as allocated)
+  int a_extent;         // rows physically present in A's storage (0 -> m, or k when MN-major); TMA zero-fills beyond
+  int b_extent;         // same for B (0 -> n, or k when MN-major)
+  void* d0;
+  long long ldd0;
+  void* d1;
+  long long ldd1;
+  const __nv_bfloat16* bias;  // [n]
+  const __nv_bfloat16* aux;   // EPI_MUL_AUX: multiplier [rows][ldaux]
+  long long ldaux;
+  float* rowsq;               // EPI_FC2: [rows][ld_rowsq] partial sum of squares per N block
+  int ld_rowsq;
+  float alpha;
+  DropoutParams drop;         // p == 0 -> disabled
+};
+
+template <int CTA_GROUP>
+struct GemmSmem {
+  static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;                 // 16 KB
+  static constexpr int B_ROWS = GEMM_BLOCK_N / CTA_GROUP;                         // rows of B this CTA loads
+  static constexpr int B_BYTES = B_ROWS * GEMM_BLOCK_K * 2;                       // 32 / 16 KB
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (CTA_GROUP == 1) ? 4 : 6;
+  static constexpr int BAR_BYTES = 1024;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + slack for 1024-B alignment
+};
+
+// ------------------------------------------------------------------------------------------------
+template <int CTA_GROUP, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const GemmParams p) {
+  using S = GemmSmem<CTA_GROUP>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + S::STAGES * S::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
+  uint64_t* full_bar = bars;                     // [STAGES]
+  uint64_t* empty_bar = bars + S::STAGES;        // [STAGES]
+  uint64_t* tmem_full_bar = bars + 2 * S::STAGES;      // [2]
+  uint64_t* tmem_empty_bar = bars + 2 * S::STAGES + 2; // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CTA_GROUP == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = (cta_rank == 0);
+
+  const int M = p.dyn_m ? min(*p.dyn_m, p.m) : p.m;
+  const int K = p.dyn_k ? min(*p.dyn_k, p.k) : p.k;
+  const int N = p.n;
+  const int num_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  const int tile_m = GEMM_BLOCK_M * CTA_GROUP;
+  const int num_m_blk = (M + tile_m - 1) / tile_m;
+  const int num_n_blk = (N + GEMM_BLOCK_N - 1) / GEMM_BLOCK_N;
+  const int num_tiles = num_m_blk * num_n_blk;
+  const int worker = blockIdx.x / CTA_GROUP;
+  const int num_workers = gridDim.x / CTA_GROUP;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < S::STAGES; ++s) {
+        mbar_init(&full_bar[s], CTA_GROUP);  // leader's expect_tx arrive (+ peer producer's arrive)
+        mbar_init(&empty_bar[s], 1);         // one tcgen05.commit
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&tmem_full_bar[a], 1);               // one tcgen05.commit
+        mbar_init(&tmem_empty_bar[a], 4 * CTA_GROUP);  // one arrive per epilogue warp of every CTA in the group
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<CTA_GROUP>(tmem_base_slot, GEMM_TMEM_COLS);
+  }
+  tcgen05_fence_before();
+  if constexpr (CTA_GROUP == 2) cluster_sync_all(); else __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0 && num_kb > 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = worker; t < num_tiles; t += num_workers) {
+        const int m_blk = t / num_n_blk, n_blk = t % num_n_blk;
+        const int m_base = (m_blk * CTA_GROUP + (int)cta_rank) * GEMM_BLOCK_M;
+        const int n_base = n_blk * GEMM_BLOCK_N + (int)cta_rank * S::B_ROWS;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem_a + stage * S::A_BYTES;
+          uint8_t* sb = smem_b + stage * S::B_BYTES;
+          const int k0 = kb * GEMM_BLOCK_K;
+          if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES * CTA_GROUP);
+          auto load = [&](void* dst, const CUtensorMap* tm, int c0, int c1) {
+            if constexpr (CTA_GROUP == 2) tma_load_2d_pair(dst, tm, &full_bar[stage], c0, c1);
+            else tma_load_2d(dst, tm, &full_bar[stage], c0, c1);
+          };
+          if constexpr (!A_MN) {
+            load(sa, &tmap_a, k0, m_base);  // box {64 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < GEMM_BLOCK_M / 64; ++j)  // box {64 m, 64 k}: one 128-B-wide slab each
+              load(sa + j * (GEMM_BLOCK_K * 128), &tmap_a, m_base + j * 64, k0);
+          }
+          if constexpr (!B_MN) {
+            load(sb, &tmap_b, k0, n_base);  // box {64 k, B_ROWS rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < S::B_ROWS / 64; ++j)
+              load(sb + j * (GEMM_BLOCK_K * 128), &tmap_b, n_base + j * 64, k0);
+          }
+          if constexpr (CTA_GROUP == 2) {
+            if (!is_leader) mbar_arrive_cluster(&full_bar[stage], 0);
+          }
+          if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer (leader CTA) ===============================
+    if (is_leader && lane == 0 && num_kb > 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M * CTA_GROUP, GEMM_BLOCK_N, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = worker; t < num_tiles; t += num_workers) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * GEMM_BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem_a + stage * S::A_BYTES);
+          const uint32_t sb = smem_u32(smem_b + stage * S::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
+            // K-major SW128: rows are 128 B, 8-row groups 1024 B apart (SBO); k-step = 32 B inside the row.
+            // MN-major SW128: each 64-element slab is [64 k][128 B]; k-step = 16 rows = 2048 B,
+            //                 8-k groups 1024 B apart (SBO), slabs BLOCK_K*128 B apart (LBO).
+            const uint64_t adesc = A_MN ? make_smem_desc_sw128(sa + k * (GEMM_UMMA_K * 128), GEMM_BLOCK_K * 128, 1024)
+                                        : make_smem_desc_sw128(sa + k * (GEMM_UMMA_K * 2), 16, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc_sw128(sb + k * (GEMM_UMMA_K * 128), GEMM_BLOCK_K * 128, 1024)
+                                        : make_smem_desc_sw128(sb + k * (GEMM_UMMA_K * 2), 16, 1024);
+            umma_bf16<CTA_GROUP>(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          if constexpr (CTA_GROUP == 2) umma_commit_pair(&empty_bar[stage], 0x3);
+          else umma_commit_1cta(&empty_bar[stage]);
+          if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+        }
+        if constexpr (CTA_GROUP == 2) umma_commit_pair(&tmem_full_bar[acc], 0x3);
+        else umma_commit_1cta(&tmem_full_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // =============================== epilogue warps ===============================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    if (num_kb > 0) {
+      for (int t = worker; t < num_tiles; t += num_workers) {
+        const int m_blk = t / num_n_blk, n_blk = t % num_n_blk;
+        const int row = (m_blk * CTA_GROUP + (int)cta_rank) * GEMM_BLOCK_M + quarter * 32 + lane;
+        const int col0 = n_blk * GEMM_BLOCK_N;
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * GEMM_BLOCK_N;
+        const bool row_valid = row < M;
+        const bool row_in_buf = row < p.rows_cap;
+        float sumsq = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < GEMM_BLOCK_N / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          const int col = col0 + c * 32;
+          if (col >= N) break;  // warp-uniform
+          const int ncols = min(32, N - col);
+          if constexpr (EPI == EPI_STORE_BF16) {
+            if (row_valid) {
+              float f[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
+              store_row_bf16(reinterpret_cast<__nv_bfloat16*>(p.d0) + (long long)row * p.ldd0 + col, f, ncols);
+            }
+          } else if constexpr (EPI == EPI_STORE_F32) {
+            if (row_valid) {
+              float f[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
+              store_row_f32(reinterpret_cast<float*>(p.d0) + (long long)row * p.ldd0 + col, f, ncols);
+            }
+          } else if constexpr (EPI == EPI_FC1 || EPI == EPI_FC2) {
+            if (row_in_buf) {
+              float val[32], der[32];
+              load_row_bf16_bcast(p.bias ? p.bias + col : nullptr, val, ncols);  // val <- bias
+              DropoutRow drop(p.drop, row, col);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float z = __uint_as_float(v[i]) + val[i];
+                float gl, gd;
+                gelu_erf_both(z, gl, gd);
+                const float kp = (row_valid && i < ncols) ? drop.keep(i) : 0.f;
+                val[i] = gl * kp;
+                der[i] = gd * kp;
+                if constexpr (EPI == EPI_FC2) {
+                  const float ar = bf16_round(val[i]);
+                  sumsq = fmaf(ar, ar, sumsq);
+                }
+              }
+              store_row_bf16(reinterpret_cast<__nv_bfloat16*>(p.d0) + (long long)row * p.ldd0 + col, val, ncols);
+              if (p.d1 != nullptr)
+                store_row_bf16(reinterpret_cast<__nv_bfloat16*>(p.d1) + (long long)row * p.ldd1 + col, der, ncols);
+            }
+          } else if constexpr (EPI == EPI_MUL_AUX) {
+            if (row_in_buf) {
+              float g[32], o[32];
+              if (row_valid) load_row_bf16(p.aux + (long long)row * p.ldaux + col, g, ncols);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = row_valid ? __uint_as_float(v[i]) * p.alpha * g[i] : 0.f;
+              store_row_bf16(reinterpret_cast<__nv_bfloat16*>(p.d0) + (long long)row * p.ldd0 + col, o, ncols);
+            }
+          }
+        }
+        if constexpr (EPI == EPI_FC2) {
+          if (row_in_buf) p.rowsq[(long long)row * p.ld_rowsq + n_blk] = sumsq;
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CTA_GROUP == 2) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+          else mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  if constexpr (CTA_GROUP == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<CTA_GROUP>(tmem_base, GEMM_TMEM_COLS);
+  }
+}
+
+}  // namespace p2t

@@ -1,0 +1,722 @@
+// HBM-bound kernels over ragged residue rows: mask -> row plan, row gather (packing), masked
+// mean/std ("mix") pooling forward with per-row L2 normalisation folded in, its backward, L2
+// normalisation of the pooled embeddings, and column sums for the bias gradients.
+//
+// Reference sites: scripts/train_contrast.py:198-248 (readout_embeddings), :354/:365 (F.normalize),
+// models/modeling_esm2llama_instruct.py:67 (per-residue F.normalize) and their autograd.
+//
+// Layout: residue rows of all sequences are PACKED back to back ([sum L_b][D], bf16); `seq_off[b]`
+// is the first packed row of sequence b (B+1 entries).  Every streaming kernel moves 16-byte
+// (8 x bf16) vectors per thread with the column index fastest across the warp, accumulates in fp32
+// and reduces in a fixed order (no floating-point atomics), so results are run-to-run identical.
+#include "common.h"
+#include "mathfn.cuh"
+#include "rows.h"
+#include <algorithm>
+
+namespace p2t {
+
+constexpr float kEpsNorm = 1e-12f;  // F.normalize eps
+
+__device__ __forceinline__ bool mask_at(const void* mask, int mask_bytes, long long i) {
+  switch (mask_bytes) {
+    case 1: return reinterpret_cast<const uint8_t*>(mask)[i] != 0;
+    case 4: return reinterpret_cast<const int32_t*>(mask)[i] != 0;
+    default: return reinterpret_cast<const long long*>(mask)[i] != 0;
+  }
+}
+
+template <int THREADS>
+__device__ __forceinline__ float block_sum(float v, float* smem /*[THREADS/32]*/) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) smem[w] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < THREADS / 32; ++i) t += smem[i];
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// row plan: counts -> offsets -> source row list
+// ------------------------------------------------------------------------------------------------
+__global__ void plan_count_kernel(const void* mask, int mask_bytes, int B, int L, int* counts) {
+  const int b = blockIdx.x;
+  int c = 0;
+  for (int r = threadIdx.x; r < L; r += blockDim.x) c += mask_at(mask, mask_bytes, (long long)b * L + r) ? 1 : 0;
+  __shared__ int sh[8];
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+    counts[b] = t;
+  }
+}
+
+// grid B, block 256.  seq_off[B+1], chunk_off[B+1] (chunks of `rc` rows), n_rows[0] = total,
+// row_src[i] = flat source row (b*L + r) of packed row i.
+__global__ void plan_fill_kernel(const void* mask, int mask_bytes, int B, int L, const int* counts, int rc,
+                                 int* seq_off, int* chunk_off, int* n_rows, int* row_src) {
+  const int b = blockIdx.x;
+  __shared__ int sh[2][8];
+  __shared__ int s_base;
+  int off = 0, coff = 0;
+  for (int i = threadIdx.x; i < b; i += blockDim.x) {
+    const int c = counts[i];
+    off += c;
+    coff += (c + rc - 1) / rc;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    off += __shfl_xor_sync(0xffffffffu, off, o);
+    coff += __shfl_xor_sync(0xffffffffu, coff, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = off; sh[1][threadIdx.x >> 5] = coff; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t0 = 0, t1 = 0;
+    for (int i = 0; i < 8; ++i) { t0 += sh[0][i]; t1 += sh[1][i]; }
+    seq_off[b] = t0;
+    chunk_off[b] = t1;
+    if (b == B - 1) {
+      const int c = counts[b];
+      seq_off[B] = t0 + c;
+      chunk_off[B] = t1 + (c + rc - 1) / rc;
+      n_rows[0] = t0 + c;
+    }
+    s_base = t0;
+  }
+  __syncthreads();
+  if (row_src == nullptr) return;
+  // ordered compaction of the valid positions of this sequence
+  int base = s_base;
+  __shared__ int wsum[8];
+  for (int r0 = 0; r0 < L; r0 += blockDim.x) {
+    const int r = r0 + threadIdx.x;
+    const bool v = (r < L) && mask_at(mask, mask_bytes, (long long)b * L + r);
+    const unsigned ball = __ballot_sync(0xffffffffu, v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) wsum[w] = __popc(ball);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+      if (i < w) before += wsum[i];
+      total += wsum[i];
+    }
+    if (v) row_src[base + before + __popc(ball & ((1u << lane) - 1u))] = b * L + r;
+    base += total;
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gather: out[i] = src[row_src[i]] for i < n; zeros for n <= i < min(cap, roundup(n, 256))
+// ------------------------------------------------------------------------------------------------
+__global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, long long ld_src,
+                                   const int* __restrict__ row_src, const int* __restrict__ n_rows, int cap, int D,
+                                   __nv_bfloat16* __restrict__ out) {
+  const int n = min(*n_rows, cap);
+  const int n_pad = min(cap, (n + 255) & ~255);
+  const int vec_per_row = D >> 3;
+  const long long total = (long long)n_pad * vec_per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(i / vec_per_row), v = (int)(i % vec_per_row);
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (row < n) val = __ldg(reinterpret_cast<const uint4*>(src + (long long)row_src[row] * ld_src) + v);
+    reinterpret_cast<uint4*>(out + (long long)row * D)[v] = val;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pooling forward, phase 1: per (row chunk, column) shifted partial moments
+//   value of element = src[row][col] * inv_norm[row]   (inv_norm from rowsq partials; 1 if rowsq == null)
+//   partial[chunk][col] = (mean_c, M2_c) over the chunk's rows
+// grid (max_chunks, ceil(D / (128*8))), block 128
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_segment(const int* __restrict__ off, int n, int x) {
+  // largest b in [0, n) with off[b] <= x   (off non-decreasing, off[0] == 0)
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (off[mid] <= x) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(128)
+pool_partial_kernel(const __nv_bfloat16* __restrict__ src, long long ld_src, const int* __restrict__ row_src,
+                    const float* __restrict__ rowsq, int nblk, const int* __restrict__ seq_off,
+                    const int* __restrict__ chunk_off, int B, int D, int rc, float2* __restrict__ partial,
+                    float* __restrict__ inv_norm_out) {
+  const int chunk = blockIdx.x;
+  if (chunk >= chunk_off[B]) return;
+  const int b = find_segment(chunk_off, B + 1, chunk);
+  const int r0 = seq_off[b] + (chunk - chunk_off[b]) * rc;
+  const int r1 = min(r0 + rc, seq_off[b + 1]);
+  const int nrows = r1 - r0;
+  extern __shared__ float s_inv[];  // [rc]
+  for (int i = threadIdx.x; i < nrows; i += blockDim.x) {
+    float inv = 1.f;
+    if (rowsq != nullptr) {
+      float s = 0.f;
+      for (int j = 0; j < nblk; ++j) s += rowsq[(long long)(r0 + i) * nblk + j];
+      inv = 1.f / fmaxf(sqrtf(s), kEpsNorm);
+      if (inv_norm_out != nullptr && blockIdx.y == 0) inv_norm_out[r0 + i] = inv;
+    }
+    s_inv[i] = inv;
+  }
+  __syncthreads();
+  const int g = blockIdx.y * blockDim.x + threadIdx.x;  // 8-column group
+  if (g * 8 >= D) return;
+  float shift[8], s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+  auto row_ptr = [&](int r) -> const uint4* {
+    const long long sr = row_src ? (long long)row_src[r] : (long long)r;
+    return reinterpret_cast<const uint4*>(src + sr * ld_src) + g;
+  };
+  auto unpack8 = [](const uint4& u, float (&f)[8]) {
+    float2 a = unpack_bf16x2(u.x), b2 = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b2.x; f[3] = b2.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+  };
+  {
+    float f[8];
+    unpack8(__ldg(row_ptr(r0)), f);
+    const float inv = s_inv[0];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) shift[i] = f[i] * inv;
+  }
+  constexpr int U = 8;
+  int r = r0 + 1;  // the first row equals the shift: contributes zero to both sums
+  for (; r + U <= r1; r += U) {
+    uint4 u[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) u[k] = __ldg(row_ptr(r + k));
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      float f[8];
+      unpack8(u[k], f);
+      const float inv = s_inv[r + k - r0];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = fmaf(f[i], inv, -shift[i]);
+        s1[i] += d;
+        s2[i] = fmaf(d, d, s2[i]);
+      }
+    }
+  }
+  for (; r < r1; ++r) {
+    float f[8];
+    unpack8(__ldg(row_ptr(r)), f);
+    const float inv = s_inv[r - r0];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float d = fmaf(f[i], inv, -shift[i]);
+      s1[i] += d;
+      s2[i] = fmaf(d, d, s2[i]);
+    }
+  }
+  const float inv_n = 1.f / (float)nrows;
+  float2* out = partial + (long long)chunk * D + g * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float dm = s1[i] * inv_n;
+    out[i] = make_float2(shift[i] + dm, fmaxf(s2[i] - s1[i] * dm, 0.f));
+  }
+}
+
+// phase 2: combine the chunks of each sequence in order (Chan), emit mean / std / mix.
+// grid (B, ceil(D/256)), block 256.  mode: 1 mean, 2 std, 3 mix.  out [B][ld_out] fp32.
+// stats[b] = (mean[D] | std[D]) is always written when `stats` != null (needed by backward).
+__global__ void pool_finalize_kernel(const float2* __restrict__ partial, const int* __restrict__ seq_off,
+                                     const int* __restrict__ chunk_off, int B, int D, int rc, int mode,
+                                     float* __restrict__ out, long long ld_out) {
+  const int b = blockIdx.x;
+  const int col = blockIdx.y * blockDim.x + threadIdx.x;
+  if (col >= D) return;
+  const int c0 = chunk_off[b], c1 = chunk_off[b + 1];
+  const int n_total = seq_off[b + 1] - seq_off[b];
+  float n = 0.f, mean = 0.f, m2 = 0.f;
+  for (int c = c0; c < c1; ++c) {
+    const float nc = (float)min(rc, n_total - (c - c0) * rc);
+    const float2 pc = partial[(long long)c * D + col];
+    const float tot = n + nc;
+    const float delta = pc.x - mean;
+    mean += delta * (nc / tot);
+    m2 += pc.y + delta * delta * (n * nc / tot);
+    n = tot;
+  }
+  float mu, sd;
+  if (n_total > 0) { mu = mean; sd = sqrtf(m2 / n); }
+  else { mu = __int_as_float(0x7fc00000); sd = mu; }  // 0/0 in the reference
+  float* o = out + (long long)b * ld_out;
+  if (mode == 1) o[col] = mu;
+  else if (mode == 2) o[col] = sd;
+  else { o[col] = mu; o[D + col] = sd; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// L2 normalisation of pooled embeddings: p = e / max(|e|, eps).  grid B, block 256.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+l2norm_fwd_kernel(const float* __restrict__ e, int E, __nv_bfloat16* __restrict__ p_bf16, float* __restrict__ p_f32,
+                  float* __restrict__ norm_out) {
+  const int b = blockIdx.x;
+  __shared__ float sh[8];
+  const float* row = e + (long long)b * E;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < E; i += 256) { const float v = row[i]; s = fmaf(v, v, s); }
+  s = block_sum<256>(s, sh);
+  const float nrm = sqrtf(s);
+  const float inv = 1.f / fmaxf(nrm, kEpsNorm);
+  if (threadIdx.x == 0 && norm_out) norm_out[b] = nrm;
+  for (int i = threadIdx.x; i < E; i += 256) {
+    const float v = row[i] * inv;
+    if (p_f32) p_f32[(long long)b * E + i] = v;
+    if (p_bf16) p_bf16[(long long)b * E + i] = __float2bfloat16_rn(v);
+  }
+}
+
+// de = (dp - p (p.dp)) / |e|   (dp/eps where the clamp is active).  grid B, block 256.
+__global__ void __launch_bounds__(256)
+l2norm_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ p, const float* __restrict__ norm, int E,
+                  float* __restrict__ de) {
+  const int b = blockIdx.x;
+  __shared__ float sh[8];
+  const float* dpr = dp + (long long)b * E;
+  const float* pr = p + (long long)b * E;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < E; i += 256) s = fmaf(dpr[i], pr[i], s);
+  s = block_sum<256>(s, sh);
+  const float nrm = norm[b];
+  const bool clamped = nrm < kEpsNorm;
+  const float inv = 1.f / fmaxf(nrm, kEpsNorm);
+  for (int i = threadIdx.x; i < E; i += 256)
+    de[(long long)b * E + i] = clamped ? dpr[i] * inv : (dpr[i] - pr[i] * s) * inv;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pooling backward, phase 1: per-sequence coefficient vectors so that  dy_r = c1 + c2 * y_r
+//   mean: c1 = dmu/n                   std: c2 = dsd/(n sd), c1 = -c2*mu         mix: both
+// grid (B, ceil(D/256)), block 256.  de [B][ld_de] fp32 holds (dmu | dsd) per mode; stats (mu | sd).
+// ------------------------------------------------------------------------------------------------
+__global__ void pool_bwd_coef_kernel(const float* __restrict__ de, long long ld_de, const float* __restrict__ stats,
+                                     long long ld_stats, const int* __restrict__ seq_off, int D, int mode,
+                                     float* __restrict__ c1, float* __restrict__ c2) {
+  const int b = blockIdx.x;
+  const int col = blockIdx.y * blockDim.x + threadIdx.x;
+  if (col >= D) return;
+  const float n = (float)(seq_off[b + 1] - seq_off[b]);
+  const float* d = de + (long long)b * ld_de;
+  const float* st = stats + (long long)b * ld_stats;
+  float dmu = 0.f, dsd = 0.f;
+  if (mode == 1) dmu = d[col];
+  else if (mode == 2) dsd = d[col];
+  else { dmu = d[col]; dsd = d[D + col]; }
+  float k1 = dmu / n, k2 = 0.f;
+  if (mode != 1) {
+    const float mu = st[col], sd = st[D + col];
+    k2 = dsd / (n * sd);  // inf/NaN when sd == 0, as autograd on the reference
+    k1 = k1 - k2 * mu;
+  }
+  c1[(long long)b * D + col] = k1;
+  c2[(long long)b * D + col] = k2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// adapter tail backward over packed rows (one warp per row):
+//   y = a * inv;  dy = c1[b] + c2[b] * y;  da = (dy - y (y.dy)) * inv;  dz2 = da * g
+// a, g bf16 [rows][D] (g = keep*GELU'(z2), a = keep*GELU(z2)); rows in [n, roundup(n,256)) are zeroed.
+// ------------------------------------------------------------------------------------------------
+template <int NV>  // 16-byte vectors per lane: D <= NV*256
+__global__ void __launch_bounds__(256)
+adapter_tail_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ g,
+                        const float* __restrict__ inv_norm, const int* __restrict__ seq_off, int B,
+                        const float* __restrict__ c1, const float* __restrict__ c2, const int* __restrict__ n_rows,
+                        int cap, int D, __nv_bfloat16* __restrict__ dz2) {
+  const int n = min(*n_rows, cap);
+  const int n_pad = min(cap, (n + 255) & ~255);
+  const int lane = threadIdx.x & 31;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  const int nvec = D >> 3;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_pad; row += warps_total) {
+    uint4* out = reinterpret_cast<uint4*>(dz2 + (long long)row * D);
+    if (row >= n) {
+      for (int v = lane; v < nvec; v += 32) out[v] = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    const int b = find_segment(seq_off, B + 1, row);
+    const float inv = inv_norm[row];
+    const uint4* ar = reinterpret_cast<const uint4*>(a + (long long)row * D);
+    const uint4* gr = reinterpret_cast<const uint4*>(g + (long long)row * D);
+    const float4* c1r = reinterpret_cast<const float4*>(c1 + (long long)b * D);
+    const float4* c2r = reinterpret_cast<const float4*>(c2 + (long long)b * D);
+    uint4 av[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int v = lane + 32 * k;
+      av[k] = (v < nvec) ? __ldg(ar + v) : make_uint4(0, 0, 0, 0);
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int v = lane + 32 * k;
+      if (v < nvec) {
+        const float4 p0 = __ldg(c1r + 2 * v), p1 = __ldg(c1r + 2 * v + 1);
+        const float4 q0 = __ldg(c2r + 2 * v), q1 = __ldg(c2r + 2 * v + 1);
+        const float k1[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+        const float k2[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        const uint32_t w[4] = {av[k].x, av[k].y, av[k].z, av[k].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = unpack_bf16x2(w[i]);
+          const float y0 = f.x * inv, y1 = f.y * inv;
+          dot = fmaf(y0, fmaf(k2[2 * i], y0, k1[2 * i]), dot);
+          dot = fmaf(y1, fmaf(k2[2 * i + 1], y1, k1[2 * i + 1]), dot);
+        }
+      }
+    }
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int v = lane + 32 * k;
+      if (v < nvec) {
+        const float4 p0 = __ldg(c1r + 2 * v), p1 = __ldg(c1r + 2 * v + 1);
+        const float4 q0 = __ldg(c2r + 2 * v), q1 = __ldg(c2r + 2 * v + 1);
+        const float k1[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+        const float k2[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        const uint4 gu = __ldg(gr + v);
+        const uint32_t w[4] = {av[k].x, av[k].y, av[k].z, av[k].w};
+        const uint32_t gw[4] = {gu.x, gu.y, gu.z, gu.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = unpack_bf16x2(w[i]);
+          const float2 gg = unpack_bf16x2(gw[i]);
+          const float y0 = f.x * inv, y1 = f.y * inv;
+          const float dy0 = fmaf(k2[2 * i], y0, k1[2 * i]), dy1 = fmaf(k2[2 * i + 1], y1, k1[2 * i + 1]);
+          const float d0 = (dy0 - y0 * dot) * inv * gg.x;
+          const float d1 = (dy1 - y1 * dot) * inv * gg.y;
+          o[i] = pack_bf16x2(d0, d1);
+        }
+        out[v] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
+// same, but the upstream gradient dy is given per row (module API: y = adapter(x) was returned)
+template <int NV>
+__global__ void __launch_bounds__(256)
+adapter_tail_bwd_dy_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ g,
+                           const float* __restrict__ inv_norm, const __nv_bfloat16* __restrict__ dy, int n, int cap,
+                           int D, __nv_bfloat16* __restrict__ dz2) {
+  const int n_pad = min(cap, (n + 255) & ~255);
+  const int lane = threadIdx.x & 31;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  const int nvec = D >> 3;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_pad; row += warps_total) {
+    uint4* out = reinterpret_cast<uint4*>(dz2 + (long long)row * D);
+    if (row >= n) {
+      for (int v = lane; v < nvec; v += 32) out[v] = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    const float inv = inv_norm[row];
+    const uint4* ar = reinterpret_cast<const uint4*>(a + (long long)row * D);
+    const uint4* gr = reinterpret_cast<const uint4*>(g + (long long)row * D);
+    const uint4* dr = reinterpret_cast<const uint4*>(dy + (long long)row * D);
+    uint4 av[NV], dv[NV];
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int v = lane + 32 * k;
+      av[k] = (v < nvec) ? __ldg(ar + v) : make_uint4(0, 0, 0, 0);
+      dv[k] = (v < nvec) ? __ldg(dr + v) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const uint32_t w[4] = {av[k].x, av[k].y, av[k].z, av[k].w};
+      const uint32_t dw[4] = {dv[k].x, dv[k].y, dv[k].z, dv[k].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16x2(w[i]);
+        const float2 d = unpack_bf16x2(dw[i]);
+        dot = fmaf(f.x * inv, d.x, dot);
+        dot = fmaf(f.y * inv, d.y, dot);
+      }
+    }
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int v = lane + 32 * k;
+      if (v < nvec) {
+        const uint4 gu = __ldg(gr + v);
+        const uint32_t w[4] = {av[k].x, av[k].y, av[k].z, av[k].w};
+        const uint32_t dw[4] = {dv[k].x, dv[k].y, dv[k].z, dv[k].w};
+        const uint32_t gw[4] = {gu.x, gu.y, gu.z, gu.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = unpack_bf16x2(w[i]);
+          const float2 d = unpack_bf16x2(dw[i]);
+          const float2 gg = unpack_bf16x2(gw[i]);
+          o[i] = pack_bf16x2((d.x - f.x * inv * dot) * inv * gg.x, (d.y - f.y * inv * dot) * inv * gg.y);
+        }
+        out[v] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
+// y[row] = a[row] * inv_norm[row]  (module API forward tail).  inv from rowsq partials.
+__global__ void __launch_bounds__(256)
+scale_rows_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ rowsq, int nblk, int n, int D,
+                  __nv_bfloat16* __restrict__ y, float* __restrict__ inv_norm_out) {
+  const int lane = threadIdx.x & 31;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  const int nvec = D >> 3;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps_total) {
+    float s = 0.f;
+    for (int j = lane; j < nblk; j += 32) s += rowsq[(long long)row * nblk + j];
+    s = warp_sum(s);
+    const float inv = 1.f / fmaxf(sqrtf(s), kEpsNorm);
+    if (lane == 0 && inv_norm_out) inv_norm_out[row] = inv;
+    const uint4* ar = reinterpret_cast<const uint4*>(a + (long long)row * D);
+    uint4* yr = reinterpret_cast<uint4*>(y + (long long)row * D);
+    for (int v = lane; v < nvec; v += 32) {
+      const uint4 u = __ldg(ar + v);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16x2(w[i]);
+        o[i] = pack_bf16x2(f.x * inv, f.y * inv);
+      }
+      yr[v] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic readout backward on a padded (B, S, D) tensor: dx[b,r] = m[b,r] (c1[b] + c2[b]*x[b,r])
+// grid-stride over 16-byte vectors; output bf16, same layout as x.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+readout_bwd_kernel(const __nv_bfloat16* __restrict__ x, const void* __restrict__ mask, int mask_bytes, int B, int S,
+                   int D, const float* __restrict__ c1, const float* __restrict__ c2, __nv_bfloat16* __restrict__ dx) {
+  const int nvec = D >> 3;
+  const long long total = (long long)B * S * nvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / nvec;
+    const int v = (int)(i % nvec);
+    const int b = (int)(row / S);
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (mask_at(mask, mask_bytes, row)) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + row * D) + v);
+      const float4 p0 = __ldg(reinterpret_cast<const float4*>(c1 + (long long)b * D) + 2 * v);
+      const float4 p1 = __ldg(reinterpret_cast<const float4*>(c1 + (long long)b * D) + 2 * v + 1);
+      const float4 q0 = __ldg(reinterpret_cast<const float4*>(c2 + (long long)b * D) + 2 * v);
+      const float4 q1 = __ldg(reinterpret_cast<const float4*>(c2 + (long long)b * D) + 2 * v + 1);
+      const float k1[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+      const float k2[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      uint32_t r[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(w[j]);
+        r[j] = pack_bf16x2(fmaf(k2[2 * j], f.x, k1[2 * j]), fmaf(k2[2 * j + 1], f.y, k1[2 * j + 1]));
+      }
+      o = make_uint4(r[0], r[1], r[2], r[3]);
+    }
+    reinterpret_cast<uint4*>(dx + row * D)[v] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sums of a packed bf16 matrix (bias gradients): two deterministic phases.
+// phase 1 grid (ceil(D/1024), nsplit), block 128: partial[split][col]; phase 2 sums the splits.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ n_rows, int n_static, int D,
+                      float* __restrict__ partial) {
+  const int n = n_rows ? min(*n_rows, n_static) : n_static;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g * 8 >= D) return;
+  const int nsplit = gridDim.y;
+  const int per = (n + nsplit - 1) / nsplit;
+  const int r0 = blockIdx.y * per, r1 = min(n, r0 + per);
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  constexpr int U = 8;
+  int r = r0;
+  for (; r + U <= r1; r += U) {
+    uint4 u[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(x + (long long)(r + k) * D) + g);
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16x2(w[i]);
+        s[2 * i] += f.x;
+        s[2 * i + 1] += f.y;
+      }
+    }
+  }
+  for (; r < r1; ++r) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (long long)r * D) + g);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = unpack_bf16x2(w[i]);
+      s[2 * i] += f.x;
+      s[2 * i + 1] += f.y;
+    }
+  }
+  float* o = partial + (long long)blockIdx.y * D + g * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = s[i];
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int nsplit, int D, __nv_bfloat16* out_bf16,
+                                    float* out_f32) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= D) return;
+  float s = 0.f;
+  for (int k = 0; k < nsplit; ++k) s += partial[(long long)k * D + col];
+  if (out_bf16) out_bf16[col] = __float2bfloat16_rn(s);
+  if (out_f32) out_f32[col] = s;
+}
+
+// 'last' readout: out[b] = x[b, sum(mask[b]) - 1]   (scripts/train_contrast.py:207-215)
+__global__ void readout_last_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ counts, int S, int D,
+                                    float* __restrict__ out) {
+  const int b = blockIdx.x;
+  int idx = counts[b] - 1;
+  if (idx < 0) idx += S;  // python negative indexing, as the reference's advanced indexing does
+  const __nv_bfloat16* row = x + ((long long)b * S + idx) * D;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) out[(long long)b * D + i] = __bfloat162float(row[i]);
+}
+
+// ================================================================================================
+// host launchers
+// ================================================================================================
+int rows_plan(const void* mask, int mask_bytes, int B, int L, int rc, int* counts, int* seq_off, int* chunk_off,
+              int* n_rows, int* row_src, cudaStream_t st) {
+  if (B <= 0 || L <= 0) return set_error(-1, "rows_plan: empty batch");
+  plan_count_kernel<<<B, 256, 0, st>>>(mask, mask_bytes, B, L, counts);
+  if (int rc_ = check_launch("plan_count_kernel")) return rc_;
+  plan_fill_kernel<<<B, 256, 0, st>>>(mask, mask_bytes, B, L, counts, rc, seq_off, chunk_off, n_rows, row_src);
+  return check_launch("plan_fill_kernel");
+}
+
+int gather_rows(const void* src, long long ld_src, const int* row_src, const int* n_rows, int cap, int D, void* out,
+                cudaStream_t st) {
+  if (D % 8) return set_error(-1, "gather_rows: D must be a multiple of 8");
+  const long long total = (long long)cap * (D / 8);
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
+  gather_rows_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), ld_src, row_src, n_rows, cap, D,
+                                             reinterpret_cast<__nv_bfloat16*>(out));
+  return check_launch("gather_rows_kernel");
+}
+
+int pool_forward(const void* src, long long ld_src, const int* row_src, const float* rowsq, int nblk,
+                 const int* seq_off, const int* chunk_off, int B, int D, int rc, int max_chunks, int mode,
+                 float2* partial, float* inv_norm_out, float* out, long long ld_out, cudaStream_t st) {
+  if (D % 8) return set_error(-1, "pool_forward: D must be a multiple of 8");
+  dim3 grid(max_chunks, (D / 8 + 127) / 128);
+  pool_partial_kernel<<<grid, 128, rc * sizeof(float), st>>>(reinterpret_cast<const __nv_bfloat16*>(src), ld_src, row_src,
+                                                             rowsq, nblk, seq_off, chunk_off, B, D, rc, partial,
+                                                             inv_norm_out);
+  if (int r = check_launch("pool_partial_kernel")) return r;
+  dim3 g2(B, (D + 255) / 256);
+  pool_finalize_kernel<<<g2, 256, 0, st>>>(partial, seq_off, chunk_off, B, D, rc, mode, out, ld_out);
+  return check_launch("pool_finalize_kernel");
+}
+
+int l2norm_forward(const float* e, int B, int E, void* p_bf16, float* p_f32, float* norm, cudaStream_t st) {
+  l2norm_fwd_kernel<<<B, 256, 0, st>>>(e, E, reinterpret_cast<__nv_bfloat16*>(p_bf16), p_f32, norm);
+  return check_launch("l2norm_fwd_kernel");
+}
+int l2norm_backward(const float* dp, const float* p, const float* norm, int B, int E, float* de, cudaStream_t st) {
+  l2norm_bwd_kernel<<<B, 256, 0, st>>>(dp, p, norm, E, de);
+  return check_launch("l2norm_bwd_kernel");
+}
+int pool_bwd_coef(const float* de, long long ld_de, const float* stats, long long ld_stats, const int* seq_off, int B,
+                  int D, int mode, float* c1, float* c2, cudaStream_t st) {
+  dim3 g(B, (D + 255) / 256);
+  pool_bwd_coef_kernel<<<g, 256, 0, st>>>(de, ld_de, stats, ld_stats, seq_off, D, mode, c1, c2);
+  return check_launch("pool_bwd_coef_kernel");
+}
+
+template <int NV>
+static int tail_bwd_launch(const void* a, const void* g, const float* inv_norm, const int* seq_off, int B,
+                           const float* c1, const float* c2, const int* n_rows, int cap, int D, void* dz2,
+                           cudaStream_t st) {
+  const int blocks = min((cap + 7) / 8, sm_count() * 8);
+  adapter_tail_bwd_kernel<NV><<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(a),
+                                                      reinterpret_cast<const __nv_bfloat16*>(g), inv_norm, seq_off, B, c1,
+                                                      c2, n_rows, cap, D, reinterpret_cast<__nv_bfloat16*>(dz2));
+  return check_launch("adapter_tail_bwd_kernel");
+}
+int adapter_tail_backward(const void* a, const void* g, const float* inv_norm, const int* seq_off, int B,
+                          const float* c1, const float* c2, const int* n_rows, int cap, int D, void* dz2,
+                          cudaStream_t st) {
+  if (D % 8 || D > 8192) return set_error(-1, "adapter_tail_backward: D must be a multiple of 8 and <= 8192");
+  if (D <= 2048) return tail_bwd_launch<8>(a, g, inv_norm, seq_off, B, c1, c2, n_rows, cap, D, dz2, st);
+  if (D <= 4096) return tail_bwd_launch<16>(a, g, inv_norm, seq_off, B, c1, c2, n_rows, cap, D, dz2, st);
+  return tail_bwd_launch<32>(a, g, inv_norm, seq_off, B, c1, c2, n_rows, cap, D, dz2, st);
+}
+
+template <int NV>
+static int tail_bwd_dy_launch(const void* a, const void* g, const float* inv_norm, const void* dy, int n, int cap, int D,
+                              void* dz2, cudaStream_t st) {
+  const int blocks = min((cap + 7) / 8, sm_count() * 8);
+  adapter_tail_bwd_dy_kernel<NV><<<blocks, 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(g), inv_norm,
+      reinterpret_cast<const __nv_bfloat16*>(dy), n, cap, D, reinterpret_cast<__nv_bfloat16*>(dz2));
+  return check_launch("adapter_tail_bwd_dy_kernel");
+}
+int adapter_tail_backward_dy(const void* a, const void* g, const float* inv_norm, const void* dy, int n, int cap, int D,
+                             void* dz2, cudaStream_t st) {
+  if (D % 8 || D > 4096) return set_error(-1, "adapter_tail_backward_dy: D must be a multiple of 8 and <= 4096");
+  if (D <= 2048) return tail_bwd_dy_launch<8>(a, g, inv_norm, dy, n, cap, D, dz2, st);
+  return tail_bwd_dy_launch<16>(a, g, inv_norm, dy, n, cap, D, dz2, st);
+}
+
+int scale_rows(const void* a, const float* rowsq, int nblk, int n, int D, void* y, float* inv_norm_out, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const int blocks = min((n + 7) / 8, sm_count() * 8);
+  scale_rows_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(a), rowsq, nblk, n, D,
+                                            reinterpret_cast<__nv_bfloat16*>(y), inv_norm_out);
+  return check_launch("scale_rows_kernel");
+}
+
+int readout_backward(const void* x, const void* mask, int mask_bytes, int B, int S, int D, const float* c1,
+                     const float* c2, void* dx, cudaStream_t st) {
+  const long long total = (long long)B * S * (D / 8);
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
+  readout_bwd_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), mask, mask_bytes, B, S, D, c1, c2,
+                                             reinterpret_cast<__nv_bfloat16*>(dx));
+  return check_launch("readout_bwd_kernel");
+}
+
+int colsum(const void* x, const int* n_rows, int n_static, int D, float* partial, int nsplit, void* out_bf16,
+           float* out_f32, cudaStream_t st) {
+  if (D % 8) return set_error(-1, "colsum: D must be a multiple of 8");
+  dim3 g((D / 8 + 127) / 128, nsplit);
+  colsum_partial_kernel<<<g, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), n_rows, n_static, D, partial);
+  if (int r = check_launch("colsum_partial_kernel")) return r;
+  colsum_final_kernel<<<(D + 255) / 256, 256, 0, st>>>(partial, nsplit, D, reinterpret_cast<__nv_bfloat16*>(out_bf16),
+                                                       out_f32);
+  return check_launch("colsum_final_kernel");
+}
+
+int readout_last(const void* x, const int* counts, int B, int S, int D, float* out, cudaStream_t st) {
+  readout_last_kernel<<<B, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), counts, S, D, out);
+  return check_launch("readout_last_kernel");
+}
+
+}  // namespace p2t

@@ -1,0 +1,128 @@
+"""The fused Stage-1 contrastive step: residue states + text hidden states -> loss, adapter grads.
+
+Mirrors `teacher_forcing_forward_pass` of the reference (scripts/train_contrast.py:313-379) from
+the point where the two frozen trunks have produced their outputs:
+
+    text branch   : hidden_states[16] (:304) -> readout 'mix' (:306-310) -> F.normalize (:354), no grad
+    protein branch: residue states -> ModalityAdapter (models/esmc_qwen_arc.py:182) -> readout 'mix'
+                    (:277-281) -> F.normalize (:365)
+    loss          : SegmentedBatchInfoNCELoss per segment, averaged (:356-379)
+
+Differences in HOW (not what): the padded (B, L, D_in) batch is packed to its valid rows on the
+device (no host sync), both adapter GEMMs run once over all rows (the segment loop only bounded
+memory in the reference; with equal segments the average of segment means IS the batch mean), and
+the handoffs between stages stay in fp32.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _core
+from .adapter import ModalityAdapter, _draw_seed
+
+
+@dataclass
+class StepAux:
+    """Side outputs of the last contrastive step (no gradient)."""
+    protein_embeddings: Optional[torch.Tensor] = None   # (B, 2*D_out) bf16, unit norm
+    text_embeddings: Optional[torch.Tensor] = None      # (B_global, 2*H) bf16, unit norm
+    argmax_row: Optional[torch.Tensor] = None           # int32 (B,)  protein -> text retrieval
+    argmax_col: Optional[torch.Tensor] = None           # int32 (B_global,) text -> protein retrieval (local rows)
+    n_rows: Optional[torch.Tensor] = None               # int32 (1,) valid residue rows
+
+
+@torch.no_grad()
+def text_embeddings(text_hidden: torch.Tensor, text_mask: torch.Tensor) -> torch.Tensor:
+    """readout 'mix' + L2 normalise of the frozen LLM's hidden states (reference :284-310, :354)."""
+    _core.require_cuda_bf16(text_hidden, "text_hidden")
+    B, T, H = text_hidden.shape
+    th = text_hidden.contiguous()
+    plan = _core.plan_rows(text_mask)
+    stats, _ = _core.pool_forward(th.view(B * T, H), plan, H, row_src=plan.row_src)
+    t_bf, _, _ = _core.l2norm_forward(stats, want_f32=False)
+    return t_bf
+
+
+class _ContrastiveStepFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, prot_mask, w1, b1, w2, b2, t_bf, labels, cfg: dict, aux: StepAux):
+        for t, name in ((x, "residue states"), (w1, "fc1.weight"), (b1, "fc1.bias"), (w2, "fc2.weight"), (b2, "fc2.bias")):
+            _core.require_cuda_bf16(t, name)
+        B, L, d_in = x.shape
+        d_out = w2.shape[0]
+        need_grad = any(ctx.needs_input_grad[2:6])
+        w1c, b1c, w2c, b2c = w1.contiguous(), b1.contiguous(), w2.contiguous(), b2.contiguous()
+        plan = _core.plan_rows(prot_mask)
+        xp = _core.gather_rows(x.contiguous().view(B * L, d_in), plan)
+        acts = _core.adapter_forward(xp, plan.rows_cap, plan.rows_cap, plan.n_rows, w1c, b1c, w2c, b2c,
+                                     cfg["dropout_p"], cfg["seed"], need_grad)
+        stats, inv_norm = _core.pool_forward(acts.a, plan, d_out, row_src=None, rowsq=acts.rowsq, nblk=acts.nblk,
+                                             want_inv_norm=True)
+        p_bf, p_f32, pnorm = _core.l2norm_forward(stats)
+        used = cfg["rows_used"]
+        hook = cfg.get("col_stats_hook")
+        res = _core.infonce_forward(p_bf[:used], t_bf, labels[:used], cfg["tau"], w_row=cfg["w_row"], w_col=cfg["w_col"],
+                                    need_grad=need_grad, want_col_argmax=True, col_stats_hook=hook,
+                                    loss_scale=cfg.get("loss_scale"))
+        aux.protein_embeddings, aux.text_embeddings = p_bf, t_bf
+        aux.argmax_row, aux.argmax_col, aux.n_rows = res.argmax_row, res.argmax_col, plan.n_rows
+        if need_grad:
+            ctx.state = (plan, acts, stats, inv_norm, p_bf, p_f32, pnorm, res, t_bf, w1c, w2c, cfg)
+        return res.loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        plan, acts, stats, inv_norm, p_bf, p_f32, pnorm, res, t_bf, w1c, w2c, cfg = ctx.state
+        ctx.state = None
+        used = cfg["rows_used"]
+        d_out = w2c.shape[0]
+        dp_used, _ = _core.infonce_backward(res, p_bf[:used], t_bf, cfg["tau"], need_dp=True, need_dt=False)
+        if used == p_bf.shape[0]:
+            dp = dp_used
+        else:  # rows dropped by the segment split get no gradient (reference :337, :357-359)
+            dp = torch.zeros_like(p_f32)
+            dp[:used] = dp_used
+        dp.mul_(dloss.to(torch.float32))
+        de = _core.l2norm_backward(dp, p_f32, pnorm)
+        c1, c2 = _core.pool_backward_coef(de, stats, plan, d_out, "mix")
+        dz2 = _core.adapter_tail_backward(acts, inv_norm, plan, c1, c2)
+        dw1, db1, dw2, db2, _ = _core.adapter_backward(acts, dz2, w1c, w2c)
+        return None, None, dw1, db1, dw2, db2, None, None, None, None
+
+
+def contrastive_step(residue_states: torch.Tensor, protein_mask: torch.Tensor, adapter: ModalityAdapter,
+                     text_hidden: Optional[torch.Tensor] = None, text_mask: Optional[torch.Tensor] = None, *,
+                     text_embeds: Optional[torch.Tensor] = None, temperature: float = 0.05,
+                     contrastive_num_segments: int = 1, symmetric: bool = False,
+                     labels: Optional[torch.Tensor] = None, aux: Optional[StepAux] = None,
+                     col_stats_hook=None, loss_scale: Optional[float] = None) -> torch.Tensor:
+    """One Stage-1 step from trunk outputs to the (differentiable) fp32 loss.
+
+    residue_states (B, L, D_in) bf16 and protein_mask (B, L) come from the frozen protein encoder
+    (models/esmc_qwen_arc.py:84-86); text_hidden (B_t, T, H) bf16 is hidden_states[16] of the frozen
+    LLM with its attention mask (scripts/train_contrast.py:304), or pass already normalised
+    `text_embeds` (B_t, 2H) — e.g. the all-gathered global negatives.  `labels[i]` is the text row
+    paired with protein i (default: i).  `contrastive_num_segments` reproduces the reference's
+    segment averaging including its dropping of the remainder rows; `symmetric` adds the
+    text->protein term.
+    """
+    if text_embeds is None:
+        if text_hidden is None or text_mask is None:
+            raise ValueError("pass either text_hidden + text_mask or text_embeds")
+        text_embeds = text_embeddings(text_hidden, text_mask)
+    B = residue_states.shape[0]
+    seg = B // contrastive_num_segments
+    if seg * contrastive_num_segments != B:
+        print("WARNING: Given batch size is not divisible by the number of segments for contrastive learning.")
+    if labels is None:
+        labels = torch.arange(B, device=residue_states.device, dtype=torch.int32)
+    p = adapter.dropout_p()
+    cfg = dict(tau=float(temperature), w_row=0.5 if symmetric else 1.0, w_col=0.5 if symmetric else 0.0,
+               dropout_p=p, seed=_draw_seed() if p > 0 else 0, rows_used=seg * contrastive_num_segments,
+               col_stats_hook=col_stats_hook, loss_scale=loss_scale)
+    aux = aux if aux is not None else StepAux()
+    return _ContrastiveStepFunction.apply(residue_states, protein_mask, adapter.fc1.weight, adapter.fc1.bias,
+                                          adapter.fc2.weight, adapter.fc2.bias, text_embeds, labels, cfg, aux)
