@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Benchmark of the Stage-1 contrastive step (BASELINE.json metric: pairs/sec + roofline fraction).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one fused contrastive step, forward AND backward, over one synthetic batch of the
+BASELINE config: residue states -> ModalityAdapter (fc1/GELU/dropout/fc2/GELU/dropout/L2-norm) ->
+'mix' readout -> L2 normalise; text hidden states -> 'mix' readout -> normalise; similarity / tau;
+InfoNCE; gradients of fc1/fc2 weights and biases.  Training mode (dropout p = 0.3) as in the
+reference's train_epoch.  N > 1 (under torchrun): every rank holds B pairs (weak scaling), text
+embeddings are all-gathered over NCCL to form global negatives.
+
+Prints ONE JSON line (rank 0).  `value` = pairs/s with inputs resident in HBM; `e2e` = the same
+through the public API with inputs in pinned host memory (H2D of the step's inputs and D2H of the
+loss inside the timed region); `roofline` = the tcgen05 GEMM kernel against the measured bf16
+peak; `cpu_baseline` = the CPU oracle timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "contrastive_step_pairs_per_sec"
+UNIT = "pairs/s"
+DEFAULT_WORKLOAD = "cfg2_esm2_3b_llama8b"
+CPU_SAMPLE_PAIRS = 4
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--eval-mode", action="store_true", help="dropout off (parity runs); default is training mode")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU oracle timing (cpu_baseline leg and --impl reference)
+# --------------------------------------------------------------------------------------------------
+def cpu_oracle_step_time(sb, pairs: int, iters: int, warmup: int):
+    """Time the CPU oracle (oracle/restatement.py: torch CPU fp32, autograd backward — the same ATen
+    kernels the reference's CPU path runs) on the first `pairs` pairs of the batch."""
+    import torch
+    from oracle import restatement as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    f = torch.float32
+    n = pairs
+    lmax = int(sb.prot_lens[:n].max())
+    x = sb.x[:n, :lmax].to(f)
+    pm = sb.prot_mask[:n, :lmax]
+    text, tm = sb.text[:n].to(f), sb.text_mask[:n]
+    params = [t.to(f).requires_grad_() for t in (sb.w1, sb.b1, sb.w2, sb.b2)]
+    times = []
+    for it in range(warmup + iters):
+        for p in params:
+            p.grad = None
+        t0 = time.perf_counter()
+        st = R.step_forward(x, pm, params[0], params[1], params[2], params[3], text, tm, 0.05, 1)
+        st.loss.backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return times, torch.get_num_threads()
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the CPU implementation of the path on the host cores (rank 0 only).
+    The reference is pure Python on PyTorch and is not present on the GPU box, so this times the
+    oracle port (same ATen CPU kernels), each step a bounded sample of the workload."""
+    if rank != 0:
+        return
+    import __graft_entry__ as entry
+    entry.load_package()
+    import importlib
+    synth = importlib.import_module("p2t_b200.synth")
+    sb = synth.make_config_batch(args.workload)
+    times, cores = cpu_oracle_step_time(sb, CPU_SAMPLE_PAIRS, args.steps, args.warmup)
+    total = sum(times)
+    value = CPU_SAMPLE_PAIRS * len(times) / total
+    cfg = synth.CONFIGS[args.workload]
+    sample = f"first {CPU_SAMPLE_PAIRS} pairs of the {args.workload} batch per step, fp32, fwd+bwd, eval-mode dropout"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "d_in": cfg["d_in"], "d_mid": cfg["d_mid"], "d_out": cfg["d_out"],
+                   "pairs_per_step": CPU_SAMPLE_PAIRS},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun the way the driver does
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    pkg = entry.load_package()
+    import importlib
+    synth = importlib.import_module("p2t_b200.synth")
+    pdist = importlib.import_module("p2t_b200.dist")
+    lib = pkg._lib
+    lib.load()  # fail loudly if the CUDA extension is missing
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = synth.CONFIGS[args.workload]
+    nbatches = 2
+    batches = [synth.make_config_batch(args.workload, seed=1234 + 17 * i, rank=rank) for i in range(nbatches)]
+    B = cfg["batch"]
+    acfg = pkg.ModalityAdapterConfig(input_dim=cfg["d_in"], intermediate_dim=cfg["d_mid"], output_dim=cfg["d_out"], dropout_rate=0.3)
+    adapter = pkg.ModalityAdapter(acfg).to(dev).to(torch.bfloat16)
+    with torch.no_grad():
+        sb0 = batches[0]
+        adapter.fc1.weight.copy_(sb0.w1); adapter.fc1.bias.copy_(sb0.b1)
+        adapter.fc2.weight.copy_(sb0.w2); adapter.fc2.bias.copy_(sb0.b2)
+    adapter.eval() if args.eval_mode else adapter.train()
+    params = [adapter.fc1.weight, adapter.fc1.bias, adapter.fc2.weight, adapter.fc2.bias]
+
+    host = [dict(x=b.x.pin_memory(), pm=b.prot_mask.pin_memory(), text=b.text.pin_memory(), tm=b.text_mask.pin_memory())
+            for b in batches]
+    resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
+    valid_rows = [int(b.prot_lens.sum()) for b in batches]
+
+    def step(inp):
+        for p in params:
+            p.grad = None
+        if world > 1:
+            loss = pdist.distributed_contrastive_step(inp["x"], inp["pm"], adapter, inp["text"], inp["tm"])
+        else:
+            loss = pkg.contrastive_step(inp["x"], inp["pm"], adapter, inp["text"], inp["tm"])
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ------------------------------ device-resident timing ------------------------------
+    for i in range(args.warmup):
+        step(resident[i % nbatches])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.gemm_timing_enable(True)
+    lib.reset_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        loss = step(resident[i % nbatches])
+    ev1.record()
+    barrier()
+    launches = lib.launch_count()
+    gemm_ms, gemm_launches = lib.gemm_timing_collect()
+    lib.gemm_timing_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    ms_per_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total / 1e3)
+    last_loss = float(loss.item())
+
+    # ------------------------------ end to end (host buffers) ------------------------------
+    e2e = None
+    if not args.no_e2e:
+        dev_in = {k: torch.empty_like(v, device=dev) for k, v in host[0].items()}
+
+        def e2e_step(h):
+            inp = {}
+            for k, v in h.items():
+                if v.shape == dev_in[k].shape:
+                    dev_in[k].copy_(v, non_blocking=True)
+                    inp[k] = dev_in[k]
+                else:
+                    inp[k] = v.to(dev, non_blocking=True)
+            l = step(inp)
+            return float(l.item())  # device -> host read of the step's result
+
+        for i in range(min(3, args.warmup)):
+            e2e_step(host[i % nbatches])
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            e2e_step(host[i % nbatches])
+        e1.record()
+        barrier()
+        e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))
+        h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+        e2e = {"value": world * B * args.steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps}
+
+    # ------------------------------ roofline of the dominant kernel ------------------------------
+    d_in, d_mid, d_out = cfg["d_in"], cfg["d_mid"], cfg["d_out"]
+    flops_per_row = 2.0 * d_in * d_mid + 2.0 * d_mid * d_out + 2.0 * d_in * d_mid + 4.0 * d_mid * d_out
+    rows_timed = sum(valid_rows[i % nbatches] for i in range(args.steps))
+    gemm_flops = flops_per_row * rows_timed
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peaks = json.load(open(peaks_path))
+        peak_tf, peak_src = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    else:
+        peak_tf, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
+    achieved_tf = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": achieved_tf, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic, "peak_source": peak_src,
+                "launches_timed": gemm_launches, "kernel_ms_per_step": gemm_ms / args.steps,
+                "kernel_share_of_step": gemm_ms / ms_total if world == 1 else None,
+                "algorithmic_flops_per_step": gemm_flops / args.steps,
+                "whole_step_frac": (gemm_flops / (ms_total / 1e3) / 1e12) / peak_tf}
+
+    if rank == 0:
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            times, cores = cpu_oracle_step_time(batches[0], CPU_SAMPLE_PAIRS, iters=3, warmup=1)
+            cpu_baseline = {"value": CPU_SAMPLE_PAIRS / min(times), "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"first {CPU_SAMPLE_PAIRS} pairs of the {args.workload} batch, fp32 oracle fwd+bwd, best of 3"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": args.workload, "d_in": d_in, "d_mid": d_mid, "d_out": d_out, "pairs_per_gpu": B,
+                       "global_pairs": world * B, "residue_len": [cfg["lmin"], cfg["lmax"]],
+                       "valid_rows_per_step": valid_rows[0], "dropout_p": 0.0 if args.eval_mode else 0.3,
+                       "parallelism": f"dp{world}", "l2": "inputs+activations per step exceed the 126 MB L2; 2 batches alternate",
+                       "cta_group": int(os.environ.get("P2T_CTA_GROUP", "2"))},
+            "loss": last_loss, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -41,6 +41,10 @@ const char* p2t_last_error(void);
 /* kernels launched by this library since the last reset (bench.py reports it as gpu_launches) */
 unsigned long long p2t_launch_count(void);
 void p2t_reset_launch_count(void);
+/* per-launch CUDA-event timing of the tcgen05 GEMM kernel on its launching stream (bench.py's
+ * roofline): enable, run, synchronise the stream, then collect the summed durations. HOST pointers. */
+void p2t_gemm_timing_enable(int on);
+int p2t_gemm_timing_collect(double* total_ms, int* launches);
 
 /* ---------------------------------------------------------------------------------------------
  * tcgen05 GEMM  D[m][n] = alpha * sum_k A[m][k] * B[n][k]      (bf16 in, fp32 accumulate in TMEM)
@@ -73,9 +77,11 @@ int p2t_gather_rows(const void* src, long long ld_src, const int* row_src, const
 /* ---------------------------------------------------------------------------------------------
  * ModalityAdapter.forward on packed rows — models/modeling_esm2llama_instruct.py:60-68.
  *   h1 = drop(GELU(x W1^T + b1))            [rows_cap][d_mid] bf16   (fc1 epilogue)
- *   g1 = keep * GELU'(x W1^T + b1)          [rows_cap][d_mid] bf16   (NULL when no backward)
- *   a  = drop(GELU(h1 W2^T + b2))           [rows_cap][d_out] bf16   (fc2 epilogue)
- *   g2 = keep * GELU'(h1 W2^T + b2)         [rows_cap][d_out] bf16   (NULL when no backward)
+ *   g1 = keep * GELU'(x W1^T + b1)          [rows_cap][d_mid] fp16   (NULL when no backward)
+ *   a  = drop(GELU(h1 W2^T + b2))           [rows_cap][d_out] fp16   (fc2 epilogue)
+ *   g2 = keep * GELU'(h1 W2^T + b2)         [rows_cap][d_out] fp16   (NULL when no backward)
+ *   (a, g1, g2 are read only by this library's streaming kernels; fp16 keeps 3 more mantissa bits
+ *    than bf16 at the same bytes.  h1 and every GEMM operand are bf16.)
  *   rowsq[row][nblk] = partial sums of a^2, nblk = ceil(d_out/256) — the per-residue L2 norm (:67)
  * x has x_rows rows allocated (TMA zero-fills beyond); outputs have rows_cap rows.
  * Weights in nn.Linear layout (out, in), bf16.  dropout_p = 0 is eval mode; otherwise a Philox
@@ -92,11 +98,12 @@ int p2t_adapter_scale_rows(const void* a, const float* rowsq, int nblk, int n, i
 
 /* ---------------------------------------------------------------------------------------------
  * readout_embeddings(..., "mean"|"std"|"mix") — scripts/train_contrast.py:217-248 — over the rows
- * listed by a plan.  `src` is bf16 [*][ld_src]; row_src == NULL means rows are already packed.
+ * listed by a plan.  `src` is bf16 (or fp16 when src_is_f16: the adapter's own `a`) [*][ld_src];
+ * row_src == NULL means rows are already packed.
  * With rowsq != NULL every row is first scaled by its inverse L2 norm (adapter output fused in).
  * partial_ws: float2 [max_chunks][D]; out: fp32 [B][ld_out] (mean | std for mix).
  * ------------------------------------------------------------------------------------------- */
-int p2t_pool_fwd(const void* src, long long ld_src, const int* row_src, const float* rowsq, int nblk,
+int p2t_pool_fwd(const void* src, int src_is_f16, long long ld_src, const int* row_src, const float* rowsq, int nblk,
                  const int* seq_off, const int* chunk_off, int B, int D, int chunk_rows, int max_chunks, int mode,
                  void* partial_ws, float* inv_norm_out, float* out, long long ld_out, void* stream);
 
@@ -140,6 +147,7 @@ int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, c
  * p2t_infonce_col_stats : per-column online (max, sum exp, argmax row) — the text->protein term
  * p2t_infonce_ce : one pass per row: loss_i, row lse, argmax, and dS written over S
  *      loss_i = w_row (lse_j S_ij - S_i,lab) + w_col (lse_col[lab] - S_i,lab);  dS scaled by inv_rn
+ *      all_cols_labelled != 0: sharded global batch, every column's positive lives on some rank
  * p2t_infonce_grad : dp = dS t / tau (fp32 [R][E]) and optionally dt = dS^T p / tau (fp32 [C][E])
  * p2t_loss_mean : loss[0] (+)= scale * sum_i row_loss[i], fixed-order reduction
  * ------------------------------------------------------------------------------------------- */
@@ -148,8 +156,8 @@ int p2t_similarity(const void* p, const void* t, int R, int C, int E, float tau,
 int p2t_infonce_col_stats(const float* S, int R, int C, float* col_max, float* col_sum, int* col_argmax,
                           int row_index_base, void* stream);
 int p2t_infonce_ce(float* S, const int* labels, int R, int C, float w_row, float w_col, float inv_rn,
-                   const float* col_max, const float* col_sum, unsigned char* col_labelled_ws, float* row_loss,
-                   float* row_lse, int* argmax_row, void* dS_bf16, int write_ds, void* stream);
+                   const float* col_max, const float* col_sum, unsigned char* col_labelled_ws, int all_cols_labelled,
+                   float* row_loss, float* row_lse, int* argmax_row, void* dS_bf16, int write_ds, void* stream);
 int p2t_infonce_grad(const float* dS, const void* dS_bf16, const void* p, const void* t, int R, int C, int E,
                      float tau, float* dp, float* dt, void* bf16_ws, int cta_group, void* stream);
 int p2t_loss_mean(const float* row_loss, int R, float scale, float* loss, int accumulate, void* stream);

@@ -139,9 +139,9 @@ def adapter_forward(x: torch.Tensor, x_rows: int, rows_cap: int, n_rows: torch.T
     dev = x.device
     bf = torch.bfloat16
     h1 = torch.empty(rows_cap, d_mid, dtype=bf, device=dev)
-    a = torch.empty(rows_cap, d_out, dtype=bf, device=dev)
-    g1 = torch.empty(rows_cap, d_mid, dtype=bf, device=dev) if need_grad else None
-    g2 = torch.empty(rows_cap, d_out, dtype=bf, device=dev) if need_grad else None
+    a = torch.empty(rows_cap, d_out, dtype=torch.float16, device=dev)
+    g1 = torch.empty(rows_cap, d_mid, dtype=torch.float16, device=dev) if need_grad else None
+    g2 = torch.empty(rows_cap, d_out, dtype=torch.float16, device=dev) if need_grad else None
     nblk = (d_out + 255) // 256
     rowsq = torch.empty(rows_cap, nblk, dtype=torch.float32, device=dev)
     _lib.call("p2t_adapter_fwd", _ptr(x), x_rows, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), d_in, d_mid, d_out,
@@ -176,12 +176,12 @@ def adapter_backward(acts: AdapterActs, dz2: torch.Tensor, w1, w2, need_dx: bool
 # --------------------------------------------------------------------------------------------------
 def pool_forward(src: torch.Tensor, plan: RowPlan, D: int, *, row_src: Optional[torch.Tensor],
                  rowsq: Optional[torch.Tensor] = None, nblk: int = 0, want_inv_norm: bool = False):
-    """(mean | std) statistics fp32 [B, 2D] of the plan's rows of `src` (bf16, row stride src.stride(0))."""
+    """(mean | std) statistics fp32 [B, 2D] of the plan's rows of `src` (bf16 or fp16, row stride src.stride(0))."""
     dev = src.device
     partial = torch.empty(plan.max_chunks, D, 2, dtype=torch.float32, device=dev)
     stats = torch.empty(plan.B, 2 * D, dtype=torch.float32, device=dev)
     inv_norm = torch.empty(plan.rows_cap, dtype=torch.float32, device=dev) if want_inv_norm else None
-    _lib.call("p2t_pool_fwd", _ptr(src), src.stride(0), _ptr(row_src), _ptr(rowsq), nblk, _ptr(plan.seq_off),
+    _lib.call("p2t_pool_fwd", _ptr(src), int(src.dtype == torch.float16), src.stride(0), _ptr(row_src), _ptr(rowsq), nblk, _ptr(plan.seq_off),
               _ptr(plan.chunk_off), plan.B, D, CHUNK_ROWS, plan.max_chunks, READOUT_MODES["mix"], _ptr(partial),
               _ptr(inv_norm), _ptr(stats), 2 * D, _stream())
     return stats, inv_norm
@@ -236,12 +236,14 @@ class InfoNCEResult:
 
 def infonce_forward(p_bf: torch.Tensor, t_bf: torch.Tensor, labels: torch.Tensor, tau: float, *, w_row: float = 1.0,
                     w_col: float = 0.0, need_grad: bool = True, want_col_argmax: bool = False,
-                    col_stats_hook=None, loss_scale: Optional[float] = None,
+                    col_stats_hook=None, loss_scale: Optional[float] = None, all_cols_labelled: bool = False,
                     cta_group: Optional[int] = None) -> InfoNCEResult:
     """loss = mean_i [ w_row (lse_j S_ij - S_i,lab) + w_col (lse_col[lab] - S_i,lab) ], S = p t^T / tau.
 
     `col_stats_hook(col_max, col_sum) -> (col_max, col_sum)` lets the multi-GPU layer merge column
     statistics across ranks before the gradient pass.  `loss_scale` overrides 1/R.
+    `all_cols_labelled`: every column has its positive on SOME rank (sharded global batch), so the
+    column term's gradient flows to all local rows, not only to columns labelled by local rows.
     """
     require_cuda_bf16(p_bf, "p")
     require_cuda_bf16(t_bf, "t")
@@ -268,7 +270,7 @@ def infonce_forward(p_bf: torch.Tensor, t_bf: torch.Tensor, labels: torch.Tensor
     dS_bf16 = torch.empty(R, C, dtype=torch.bfloat16, device=dev) if (need_grad and big) else None
     scale = (1.0 / R) if loss_scale is None else float(loss_scale)
     _lib.call("p2t_infonce_ce", _ptr(S), _ptr(labels32), R, C, float(w_row), float(w_col), scale, _ptr(col_max),
-              _ptr(col_sum), _ptr(marks), _ptr(row_loss), _ptr(row_lse), _ptr(argmax_row), _ptr(dS_bf16),
+              _ptr(col_sum), _ptr(marks), int(all_cols_labelled), _ptr(row_loss), _ptr(row_lse), _ptr(argmax_row), _ptr(dS_bf16),
               int(need_grad), _stream())
     loss = torch.empty((), dtype=torch.float32, device=dev)
     _lib.call("p2t_loss_mean", _ptr(row_loss), R, scale, _ptr(loss), 0, _stream())

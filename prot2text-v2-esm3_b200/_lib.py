@@ -20,7 +20,7 @@ SIGNATURES = {
     "p2t_gather_rows": [_vp, _ll, _vp, _vp, _i, _i, _vp, _vp],
     "p2t_adapter_fwd": [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _ull, _i, _vp],
     "p2t_adapter_scale_rows": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp],
-    "p2t_pool_fwd": [_vp, _ll, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _ll, _vp],
+    "p2t_pool_fwd": [_vp, _i, _ll, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _ll, _vp],
     "p2t_readout_last": [_vp, _vp, _i, _i, _i, _vp, _vp],
     "p2t_l2norm_fwd": [_vp, _i, _i, _vp, _vp, _vp, _vp],
     "p2t_l2norm_bwd": [_vp, _vp, _vp, _i, _i, _vp, _vp],
@@ -31,16 +31,18 @@ SIGNATURES = {
     "p2t_adapter_bwd": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "p2t_similarity": [_vp, _vp, _i, _i, _i, _f, _vp, _i, _vp],
     "p2t_infonce_col_stats": [_vp, _i, _i, _vp, _vp, _vp, _i, _vp],
-    "p2t_infonce_ce": [_vp, _vp, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+    "p2t_infonce_ce": [_vp, _vp, _i, _i, _f, _f, _f, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp],
     "p2t_infonce_grad": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _i, _vp],
     "p2t_loss_mean": [_vp, _i, _f, _vp, _i, _vp],
     "p2t_f32_to_bf16": [_vp, _ll, _vp, _vp],
     "p2t_bf16_to_f32": [_vp, _ll, _vp, _vp],
     "p2t_colsum": [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp],
     "p2t_dropout_mask": [_i, _i, _f, _ull, _i, _vp, _vp],
+    "p2t_gemm_timing_collect": [C.POINTER(C.c_double), C.POINTER(C.c_int)],
 }
 NON_STATUS = {"p2t_abi_version": (_i, []), "p2t_last_error": (C.c_char_p, []),
-              "p2t_launch_count": (_ull, []), "p2t_reset_launch_count": (None, [])}
+              "p2t_launch_count": (_ull, []), "p2t_reset_launch_count": (None, []),
+              "p2t_gemm_timing_enable": (None, [_i])}
 
 _lib = None
 
@@ -86,3 +88,14 @@ def launch_count() -> int:
 
 def reset_launch_count() -> None:
     load().p2t_reset_launch_count()
+
+
+def gemm_timing_enable(on: bool) -> None:
+    load().p2t_gemm_timing_enable(int(on))
+
+
+def gemm_timing_collect():
+    """(total GEMM-kernel milliseconds, number of GEMM launches) since enable; synchronise first."""
+    ms, n = C.c_double(0.0), C.c_int(0)
+    call("p2t_gemm_timing_collect", C.byref(ms), C.byref(n))
+    return ms.value, n.value

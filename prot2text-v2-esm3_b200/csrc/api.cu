@@ -57,6 +57,11 @@ int p2t_abi_version(void) { return P2T_ABI_VERSION; }
 const char* p2t_last_error(void) { return last_error(); }
 unsigned long long p2t_launch_count(void) { return launches(); }
 void p2t_reset_launch_count(void) { reset_launches(); }
+void p2t_gemm_timing_enable(int on) { gemm_timing_enable(on != 0); }
+int p2t_gemm_timing_collect(double* total_ms, int* launches) {
+  if (!total_ms || !launches) return set_error(-1, "p2t_gemm_timing_collect: null pointer");
+  return gemm_timing_collect(total_ms, launches);
+}
 
 int p2t_gemm_bf16(const void* a, long long lda, int a_mn_major, const void* b, long long ldb, int b_mn_major,
                   void* d, long long ldd, int d_is_f32, int m, int n, int k, float alpha, const int* dyn_m,
@@ -112,13 +117,13 @@ int p2t_adapter_scale_rows(const void* a, const float* rowsq, int nblk, int n, i
   return scale_rows(a, rowsq, nblk, n, d_out, y, inv_norm, S(stream));
 }
 
-int p2t_pool_fwd(const void* src, long long ld_src, const int* row_src, const float* rowsq, int nblk,
+int p2t_pool_fwd(const void* src, int src_is_f16, long long ld_src, const int* row_src, const float* rowsq, int nblk,
                  const int* seq_off, const int* chunk_off, int B, int D, int chunk_rows, int max_chunks, int mode,
                  void* partial_ws, float* inv_norm_out, float* out, long long ld_out, void* stream) {
   if (!src || !seq_off || !chunk_off || !partial_ws || !out) return set_error(-1, "p2t_pool_fwd: null pointer");
   if (mode < 1 || mode > 3) return set_error(-1, "p2t_pool_fwd: mode must be MEAN, STD or MIX");
   if (max_chunks <= 0) return 0;
-  return pool_forward(src, ld_src, row_src, rowsq, nblk, seq_off, chunk_off, B, D, chunk_rows, max_chunks, mode,
+  return pool_forward(src, src_is_f16 != 0, ld_src, row_src, rowsq, nblk, seq_off, chunk_off, B, D, chunk_rows, max_chunks, mode,
                       reinterpret_cast<float2*>(partial_ws), inv_norm_out, out, ld_out, S(stream));
 }
 
@@ -173,7 +178,7 @@ int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, c
     GemmParams p = base_params(rows_cap, d_mid, d_out);
     p.dyn_m = n_rows_dev;
     p.d0 = dz1; p.ldd0 = d_mid;
-    p.aux = reinterpret_cast<const __nv_bfloat16*>(g1); p.ldaux = d_mid;
+    p.aux = reinterpret_cast<const __half*>(g1); p.ldaux = d_mid;
     if (int rc = launch_gemm(dz2, d_out, false, w2, d_mid, true, EPI_MUL_AUX, p, cta_group, st)) return rc;
   }
   // dW2 = dz2^T h1           both operands MN-major, K = residue rows
@@ -222,12 +227,18 @@ int p2t_infonce_col_stats(const float* Sm, int R, int C, float* col_max, float* 
 }
 
 int p2t_infonce_ce(float* Sm, const int* labels, int R, int C, float w_row, float w_col, float inv_rn,
-                   const float* col_max, const float* col_sum, unsigned char* col_labelled_ws, float* row_loss,
+                   const float* col_max, const float* col_sum, unsigned char* col_labelled_ws, int all_cols_labelled,
+                   float* row_loss,
                    float* row_lse, int* argmax_row, void* dS_bf16, int write_ds, void* stream) {
   if (!Sm || !labels || !row_loss) return set_error(-1, "p2t_infonce_ce: null pointer");
   if (w_col != 0.f) {
     if (!col_max || !col_sum || !col_labelled_ws) return set_error(-1, "p2t_infonce_ce: column statistics required");
-    if (int rc = mark_labelled(labels, R, C, col_labelled_ws, S(stream))) return rc;
+    if (all_cols_labelled) {
+      cudaError_t e = cudaMemsetAsync(col_labelled_ws, 1, C, S(stream));
+      if (e != cudaSuccess) return set_error((int)e, "memset: %s", cudaGetErrorString(e));
+    } else if (int rc = mark_labelled(labels, R, C, col_labelled_ws, S(stream))) {
+      return rc;
+    }
   }
   return ce_rows(Sm, labels, R, C, w_row, w_col, inv_rn, col_max, col_sum, col_labelled_ws, row_loss, row_lse,
                  argmax_row, dS_bf16, write_ds, S(stream));

@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <vector>
 
 namespace p2t {
 
@@ -26,5 +27,38 @@ int check_launch(const char* what) {
 const char* last_error() { return g_err; }
 unsigned long long launches() { return g_launches.load(std::memory_order_relaxed); }
 void reset_launches() { g_launches.store(0, std::memory_order_relaxed); }
+
+
+// ---- GEMM launch timing: event pairs recorded around each GEMM launch, resolved on demand ----
+static bool g_timing = false;
+static std::vector<cudaEvent_t> g_ev;  // begin/end pairs
+static size_t g_ev_used = 0;
+bool gemm_timing_enabled() { return g_timing; }
+void gemm_timing_record(cudaStream_t st, bool begin) {
+  (void)begin;
+  if (g_ev_used == g_ev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    g_ev.push_back(e);
+  }
+  cudaEventRecord(g_ev[g_ev_used++], st);
+}
+void gemm_timing_enable(bool on) { g_timing = on; g_ev_used = 0; }
+// sum of (end - begin) over recorded pairs, in ms; caller must have synchronised the stream
+int gemm_timing_collect(double* total_ms, int* pairs) {
+  double t = 0.0;
+  int n = 0;
+  for (size_t i = 0; i + 1 < g_ev_used; i += 2) {
+    float ms = 0.f;
+    cudaError_t e = cudaEventElapsedTime(&ms, g_ev[i], g_ev[i + 1]);
+    if (e != cudaSuccess) return set_error((int)e, "cudaEventElapsedTime: %s", cudaGetErrorString(e));
+    t += ms;
+    ++n;
+  }
+  *total_ms = t;
+  *pairs = n;
+  g_ev_used = 0;
+  return 0;
+}
 
 }  // namespace p2t

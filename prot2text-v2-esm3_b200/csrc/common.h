@@ -14,4 +14,8 @@ int check_launch(const char* what);
 
 int sm_count();
 
+// Optional per-launch timing of the GEMM kernel with CUDA events on the launching stream (bench.py's roofline).
+bool gemm_timing_enabled();
+void gemm_timing_record(cudaStream_t st, bool begin);
+
 }  // namespace p2t

@@ -76,7 +76,10 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  const bool timed = gemm_timing_enabled();
+  if (timed) gemm_timing_record(stream, true);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+  if (timed) gemm_timing_record(stream, false);
   if (e != cudaSuccess) return set_error((int)e, "GEMM launch failed: %s", cudaGetErrorString(e));
   count_launch();
   return 0;

@@ -14,9 +14,11 @@
 //
 // Epilogues (reference sites in models/modeling_esm2llama_instruct.py:60-68 and its autograd):
 //   EPI_STORE_BF16 / EPI_STORE_F32 : D = alpha * acc
-//   EPI_FC1    : z1 = acc + b1;  D0 = h1 = keep*GELU(z1) (bf16);  D1 = g1 = keep*GELU'(z1) (bf16)   (:62-63)
-//   EPI_FC2    : z2 = acc + b2;  D0 = a  = keep*GELU(z2) (bf16);  D1 = g2 = keep*GELU'(z2) (bf16);
-//                rowsq[row][n_blk] = sum_cols a^2 (of the bf16-rounded a)                        (:65-67)
+//   EPI_FC1    : z1 = acc + b1;  D0 = h1 = keep*GELU(z1) (bf16);  D1 = g1 = keep*GELU'(z1) (fp16)   (:62-63)
+//   EPI_FC2    : z2 = acc + b2;  D0 = a  = keep*GELU(z2) (fp16);  D1 = g2 = keep*GELU'(z2) (fp16);
+//                rowsq[row][n_blk] = sum_cols a^2 (of the fp16-rounded a)                        (:65-67)
+//   (fp16 for tensors only our own streaming kernels read: bf16's 8-bit mantissa adds rounding noise
+//    of 2^-9*|a| to every residue, which inflates the pooled std and its 1/std backward)
 //   EPI_MUL_AUX: D0 = alpha * acc * aux   (fc2 dgrad chained into GELU'(z1): aux = g1)
 // Storing (value, derivative) pairs instead of the pre-activation keeps every later HBM-bound pass
 // free of erf/exp and of Philox re-generation: the dropout multiplier is folded into both.
@@ -48,7 +50,7 @@ struct GemmParams {
   void* d1;
   long long ldd1;
   const __nv_bfloat16* bias;  // [n]
-  const __nv_bfloat16* aux;   // EPI_MUL_AUX: multiplier [rows][ldaux]
+  const __half* aux;          // EPI_MUL_AUX: fp16 multiplier [rows][ldaux]
   long long ldaux;
   float* rowsq;               // EPI_FC2: [rows][ld_rowsq] partial sum of squares per N block
   int ld_rowsq;
@@ -107,7 +109,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < S::STAGES; ++s) {
-        mbar_init(&full_bar[s], CTA_GROUP);  // leader's expect_tx arrive (+ peer producer's arrive)
+        mbar_init(&full_bar[s], 1);          // the leader's expect_tx arrive; both CTAs' TMA bytes complete_tx on it
         mbar_init(&empty_bar[s], 1);         // one tcgen05.commit
       }
       for (int a = 0; a < 2; ++a) {
@@ -156,9 +158,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
             for (int j = 0; j < S::B_ROWS / 64; ++j)
               load(sb + j * (GEMM_BLOCK_K * 128), &tmap_b, n_base + j * 64, k0);
-          }
-          if constexpr (CTA_GROUP == 2) {
-            if (!is_leader) mbar_arrive_cluster(&full_bar[stage], 0);
           }
           if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -253,18 +252,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 val[i] = gl * kp;
                 der[i] = gd * kp;
                 if constexpr (EPI == EPI_FC2) {
-                  const float ar = bf16_round(val[i]);
+                  const float ar = f16_round(val[i]);
                   sumsq = fmaf(ar, ar, sumsq);
                 }
               }
-              store_row_bf16(reinterpret_cast<__nv_bfloat16*>(p.d0) + (long long)row * p.ldd0 + col, val, ncols);
+              if constexpr (EPI == EPI_FC1)  // h1 feeds the next GEMM: bf16
+                store_row_bf16(reinterpret_cast<__nv_bfloat16*>(p.d0) + (long long)row * p.ldd0 + col, val, ncols);
+              else                           // a is read only by our own streaming kernels: fp16
+                store_row_f16(reinterpret_cast<__half*>(p.d0) + (long long)row * p.ldd0 + col, val, ncols);
               if (p.d1 != nullptr)
-                store_row_bf16(reinterpret_cast<__nv_bfloat16*>(p.d1) + (long long)row * p.ldd1 + col, der, ncols);
+                store_row_f16(reinterpret_cast<__half*>(p.d1) + (long long)row * p.ldd1 + col, der, ncols);
             }
           } else if constexpr (EPI == EPI_MUL_AUX) {
             if (row_in_buf) {
               float g[32], o[32];
-              if (row_valid) load_row_bf16(p.aux + (long long)row * p.ldaux + col, g, ncols);
+              if (row_valid) load_row_f16(p.aux + (long long)row * p.ldaux + col, g, ncols);
 #pragma unroll
               for (int i = 0; i < 32; ++i) o[i] = row_valid ? __uint_as_float(v[i]) * p.alpha * g[i] : 0.f;
               store_row_bf16(reinterpret_cast<__nv_bfloat16*>(p.d0) + (long long)row * p.ldd0 + col, o, ncols);

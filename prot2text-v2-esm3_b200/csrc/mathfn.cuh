@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace p2t {
@@ -92,6 +93,54 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
+}
+
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t u) {
+  __half2 v = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(v);
+}
+template <bool F16>
+__device__ __forceinline__ float2 unpack_h2(uint32_t u) {
+  if constexpr (F16) return unpack_f16x2(u); else return unpack_bf16x2(u);
+}
+__device__ __forceinline__ float f16_round(float x) { return __half2float(__float2half_rn(x)); }
+
+// fp16 flavour of the 32-element row fragment helpers (activations private to our own kernels are
+// kept in fp16: same bytes as bf16, 8x finer mantissa; GEMM operands stay bf16)
+__device__ __forceinline__ void store_row_f16(__half* dst, const float (&f)[32], int ncols) {
+  if (ncols == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 u;
+      u.x = pack_f16x2(f[8 * q + 0], f[8 * q + 1]);
+      u.y = pack_f16x2(f[8 * q + 2], f[8 * q + 3]);
+      u.z = pack_f16x2(f[8 * q + 4], f[8 * q + 5]);
+      u.w = pack_f16x2(f[8 * q + 6], f[8 * q + 7]);
+      reinterpret_cast<uint4*>(dst)[q] = u;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < ncols) dst[i] = __float2half_rn(f[i]);
+  }
+}
+__device__ __forceinline__ void load_row_f16(const __half* src, float (&f)[32], int ncols) {
+  if (ncols == 32 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + q);
+      float2 a = unpack_f16x2(u.x), b = unpack_f16x2(u.y), c = unpack_f16x2(u.z), d = unpack_f16x2(u.w);
+      f[8 * q + 0] = a.x; f[8 * q + 1] = a.y; f[8 * q + 2] = b.x; f[8 * q + 3] = b.y;
+      f[8 * q + 4] = c.x; f[8 * q + 5] = c.y; f[8 * q + 6] = d.x; f[8 * q + 7] = d.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = (i < ncols) ? __half2float(src[i]) : 0.f;
+  }
 }
 
 __device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, const float (&f)[32], int ncols) {

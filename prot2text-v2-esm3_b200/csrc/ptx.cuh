@@ -61,7 +61,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // arrive on the barrier at the same smem offset inside CTA `rank` of the cluster
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
   uint32_t remote = mapa_shared(smem_u32(bar), rank);
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;

@@ -146,6 +146,7 @@ __device__ __forceinline__ int find_segment(const int* __restrict__ off, int n, 
   return lo;
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(128)
 pool_partial_kernel(const __nv_bfloat16* __restrict__ src, long long ld_src, const int* __restrict__ row_src,
                     const float* __restrict__ rowsq, int nblk, const int* __restrict__ seq_off,
@@ -179,7 +180,7 @@ pool_partial_kernel(const __nv_bfloat16* __restrict__ src, long long ld_src, con
     return reinterpret_cast<const uint4*>(src + sr * ld_src) + g;
   };
   auto unpack8 = [](const uint4& u, float (&f)[8]) {
-    float2 a = unpack_bf16x2(u.x), b2 = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    float2 a = unpack_h2<F16>(u.x), b2 = unpack_h2<F16>(u.y), c = unpack_h2<F16>(u.z), d = unpack_h2<F16>(u.w);
     f[0] = a.x; f[1] = a.y; f[2] = b2.x; f[3] = b2.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
   };
   {
@@ -329,11 +330,11 @@ __global__ void pool_bwd_coef_kernel(const float* __restrict__ de, long long ld_
 // ------------------------------------------------------------------------------------------------
 // adapter tail backward over packed rows (one warp per row):
 //   y = a * inv;  dy = c1[b] + c2[b] * y;  da = (dy - y (y.dy)) * inv;  dz2 = da * g
-// a, g bf16 [rows][D] (g = keep*GELU'(z2), a = keep*GELU(z2)); rows in [n, roundup(n,256)) are zeroed.
+// a, g fp16 [rows][D] (g = keep*GELU'(z2), a = keep*GELU(z2)); dz2 bf16; rows in [n, roundup(n,256)) are zeroed.
 // ------------------------------------------------------------------------------------------------
 template <int NV>  // 16-byte vectors per lane: D <= NV*256
 __global__ void __launch_bounds__(256)
-adapter_tail_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ g,
+adapter_tail_bwd_kernel(const __half* __restrict__ a, const __half* __restrict__ g,
                         const float* __restrict__ inv_norm, const int* __restrict__ seq_off, int B,
                         const float* __restrict__ c1, const float* __restrict__ c2, const int* __restrict__ n_rows,
                         int cap, int D, __nv_bfloat16* __restrict__ dz2) {
@@ -372,7 +373,7 @@ adapter_tail_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16
         const uint32_t w[4] = {av[k].x, av[k].y, av[k].z, av[k].w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float2 f = unpack_bf16x2(w[i]);
+          const float2 f = unpack_f16x2(w[i]);
           const float y0 = f.x * inv, y1 = f.y * inv;
           dot = fmaf(y0, fmaf(k2[2 * i], y0, k1[2 * i]), dot);
           dot = fmaf(y1, fmaf(k2[2 * i + 1], y1, k1[2 * i + 1]), dot);
@@ -394,8 +395,8 @@ adapter_tail_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16
         uint32_t o[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float2 f = unpack_bf16x2(w[i]);
-          const float2 gg = unpack_bf16x2(gw[i]);
+          const float2 f = unpack_f16x2(w[i]);
+          const float2 gg = unpack_f16x2(gw[i]);
           const float y0 = f.x * inv, y1 = f.y * inv;
           const float dy0 = fmaf(k2[2 * i], y0, k1[2 * i]), dy1 = fmaf(k2[2 * i + 1], y1, k1[2 * i + 1]);
           const float d0 = (dy0 - y0 * dot) * inv * gg.x;
@@ -411,7 +412,7 @@ adapter_tail_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16
 // same, but the upstream gradient dy is given per row (module API: y = adapter(x) was returned)
 template <int NV>
 __global__ void __launch_bounds__(256)
-adapter_tail_bwd_dy_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ g,
+adapter_tail_bwd_dy_kernel(const __half* __restrict__ a, const __half* __restrict__ g,
                            const float* __restrict__ inv_norm, const __nv_bfloat16* __restrict__ dy, int n, int cap,
                            int D, __nv_bfloat16* __restrict__ dz2) {
   const int n_pad = min(cap, (n + 255) & ~255);
@@ -442,7 +443,7 @@ adapter_tail_bwd_dy_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloa
       const uint32_t dw[4] = {dv[k].x, dv[k].y, dv[k].z, dv[k].w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float2 f = unpack_bf16x2(w[i]);
+        const float2 f = unpack_f16x2(w[i]);
         const float2 d = unpack_bf16x2(dw[i]);
         dot = fmaf(f.x * inv, d.x, dot);
         dot = fmaf(f.y * inv, d.y, dot);
@@ -460,9 +461,9 @@ adapter_tail_bwd_dy_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloa
         uint32_t o[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float2 f = unpack_bf16x2(w[i]);
+          const float2 f = unpack_f16x2(w[i]);
           const float2 d = unpack_bf16x2(dw[i]);
-          const float2 gg = unpack_bf16x2(gw[i]);
+          const float2 gg = unpack_f16x2(gw[i]);
           o[i] = pack_bf16x2((d.x - f.x * inv * dot) * inv * gg.x, (d.y - f.y * inv * dot) * inv * gg.y);
         }
         out[v] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -473,7 +474,7 @@ adapter_tail_bwd_dy_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloa
 
 // y[row] = a[row] * inv_norm[row]  (module API forward tail).  inv from rowsq partials.
 __global__ void __launch_bounds__(256)
-scale_rows_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ rowsq, int nblk, int n, int D,
+scale_rows_kernel(const __half* __restrict__ a, const float* __restrict__ rowsq, int nblk, int n, int D,
                   __nv_bfloat16* __restrict__ y, float* __restrict__ inv_norm_out) {
   const int lane = threadIdx.x & 31;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
@@ -492,7 +493,7 @@ scale_rows_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__
       uint32_t o[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float2 f = unpack_bf16x2(w[i]);
+        const float2 f = unpack_f16x2(w[i]);
         o[i] = pack_bf16x2(f.x * inv, f.y * inv);
       }
       yr[v] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -622,14 +623,19 @@ int gather_rows(const void* src, long long ld_src, const int* row_src, const int
   return check_launch("gather_rows_kernel");
 }
 
-int pool_forward(const void* src, long long ld_src, const int* row_src, const float* rowsq, int nblk,
+int pool_forward(const void* src, bool src_is_f16, long long ld_src, const int* row_src, const float* rowsq, int nblk,
                  const int* seq_off, const int* chunk_off, int B, int D, int rc, int max_chunks, int mode,
                  float2* partial, float* inv_norm_out, float* out, long long ld_out, cudaStream_t st) {
   if (D % 8) return set_error(-1, "pool_forward: D must be a multiple of 8");
   dim3 grid(max_chunks, (D / 8 + 127) / 128);
-  pool_partial_kernel<<<grid, 128, rc * sizeof(float), st>>>(reinterpret_cast<const __nv_bfloat16*>(src), ld_src, row_src,
-                                                             rowsq, nblk, seq_off, chunk_off, B, D, rc, partial,
-                                                             inv_norm_out);
+  if (src_is_f16)
+    pool_partial_kernel<true><<<grid, 128, rc * sizeof(float), st>>>(reinterpret_cast<const __nv_bfloat16*>(src), ld_src,
+                                                                     row_src, rowsq, nblk, seq_off, chunk_off, B, D, rc,
+                                                                     partial, inv_norm_out);
+  else
+    pool_partial_kernel<false><<<grid, 128, rc * sizeof(float), st>>>(reinterpret_cast<const __nv_bfloat16*>(src), ld_src,
+                                                                      row_src, rowsq, nblk, seq_off, chunk_off, B, D, rc,
+                                                                      partial, inv_norm_out);
   if (int r = check_launch("pool_partial_kernel")) return r;
   dim3 g2(B, (D + 255) / 256);
   pool_finalize_kernel<<<g2, 256, 0, st>>>(partial, seq_off, chunk_off, B, D, rc, mode, out, ld_out);
@@ -656,8 +662,8 @@ static int tail_bwd_launch(const void* a, const void* g, const float* inv_norm, 
                            const float* c1, const float* c2, const int* n_rows, int cap, int D, void* dz2,
                            cudaStream_t st) {
   const int blocks = min((cap + 7) / 8, sm_count() * 8);
-  adapter_tail_bwd_kernel<NV><<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(a),
-                                                      reinterpret_cast<const __nv_bfloat16*>(g), inv_norm, seq_off, B, c1,
+  adapter_tail_bwd_kernel<NV><<<blocks, 256, 0, st>>>(reinterpret_cast<const __half*>(a),
+                                                      reinterpret_cast<const __half*>(g), inv_norm, seq_off, B, c1,
                                                       c2, n_rows, cap, D, reinterpret_cast<__nv_bfloat16*>(dz2));
   return check_launch("adapter_tail_bwd_kernel");
 }
@@ -675,7 +681,7 @@ static int tail_bwd_dy_launch(const void* a, const void* g, const float* inv_nor
                               void* dz2, cudaStream_t st) {
   const int blocks = min((cap + 7) / 8, sm_count() * 8);
   adapter_tail_bwd_dy_kernel<NV><<<blocks, 256, 0, st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(g), inv_norm,
+      reinterpret_cast<const __half*>(a), reinterpret_cast<const __half*>(g), inv_norm,
       reinterpret_cast<const __nv_bfloat16*>(dy), n, cap, D, reinterpret_cast<__nv_bfloat16*>(dz2));
   return check_launch("adapter_tail_bwd_dy_kernel");
 }
@@ -689,7 +695,7 @@ int adapter_tail_backward_dy(const void* a, const void* g, const float* inv_norm
 int scale_rows(const void* a, const float* rowsq, int nblk, int n, int D, void* y, float* inv_norm_out, cudaStream_t st) {
   if (n <= 0) return 0;
   const int blocks = min((n + 7) / 8, sm_count() * 8);
-  scale_rows_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(a), rowsq, nblk, n, D,
+  scale_rows_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __half*>(a), rowsq, nblk, n, D,
                                             reinterpret_cast<__nv_bfloat16*>(y), inv_norm_out);
   return check_launch("scale_rows_kernel");
 }

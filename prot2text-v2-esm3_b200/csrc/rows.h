@@ -11,7 +11,7 @@ int rows_plan(const void* mask, int mask_bytes, int B, int L, int rc, int* count
               int* n_rows, int* row_src, cudaStream_t st);
 int gather_rows(const void* src, long long ld_src, const int* row_src, const int* n_rows, int cap, int D, void* out,
                 cudaStream_t st);
-int pool_forward(const void* src, long long ld_src, const int* row_src, const float* rowsq, int nblk,
+int pool_forward(const void* src, bool src_is_f16, long long ld_src, const int* row_src, const float* rowsq, int nblk,
                  const int* seq_off, const int* chunk_off, int B, int D, int rc, int max_chunks, int mode,
                  float2* partial, float* inv_norm_out, float* out, long long ld_out, cudaStream_t st);
 int l2norm_forward(const float* e, int B, int E, void* p_bf16, float* p_f32, float* norm, cudaStream_t st);
@@ -49,5 +49,7 @@ int launch_gemm(const void* a, long long lda, bool a_mn, const void* b, long lon
 const char* last_error();
 unsigned long long launches();
 void reset_launches();
+void gemm_timing_enable(bool on);
+int gemm_timing_collect(double* total_ms, int* pairs);
 
 }  // namespace p2t

@@ -1,0 +1,67 @@
+"""Multi-GPU form of the contrastive step: one process per GPU, batch sharded across ranks,
+normalised text embeddings all-gathered over NCCL/NVLink to form global negatives (north_star;
+the reference itself computes a local-only loss per rank and lets DDP average adapter grads,
+scripts/train_contrast.py:551-556,611-614 — SURVEY.md D6).
+
+Rank k holds pairs [k*B, (k+1)*B): it pools/projects its own rows, gathers t from all ranks and
+computes the B x B_global block S_k = p_k T^T / tau.  The protein->text (row) term is then fully
+local.  For the symmetric form only the per-column (max, sum-exp) statistics — 2*B_global floats —
+cross ranks; because the text side carries no gradient (frozen LLM, :348-354) no E-wide gradient
+has to be reduce-scattered.  When a caller does want d(loss)/d(text embeddings), `reduce_scatter_text_grad`
+implements north_star's reduce-scatter of the gathered embeddings' gradient.
+
+The returned loss is the LOCAL mean; averaging adapter grads across ranks (DDP) yields the
+gradient of the global-batch mean loss.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import step as _step
+
+
+def all_gather_embeddings(t_local: torch.Tensor, group=None) -> torch.Tensor:
+    """(B, E) per rank -> (W*B, E), rank-major.  One NCCL all-gather (B*E*2 bytes per rank)."""
+    world = dist.get_world_size(group)
+    out = torch.empty(world * t_local.shape[0], t_local.shape[1], dtype=t_local.dtype, device=t_local.device)
+    dist.all_gather_into_tensor(out, t_local.contiguous(), group=group)
+    return out
+
+
+def merge_column_stats(col_max: torch.Tensor, col_sum: torch.Tensor, group=None):
+    """Combine per-rank online-softmax column statistics: M = max_k m_k, S = sum_k s_k exp(m_k - M)."""
+    world = dist.get_world_size(group)
+    packed = torch.stack([col_max, col_sum])  # (2, C)
+    gathered = torch.empty(world * 2, col_max.shape[0], dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(gathered, packed, group=group)
+    gathered = gathered.view(world, 2, -1)
+    m_all, s_all = gathered[:, 0], gathered[:, 1]
+    m = m_all.max(dim=0).values
+    s = (s_all * torch.exp(m_all - m)).sum(dim=0)
+    return m, s
+
+
+def reduce_scatter_text_grad(dt_full: torch.Tensor, group=None) -> torch.Tensor:
+    """(W*B, E) local contribution to d(loss)/d(gathered text) -> (B, E) summed over ranks."""
+    world = dist.get_world_size(group)
+    out = torch.empty(dt_full.shape[0] // world, dt_full.shape[1], dtype=dt_full.dtype, device=dt_full.device)
+    dist.reduce_scatter_tensor(out, dt_full.contiguous(), op=dist.ReduceOp.SUM, group=group)
+    return out
+
+
+def distributed_contrastive_step(residue_states, protein_mask, adapter, text_hidden, text_mask, *,
+                                 temperature: float = 0.05, symmetric: bool = False, group=None,
+                                 aux: Optional[_step.StepAux] = None) -> torch.Tensor:
+    """Sharded-batch contrastive step with all-gathered negatives; returns the local mean loss."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    t_local = _step.text_embeddings(text_hidden, text_mask)
+    t_global = all_gather_embeddings(t_local, group) if world > 1 else t_local
+    B = residue_states.shape[0]
+    labels = torch.arange(rank * B, (rank + 1) * B, device=residue_states.device, dtype=torch.int32)
+    hook = (lambda m, s: merge_column_stats(m, s, group)) if (symmetric and world > 1) else None
+    return _step.contrastive_step(residue_states, protein_mask, adapter, text_embeds=t_global,
+                                  temperature=temperature, symmetric=symmetric, labels=labels, aux=aux,
+                                  col_stats_hook=hook, all_cols_labelled=symmetric and world > 1)

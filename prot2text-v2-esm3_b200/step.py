@@ -66,7 +66,8 @@ class _ContrastiveStepFunction(torch.autograd.Function):
         hook = cfg.get("col_stats_hook")
         res = _core.infonce_forward(p_bf[:used], t_bf, labels[:used], cfg["tau"], w_row=cfg["w_row"], w_col=cfg["w_col"],
                                     need_grad=need_grad, want_col_argmax=True, col_stats_hook=hook,
-                                    loss_scale=cfg.get("loss_scale"))
+                                    loss_scale=cfg.get("loss_scale"),
+                                    all_cols_labelled=cfg.get("all_cols_labelled", False))
         aux.protein_embeddings, aux.text_embeddings = p_bf, t_bf
         aux.argmax_row, aux.argmax_col, aux.n_rows = res.argmax_row, res.argmax_col, plan.n_rows
         if need_grad:
@@ -98,7 +99,8 @@ def contrastive_step(residue_states: torch.Tensor, protein_mask: torch.Tensor, a
                      text_embeds: Optional[torch.Tensor] = None, temperature: float = 0.05,
                      contrastive_num_segments: int = 1, symmetric: bool = False,
                      labels: Optional[torch.Tensor] = None, aux: Optional[StepAux] = None,
-                     col_stats_hook=None, loss_scale: Optional[float] = None) -> torch.Tensor:
+                     col_stats_hook=None, loss_scale: Optional[float] = None,
+                     all_cols_labelled: bool = False) -> torch.Tensor:
     """One Stage-1 step from trunk outputs to the (differentiable) fp32 loss.
 
     residue_states (B, L, D_in) bf16 and protein_mask (B, L) come from the frozen protein encoder
@@ -122,7 +124,7 @@ def contrastive_step(residue_states: torch.Tensor, protein_mask: torch.Tensor, a
     p = adapter.dropout_p()
     cfg = dict(tau=float(temperature), w_row=0.5 if symmetric else 1.0, w_col=0.5 if symmetric else 0.0,
                dropout_p=p, seed=_draw_seed() if p > 0 else 0, rows_used=seg * contrastive_num_segments,
-               col_stats_hook=col_stats_hook, loss_scale=loss_scale)
+               col_stats_hook=col_stats_hook, loss_scale=loss_scale, all_cols_labelled=all_cols_labelled)
     aux = aux if aux is not None else StepAux()
     return _ContrastiveStepFunction.apply(residue_states, protein_mask, adapter.fc1.weight, adapter.fc1.bias,
                                           adapter.fc2.weight, adapter.fc2.bias, text_embeds, labels, cfg, aux)
