@@ -63,10 +63,11 @@ int p2t_gemm_bf16(const void* a, long long lda, int a_mn_major, const void* b, l
  * reference passes int64, scripts/train_contrast.py:270-275 / dataset collaters).  Any mask
  * pattern is accepted (right padded, left padded, holes).
  *   counts[B], seq_off[B+1], chunk_off[B+1] (pooling chunks of `chunk_rows` rows), n_rows_dev[1],
- *   row_src[>= sum(mask)] = flat source row b*L + r of each packed row (may be NULL).
+ *   row_src[>= sum(mask)] = flat source row b*L + r of each packed row (may be NULL),
+ *   chunk_seq[>= ceil(B*L/chunk_rows)+B] = sequence owning each pooling chunk (may be NULL).
  * ------------------------------------------------------------------------------------------- */
 int p2t_rows_plan(const void* mask, int mask_bytes, int B, int L, int chunk_rows, int* counts, int* seq_off,
-                  int* chunk_off, int* n_rows_dev, int* row_src, void* stream);
+                  int* chunk_off, int* n_rows_dev, int* row_src, int* chunk_seq, void* stream);
 
 /* out[i] = src[row_src[i]] (bf16 rows of D elements), zero rows from n_rows up to the next multiple
  * of 256 (<= rows_cap).  Packs the padded (B, L, D_in) residue states that
@@ -82,7 +83,7 @@ int p2t_gather_rows(const void* src, long long ld_src, const int* row_src, const
  *   g2 = keep * GELU'(h1 W2^T + b2)         [rows_cap][d_out] fp16   (NULL when no backward)
  *   (a, g1, g2 are read only by this library's streaming kernels; fp16 keeps 3 more mantissa bits
  *    than bf16 at the same bytes.  h1 and every GEMM operand are bf16.)
- *   rowsq[row][nblk] = partial sums of a^2, nblk = ceil(d_out/256) — the per-residue L2 norm (:67)
+ *   rowsq[row][nblk] = partial sums of a^2, nblk = 4*ceil(d_out/256) — the per-residue L2 norm (:67)
  * x has x_rows rows allocated (TMA zero-fills beyond); outputs have rows_cap rows.
  * Weights in nn.Linear layout (out, in), bf16.  dropout_p = 0 is eval mode; otherwise a Philox
  * mask keyed by (seed, layer, row, column) with multiplier 1/(1-p) (nn.Dropout, :63,:66).
@@ -96,16 +97,20 @@ int p2t_adapter_fwd(const void* x, int x_rows, const void* w1, const void* b1, c
 int p2t_adapter_scale_rows(const void* a, const float* rowsq, int nblk, int n, int d_out, void* y, float* inv_norm,
                            void* stream);
 
+/* inv_norm[row] = 1 / max(sqrt(sum_j rowsq[row][j]), 1e-12) for row < n_rows: the per-residue
+ * F.normalize denominator of models/modeling_esm2llama_instruct.py:67 */
+int p2t_row_inv_norm(const float* rowsq, int nblk, const int* n_rows_dev, int rows_cap, float* inv_norm, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * readout_embeddings(..., "mean"|"std"|"mix") — scripts/train_contrast.py:217-248 — over the rows
  * listed by a plan.  `src` is bf16 (or fp16 when src_is_f16: the adapter's own `a`) [*][ld_src];
- * row_src == NULL means rows are already packed.
- * With rowsq != NULL every row is first scaled by its inverse L2 norm (adapter output fused in).
+ * row_src == NULL means rows are already packed.  With inv_norm != NULL every row is first scaled
+ * by inv_norm[row] (adapter output: normalise fused into the pooling pass).
  * partial_ws: float2 [max_chunks][D]; out: fp32 [B][ld_out] (mean | std for mix).
  * ------------------------------------------------------------------------------------------- */
-int p2t_pool_fwd(const void* src, int src_is_f16, long long ld_src, const int* row_src, const float* rowsq, int nblk,
-                 const int* seq_off, const int* chunk_off, int B, int D, int chunk_rows, int max_chunks, int mode,
-                 void* partial_ws, float* inv_norm_out, float* out, long long ld_out, void* stream);
+int p2t_pool_fwd(const void* src, int src_is_f16, long long ld_src, const int* row_src, const float* inv_norm,
+                 const int* seq_off, const int* chunk_off, const int* chunk_seq, int B, int D, int chunk_rows,
+                 int max_chunks, int mode, void* partial_ws, float* out, long long ld_out, void* stream);
 
 /* readout_embeddings(..., "last") — :207-215 — out fp32 [B][D] from padded x [B][S][D] */
 int p2t_readout_last(const void* x, const int* counts, int B, int S, int D, float* out, void* stream);
@@ -123,9 +128,12 @@ int p2t_readout_bwd(const void* x, const void* mask, int mask_bytes, int B, int 
                     const float* c2, void* dx, void* stream);
 
 /* backward through normalise -> GELU(fc2) on packed rows (autograd of :65-67):
- *   dz2 = ((dy - y (y.dy)) / |a|) * g2,  dy = c1[b] + c2[b]*y   (pooled)   or given per row (_dy) */
-int p2t_adapter_tail_bwd(const void* a, const void* g2, const float* inv_norm, const int* seq_off, int B,
-                         const float* c1, const float* c2, const int* n_rows_dev, int rows_cap, int d_out, void* dz2,
+ *   dz2 = ((dy - y (y.dy)) / |a|) * g2,  dy = c1[b] + c2[b]*y   (pooled)   or given per row (_dy)
+ * The pooled form runs one CTA per pooling chunk and also emits db2 = colsum(dz2) (colsum_ws: fp32
+ * [max_chunks][d_out]; db2 bf16 [d_out], may be NULL). */
+int p2t_adapter_tail_bwd(const void* a, const void* g2, const float* inv_norm, const int* seq_off, const int* chunk_off,
+                         const int* chunk_seq, int B, const float* c1, const float* c2, const int* n_rows_dev,
+                         int rows_cap, int d_out, int chunk_rows, int max_chunks, void* dz2, float* colsum_ws, void* db2,
                          void* stream);
 int p2t_adapter_tail_bwd_dy(const void* a, const void* g2, const float* inv_norm, const void* dy, int n,
                             int rows_cap, int d_out, void* dz2, void* stream);
@@ -134,8 +142,8 @@ int p2t_adapter_tail_bwd_dy(const void* a, const void* g2, const float* inv_norm
  * backward GEMMs of the adapter (autograd of :62-65; scripts/train_contrast.py:448):
  *   dz1 = (dz2 W2) * g1;  dW2 = dz2^T h1;  db2 = colsum dz2;  dW1 = dz1^T x;  db1 = colsum dz1
  *   dx  = dz1 W1 (only when dx != NULL; the encoder is frozen in Stage 1, :186)
- * Gradients are written (not accumulated) in bf16, nn.Linear layout.  colsum_ws: fp32
- * [64][max(d_mid, d_out)] scratch.
+ * Gradients are written (not accumulated) in bf16, nn.Linear layout.  db1/db2/dx may be NULL (db2
+ * is normally produced by p2t_adapter_tail_bwd).  colsum_ws: fp32 [ceil(rows_cap/64)][max(d_mid, d_out)].
  * ------------------------------------------------------------------------------------------- */
 int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, const void* h1, const void* g1, const void* dz2,
                     int d_in, int d_mid, int d_out, int rows_cap, const int* n_rows_dev, void* dz1, void* dw1,
@@ -143,29 +151,32 @@ int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, c
 
 /* ---------------------------------------------------------------------------------------------
  * InfoNCE — scripts/train_contrast.py:86-91 (BatchInfoNCELoss), :100-114 (Segmented...).
- * p2t_similarity : S[R][C] = (p . t^T) / tau   (fp32; bf16 unit-norm inputs [R][E], [C][E])
+ * p2t_similarity : S[R][C] = (p . t^T) / tau   (fp32 out; unit-norm inputs [R][E], [C][E] as bf16 and/or
+ *      fp32 — small problems use the fp32 copies on CUDA cores when given, large ones the bf16 tcgen05 GEMM)
  * p2t_infonce_col_stats : per-column online (max, sum exp, argmax row) — the text->protein term
  * p2t_infonce_ce : one pass per row: loss_i, row lse, argmax, and dS written over S
  *      loss_i = w_row (lse_j S_ij - S_i,lab) + w_col (lse_col[lab] - S_i,lab);  dS scaled by inv_rn
  *      all_cols_labelled != 0: sharded global batch, every column's positive lives on some rank
- * p2t_infonce_grad : dp = dS t / tau (fp32 [R][E]) and optionally dt = dS^T p / tau (fp32 [C][E])
+ * p2t_infonce_grad : dp = dS t / tau (fp32 [R][E]) and optionally dt = dS^T p / tau (fp32 [C][E]); same
+ *      bf16 / fp32 operand convention as p2t_similarity
  * p2t_loss_mean : loss[0] (+)= scale * sum_i row_loss[i], fixed-order reduction
  * ------------------------------------------------------------------------------------------- */
-int p2t_similarity(const void* p, const void* t, int R, int C, int E, float tau, float* S, int cta_group,
-                   void* stream);
+int p2t_similarity(const void* p, const void* t, const float* p_f32, const float* t_f32, int R, int C, int E, float tau,
+                   float* S, int cta_group, void* stream);
 int p2t_infonce_col_stats(const float* S, int R, int C, float* col_max, float* col_sum, int* col_argmax,
                           int row_index_base, void* stream);
 int p2t_infonce_ce(float* S, const int* labels, int R, int C, float w_row, float w_col, float inv_rn,
                    const float* col_max, const float* col_sum, unsigned char* col_labelled_ws, int all_cols_labelled,
                    float* row_loss, float* row_lse, int* argmax_row, void* dS_bf16, int write_ds, void* stream);
-int p2t_infonce_grad(const float* dS, const void* dS_bf16, const void* p, const void* t, int R, int C, int E,
-                     float tau, float* dp, float* dt, void* bf16_ws, int cta_group, void* stream);
+int p2t_infonce_grad(const float* dS, const void* dS_bf16, const void* p, const void* t, const float* p_f32,
+                     const float* t_f32, int R, int C, int E, float tau, float* dp, float* dt, int cta_group,
+                     void* stream);
 int p2t_loss_mean(const float* row_loss, int R, float scale, float* loss, int accumulate, void* stream);
 
 /* dtype helpers used by the host layer around the fp32 <-> bf16 boundaries */
 int p2t_f32_to_bf16(const float* in, long long n, void* out, void* stream);
 int p2t_bf16_to_f32(const void* in, long long n, float* out, void* stream);
-/* deterministic column sums of a packed bf16 matrix (bias gradients) */
+/* deterministic column sums of a packed bf16 matrix (bias gradients); ws: fp32 [ceil(n_static/64)][D] */
 int p2t_colsum(const void* x, const int* n_rows_dev, int n_static, int D, float* ws, void* out_bf16, float* out_f32,
                void* stream);
 /* debug/test aid: the dropout keep-multipliers the kernels use, as fp32 [rows][cols] */

@@ -55,6 +55,7 @@ class RowPlan:
     chunk_off: torch.Tensor   # int32 [B+1]
     n_rows: torch.Tensor      # int32 [1] (device)
     row_src: Optional[torch.Tensor]  # int32 [B*L]
+    chunk_seq: torch.Tensor   # int32 [max_chunks] sequence owning each pooling chunk
     rows_cap: int             # allocation size for packed buffers
     max_chunks: int           # upper bound on pooling chunks
 
@@ -75,10 +76,12 @@ def plan_rows(mask: torch.Tensor, want_row_src: bool = True) -> RowPlan:
     ints = torch.empty(3 * (B + 1) + 1, dtype=torch.int32, device=dev)
     counts, seq_off, chunk_off, n_rows = ints[:B], ints[B + 1:2 * B + 2], ints[2 * B + 2:3 * B + 3], ints[3 * B + 3:]
     row_src = torch.empty(B * L, dtype=torch.int32, device=dev) if want_row_src else None
+    max_chunks = (B * L + CHUNK_ROWS - 1) // CHUNK_ROWS + B
+    chunk_seq = torch.empty(max_chunks, dtype=torch.int32, device=dev)
     _lib.call("p2t_rows_plan", _ptr(mask), nbytes, B, L, CHUNK_ROWS, _ptr(counts), _ptr(seq_off), _ptr(chunk_off),
-              _ptr(n_rows), _ptr(row_src), _stream())
+              _ptr(n_rows), _ptr(row_src), _ptr(chunk_seq), _stream())
     return RowPlan(B=B, L=L, counts=counts, seq_off=seq_off, chunk_off=chunk_off, n_rows=n_rows, row_src=row_src,
-                   rows_cap=_round_up(B * L, ROW_ALIGN), max_chunks=(B * L + CHUNK_ROWS - 1) // CHUNK_ROWS + B)
+                   chunk_seq=chunk_seq, rows_cap=_round_up(B * L, ROW_ALIGN), max_chunks=max_chunks)
 
 
 def dense_plan(B: int, L: int, device) -> RowPlan:
@@ -142,7 +145,7 @@ def adapter_forward(x: torch.Tensor, x_rows: int, rows_cap: int, n_rows: torch.T
     a = torch.empty(rows_cap, d_out, dtype=torch.float16, device=dev)
     g1 = torch.empty(rows_cap, d_mid, dtype=torch.float16, device=dev) if need_grad else None
     g2 = torch.empty(rows_cap, d_out, dtype=torch.float16, device=dev) if need_grad else None
-    nblk = (d_out + 255) // 256
+    nblk = 4 * ((d_out + 255) // 256)
     rowsq = torch.empty(rows_cap, nblk, dtype=torch.float32, device=dev)
     _lib.call("p2t_adapter_fwd", _ptr(x), x_rows, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), d_in, d_mid, d_out,
               rows_cap, _ptr(n_rows), _ptr(h1), _ptr(g1), _ptr(a), _ptr(g2), _ptr(rowsq), float(dropout_p),
@@ -151,9 +154,9 @@ def adapter_forward(x: torch.Tensor, x_rows: int, rows_cap: int, n_rows: torch.T
                        n_rows=n_rows)
 
 
-def adapter_backward(acts: AdapterActs, dz2: torch.Tensor, w1, w2, need_dx: bool = False,
+def adapter_backward(acts: AdapterActs, dz2: torch.Tensor, w1, w2, need_dx: bool = False, need_db2: bool = True,
                      cta_group: Optional[int] = None):
-    """Returns (dw1, db1, dw2, db2, dx_or_None) in bf16, nn.Linear layout."""
+    """Returns (dw1, db1, dw2, db2_or_None, dx_or_None) in bf16, nn.Linear layout."""
     d_mid, d_in = w1.shape
     d_out = w2.shape[0]
     dev = dz2.device
@@ -162,9 +165,9 @@ def adapter_backward(acts: AdapterActs, dz2: torch.Tensor, w1, w2, need_dx: bool
     dw1 = torch.empty(d_mid, d_in, dtype=bf, device=dev)
     db1 = torch.empty(d_mid, dtype=bf, device=dev)
     dw2 = torch.empty(d_out, d_mid, dtype=bf, device=dev)
-    db2 = torch.empty(d_out, dtype=bf, device=dev)
+    db2 = torch.empty(d_out, dtype=bf, device=dev) if need_db2 else None
     dx = torch.empty(acts.rows_cap, d_in, dtype=bf, device=dev) if need_dx else None
-    ws = torch.empty(64, max(d_mid, d_out), dtype=torch.float32, device=dev)
+    ws = torch.empty((acts.rows_cap + 63) // 64, max(d_mid, d_out) if need_db2 else d_mid, dtype=torch.float32, device=dev)
     _lib.call("p2t_adapter_bwd", _ptr(acts.x), acts.x_rows, _ptr(w1), _ptr(w2), _ptr(acts.h1), _ptr(acts.g1),
               _ptr(dz2), d_in, d_mid, d_out, acts.rows_cap, _ptr(acts.n_rows), _ptr(dz1), _ptr(dw1), _ptr(db1),
               _ptr(dw2), _ptr(db2), _ptr(dx), _ptr(ws), cta_group or default_cta_group(), _stream())
@@ -174,17 +177,24 @@ def adapter_backward(acts: AdapterActs, dz2: torch.Tensor, w1, w2, need_dx: bool
 # --------------------------------------------------------------------------------------------------
 # pooling / normalisation
 # --------------------------------------------------------------------------------------------------
+def row_inv_norm(acts: "AdapterActs") -> torch.Tensor:
+    """1 / max(|a_row|, 1e-12) per packed row, from the fc2 epilogue's partial sums of squares."""
+    inv = torch.empty(acts.rows_cap, dtype=torch.float32, device=acts.a.device)
+    _lib.call("p2t_row_inv_norm", _ptr(acts.rowsq), acts.nblk, _ptr(acts.n_rows), acts.rows_cap, _ptr(inv), _stream())
+    return inv
+
+
 def pool_forward(src: torch.Tensor, plan: RowPlan, D: int, *, row_src: Optional[torch.Tensor],
-                 rowsq: Optional[torch.Tensor] = None, nblk: int = 0, want_inv_norm: bool = False):
-    """(mean | std) statistics fp32 [B, 2D] of the plan's rows of `src` (bf16 or fp16, row stride src.stride(0))."""
+                 inv_norm: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(mean | std) statistics fp32 [B, 2D] of the plan's rows of `src` (bf16 or fp16, row stride src.stride(0)),
+    each row optionally scaled by inv_norm[row] first."""
     dev = src.device
     partial = torch.empty(plan.max_chunks, D, 2, dtype=torch.float32, device=dev)
     stats = torch.empty(plan.B, 2 * D, dtype=torch.float32, device=dev)
-    inv_norm = torch.empty(plan.rows_cap, dtype=torch.float32, device=dev) if want_inv_norm else None
-    _lib.call("p2t_pool_fwd", _ptr(src), int(src.dtype == torch.float16), src.stride(0), _ptr(row_src), _ptr(rowsq), nblk, _ptr(plan.seq_off),
-              _ptr(plan.chunk_off), plan.B, D, CHUNK_ROWS, plan.max_chunks, READOUT_MODES["mix"], _ptr(partial),
-              _ptr(inv_norm), _ptr(stats), 2 * D, _stream())
-    return stats, inv_norm
+    _lib.call("p2t_pool_fwd", _ptr(src), int(src.dtype == torch.float16), src.stride(0), _ptr(row_src), _ptr(inv_norm),
+              _ptr(plan.seq_off), _ptr(plan.chunk_off), _ptr(plan.chunk_seq), plan.B, D, CHUNK_ROWS, plan.max_chunks,
+              READOUT_MODES["mix"], _ptr(partial), _ptr(stats), 2 * D, _stream())
+    return stats
 
 
 def l2norm_forward(e: torch.Tensor, want_f32: bool = True):
@@ -194,6 +204,12 @@ def l2norm_forward(e: torch.Tensor, want_f32: bool = True):
     norm = torch.empty(B, dtype=torch.float32, device=e.device)
     _lib.call("p2t_l2norm_fwd", _ptr(e), B, E, _ptr(p_bf), _ptr(p_f32), _ptr(norm), _stream())
     return p_bf, p_f32, norm
+
+
+def to_bf16(x_f32: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(x_f32.shape, dtype=torch.bfloat16, device=x_f32.device)
+    _lib.call("p2t_f32_to_bf16", _ptr(x_f32), x_f32.numel(), _ptr(out), _stream())
+    return out
 
 
 def l2norm_backward(dp: torch.Tensor, p_f32: torch.Tensor, norm: torch.Tensor) -> torch.Tensor:
@@ -211,12 +227,17 @@ def pool_backward_coef(de: torch.Tensor, stats: torch.Tensor, plan: RowPlan, D: 
     return c1, c2
 
 
-def adapter_tail_backward(acts: AdapterActs, inv_norm: torch.Tensor, plan: RowPlan, c1, c2) -> torch.Tensor:
+def adapter_tail_backward(acts: AdapterActs, inv_norm: torch.Tensor, plan: RowPlan, c1, c2):
+    """dz2 (bf16 [rows_cap, d_out]) and db2 = colsum(dz2) (bf16 [d_out])."""
     d_out = acts.a.shape[1]
-    dz2 = torch.empty(acts.rows_cap, d_out, dtype=torch.bfloat16, device=acts.a.device)
-    _lib.call("p2t_adapter_tail_bwd", _ptr(acts.a), _ptr(acts.g2), _ptr(inv_norm), _ptr(plan.seq_off), plan.B,
-              _ptr(c1), _ptr(c2), _ptr(acts.n_rows), acts.rows_cap, d_out, _ptr(dz2), _stream())
-    return dz2
+    dev = acts.a.device
+    dz2 = torch.empty(acts.rows_cap, d_out, dtype=torch.bfloat16, device=dev)
+    ws = torch.empty(plan.max_chunks + 8, d_out, dtype=torch.float32, device=dev)
+    db2 = torch.empty(d_out, dtype=torch.bfloat16, device=dev)
+    _lib.call("p2t_adapter_tail_bwd", _ptr(acts.a), _ptr(acts.g2), _ptr(inv_norm), _ptr(plan.seq_off),
+              _ptr(plan.chunk_off), _ptr(plan.chunk_seq), plan.B, _ptr(c1), _ptr(c2), _ptr(acts.n_rows), acts.rows_cap,
+              d_out, CHUNK_ROWS, plan.max_chunks, _ptr(dz2), _ptr(ws), _ptr(db2), _stream())
+    return dz2, db2
 
 
 # --------------------------------------------------------------------------------------------------
@@ -236,6 +257,7 @@ class InfoNCEResult:
 
 def infonce_forward(p_bf: torch.Tensor, t_bf: torch.Tensor, labels: torch.Tensor, tau: float, *, w_row: float = 1.0,
                     w_col: float = 0.0, need_grad: bool = True, want_col_argmax: bool = False,
+                    p_f32: Optional[torch.Tensor] = None, t_f32: Optional[torch.Tensor] = None,
                     col_stats_hook=None, loss_scale: Optional[float] = None, all_cols_labelled: bool = False,
                     cta_group: Optional[int] = None) -> InfoNCEResult:
     """loss = mean_i [ w_row (lse_j S_ij - S_i,lab) + w_col (lse_col[lab] - S_i,lab) ], S = p t^T / tau.
@@ -244,6 +266,9 @@ def infonce_forward(p_bf: torch.Tensor, t_bf: torch.Tensor, labels: torch.Tensor
     statistics across ranks before the gradient pass.  `loss_scale` overrides 1/R.
     `all_cols_labelled`: every column has its positive on SOME rank (sharded global batch), so the
     column term's gradient flows to all local rows, not only to columns labelled by local rows.
+    `p_f32`/`t_f32`: fp32 copies of the embeddings; when given, small problems (CUDA-core path) use
+    them instead of the bf16 tensors (see infonce.cu: near-parallel embeddings make bf16 rounding of
+    p/t the dominant gradient error).
     """
     require_cuda_bf16(p_bf, "p")
     require_cuda_bf16(t_bf, "t")
@@ -253,7 +278,8 @@ def infonce_forward(p_bf: torch.Tensor, t_bf: torch.Tensor, labels: torch.Tensor
     cg = cta_group or default_cta_group()
     labels32 = labels.to(device=dev, dtype=torch.int32).contiguous()
     S = torch.empty(R, C, dtype=torch.float32, device=dev)
-    _lib.call("p2t_similarity", _ptr(p_bf), _ptr(t_bf), R, C, E, float(tau), _ptr(S), cg, _stream())
+    _lib.call("p2t_similarity", _ptr(p_bf), _ptr(t_bf), _ptr(p_f32), _ptr(t_f32), R, C, E, float(tau), _ptr(S), cg,
+              _stream())
     col_max = col_sum = argmax_col = marks = None
     if w_col != 0.0 or want_col_argmax:
         col_max = torch.empty(C, dtype=torch.float32, device=dev)
@@ -279,14 +305,15 @@ def infonce_forward(p_bf: torch.Tensor, t_bf: torch.Tensor, labels: torch.Tensor
 
 
 def infonce_backward(res: InfoNCEResult, p_bf, t_bf, tau: float, need_dp: bool = True, need_dt: bool = False,
+                     p_f32: Optional[torch.Tensor] = None, t_f32: Optional[torch.Tensor] = None,
                      cta_group: Optional[int] = None):
     R, E = p_bf.shape
     C = t_bf.shape[0]
     dev = p_bf.device
     dp = torch.empty(R, E, dtype=torch.float32, device=dev) if need_dp else None
     dt = torch.empty(C, E, dtype=torch.float32, device=dev) if need_dt else None
-    _lib.call("p2t_infonce_grad", _ptr(res.dS), _ptr(res.dS_bf16), _ptr(p_bf), _ptr(t_bf), R, C, E, float(tau),
-              _ptr(dp), _ptr(dt), None, cta_group or default_cta_group(), _stream())
+    _lib.call("p2t_infonce_grad", _ptr(res.dS), _ptr(res.dS_bf16), _ptr(p_bf), _ptr(t_bf), _ptr(p_f32), _ptr(t_f32),
+              R, C, E, float(tau), _ptr(dp), _ptr(dt), cta_group or default_cta_group(), _stream())
     return dp, dt
 
 

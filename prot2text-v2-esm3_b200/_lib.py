@@ -16,23 +16,24 @@ _vp, _i, _ll, _f, _ull = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulong
 # name -> argument ctypes, in header order (include/p2t_b200.h)
 SIGNATURES = {
     "p2t_gemm_bf16": [_vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp],
-    "p2t_rows_plan": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "p2t_rows_plan": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "p2t_row_inv_norm": [_vp, _i, _vp, _i, _vp, _vp],
     "p2t_gather_rows": [_vp, _ll, _vp, _vp, _i, _i, _vp, _vp],
     "p2t_adapter_fwd": [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _ull, _i, _vp],
     "p2t_adapter_scale_rows": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp],
-    "p2t_pool_fwd": [_vp, _i, _ll, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _ll, _vp],
+    "p2t_pool_fwd": [_vp, _i, _ll, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _ll, _vp],
     "p2t_readout_last": [_vp, _vp, _i, _i, _i, _vp, _vp],
     "p2t_l2norm_fwd": [_vp, _i, _i, _vp, _vp, _vp, _vp],
     "p2t_l2norm_bwd": [_vp, _vp, _vp, _i, _i, _vp, _vp],
     "p2t_pool_bwd_coef": [_vp, _ll, _vp, _ll, _vp, _i, _i, _i, _vp, _vp, _vp],
     "p2t_readout_bwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
-    "p2t_adapter_tail_bwd": [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp],
+    "p2t_adapter_tail_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "p2t_adapter_tail_bwd_dy": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp],
     "p2t_adapter_bwd": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
-    "p2t_similarity": [_vp, _vp, _i, _i, _i, _f, _vp, _i, _vp],
+    "p2t_similarity": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i, _vp],
     "p2t_infonce_col_stats": [_vp, _i, _i, _vp, _vp, _vp, _i, _vp],
     "p2t_infonce_ce": [_vp, _vp, _i, _i, _f, _f, _f, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp],
-    "p2t_infonce_grad": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _i, _vp],
+    "p2t_infonce_grad": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _i, _vp],
     "p2t_loss_mean": [_vp, _i, _f, _vp, _i, _vp],
     "p2t_f32_to_bf16": [_vp, _ll, _vp, _vp],
     "p2t_bf16_to_f32": [_vp, _ll, _vp, _vp],

@@ -75,11 +75,11 @@ int p2t_gemm_bf16(const void* a, long long lda, int a_mn_major, const void* b, l
 }
 
 int p2t_rows_plan(const void* mask, int mask_bytes, int B, int L, int chunk_rows, int* counts, int* seq_off,
-                  int* chunk_off, int* n_rows_dev, int* row_src, void* stream) {
+                  int* chunk_off, int* n_rows_dev, int* row_src, int* chunk_seq, void* stream) {
   if (!mask || !counts || !seq_off || !chunk_off || !n_rows_dev) return set_error(-1, "p2t_rows_plan: null pointer");
   if (mask_bytes != 1 && mask_bytes != 4 && mask_bytes != 8) return set_error(-1, "p2t_rows_plan: mask_bytes must be 1, 4 or 8");
   if (chunk_rows <= 0) return set_error(-1, "p2t_rows_plan: chunk_rows must be positive");
-  return rows_plan(mask, mask_bytes, B, L, chunk_rows, counts, seq_off, chunk_off, n_rows_dev, row_src, S(stream));
+  return rows_plan(mask, mask_bytes, B, L, chunk_rows, counts, seq_off, chunk_off, n_rows_dev, row_src, chunk_seq, S(stream));
 }
 
 int p2t_gather_rows(const void* src, long long ld_src, const int* row_src, const int* n_rows_dev, int rows_cap,
@@ -105,7 +105,7 @@ int p2t_adapter_fwd(const void* x, int x_rows, const void* w1, const void* b1, c
   q.dyn_m = n_rows_dev;
   q.d0 = a; q.ldd0 = d_out; q.d1 = g2; q.ldd1 = d_out;
   q.bias = reinterpret_cast<const __nv_bfloat16*>(b2);
-  q.rowsq = rowsq; q.ld_rowsq = (d_out + GEMM_BLOCK_N - 1) / GEMM_BLOCK_N;
+  q.rowsq = rowsq; q.ld_rowsq = (GEMM_EPI_WARPS / 4) * ((d_out + GEMM_BLOCK_N - 1) / GEMM_BLOCK_N);
   q.drop = make_dropout(dropout_p, seed, 2);
   return launch_gemm(h1, d_mid, false, w2, d_mid, false, EPI_FC2, q, cta_group, S(stream));
 }
@@ -117,14 +117,19 @@ int p2t_adapter_scale_rows(const void* a, const float* rowsq, int nblk, int n, i
   return scale_rows(a, rowsq, nblk, n, d_out, y, inv_norm, S(stream));
 }
 
-int p2t_pool_fwd(const void* src, int src_is_f16, long long ld_src, const int* row_src, const float* rowsq, int nblk,
-                 const int* seq_off, const int* chunk_off, int B, int D, int chunk_rows, int max_chunks, int mode,
-                 void* partial_ws, float* inv_norm_out, float* out, long long ld_out, void* stream) {
-  if (!src || !seq_off || !chunk_off || !partial_ws || !out) return set_error(-1, "p2t_pool_fwd: null pointer");
+int p2t_row_inv_norm(const float* rowsq, int nblk, const int* n_rows_dev, int rows_cap, float* inv_norm, void* stream) {
+  if (!rowsq || !n_rows_dev || !inv_norm) return set_error(-1, "p2t_row_inv_norm: null pointer");
+  return row_inv_norm(rowsq, nblk, n_rows_dev, rows_cap, inv_norm, S(stream));
+}
+
+int p2t_pool_fwd(const void* src, int src_is_f16, long long ld_src, const int* row_src, const float* inv_norm,
+                 const int* seq_off, const int* chunk_off, const int* chunk_seq, int B, int D, int chunk_rows,
+                 int max_chunks, int mode, void* partial_ws, float* out, long long ld_out, void* stream) {
+  if (!src || !seq_off || !chunk_off || !chunk_seq || !partial_ws || !out) return set_error(-1, "p2t_pool_fwd: null pointer");
   if (mode < 1 || mode > 3) return set_error(-1, "p2t_pool_fwd: mode must be MEAN, STD or MIX");
   if (max_chunks <= 0) return 0;
-  return pool_forward(src, src_is_f16 != 0, ld_src, row_src, rowsq, nblk, seq_off, chunk_off, B, D, chunk_rows, max_chunks, mode,
-                      reinterpret_cast<float2*>(partial_ws), inv_norm_out, out, ld_out, S(stream));
+  return pool_forward(src, src_is_f16 != 0, ld_src, row_src, inv_norm, seq_off, chunk_off, chunk_seq, B, D, chunk_rows,
+                      max_chunks, mode, reinterpret_cast<float2*>(partial_ws), out, ld_out, S(stream));
 }
 
 int p2t_readout_last(const void* x, const int* counts, int B, int S_, int D, float* out, void* stream) {
@@ -154,12 +159,14 @@ int p2t_readout_bwd(const void* x, const void* mask, int mask_bytes, int B, int 
   return readout_backward(x, mask, mask_bytes, B, S_, D, c1, c2, dx, S(stream));
 }
 
-int p2t_adapter_tail_bwd(const void* a, const void* g2, const float* inv_norm, const int* seq_off, int B,
-                         const float* c1, const float* c2, const int* n_rows_dev, int rows_cap, int d_out, void* dz2,
+int p2t_adapter_tail_bwd(const void* a, const void* g2, const float* inv_norm, const int* seq_off, const int* chunk_off,
+                         const int* chunk_seq, int B, const float* c1, const float* c2, const int* n_rows_dev,
+                         int rows_cap, int d_out, int chunk_rows, int max_chunks, void* dz2, float* colsum_ws, void* db2,
                          void* stream) {
-  if (!a || !g2 || !inv_norm || !seq_off || !c1 || !c2 || !n_rows_dev || !dz2)
+  if (!a || !g2 || !inv_norm || !seq_off || !chunk_off || !chunk_seq || !c1 || !c2 || !n_rows_dev || !dz2)
     return set_error(-1, "p2t_adapter_tail_bwd: null pointer");
-  return adapter_tail_backward(a, g2, inv_norm, seq_off, B, c1, c2, n_rows_dev, rows_cap, d_out, dz2, S(stream));
+  return adapter_tail_backward(a, g2, inv_norm, seq_off, chunk_off, chunk_seq, B, c1, c2, n_rows_dev, rows_cap, d_out,
+                               chunk_rows, max_chunks, dz2, colsum_ws, db2, S(stream));
 }
 int p2t_adapter_tail_bwd_dy(const void* a, const void* g2, const float* inv_norm, const void* dy, int n,
                             int rows_cap, int d_out, void* dz2, void* stream) {
@@ -196,8 +203,8 @@ int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, c
     p.b_extent = x_rows;
     if (int rc = launch_gemm(dz1, d_mid, true, x, d_in, true, EPI_STORE_BF16, p, cta_group, st)) return rc;
   }
-  if (db2) if (int rc = colsum(dz2, n_rows_dev, rows_cap, d_out, colsum_ws, 64, db2, nullptr, st)) return rc;
-  if (db1) if (int rc = colsum(dz1, n_rows_dev, rows_cap, d_mid, colsum_ws, 64, db1, nullptr, st)) return rc;
+  if (db2) if (int rc = colsum(dz2, n_rows_dev, rows_cap, d_out, colsum_ws, db2, nullptr, st)) return rc;
+  if (db1) if (int rc = colsum(dz1, n_rows_dev, rows_cap, d_mid, colsum_ws, db1, nullptr, st)) return rc;
   if (dx) {
     if (!w1) return set_error(-1, "p2t_adapter_bwd: w1 required for dx");
     GemmParams p = base_params(rows_cap, d_in, d_mid);
@@ -210,11 +217,14 @@ int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, c
 
 static bool small_problem(int R, int C, int E) { return (long long)R * C * E <= (1LL << 26); }
 
-int p2t_similarity(const void* p, const void* t, int R, int C, int E, float tau, float* Sm, int cta_group,
-                   void* stream) {
-  if (!p || !t || !Sm) return set_error(-1, "p2t_similarity: null pointer");
+int p2t_similarity(const void* p, const void* t, const float* p_f32, const float* t_f32, int R, int C, int E, float tau,
+                   float* Sm, int cta_group, void* stream) {
+  if (!Sm || (!(p && t) && !(p_f32 && t_f32))) return set_error(-1, "p2t_similarity: null pointer");
   if (tau <= 0.f) return set_error(-1, "p2t_similarity: temperature must be positive");
-  if (small_problem(R, C, E)) return sim_small(p, t, R, C, E, 1.f / tau, Sm, S(stream));
+  if (small_problem(R, C, E) || !(p && t)) {
+    if (p_f32 && t_f32) return sim_small(p_f32, t_f32, true, R, C, E, 1.f / tau, Sm, S(stream));
+    return sim_small(p, t, false, R, C, E, 1.f / tau, Sm, S(stream));
+  }
   GemmParams q = base_params(R, C, E);
   q.d0 = Sm; q.ldd0 = C; q.alpha = 1.f / tau;
   return launch_gemm(p, E, false, t, E, false, EPI_STORE_F32, q, cta_group, S(stream));
@@ -244,16 +254,20 @@ int p2t_infonce_ce(float* Sm, const int* labels, int R, int C, float w_row, floa
                  argmax_row, dS_bf16, write_ds, S(stream));
 }
 
-int p2t_infonce_grad(const float* dS, const void* dS_bf16, const void* p, const void* t, int R, int C, int E,
-                     float tau, float* dp, float* dt, void* bf16_ws, int cta_group, void* stream) {
-  if (!dS || !t) return set_error(-1, "p2t_infonce_grad: null pointer");
+int p2t_infonce_grad(const float* dS, const void* dS_bf16, const void* p, const void* t, const float* p_f32,
+                     const float* t_f32, int R, int C, int E, float tau, float* dp, float* dt, int cta_group,
+                     void* stream) {
+  if (!dS) return set_error(-1, "p2t_infonce_grad: null pointer");
   cudaStream_t st = S(stream);
-  (void)bf16_ws;
-  if (small_problem(R, C, E) || (C % 8) || !dS_bf16) {
-    if (dp) if (int rc = contract_small(dS, C, false, t, R, C, E, 1.f / tau, dp, st)) return rc;
+  const bool gemm_ok = !small_problem(R, C, E) && (C % 8 == 0) && dS_bf16 && (!dp || t) && (!dt || p);
+  if (!gemm_ok) {
+    if (dp) {
+      if (!t && !t_f32) return set_error(-1, "p2t_infonce_grad: t required for dp");
+      if (int rc = contract_small(dS, C, false, t_f32 ? (const void*)t_f32 : t, t_f32 != nullptr, R, C, E, 1.f / tau, dp, st)) return rc;
+    }
     if (dt) {
-      if (!p) return set_error(-1, "p2t_infonce_grad: p required for dt");
-      if (int rc = contract_small(dS, C, true, p, C, R, E, 1.f / tau, dt, st)) return rc;
+      if (!p && !p_f32) return set_error(-1, "p2t_infonce_grad: p required for dt");
+      if (int rc = contract_small(dS, C, true, p_f32 ? (const void*)p_f32 : p, p_f32 != nullptr, C, R, E, 1.f / tau, dt, st)) return rc;
     }
     return 0;
   }
@@ -263,7 +277,6 @@ int p2t_infonce_grad(const float* dS, const void* dS_bf16, const void* p, const 
     if (int rc = launch_gemm(dS_bf16, C, false, t, E, true, EPI_STORE_F32, q, cta_group, st)) return rc;
   }
   if (dt) {  // dt[j][e] = sum_i dS[i][j] p[i][e]: A[m=j][k=i] (MN-major), B[n=e][k=i] (MN-major)
-    if (!p) return set_error(-1, "p2t_infonce_grad: p required for dt");
     GemmParams q = base_params(C, E, R);
     q.d0 = dt; q.ldd0 = E; q.alpha = 1.f / tau;
     if (int rc = launch_gemm(dS_bf16, C, true, p, E, true, EPI_STORE_F32, q, cta_group, st)) return rc;
@@ -287,7 +300,7 @@ int p2t_bf16_to_f32(const void* in, long long n, float* out, void* stream) {
 int p2t_colsum(const void* x, const int* n_rows_dev, int n_static, int D, float* ws, void* out_bf16, float* out_f32,
                void* stream) {
   if (!x || !ws) return set_error(-1, "p2t_colsum: null pointer");
-  return colsum(x, n_rows_dev, n_static, D, ws, 64, out_bf16, out_f32, S(stream));
+  return colsum(x, n_rows_dev, n_static, D, ws, out_bf16, out_f32, S(stream));
 }
 int p2t_dropout_mask(int rows, int cols, float dropout_p, unsigned long long seed, int layer, float* out,
                      void* stream) {

@@ -18,6 +18,41 @@ namespace p2t {
 // small-problem similarity on CUDA cores: S[i][j] = alpha * sum_e p[i][e] t[j][e]
 // one warp per (i, 4 consecutive j); 16-byte loads.  (large problems use the tcgen05 GEMM)
 // ------------------------------------------------------------------------------------------------
+// fp32-embedding flavour: random-init / early-training embeddings are nearly parallel (loss ~ ln B), so the
+// informative part of S and of dp = dS t is a small difference of large common components; rounding p and t
+// to bf16 costs ~1 % of that difference.  The fused step therefore keeps p and t in fp32 on this path.
+__global__ void __launch_bounds__(256)
+sim_small_f32_kernel(const float* __restrict__ p, const float* __restrict__ t, int R, int C, int E, float alpha,
+                     float* __restrict__ S) {
+  const int lane = threadIdx.x & 31;
+  const int cgroups = (C + 3) / 4;
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp_id >= (long long)R * cgroups) return;
+  const int i = (int)(warp_id / cgroups), j0 = (int)(warp_id % cgroups) * 4;
+  const float4* pr = reinterpret_cast<const float4*>(p + (long long)i * E);
+  const float4* tr[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) tr[q] = reinterpret_cast<const float4*>(t + (long long)min(j0 + q, C - 1) * E);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int nvec = E >> 2;
+  for (int v = lane; v < nvec; v += 32) {
+    const float4 a = __ldg(pr + v);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 b = __ldg(tr[q] + v);
+      acc[q] = fmaf(a.x, b.x, acc[q]);
+      acc[q] = fmaf(a.y, b.y, acc[q]);
+      acc[q] = fmaf(a.z, b.z, acc[q]);
+      acc[q] = fmaf(a.w, b.w, acc[q]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float s = warp_sum(acc[q]);
+    if (lane == 0 && j0 + q < C) S[(long long)i * C + j0 + q] = s * alpha;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 sim_small_kernel(const __nv_bfloat16* __restrict__ p, const __nv_bfloat16* __restrict__ t, int R, int C, int E,
                  float alpha, float* __restrict__ S) {
@@ -183,9 +218,9 @@ __global__ void mark_labelled_kernel(const int* __restrict__ labels, int R, int 
 //   (dp = dS t / tau with W = dS [R][C], X = t [C][E];  dt = dS^T p / tau with W read transposed)
 // thread = (row i, 8 columns e); grid (ceil(E/8/256), R)
 // ------------------------------------------------------------------------------------------------
-template <bool TRANSPOSE_W>
+template <bool TRANSPOSE_W, bool X_F32>
 __global__ void __launch_bounds__(256)
-contract_small_kernel(const float* __restrict__ W, int ldw, const __nv_bfloat16* __restrict__ X, int n_out, int n_red,
+contract_small_kernel(const float* __restrict__ W, int ldw, const void* __restrict__ Xv, int n_out, int n_red,
                       int E, float alpha, float* __restrict__ out) {
   const int i = blockIdx.y;
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -193,13 +228,20 @@ contract_small_kernel(const float* __restrict__ W, int ldw, const __nv_bfloat16*
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int j = 0; j < n_red; ++j) {
     const float w = TRANSPOSE_W ? W[(long long)j * ldw + i] : W[(long long)i * ldw + j];
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(X + (long long)j * E) + v);
-    const uint32_t x[4] = {u.x, u.y, u.z, u.w};
+    if constexpr (X_F32) {
+      const float4* xr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(Xv) + (long long)j * E) + 2 * v;
+      const float4 a = __ldg(xr), b = __ldg(xr + 1);
+      acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]); acc[2] = fmaf(w, a.z, acc[2]); acc[3] = fmaf(w, a.w, acc[3]);
+      acc[4] = fmaf(w, b.x, acc[4]); acc[5] = fmaf(w, b.y, acc[5]); acc[6] = fmaf(w, b.z, acc[6]); acc[7] = fmaf(w, b.w, acc[7]);
+    } else {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(Xv) + (long long)j * E) + v);
+      const uint32_t x[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 f = unpack_bf16x2(x[k]);
-      acc[2 * k] = fmaf(w, f.x, acc[2 * k]);
-      acc[2 * k + 1] = fmaf(w, f.y, acc[2 * k + 1]);
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16x2(x[k]);
+        acc[2 * k] = fmaf(w, f.x, acc[2 * k]);
+        acc[2 * k + 1] = fmaf(w, f.y, acc[2 * k + 1]);
+      }
     }
   }
   float4* o = reinterpret_cast<float4*>(out + (long long)i * E) + 2 * v;
@@ -219,12 +261,16 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, long lo
 }
 
 // ================================================================================================
-int sim_small(const void* p, const void* t, int R, int C, int E, float alpha, float* S, cudaStream_t st) {
+int sim_small(const void* p, const void* t, bool in_f32, int R, int C, int E, float alpha, float* S, cudaStream_t st) {
   if (E % 8) return set_error(-1, "similarity: E must be a multiple of 8");
   const long long warps = (long long)R * ((C + 3) / 4);
   const int blocks = (int)((warps + 7) / 8);
-  sim_small_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(p),
-                                           reinterpret_cast<const __nv_bfloat16*>(t), R, C, E, alpha, S);
+  if (in_f32)
+    sim_small_f32_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(p), reinterpret_cast<const float*>(t), R,
+                                                 C, E, alpha, S);
+  else
+    sim_small_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(p),
+                                             reinterpret_cast<const __nv_bfloat16*>(t), R, C, E, alpha, S);
   return check_launch("sim_small_kernel");
 }
 
@@ -255,16 +301,17 @@ int loss_mean(const float* row_loss, int R, float scale, float* loss, int accumu
   return check_launch("loss_mean_kernel");
 }
 
-int contract_small(const float* W, int ldw, bool transpose_w, const void* X, int n_out, int n_red, int E, float alpha,
-                   float* out, cudaStream_t st) {
+int contract_small(const float* W, int ldw, bool transpose_w, const void* X, bool x_f32, int n_out, int n_red, int E,
+                   float alpha, float* out, cudaStream_t st) {
   if (E % 8) return set_error(-1, "contract: E must be a multiple of 8");
   dim3 g((E / 8 + 255) / 256, n_out);
-  if (transpose_w)
-    contract_small_kernel<true><<<g, 256, 0, st>>>(W, ldw, reinterpret_cast<const __nv_bfloat16*>(X), n_out, n_red, E,
-                                                   alpha, out);
-  else
-    contract_small_kernel<false><<<g, 256, 0, st>>>(W, ldw, reinterpret_cast<const __nv_bfloat16*>(X), n_out, n_red, E,
-                                                    alpha, out);
+  if (transpose_w) {
+    if (x_f32) contract_small_kernel<true, true><<<g, 256, 0, st>>>(W, ldw, X, n_out, n_red, E, alpha, out);
+    else contract_small_kernel<true, false><<<g, 256, 0, st>>>(W, ldw, X, n_out, n_red, E, alpha, out);
+  } else {
+    if (x_f32) contract_small_kernel<false, true><<<g, 256, 0, st>>>(W, ldw, X, n_out, n_red, E, alpha, out);
+    else contract_small_kernel<false, false><<<g, 256, 0, st>>>(W, ldw, X, n_out, n_red, E, alpha, out);
+  }
   return check_launch("contract_small_kernel");
 }
 

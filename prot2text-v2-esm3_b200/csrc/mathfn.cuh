@@ -25,6 +25,33 @@ __device__ __forceinline__ void gelu_erf_both(float z, float& val, float& der) {
   val = z * cdf;
   der = fmaf(z, pdf, cdf);
 }
+// Fast erf-form GELU pair for the GEMM epilogues.  Same function as above (z*Phi(z), Phi via erf — NOT the
+// tanh approximation), with erfc evaluated by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, below fp32 erff's
+// own error for O(1) arguments and 4 orders of magnitude below the bf16/fp16 resolution of the stored result).
+// exp(-z^2/2) is shared between erfc and the Gaussian density, so value + derivative cost one ex2 + one rcp.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void gelu_erf_both_fast(float z, float& val, float& der) {
+  const float ax = fabsf(z) * 0.70710678118654752f;
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
+  const float e = ex2_approx(z * z * -0.72134752044448170f);  // exp(-z^2/2)
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float half_erfc = 0.5f * poly * t * e;  // 0.5*erfc(|z|/sqrt2)
+  const float cdf = (z >= 0.f) ? 1.0f - half_erfc : half_erfc;
+  val = z * cdf;
+  der = fmaf(z * 0.39894228040143268f, e, cdf);
+}
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 // ------------------------------------------------------------------------------------------------
@@ -60,6 +87,16 @@ __device__ __forceinline__ void dropout_keep8(const DropoutParams& d, uint32_t r
   }
   const uint4 r = philox4x32_10(make_uint4(row, g, d.layer, 0u),
                                 make_uint2(static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32)));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    keep[2 * i] = ((w[i] & 0xFFFFu) >= d.threshold) ? d.scale : 0.0f;
+    keep[2 * i + 1] = ((w[i] >> 16) >= d.threshold) ? d.scale : 0.0f;
+  }
+}
+
+// same, from an already generated Philox block
+__device__ __forceinline__ void dropout_keep8_from(const DropoutParams& d, const uint4& r, float (&keep)[8]) {
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {

@@ -60,10 +60,10 @@ __global__ void plan_count_kernel(const void* mask, int mask_bytes, int B, int L
 // grid B, block 256.  seq_off[B+1], chunk_off[B+1] (chunks of `rc` rows), n_rows[0] = total,
 // row_src[i] = flat source row (b*L + r) of packed row i.
 __global__ void plan_fill_kernel(const void* mask, int mask_bytes, int B, int L, const int* counts, int rc,
-                                 int* seq_off, int* chunk_off, int* n_rows, int* row_src) {
+                                 int* seq_off, int* chunk_off, int* n_rows, int* row_src, int* chunk_seq) {
   const int b = blockIdx.x;
   __shared__ int sh[2][8];
-  __shared__ int s_base;
+  __shared__ int s_base, s_cbase;
   int off = 0, coff = 0;
   for (int i = threadIdx.x; i < b; i += blockDim.x) {
     const int c = counts[i];
@@ -88,8 +88,13 @@ __global__ void plan_fill_kernel(const void* mask, int mask_bytes, int B, int L,
       n_rows[0] = t0 + c;
     }
     s_base = t0;
+    s_cbase = t1;
   }
   __syncthreads();
+  if (chunk_seq != nullptr) {
+    const int nchunks = (counts[b] + rc - 1) / rc;
+    for (int j = threadIdx.x; j < nchunks; j += blockDim.x) chunk_seq[s_cbase + j] = b;
+  }
   if (row_src == nullptr) return;
   // ordered compaction of the valid positions of this sequence
   int base = s_base;
@@ -146,86 +151,110 @@ __device__ __forceinline__ int find_segment(const int* __restrict__ off, int n, 
   return lo;
 }
 
+// inverse L2 norm of each adapter output row from the fc2 epilogue's partial sums of squares
+__global__ void row_inv_norm_kernel(const float* __restrict__ rowsq, int nblk, const int* __restrict__ n_rows, int cap,
+                                    float* __restrict__ inv_norm) {
+  const int n = min(*n_rows, cap);
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < nblk; ++j) s += rowsq[(long long)r * nblk + j];
+    inv_norm[r] = 1.f / fmaxf(sqrtf(s), kEpsNorm);
+  }
+}
+
 template <bool F16>
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const float2 a = unpack_h2<F16>(u.x), b = unpack_h2<F16>(u.y), c = unpack_h2<F16>(u.z), d = unpack_h2<F16>(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+// grid (max_chunks, ceil(D/256)), block 256 = 64 column groups (4 columns = one 8-byte load each) x 4 row
+// subsets.  A chunk has <= 64 rows, so a thread owns <= 16 rows: it issues ALL 16 loads at once (a single level
+// of memory latency after the chunk lookup), then does an exact two-pass mean / M2 in registers; the 4 subsets
+// are merged with Chan's formula through shared memory.  Small per-thread state (~50 registers) keeps 4+ CTAs
+// resident per SM, i.e. >100 KB of loads in flight per SM.
+template <bool F16>
+__global__ void __launch_bounds__(256, 2)
 pool_partial_kernel(const __nv_bfloat16* __restrict__ src, long long ld_src, const int* __restrict__ row_src,
-                    const float* __restrict__ rowsq, int nblk, const int* __restrict__ seq_off,
-                    const int* __restrict__ chunk_off, int B, int D, int rc, float2* __restrict__ partial,
-                    float* __restrict__ inv_norm_out) {
+                    const float* __restrict__ inv_norm, const int* __restrict__ seq_off,
+                    const int* __restrict__ chunk_off, const int* __restrict__ chunk_seq, int B, int D, int rc,
+                    float2* __restrict__ partial) {
   const int chunk = blockIdx.x;
   if (chunk >= chunk_off[B]) return;
-  const int b = find_segment(chunk_off, B + 1, chunk);
+  const int b = chunk_seq[chunk];
   const int r0 = seq_off[b] + (chunk - chunk_off[b]) * rc;
   const int r1 = min(r0 + rc, seq_off[b + 1]);
-  const int nrows = r1 - r0;
-  extern __shared__ float s_inv[];  // [rc]
-  for (int i = threadIdx.x; i < nrows; i += blockDim.x) {
-    float inv = 1.f;
-    if (rowsq != nullptr) {
-      float s = 0.f;
-      for (int j = 0; j < nblk; ++j) s += rowsq[(long long)(r0 + i) * nblk + j];
-      inv = 1.f / fmaxf(sqrtf(s), kEpsNorm);
-      if (inv_norm_out != nullptr && blockIdx.y == 0) inv_norm_out[r0 + i] = inv;
+  const int cgl = threadIdx.x & 63, sub = threadIdx.x >> 6;  // sub in [0, 4)
+  const int g = blockIdx.y * 64 + cgl;                       // 4-column group
+  const bool active = g * 4 < D;
+  constexpr int RPT = 16, NSUB = 4;
+  __shared__ float comb[NSUB - 1][64][9];
+  __shared__ float comb_n[NSUB - 1];
+  float mean[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f};
+  int cnt = 0;
+  for (int r = r0 + sub; r < r1; r += NSUB) ++cnt;
+  if (active && cnt > 0) {
+    uint2 u[RPT];
+    float sc[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      const int r = r0 + sub + NSUB * k;
+      if (r < r1) {
+        const long long sr = row_src ? (long long)row_src[r] : (long long)r;
+        u[k] = __ldg(reinterpret_cast<const uint2*>(src + sr * ld_src) + g);
+        sc[k] = inv_norm ? __ldg(inv_norm + r) : 1.f;
+      } else {
+        u[k] = make_uint2(0, 0);
+        sc[k] = 0.f;
+      }
     }
-    s_inv[i] = inv;
-  }
-  __syncthreads();
-  const int g = blockIdx.y * blockDim.x + threadIdx.x;  // 8-column group
-  if (g * 8 >= D) return;
-  float shift[8], s1[8], s2[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
-  auto row_ptr = [&](int r) -> const uint4* {
-    const long long sr = row_src ? (long long)row_src[r] : (long long)r;
-    return reinterpret_cast<const uint4*>(src + sr * ld_src) + g;
-  };
-  auto unpack8 = [](const uint4& u, float (&f)[8]) {
-    float2 a = unpack_h2<F16>(u.x), b2 = unpack_h2<F16>(u.y), c = unpack_h2<F16>(u.z), d = unpack_h2<F16>(u.w);
-    f[0] = a.x; f[1] = a.y; f[2] = b2.x; f[3] = b2.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
-  };
-  {
-    float f[8];
-    unpack8(__ldg(row_ptr(r0)), f);
-    const float inv = s_inv[0];
+    for (int k = 0; k < RPT; ++k) {
+      const float2 lo = unpack_h2<F16>(u[k].x), hi = unpack_h2<F16>(u[k].y);
+      mean[0] = fmaf(lo.x, sc[k], mean[0]);  // absent rows: sc == 0, exact zeros
+      mean[1] = fmaf(lo.y, sc[k], mean[1]);
+      mean[2] = fmaf(hi.x, sc[k], mean[2]);
+      mean[3] = fmaf(hi.y, sc[k], mean[3]);
+    }
+    const float inv_cnt = 1.f / (float)cnt;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) shift[i] = f[i] * inv;
-  }
-  constexpr int U = 8;
-  int r = r0 + 1;  // the first row equals the shift: contributes zero to both sums
-  for (; r + U <= r1; r += U) {
-    uint4 u[U];
+    for (int i = 0; i < 4; ++i) mean[i] *= inv_cnt;
 #pragma unroll
-    for (int k = 0; k < U; ++k) u[k] = __ldg(row_ptr(r + k));
-#pragma unroll
-    for (int k = 0; k < U; ++k) {
-      float f[8];
-      unpack8(u[k], f);
-      const float inv = s_inv[r + k - r0];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float d = fmaf(f[i], inv, -shift[i]);
-        s1[i] += d;
-        s2[i] = fmaf(d, d, s2[i]);
+    for (int k = 0; k < RPT; ++k) {
+      if (k < cnt) {
+        const float2 lo = unpack_h2<F16>(u[k].x), hi = unpack_h2<F16>(u[k].y);
+        const float d0 = fmaf(lo.x, sc[k], -mean[0]), d1 = fmaf(lo.y, sc[k], -mean[1]);
+        const float d2 = fmaf(hi.x, sc[k], -mean[2]), d3 = fmaf(hi.y, sc[k], -mean[3]);
+        m2[0] = fmaf(d0, d0, m2[0]); m2[1] = fmaf(d1, d1, m2[1]); m2[2] = fmaf(d2, d2, m2[2]); m2[3] = fmaf(d3, d3, m2[3]);
       }
     }
   }
-  for (; r < r1; ++r) {
-    float f[8];
-    unpack8(__ldg(row_ptr(r)), f);
-    const float inv = s_inv[r - r0];
+  if (sub > 0) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float d = fmaf(f[i], inv, -shift[i]);
-      s1[i] += d;
-      s2[i] = fmaf(d, d, s2[i]);
-    }
+    for (int i = 0; i < 4; ++i) { comb[sub - 1][cgl][i] = mean[i]; comb[sub - 1][cgl][4 + i] = m2[i]; }
+    if (cgl == 0) comb_n[sub - 1] = (float)cnt;
   }
-  const float inv_n = 1.f / (float)nrows;
-  float2* out = partial + (long long)chunk * D + g * 8;
+  __syncthreads();
+  if (sub == 0 && active) {
+    float n = (float)cnt;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float dm = s1[i] * inv_n;
-    out[i] = make_float2(shift[i] + dm, fmaxf(s2[i] - s1[i] * dm, 0.f));
+    for (int k = 0; k < NSUB - 1; ++k) {
+      const float nk = comb_n[k];
+      if (nk > 0.f) {
+        const float tot = n + nk;
+        const float w = nk / tot, w2 = n * nk / tot;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float delta = comb[k][cgl][i] - mean[i];
+          mean[i] = fmaf(delta, w, mean[i]);
+          m2[i] += comb[k][cgl][4 + i] + delta * delta * w2;
+        }
+        n = tot;
+      }
+    }
+    float4* out = reinterpret_cast<float4*>(partial + (long long)chunk * D + g * 4);
+    out[0] = make_float4(mean[0], m2[0], mean[1], m2[1]);
+    out[1] = make_float4(mean[2], m2[2], mean[3], m2[3]);
   }
 }
 
@@ -328,84 +357,158 @@ __global__ void pool_bwd_coef_kernel(const float* __restrict__ de, long long ld_
 }
 
 // ------------------------------------------------------------------------------------------------
-// adapter tail backward over packed rows (one warp per row):
+// adapter tail backward over packed rows, one CTA per pooling chunk (<= rc rows of ONE sequence):
 //   y = a * inv;  dy = c1[b] + c2[b] * y;  da = (dy - y (y.dy)) * inv;  dz2 = da * g
-// a, g fp16 [rows][D] (g = keep*GELU'(z2), a = keep*GELU(z2)); dz2 bf16; rows in [n, roundup(n,256)) are zeroed.
+// thread = 8 columns (c1/c2 of the sequence live in registers), 2 rows per batch, double-buffered so that 8
+// independent 16-byte loads are in flight per thread; the per-row dot product y.dy is a block reduction.
+// The column sums of dz2 (the fc2 bias gradient) accumulate in registers and leave as one partial
+// row per chunk.  a, g fp16 [rows][D]; dz2 bf16.  CTAs beyond the last chunk zero the rows in
+// [n, roundup(n,256)) so the weight-gradient GEMMs can run their K loop over whole 64-row blocks.
 // ------------------------------------------------------------------------------------------------
-template <int NV>  // 16-byte vectors per lane: D <= NV*256
-__global__ void __launch_bounds__(256)
-adapter_tail_bwd_kernel(const __half* __restrict__ a, const __half* __restrict__ g,
-                        const float* __restrict__ inv_norm, const int* __restrict__ seq_off, int B,
-                        const float* __restrict__ c1, const float* __restrict__ c2, const int* __restrict__ n_rows,
-                        int cap, int D, __nv_bfloat16* __restrict__ dz2) {
-  const int n = min(*n_rows, cap);
-  const int n_pad = min(cap, (n + 255) & ~255);
-  const int lane = threadIdx.x & 31;
-  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+constexpr int TAIL_R = 2;
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+adapter_tail_bwd_kernel(const __half* __restrict__ a, const __half* __restrict__ g, const float* __restrict__ inv_norm,
+                        const int* __restrict__ seq_off, const int* __restrict__ chunk_off,
+                        const int* __restrict__ chunk_seq, int B, const float* __restrict__ c1,
+                        const float* __restrict__ c2, const int* __restrict__ n_rows, int cap, int D, int rc,
+                        __nv_bfloat16* __restrict__ dz2, float* __restrict__ colsum_partial) {
+  const int chunk = blockIdx.x;
+  const int total_chunks = chunk_off[B];
   const int nvec = D >> 3;
-  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_pad; row += warps_total) {
-    uint4* out = reinterpret_cast<uint4*>(dz2 + (long long)row * D);
-    if (row >= n) {
-      for (int v = lane; v < nvec; v += 32) out[v] = make_uint4(0, 0, 0, 0);
-      continue;
+  const int tid = threadIdx.x;
+  if (chunk >= total_chunks) {
+    const int n = min(*n_rows, cap);
+    const int n_pad = min(cap, (n + 255) & ~255);
+    const int extra = gridDim.x - total_chunks;
+    for (int row = n + (chunk - total_chunks); row < n_pad; row += extra)
+      if (tid < nvec) reinterpret_cast<uint4*>(dz2 + (long long)row * D)[tid] = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  const int b = chunk_seq[chunk];
+  const int r0 = seq_off[b] + (chunk - chunk_off[b]) * rc;
+  const int r1 = min(r0 + rc, seq_off[b + 1]);
+  const bool active = tid < nvec;
+  const int warp = tid >> 5, lane = tid & 31;
+  constexpr int NWARPS = THREADS / 32;
+  __shared__ float red[2][NWARPS][TAIL_R];
+  float k1[8], k2[8], csum[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { k1[i] = 0.f; k2[i] = 0.f; csum[i] = 0.f; }
+  if (active) {
+    const float4* p1 = reinterpret_cast<const float4*>(c1 + (long long)b * D) + 2 * tid;
+    const float4* p2 = reinterpret_cast<const float4*>(c2 + (long long)b * D) + 2 * tid;
+    const float4 x0 = __ldg(p1), x1 = __ldg(p1 + 1), y0 = __ldg(p2), y1 = __ldg(p2 + 1);
+    k1[0] = x0.x; k1[1] = x0.y; k1[2] = x0.z; k1[3] = x0.w; k1[4] = x1.x; k1[5] = x1.y; k1[6] = x1.z; k1[7] = x1.w;
+    k2[0] = y0.x; k2[1] = y0.y; k2[2] = y0.z; k2[3] = y0.w; k2[4] = y1.x; k2[5] = y1.y; k2[6] = y1.z; k2[7] = y1.w;
+  }
+  struct Batch {
+    uint4 av[TAIL_R], gv[TAIL_R];
+    float inv[TAIL_R];
+  };
+  auto load = [&](Batch& bt, int rb) {
+#pragma unroll
+    for (int q = 0; q < TAIL_R; ++q) {
+      const int r = min(rb + q, r1 - 1);
+      bt.av[q] = active ? __ldg(reinterpret_cast<const uint4*>(a + (long long)r * D) + tid) : make_uint4(0, 0, 0, 0);
+      bt.gv[q] = active ? __ldg(reinterpret_cast<const uint4*>(g + (long long)r * D) + tid) : make_uint4(0, 0, 0, 0);
+      bt.inv[q] = inv_norm[r];
     }
-    const int b = find_segment(seq_off, B + 1, row);
-    const float inv = inv_norm[row];
-    const uint4* ar = reinterpret_cast<const uint4*>(a + (long long)row * D);
-    const uint4* gr = reinterpret_cast<const uint4*>(g + (long long)row * D);
-    const float4* c1r = reinterpret_cast<const float4*>(c1 + (long long)b * D);
-    const float4* c2r = reinterpret_cast<const float4*>(c2 + (long long)b * D);
-    uint4 av[NV];
+  };
+  auto process = [&](const Batch& bt, int rb, int buf) {
+    float dot[TAIL_R];
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int v = lane + 32 * k;
-      av[k] = (v < nvec) ? __ldg(ar + v) : make_uint4(0, 0, 0, 0);
+    for (int q = 0; q < TAIL_R; ++q) {
+      float f[8];
+      unpack8<true>(bt.av[q], f);
+      float d = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float y = f[i] * bt.inv[q];
+        d = fmaf(y, fmaf(k2[i], y, k1[i]), d);
+      }
+      dot[q] = warp_sum(d);
     }
-    float dot = 0.f;
+    if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int v = lane + 32 * k;
-      if (v < nvec) {
-        const float4 p0 = __ldg(c1r + 2 * v), p1 = __ldg(c1r + 2 * v + 1);
-        const float4 q0 = __ldg(c2r + 2 * v), q1 = __ldg(c2r + 2 * v + 1);
-        const float k1[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-        const float k2[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-        const uint32_t w[4] = {av[k].x, av[k].y, av[k].z, av[k].w};
+      for (int q = 0; q < TAIL_R; ++q) red[buf][warp][q] = dot[q];
+    }
+    __syncthreads();  // the only barrier per batch: every thread then adds the NWARPS partials itself (smem broadcasts)
+    float totq[TAIL_R];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = unpack_f16x2(w[i]);
-          const float y0 = f.x * inv, y1 = f.y * inv;
-          dot = fmaf(y0, fmaf(k2[2 * i], y0, k1[2 * i]), dot);
-          dot = fmaf(y1, fmaf(k2[2 * i + 1], y1, k1[2 * i + 1]), dot);
+    for (int q = 0; q < TAIL_R; ++q) totq[q] = 0.f;
+#pragma unroll
+    for (int w = 0; w < NWARPS; ++w) {
+#pragma unroll
+      for (int q = 0; q < TAIL_R; ++q) totq[q] += red[buf][w][q];
+    }
+#pragma unroll
+    for (int q = 0; q < TAIL_R; ++q) {
+      if (active && rb + q < r1) {
+        const float dt = totq[q];
+        float f[8], gg[8], o[8];
+        unpack8<true>(bt.av[q], f);
+        unpack8<true>(bt.gv[q], gg);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float y = f[i] * bt.inv[q];
+          const float dy = fmaf(k2[i], y, k1[i]);
+          o[i] = (dy - y * dt) * bt.inv[q] * gg[i];
+          csum[i] += o[i];
         }
+        reinterpret_cast<uint4*>(dz2 + (long long)(rb + q) * D)[tid] =
+            make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
       }
     }
-    dot = warp_sum(dot);
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int v = lane + 32 * k;
-      if (v < nvec) {
-        const float4 p0 = __ldg(c1r + 2 * v), p1 = __ldg(c1r + 2 * v + 1);
-        const float4 q0 = __ldg(c2r + 2 * v), q1 = __ldg(c2r + 2 * v + 1);
-        const float k1[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-        const float k2[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-        const uint4 gu = __ldg(gr + v);
-        const uint32_t w[4] = {av[k].x, av[k].y, av[k].z, av[k].w};
-        const uint32_t gw[4] = {gu.x, gu.y, gu.z, gu.w};
-        uint32_t o[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = unpack_f16x2(w[i]);
-          const float2 gg = unpack_f16x2(gw[i]);
-          const float y0 = f.x * inv, y1 = f.y * inv;
-          const float dy0 = fmaf(k2[2 * i], y0, k1[2 * i]), dy1 = fmaf(k2[2 * i + 1], y1, k1[2 * i + 1]);
-          const float d0 = (dy0 - y0 * dot) * inv * gg.x;
-          const float d1 = (dy1 - y1 * dot) * inv * gg.y;
-          o[i] = pack_bf16x2(d0, d1);
-        }
-        out[v] = make_uint4(o[0], o[1], o[2], o[3]);
-      }
+  };
+  // double-buffered: the loads of batch i+1 are in flight while batch i is reduced and written
+  Batch b0, b1;
+  load(b0, r0);
+  for (int rb = r0; rb < r1; rb += 2 * TAIL_R) {
+    if (rb + TAIL_R < r1) load(b1, rb + TAIL_R);
+    process(b0, rb, 0);
+    if (rb + TAIL_R < r1) {
+      if (rb + 2 * TAIL_R < r1) load(b0, rb + 2 * TAIL_R);
+      process(b1, rb + TAIL_R, 1);
     }
+  }
+  if (active && colsum_partial != nullptr) {
+    float4* o = reinterpret_cast<float4*>(colsum_partial + (long long)chunk * D) + 2 * tid;
+    o[0] = make_float4(csum[0], csum[1], csum[2], csum[3]);
+    o[1] = make_float4(csum[4], csum[5], csum[6], csum[7]);
+  }
+}
+
+// sum `nparts` partial rows: out[col] = sum_k partial[k][col].  grid ceil(D/32), block (32, 8): thread (x, y)
+// adds parts y, y+8, ... of column 32*blockIdx.x + x, then the 8 lanes are merged in shared memory (fixed order).
+__device__ __forceinline__ float sum_parts(const float* __restrict__ partial, int nparts, int D, int col) {
+  float s0 = 0.f, s1 = 0.f;
+  int k = threadIdx.y;
+  for (; k + 8 < nparts; k += 16) {
+    s0 += partial[(long long)k * D + col];
+    s1 += partial[(long long)(k + 8) * D + col];
+  }
+  if (k < nparts) s0 += partial[(long long)k * D + col];
+  return s0 + s1;
+}
+__global__ void __launch_bounds__(256)
+parts_colsum_final_kernel(const float* __restrict__ partial, const int* __restrict__ chunk_off, int B,
+                          const int* __restrict__ n_rows, int n_static, int D, __nv_bfloat16* __restrict__ out_bf16,
+                          float* __restrict__ out_f32) {
+  // number of partial rows: chunk_off[B] (pooling chunks) or ceil(n/64) (plain 64-row blocks)
+  int nparts;
+  if (chunk_off != nullptr) nparts = chunk_off[B];
+  else nparts = ((n_rows ? min(*n_rows, n_static) : n_static) + 63) / 64;
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  __shared__ float sm[8][33];
+  sm[threadIdx.y][threadIdx.x] = (col < D) ? sum_parts(partial, nparts, D, col) : 0.f;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < D) {
+    float s = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) s += sm[y][threadIdx.x];
+    if (out_bf16) out_bf16[col] = __float2bfloat16_rn(s);
+    if (out_f32) out_f32[col] = s;
   }
 }
 
@@ -538,59 +641,46 @@ readout_bwd_kernel(const __nv_bfloat16* __restrict__ x, const void* __restrict__
 
 // ------------------------------------------------------------------------------------------------
 // column sums of a packed bf16 matrix (bias gradients): two deterministic phases.
-// phase 1 grid (ceil(D/1024), nsplit), block 128: partial[split][col]; phase 2 sums the splits.
+// phase 1 grid (ceil(cap/64), ceil(D/512)), block 256 = 64 column groups x 4 row subsets over a 64-row
+// block -> partial[block][col]; phase 2 sums the row blocks below ceil(n/64) in a fixed order.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ n_rows, int n_static, int D,
                       float* __restrict__ partial) {
   const int n = n_rows ? min(*n_rows, n_static) : n_static;
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g * 8 >= D) return;
-  const int nsplit = gridDim.y;
-  const int per = (n + nsplit - 1) / nsplit;
-  const int r0 = blockIdx.y * per, r1 = min(n, r0 + per);
+  const int r0 = blockIdx.x * 64, r1 = min(n, r0 + 64);
+  if (r0 >= n) return;
+  const int cgl = threadIdx.x & 63, sub = threadIdx.x >> 6;
+  const int g = blockIdx.y * 64 + cgl;
+  const bool active = g * 8 < D;
+  __shared__ float comb[3][64][9];
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  constexpr int U = 8;
-  int r = r0;
-  for (; r + U <= r1; r += U) {
-    uint4 u[U];
+  if (active) {
+    uint4 u[16];
 #pragma unroll
-    for (int k = 0; k < U; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(x + (long long)(r + k) * D) + g);
+    for (int k = 0; k < 16; ++k) {
+      const int r = r0 + sub + 4 * k;
+      u[k] = (r < r1) ? __ldg(reinterpret_cast<const uint4*>(x + (long long)r * D) + g) : make_uint4(0, 0, 0, 0);
+    }
 #pragma unroll
-    for (int k = 0; k < U; ++k) {
-      const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+    for (int k = 0; k < 16; ++k) {
+      float f[8];
+      unpack8<false>(u[k], f);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = unpack_bf16x2(w[i]);
-        s[2 * i] += f.x;
-        s[2 * i + 1] += f.y;
-      }
+      for (int i = 0; i < 8; ++i) s[i] += f[i];
     }
   }
-  for (; r < r1; ++r) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (long long)r * D) + g);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  if (sub > 0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = unpack_bf16x2(w[i]);
-      s[2 * i] += f.x;
-      s[2 * i + 1] += f.y;
-    }
+    for (int i = 0; i < 8; ++i) comb[sub - 1][cgl][i] = s[i];
   }
-  float* o = partial + (long long)blockIdx.y * D + g * 8;
+  __syncthreads();
+  if (sub == 0 && active) {
+    float* o = partial + (long long)blockIdx.x * D + g * 8;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = s[i];
+    for (int i = 0; i < 8; ++i) o[i] = s[i] + comb[0][cgl][i] + comb[1][cgl][i] + comb[2][cgl][i];
+  }
 }
-__global__ void colsum_final_kernel(const float* __restrict__ partial, int nsplit, int D, __nv_bfloat16* out_bf16,
-                                    float* out_f32) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= D) return;
-  float s = 0.f;
-  for (int k = 0; k < nsplit; ++k) s += partial[(long long)k * D + col];
-  if (out_bf16) out_bf16[col] = __float2bfloat16_rn(s);
-  if (out_f32) out_f32[col] = s;
-}
-
 // 'last' readout: out[b] = x[b, sum(mask[b]) - 1]   (scripts/train_contrast.py:207-215)
 __global__ void readout_last_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ counts, int S, int D,
                                     float* __restrict__ out) {
@@ -605,11 +695,11 @@ __global__ void readout_last_kernel(const __nv_bfloat16* __restrict__ x, const i
 // host launchers
 // ================================================================================================
 int rows_plan(const void* mask, int mask_bytes, int B, int L, int rc, int* counts, int* seq_off, int* chunk_off,
-              int* n_rows, int* row_src, cudaStream_t st) {
+              int* n_rows, int* row_src, int* chunk_seq, cudaStream_t st) {
   if (B <= 0 || L <= 0) return set_error(-1, "rows_plan: empty batch");
   plan_count_kernel<<<B, 256, 0, st>>>(mask, mask_bytes, B, L, counts);
   if (int rc_ = check_launch("plan_count_kernel")) return rc_;
-  plan_fill_kernel<<<B, 256, 0, st>>>(mask, mask_bytes, B, L, counts, rc, seq_off, chunk_off, n_rows, row_src);
+  plan_fill_kernel<<<B, 256, 0, st>>>(mask, mask_bytes, B, L, counts, rc, seq_off, chunk_off, n_rows, row_src, chunk_seq);
   return check_launch("plan_fill_kernel");
 }
 
@@ -623,19 +713,22 @@ int gather_rows(const void* src, long long ld_src, const int* row_src, const int
   return check_launch("gather_rows_kernel");
 }
 
-int pool_forward(const void* src, bool src_is_f16, long long ld_src, const int* row_src, const float* rowsq, int nblk,
-                 const int* seq_off, const int* chunk_off, int B, int D, int rc, int max_chunks, int mode,
-                 float2* partial, float* inv_norm_out, float* out, long long ld_out, cudaStream_t st) {
+int row_inv_norm(const float* rowsq, int nblk, const int* n_rows, int cap, float* inv_norm, cudaStream_t st) {
+  const int blocks = std::min((cap + 255) / 256, sm_count() * 8);
+  row_inv_norm_kernel<<<blocks, 256, 0, st>>>(rowsq, nblk, n_rows, cap, inv_norm);
+  return check_launch("row_inv_norm_kernel");
+}
+
+int pool_forward(const void* src, bool src_is_f16, long long ld_src, const int* row_src, const float* inv_norm,
+                 const int* seq_off, const int* chunk_off, const int* chunk_seq, int B, int D, int rc, int max_chunks,
+                 int mode, float2* partial, float* out, long long ld_out, cudaStream_t st) {
   if (D % 8) return set_error(-1, "pool_forward: D must be a multiple of 8");
-  dim3 grid(max_chunks, (D / 8 + 127) / 128);
+  dim3 grid(max_chunks, (D / 4 + 63) / 64);
+  const __nv_bfloat16* sp = reinterpret_cast<const __nv_bfloat16*>(src);
   if (src_is_f16)
-    pool_partial_kernel<true><<<grid, 128, rc * sizeof(float), st>>>(reinterpret_cast<const __nv_bfloat16*>(src), ld_src,
-                                                                     row_src, rowsq, nblk, seq_off, chunk_off, B, D, rc,
-                                                                     partial, inv_norm_out);
+    pool_partial_kernel<true><<<grid, 256, 0, st>>>(sp, ld_src, row_src, inv_norm, seq_off, chunk_off, chunk_seq, B, D, rc, partial);
   else
-    pool_partial_kernel<false><<<grid, 128, rc * sizeof(float), st>>>(reinterpret_cast<const __nv_bfloat16*>(src), ld_src,
-                                                                      row_src, rowsq, nblk, seq_off, chunk_off, B, D, rc,
-                                                                      partial, inv_norm_out);
+    pool_partial_kernel<false><<<grid, 256, 0, st>>>(sp, ld_src, row_src, inv_norm, seq_off, chunk_off, chunk_seq, B, D, rc, partial);
   if (int r = check_launch("pool_partial_kernel")) return r;
   dim3 g2(B, (D + 255) / 256);
   pool_finalize_kernel<<<g2, 256, 0, st>>>(partial, seq_off, chunk_off, B, D, rc, mode, out, ld_out);
@@ -657,23 +750,28 @@ int pool_bwd_coef(const float* de, long long ld_de, const float* stats, long lon
   return check_launch("pool_bwd_coef_kernel");
 }
 
-template <int NV>
-static int tail_bwd_launch(const void* a, const void* g, const float* inv_norm, const int* seq_off, int B,
-                           const float* c1, const float* c2, const int* n_rows, int cap, int D, void* dz2,
-                           cudaStream_t st) {
-  const int blocks = min((cap + 7) / 8, sm_count() * 8);
-  adapter_tail_bwd_kernel<NV><<<blocks, 256, 0, st>>>(reinterpret_cast<const __half*>(a),
-                                                      reinterpret_cast<const __half*>(g), inv_norm, seq_off, B, c1,
-                                                      c2, n_rows, cap, D, reinterpret_cast<__nv_bfloat16*>(dz2));
-  return check_launch("adapter_tail_bwd_kernel");
-}
-int adapter_tail_backward(const void* a, const void* g, const float* inv_norm, const int* seq_off, int B,
-                          const float* c1, const float* c2, const int* n_rows, int cap, int D, void* dz2,
-                          cudaStream_t st) {
+int adapter_tail_backward(const void* a, const void* g, const float* inv_norm, const int* seq_off, const int* chunk_off,
+                          const int* chunk_seq, int B, const float* c1, const float* c2, const int* n_rows, int cap, int D,
+                          int rc, int max_chunks, void* dz2, float* colsum_partial, void* db2, cudaStream_t st) {
   if (D % 8 || D > 8192) return set_error(-1, "adapter_tail_backward: D must be a multiple of 8 and <= 8192");
-  if (D <= 2048) return tail_bwd_launch<8>(a, g, inv_norm, seq_off, B, c1, c2, n_rows, cap, D, dz2, st);
-  if (D <= 4096) return tail_bwd_launch<16>(a, g, inv_norm, seq_off, B, c1, c2, n_rows, cap, D, dz2, st);
-  return tail_bwd_launch<32>(a, g, inv_norm, seq_off, B, c1, c2, n_rows, cap, D, dz2, st);
+  const __half* ap = reinterpret_cast<const __half*>(a);
+  const __half* gp = reinterpret_cast<const __half*>(g);
+  __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(dz2);
+  const int grid = max_chunks + 8;
+  if (D <= 2048)
+    adapter_tail_bwd_kernel<256><<<grid, 256, 0, st>>>(ap, gp, inv_norm, seq_off, chunk_off, chunk_seq, B, c1, c2, n_rows, cap, D, rc, op, colsum_partial);
+  else if (D <= 4096)
+    adapter_tail_bwd_kernel<512><<<grid, 512, 0, st>>>(ap, gp, inv_norm, seq_off, chunk_off, chunk_seq, B, c1, c2, n_rows, cap, D, rc, op, colsum_partial);
+  else
+    adapter_tail_bwd_kernel<1024><<<grid, 1024, 0, st>>>(ap, gp, inv_norm, seq_off, chunk_off, chunk_seq, B, c1, c2, n_rows, cap, D, rc, op, colsum_partial);
+  if (int r = check_launch("adapter_tail_bwd_kernel")) return r;
+  if (db2 != nullptr) {
+    if (!colsum_partial) return set_error(-1, "adapter_tail_backward: db2 needs the partial workspace");
+    parts_colsum_final_kernel<<<(D + 31) / 32, dim3(32, 8), 0, st>>>(colsum_partial, chunk_off, B, nullptr, 0, D,
+                                                                     reinterpret_cast<__nv_bfloat16*>(db2), nullptr);
+    return check_launch("parts_colsum_final_kernel");
+  }
+  return 0;
 }
 
 template <int NV>
@@ -709,15 +807,16 @@ int readout_backward(const void* x, const void* mask, int mask_bytes, int B, int
   return check_launch("readout_bwd_kernel");
 }
 
-int colsum(const void* x, const int* n_rows, int n_static, int D, float* partial, int nsplit, void* out_bf16,
-           float* out_f32, cudaStream_t st) {
+int colsum(const void* x, const int* n_rows, int n_static, int D, float* partial, void* out_bf16, float* out_f32,
+           cudaStream_t st) {
   if (D % 8) return set_error(-1, "colsum: D must be a multiple of 8");
-  dim3 g((D / 8 + 127) / 128, nsplit);
-  colsum_partial_kernel<<<g, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), n_rows, n_static, D, partial);
+  if (n_static <= 0) return set_error(-1, "colsum: empty matrix");
+  dim3 g((n_static + 63) / 64, (D / 8 + 63) / 64);
+  colsum_partial_kernel<<<g, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), n_rows, n_static, D, partial);
   if (int r = check_launch("colsum_partial_kernel")) return r;
-  colsum_final_kernel<<<(D + 255) / 256, 256, 0, st>>>(partial, nsplit, D, reinterpret_cast<__nv_bfloat16*>(out_bf16),
-                                                       out_f32);
-  return check_launch("colsum_final_kernel");
+  parts_colsum_final_kernel<<<(D + 31) / 32, dim3(32, 8), 0, st>>>(partial, nullptr, 0, n_rows, n_static, D,
+                                                                   reinterpret_cast<__nv_bfloat16*>(out_bf16), out_f32);
+  return check_launch("parts_colsum_final_kernel");
 }
 
 int readout_last(const void* x, const int* counts, int B, int S, int D, float* out, cudaStream_t st) {

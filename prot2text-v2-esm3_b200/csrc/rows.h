@@ -8,29 +8,30 @@ namespace p2t {
 struct GemmParams;
 
 int rows_plan(const void* mask, int mask_bytes, int B, int L, int rc, int* counts, int* seq_off, int* chunk_off,
-              int* n_rows, int* row_src, cudaStream_t st);
+              int* n_rows, int* row_src, int* chunk_seq, cudaStream_t st);
+int row_inv_norm(const float* rowsq, int nblk, const int* n_rows, int cap, float* inv_norm, cudaStream_t st);
 int gather_rows(const void* src, long long ld_src, const int* row_src, const int* n_rows, int cap, int D, void* out,
                 cudaStream_t st);
-int pool_forward(const void* src, bool src_is_f16, long long ld_src, const int* row_src, const float* rowsq, int nblk,
-                 const int* seq_off, const int* chunk_off, int B, int D, int rc, int max_chunks, int mode,
-                 float2* partial, float* inv_norm_out, float* out, long long ld_out, cudaStream_t st);
+int pool_forward(const void* src, bool src_is_f16, long long ld_src, const int* row_src, const float* inv_norm,
+                 const int* seq_off, const int* chunk_off, const int* chunk_seq, int B, int D, int rc, int max_chunks,
+                 int mode, float2* partial, float* out, long long ld_out, cudaStream_t st);
 int l2norm_forward(const float* e, int B, int E, void* p_bf16, float* p_f32, float* norm, cudaStream_t st);
 int l2norm_backward(const float* dp, const float* p, const float* norm, int B, int E, float* de, cudaStream_t st);
 int pool_bwd_coef(const float* de, long long ld_de, const float* stats, long long ld_stats, const int* seq_off, int B,
                   int D, int mode, float* c1, float* c2, cudaStream_t st);
-int adapter_tail_backward(const void* a, const void* g, const float* inv_norm, const int* seq_off, int B,
-                          const float* c1, const float* c2, const int* n_rows, int cap, int D, void* dz2,
-                          cudaStream_t st);
+int adapter_tail_backward(const void* a, const void* g, const float* inv_norm, const int* seq_off, const int* chunk_off,
+                          const int* chunk_seq, int B, const float* c1, const float* c2, const int* n_rows, int cap, int D,
+                          int rc, int max_chunks, void* dz2, float* colsum_partial, void* db2, cudaStream_t st);
 int adapter_tail_backward_dy(const void* a, const void* g, const float* inv_norm, const void* dy, int n, int cap, int D,
                              void* dz2, cudaStream_t st);
 int scale_rows(const void* a, const float* rowsq, int nblk, int n, int D, void* y, float* inv_norm_out, cudaStream_t st);
 int readout_backward(const void* x, const void* mask, int mask_bytes, int B, int S, int D, const float* c1,
                      const float* c2, void* dx, cudaStream_t st);
-int colsum(const void* x, const int* n_rows, int n_static, int D, float* partial, int nsplit, void* out_bf16,
-           float* out_f32, cudaStream_t st);
+int colsum(const void* x, const int* n_rows, int n_static, int D, float* partial, void* out_bf16, float* out_f32,
+           cudaStream_t st);
 int readout_last(const void* x, const int* counts, int B, int S, int D, float* out, cudaStream_t st);
 
-int sim_small(const void* p, const void* t, int R, int C, int E, float alpha, float* S, cudaStream_t st);
+int sim_small(const void* p, const void* t, bool in_f32, int R, int C, int E, float alpha, float* S, cudaStream_t st);
 int col_stats(const float* S, int R, int C, float* col_max, float* col_sum, int* col_argmax, int row_index_base,
               cudaStream_t st);
 int mark_labelled(const int* labels, int R, int C, unsigned char* marks, cudaStream_t st);
@@ -38,8 +39,8 @@ int ce_rows(float* S, const int* labels, int R, int C, float w_row, float w_col,
             const float* col_sum, const unsigned char* col_labelled, float* row_loss, float* row_lse, int* argmax_row,
             void* dS_bf16, int write_ds, cudaStream_t st);
 int loss_mean(const float* row_loss, int R, float scale, float* loss, int accumulate, cudaStream_t st);
-int contract_small(const float* W, int ldw, bool transpose_w, const void* X, int n_out, int n_red, int E, float alpha,
-                   float* out, cudaStream_t st);
+int contract_small(const float* W, int ldw, bool transpose_w, const void* X, bool x_f32, int n_out, int n_red, int E,
+                   float alpha, float* out, cudaStream_t st);
 int convert_f32_to_bf16(const float* in, long long n, void* out, cudaStream_t st);
 int convert_bf16_to_f32(const void* in, long long n, float* out, cudaStream_t st);
 

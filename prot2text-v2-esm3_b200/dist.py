@@ -57,7 +57,7 @@ def distributed_contrastive_step(residue_states, protein_mask, adapter, text_hid
                                  aux: Optional[_step.StepAux] = None) -> torch.Tensor:
     """Sharded-batch contrastive step with all-gathered negatives; returns the local mean loss."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    t_local = _step.text_embeddings(text_hidden, text_mask)
+    t_local = _step.text_embeddings(text_hidden, text_mask, dtype=torch.float32)
     t_global = all_gather_embeddings(t_local, group) if world > 1 else t_local
     B = residue_states.shape[0]
     labels = torch.arange(rank * B, (rank + 1) * B, device=residue_states.device, dtype=torch.int32)

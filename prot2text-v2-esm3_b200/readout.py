@@ -15,7 +15,7 @@ class _ReadoutFunction(torch.autograd.Function):
         B, S, D = embeddings.shape
         emb = embeddings.contiguous()
         plan = _core.plan_rows(attention_mask)
-        stats, _ = _core.pool_forward(emb.view(B * S, D), plan, D, row_src=plan.row_src)
+        stats = _core.pool_forward(emb.view(B * S, D), plan, D, row_src=plan.row_src)
         if readout_fn == "mean":
             out = stats[:, :D]
         elif readout_fn == "std":

@@ -35,20 +35,23 @@ class StepAux:
 
 
 @torch.no_grad()
-def text_embeddings(text_hidden: torch.Tensor, text_mask: torch.Tensor) -> torch.Tensor:
-    """readout 'mix' + L2 normalise of the frozen LLM's hidden states (reference :284-310, :354)."""
+def text_embeddings(text_hidden: torch.Tensor, text_mask: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
+    """readout 'mix' + L2 normalise of the frozen LLM's hidden states (reference :284-310, :354).
+
+    Returns (B, 2H) unit-norm embeddings in `dtype`: bfloat16 like the reference, or float32 — the
+    fused step keeps the fp32 copy for the loss gradient (see csrc/infonce.cu)."""
     _core.require_cuda_bf16(text_hidden, "text_hidden")
     B, T, H = text_hidden.shape
     th = text_hidden.contiguous()
     plan = _core.plan_rows(text_mask)
-    stats, _ = _core.pool_forward(th.view(B * T, H), plan, H, row_src=plan.row_src)
-    t_bf, _, _ = _core.l2norm_forward(stats, want_f32=False)
-    return t_bf
+    stats = _core.pool_forward(th.view(B * T, H), plan, H, row_src=plan.row_src)
+    t_bf, t_f32, _ = _core.l2norm_forward(stats, want_f32=(dtype == torch.float32))
+    return t_f32 if dtype == torch.float32 else t_bf
 
 
 class _ContrastiveStepFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, prot_mask, w1, b1, w2, b2, t_bf, labels, cfg: dict, aux: StepAux):
+    def forward(ctx, x, prot_mask, w1, b1, w2, b2, t_in, labels, cfg: dict, aux: StepAux):
         for t, name in ((x, "residue states"), (w1, "fc1.weight"), (b1, "fc1.bias"), (w2, "fc2.weight"), (b2, "fc2.bias")):
             _core.require_cuda_bf16(t, name)
         B, L, d_in = x.shape
@@ -59,28 +62,36 @@ class _ContrastiveStepFunction(torch.autograd.Function):
         xp = _core.gather_rows(x.contiguous().view(B * L, d_in), plan)
         acts = _core.adapter_forward(xp, plan.rows_cap, plan.rows_cap, plan.n_rows, w1c, b1c, w2c, b2c,
                                      cfg["dropout_p"], cfg["seed"], need_grad)
-        stats, inv_norm = _core.pool_forward(acts.a, plan, d_out, row_src=None, rowsq=acts.rowsq, nblk=acts.nblk,
-                                             want_inv_norm=True)
+        inv_norm = _core.row_inv_norm(acts)
+        stats = _core.pool_forward(acts.a, plan, d_out, row_src=None, inv_norm=inv_norm)
         p_bf, p_f32, pnorm = _core.l2norm_forward(stats)
+        if t_in.dtype == torch.float32:
+            t_f32 = t_in.contiguous()
+            t_bf = _core.to_bf16(t_f32)
+        else:
+            _core.require_cuda_bf16(t_in, "text_embeds")
+            t_f32, t_bf = None, t_in.contiguous()
         used = cfg["rows_used"]
         hook = cfg.get("col_stats_hook")
         res = _core.infonce_forward(p_bf[:used], t_bf, labels[:used], cfg["tau"], w_row=cfg["w_row"], w_col=cfg["w_col"],
                                     need_grad=need_grad, want_col_argmax=True, col_stats_hook=hook,
+                                    p_f32=p_f32[:used] if t_f32 is not None else None, t_f32=t_f32,
                                     loss_scale=cfg.get("loss_scale"),
                                     all_cols_labelled=cfg.get("all_cols_labelled", False))
         aux.protein_embeddings, aux.text_embeddings = p_bf, t_bf
         aux.argmax_row, aux.argmax_col, aux.n_rows = res.argmax_row, res.argmax_col, plan.n_rows
         if need_grad:
-            ctx.state = (plan, acts, stats, inv_norm, p_bf, p_f32, pnorm, res, t_bf, w1c, w2c, cfg)
+            ctx.state = (plan, acts, stats, inv_norm, p_bf, p_f32, pnorm, res, t_bf, t_f32, w1c, w2c, cfg)
         return res.loss
 
     @staticmethod
     def backward(ctx, dloss):
-        plan, acts, stats, inv_norm, p_bf, p_f32, pnorm, res, t_bf, w1c, w2c, cfg = ctx.state
+        plan, acts, stats, inv_norm, p_bf, p_f32, pnorm, res, t_bf, t_f32, w1c, w2c, cfg = ctx.state
         ctx.state = None
         used = cfg["rows_used"]
         d_out = w2c.shape[0]
-        dp_used, _ = _core.infonce_backward(res, p_bf[:used], t_bf, cfg["tau"], need_dp=True, need_dt=False)
+        dp_used, _ = _core.infonce_backward(res, p_bf[:used], t_bf, cfg["tau"], need_dp=True, need_dt=False,
+                                            p_f32=p_f32[:used] if t_f32 is not None else None, t_f32=t_f32)
         if used == p_bf.shape[0]:
             dp = dp_used
         else:  # rows dropped by the segment split get no gradient (reference :337, :357-359)
@@ -89,8 +100,8 @@ class _ContrastiveStepFunction(torch.autograd.Function):
         dp.mul_(dloss.to(torch.float32))
         de = _core.l2norm_backward(dp, p_f32, pnorm)
         c1, c2 = _core.pool_backward_coef(de, stats, plan, d_out, "mix")
-        dz2 = _core.adapter_tail_backward(acts, inv_norm, plan, c1, c2)
-        dw1, db1, dw2, db2, _ = _core.adapter_backward(acts, dz2, w1c, w2c)
+        dz2, db2 = _core.adapter_tail_backward(acts, inv_norm, plan, c1, c2)
+        dw1, db1, dw2, _, _ = _core.adapter_backward(acts, dz2, w1c, w2c, need_db2=False)
         return None, None, dw1, db1, dw2, db2, None, None, None, None
 
 
@@ -106,7 +117,7 @@ def contrastive_step(residue_states: torch.Tensor, protein_mask: torch.Tensor, a
     residue_states (B, L, D_in) bf16 and protein_mask (B, L) come from the frozen protein encoder
     (models/esmc_qwen_arc.py:84-86); text_hidden (B_t, T, H) bf16 is hidden_states[16] of the frozen
     LLM with its attention mask (scripts/train_contrast.py:304), or pass already normalised
-    `text_embeds` (B_t, 2H) — e.g. the all-gathered global negatives.  `labels[i]` is the text row
+    `text_embeds` (B_t, 2H), float32 (preferred) or bfloat16 — e.g. the all-gathered global negatives.  `labels[i]` is the text row
     paired with protein i (default: i).  `contrastive_num_segments` reproduces the reference's
     segment averaging including its dropping of the remainder rows; `symmetric` adds the
     text->protein term.
@@ -114,7 +125,7 @@ def contrastive_step(residue_states: torch.Tensor, protein_mask: torch.Tensor, a
     if text_embeds is None:
         if text_hidden is None or text_mask is None:
             raise ValueError("pass either text_hidden + text_mask or text_embeds")
-        text_embeds = text_embeddings(text_hidden, text_mask)
+        text_embeds = text_embeddings(text_hidden, text_mask, dtype=torch.float32)
     B = residue_states.shape[0]
     seg = B // contrastive_num_segments
     if seg * contrastive_num_segments != B:

@@ -52,7 +52,7 @@ def test_argument_errors_are_reported_without_a_gpu(built):
     with pytest.raises(built.P2TError, match="null pointer"):
         built._lib.call("p2t_l2norm_fwd", None, 1, 8, None, None, None, None)
     with pytest.raises(built.P2TError, match="mask_bytes"):
-        built._lib.call("p2t_rows_plan", 1, 3, 1, 1, 64, 1, 1, 1, 1, None, None)
+        built._lib.call("p2t_rows_plan", 1, 3, 1, 1, 64, 1, 1, 1, 1, None, None, None)
 
 
 def test_sass_is_blackwell_native(built):

@@ -13,7 +13,7 @@ import __graft_entry__ as entry
 
 def main():
     cg, a_mn, b_mn, m, n, k = (int(v) for v in sys.argv[1:7])
-    f32 = len(sys.argv) > 7 and sys.argv[7] == "f32"
+    f32 = len(sys.argv) > 7 and "f32" in sys.argv[7:]
     pkg = entry.load_package()
     core = sys.modules["p2t_b200._core"]
     torch.manual_seed(0)

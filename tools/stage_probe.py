@@ -20,7 +20,7 @@ def rel(a, b):
 
 
 def cos(a, b):
-    return torch.nn.functional.cosine_similarity(a.float().cpu().flatten(), b.float().cpu().flatten(), dim=0).item()
+    return torch.nn.functional.cosine_similarity(a.double().cpu().flatten(), b.double().cpu().flatten(), dim=0).item()
 
 
 def main():
@@ -60,7 +60,8 @@ def main():
     print(f"rowsq: rel={rel(acts.rowsq[:n].sum(1), tr.a[valid].pow(2).sum(-1)):.3e}")
 
     # 3/4. pool + normalise
-    stats, inv_norm = core.pool_forward(acts.a, plan, d_out, row_src=None, rowsq=acts.rowsq, nblk=acts.nblk, want_inv_norm=True)
+    inv_norm = core.row_inv_norm(acts)
+    stats = core.pool_forward(acts.a, plan, d_out, row_src=None, inv_norm=inv_norm)
     p_bf, p_f32, pn = core.l2norm_forward(stats)
     torch.cuda.synchronize()
     print(f"pool: mean rel={rel(stats[:, :d_out], st.e_prot[:, :d_out]):.3e} std rel={rel(stats[:, d_out:], st.e_prot[:, d_out:]):.3e} p rel={rel(p_f32, st.p):.3e}")
@@ -97,8 +98,47 @@ def main():
     print(f"step: loss {loss.item():.6f} oracle {st.loss.item():.6f} rel={abs(loss.item() - st.loss.item()) / abs(st.loss.item()):.3e}")
     for k, prm in (("fc1.weight", ad.fc1.weight), ("fc1.bias", ad.fc1.bias), ("fc2.weight", ad.fc2.weight), ("fc2.bias", ad.fc2.bias)):
         print(f"  grad {k}: cos={cos(prm.grad, gr[k]):.6f} maxrel={rel(prm.grad, gr[k]):.3e}")
+    # same comparison against an oracle that rounds h1 exactly where the kernel does (bf16 operand of fc2)
+    for hdt in (torch.bfloat16, torch.float16):
+        w1f, b1f, w2f, b2f = (t.to(f).requires_grad_() for t in (sb.w1, sb.b1, sb.w2, sb.b2))
+        z1 = sb.x.to(f) @ w1f.t() + b1f
+        h1 = R.gelu_erf(z1)
+        h1 = h1 + (h1.detach().to(hdt).to(f) - h1.detach())  # straight-through rounding
+        a_ = R.gelu_erf(h1 @ w2f.t() + b2f)
+        y_ = a_ / a_.pow(2).sum(-1, keepdim=True).sqrt().clamp_min(1e-12)
+        p_, _ = R.l2_normalize(R.readout(y_, sb.prot_mask, "mix"))
+        lo_ = R.infonce_rows(p_, st.t, torch.arange(B), 0.05)
+        gs = torch.autograd.grad(lo_, (w1f, b1f, w2f, b2f))
+        print(f"  vs oracle with h1 rounded to {str(hdt).split('.')[-1]}: loss rel={abs(loss.item() - lo_.item()) / abs(lo_.item()):.3e}")
+        for (k, prm), g_ in zip((("fc1.weight", ad.fc1.weight), ("fc1.bias", ad.fc1.bias), ("fc2.weight", ad.fc2.weight), ("fc2.bias", ad.fc2.bias)), gs):
+            print(f"    grad {k}: cos={cos(prm.grad, g_):.6f} maxrel={rel(prm.grad, g_):.3e}   [oracle-vs-oracle: cos={cos(g_, gr[k]):.6f} maxrel={rel(g_, gr[k]):.3e}]")
     am_r, am_c = R.retrieval_argmax(st.p, st.t)
     print(f"  argmax_row ok={torch.equal(aux.argmax_row.cpu().long(), am_r)} argmax_col ok={torch.equal(aux.argmax_col.cpu().long(), am_c)}")
+
+    # 7b. the backward chain stage by stage (same kernels the fused step calls)
+    labels_i = torch.arange(B, dtype=torch.int32, device=dev)
+    t_f32 = pkg.text_embeddings(sb.text.to(dev), sb.text_mask.to(dev), dtype=torch.float32)
+    res = core.infonce_forward(p_bf, t_bf, labels_i, 0.05, need_grad=True, p_f32=p_f32, t_f32=t_f32)
+    dp, _ = core.infonce_backward(res, p_bf, t_bf, 0.05, p_f32=p_f32, t_f32=t_f32)
+    de = core.l2norm_backward(dp, p_f32, pn)
+    c1, c2 = core.pool_backward_coef(de, stats, plan, d_out, "mix")
+    dz2, db2 = core.adapter_tail_backward(acts, inv_norm, plan, c1, c2)
+    torch.cuda.synchronize()
+    nseq = sb.prot_lens.to(f)[:, None]
+    mu_o, sd_o = st.e_prot[:, :d_out], st.e_prot[:, d_out:]
+    c2o = gr["de"][:, d_out:] / (nseq * sd_o)
+    c1o = gr["de"][:, :d_out] / nseq - c2o * mu_o
+    dz2o = gr["dz2"].view(B, L, d_out)[valid]
+    print(f"bwd chain: dp rel={rel(dp, gr['dp']):.3e} cos={cos(dp, gr['dp']):.6f} | de rel={rel(de, gr['de']):.3e} cos={cos(de, gr['de']):.6f} | "
+          f"c1 rel={rel(c1, c1o):.3e} c2 rel={rel(c2, c2o):.3e} cos={cos(c2, c2o):.6f}")
+    print(f"           dz2 rel={rel(dz2[:n], dz2o):.3e} cos={cos(dz2[:n], dz2o):.6f} db2 cos={cos(db2, gr['fc2.bias']):.6f}")
+    # dz2 recomputed by the oracle from OUR c1/c2/y (isolates the tail kernel itself)
+    yv = tr.y[valid]
+    seq_id = torch.repeat_interleave(torch.arange(B), sb.prot_lens)
+    dy_ours = c1.cpu()[seq_id] + c2.cpu()[seq_id] * yv
+    da = (dy_ours - yv * (yv * dy_ours).sum(-1, keepdim=True)) / tr.norm[valid]
+    dz2_mix = da * R.gelu_erf_grad(tr.z2[valid])
+    print(f"           dz2 vs oracle-tail(our c1,c2): rel={rel(dz2[:n], dz2_mix):.3e} cos={cos(dz2[:n], dz2_mix):.6f}")
 
     # 8. module API: y = adapter(x) and its backward
     ad.zero_grad()
