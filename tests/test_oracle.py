@@ -120,6 +120,64 @@ def test_step_matches_reference_teacher_forcing_forward_pass(golden_dir, tag, dt
         _close(v, ref, rtol=rtol * 10, atol=ref.abs().max().item() * rtol)
 
 
+def _fork_mask_step(g, nseg):
+    """Same step through R.step_forward with ONE padded batch and the mask the fork effectively applies
+    (every segment pooled over its own padded length) — the form the CUDA path is driven with."""
+    lens = [int(v) for v in g["lens"]]
+    bsz, d_in = len(lens), g["x0"].shape[1]
+    seg = bsz // nseg
+    lmax = max(lens)
+    x = torch.zeros(bsz, lmax, d_in)
+    mask = torch.zeros(bsz, lmax, dtype=torch.long)
+    for b, n in enumerate(lens):
+        x[b, :n] = g[f"x{b}"]
+        ids = range((b // seg) * seg, (b // seg + 1) * seg) if b < seg * nseg else [b]
+        mask[b, : max(lens[i] for i in ids)] = 1
+    w1, b1, w2, b2 = (g["sd." + k] for k in ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"))
+    st = R.step_forward(x, mask, w1, b1, w2, b2, g["text"], g["tmask"], 0.05, nseg)
+    return st, R.step_backward(st, x, mask, w1, w2, 0.05, nseg)
+
+
+@pytest.mark.parametrize("nseg", [1, 2, 3, 4])
+def test_grid_step_fixture_matches_oracle(golden_dir, nseg):
+    """bf16-grid fixture of the real teacher_forcing_forward_pass (incl. nseg=3, which drops 2 of 8 rows)."""
+    g = _load(golden_dir, "grid_step.npz")
+    st, grads = _fork_mask_step(g, nseg)
+    _close(st.loss, g[f"seg{nseg}.loss"], rtol=2e-5, atol=0)
+    for k in ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"):
+        ref = g[f"seg{nseg}.grad.{k}"]
+        _close(grads[k], ref, rtol=2e-3, atol=ref.abs().max().item() * 2e-4)
+    if nseg == 1:
+        _close(st.p, g["p"], rtol=1e-4, atol=1e-6)
+
+
+def test_grid_fixtures_match_oracle(golden_dir):
+    g = _load(golden_dir, "grid_adapter.npz")
+    w1, b1, w2, b2 = (g["sd." + k] for k in ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"))
+    tr = R.adapter_rows(g["x"].reshape(-1, 24), w1, b1, w2, b2)
+    _close(tr.y.reshape(g["y"].shape), g["y"])
+    grads = R.adapter_rows_backward(tr, g["gy"].reshape(-1, 32), w1, w2, need_dx=True)
+    for k in ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"):
+        _close(grads[k], g["grad." + k], rtol=1e-4, atol=1e-5)
+    _close(grads["dx"].reshape(g["grad.x"].shape), g["grad.x"], rtol=1e-4, atol=1e-5)
+    g = _load(golden_dir, "grid_readout.npz")
+    for mname in ("right", "left", "holes"):
+        for fn in ("last", "mean", "std", "mix"):
+            if f"out.{mname}.{fn}" not in g:
+                continue
+            _close(R.readout(g["emb"], g["mask_" + mname], fn), g[f"out.{mname}.{fn}"])
+            _close(R.readout_backward(g["emb"], g["mask_" + mname], fn, g[f"gout.{mname}.{fn}"]), g[f"gemb.{mname}.{fn}"],
+                   rtol=1e-4, atol=1e-5)
+    g = _load(golden_dir, "grid_losses.npz")
+    p, t = g["p"], g["t"]
+    diag = torch.arange(p.shape[0])
+    _close(R.infonce_rows(p, t, diag, 0.05), g["batch.loss"], rtol=1e-4)
+    _close(R.infonce_cols(p, t, diag, 0.05), g["swapped.loss"], rtol=1e-4)
+    _close(R.infonce_rows(p[3:8], t, g["seg.labels"].long(), float(g["seg.temperature"])), g["seg.loss"], rtol=1e-4)
+    am_r, am_c = R.retrieval_argmax(p, t)
+    assert torch.equal(am_r, g["argmax_row"]) and torch.equal(am_c, g["argmax_col"])  # index work: bit-exact
+
+
 def test_step_closed_form_backward_agrees_with_autograd():
     """Second witness: the hand-derived backward equals autograd on the restatement (fp64)."""
     torch.manual_seed(5)
