@@ -239,7 +239,7 @@ def main():
     ev1.record()
     barrier()
     launches = lib.launch_count()
-    gemm_ms, gemm_launches = lib.gemm_timing_collect()
+    gemm_ms, gemm_launches, gemm_each = lib.gemm_timing_collect()
     lib.gemm_timing_enable(False)
     clocks = sampler.stop() if rank == 0 else None
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
@@ -290,6 +290,11 @@ def main():
     else:
         peak_tf, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
     achieved_tf = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    # mean duration of each of the step's GEMM launches, in launch order: fc1, fc2, fc2-dgrad, dW2, dW1
+    per_step = gemm_launches // args.steps if args.steps else 0
+    per_gemm_us = None
+    if per_step and per_step * args.steps == gemm_launches and len(gemm_each) == gemm_launches:
+        per_gemm_us = [round(1e3 * sum(gemm_each[i::per_step]) / args.steps, 1) for i in range(per_step)]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
@@ -299,6 +304,7 @@ def main():
                 "launches_timed": gemm_launches, "kernel_ms_per_step": gemm_ms / args.steps,
                 "kernel_share_of_step": gemm_ms / ms_total if world == 1 else None,
                 "algorithmic_flops_per_step": gemm_flops / args.steps,
+                "per_gemm_us": per_gemm_us,
                 "whole_step_frac": (gemm_flops / (ms_total / 1e3) / 1e12) / peak_tf}
 
     if rank == 0:

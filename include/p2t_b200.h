@@ -42,9 +42,10 @@ const char* p2t_last_error(void);
 unsigned long long p2t_launch_count(void);
 void p2t_reset_launch_count(void);
 /* per-launch CUDA-event timing of the tcgen05 GEMM kernel on its launching stream (bench.py's
- * roofline): enable, run, synchronise the stream, then collect the summed durations. HOST pointers. */
+ * roofline): enable, run, synchronise the stream, then collect the summed durations and (optionally, up to
+ * each_cap entries in launch order) every launch's own duration. HOST pointers. */
 void p2t_gemm_timing_enable(int on);
-int p2t_gemm_timing_collect(double* total_ms, int* launches);
+int p2t_gemm_timing_collect(double* total_ms, int* launches, double* each_ms, int each_cap);
 
 /* ---------------------------------------------------------------------------------------------
  * tcgen05 GEMM  D[m][n] = alpha * sum_k A[m][k] * B[n][k]      (bf16 in, fp32 accumulate in TMEM)
@@ -53,10 +54,15 @@ int p2t_gemm_timing_collect(double* total_ms, int* launches);
  * a_mn_major = 0: A stored [m][lda] (K contiguous); 1: A stored [k][lda] (M contiguous). Same for B.
  * d_is_f32 selects fp32 or bf16 output.  dyn_m / dyn_k: optional device int32 overriding m / k
  * (must be <= the static value).  cta_group: 1 = one SM per tile (128x256), 2 = CTA pair (256x256).
+ * gemm_ws: optional scratch of p2t_gemm_workspace_bytes() bytes (16-byte aligned, contents
+ * irrelevant).  When given and M is static, the tiles of an incomplete last wave are cut along K
+ * so that all SMs stay busy; the partial tiles are summed in a fixed order through the scratch
+ * (same result layout, deterministic).  NULL = whole tiles only.
  * ------------------------------------------------------------------------------------------- */
+unsigned long long p2t_gemm_workspace_bytes(void);
 int p2t_gemm_bf16(const void* a, long long lda, int a_mn_major, const void* b, long long ldb, int b_mn_major,
                   void* d, long long ldd, int d_is_f32, int m, int n, int k, float alpha, const int* dyn_m,
-                  const int* dyn_k, int cta_group, void* stream);
+                  const int* dyn_k, void* gemm_ws, int cta_group, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Ragged row plan from a {0,1} attention mask [B][L] (mask_bytes = 1, 4 or 8 per element; the
@@ -144,10 +150,12 @@ int p2t_adapter_tail_bwd_dy(const void* a, const void* g2, const float* inv_norm
  *   dx  = dz1 W1 (only when dx != NULL; the encoder is frozen in Stage 1, :186)
  * Gradients are written (not accumulated) in bf16, nn.Linear layout.  db1/db2/dx may be NULL (db2
  * is normally produced by p2t_adapter_tail_bwd).  colsum_ws: fp32 [ceil(rows_cap/64)][max(d_mid, d_out)].
+ * gemm_ws: optional split-K scratch for the two weight-gradient GEMMs (see p2t_gemm_bf16).
  * ------------------------------------------------------------------------------------------- */
 int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, const void* h1, const void* g1, const void* dz2,
                     int d_in, int d_mid, int d_out, int rows_cap, const int* n_rows_dev, void* dz1, void* dw1,
-                    void* db1, void* dw2, void* db2, void* dx, float* colsum_ws, int cta_group, void* stream);
+                    void* db1, void* dw2, void* db2, void* dx, float* colsum_ws, void* gemm_ws, int cta_group,
+                    void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * InfoNCE — scripts/train_contrast.py:86-91 (BatchInfoNCELoss), :100-114 (Segmented...).

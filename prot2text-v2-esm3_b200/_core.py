@@ -102,9 +102,18 @@ def gather_rows(x2d: torch.Tensor, plan: RowPlan) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------------
 # GEMM
 # --------------------------------------------------------------------------------------------------
+def gemm_workspace(device) -> Optional[torch.Tensor]:
+    """Scratch for split-K GEMM tails (flags + raw accumulator slots); None when P2T_STREAMK=0."""
+    import os
+    if os.environ.get("P2T_STREAMK", "1") == "0":
+        return None
+    return torch.empty(int(_lib.load().p2t_gemm_workspace_bytes()), dtype=torch.uint8, device=device)
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, m: int, n: int, k: int, *, a_mn: bool = False, b_mn: bool = False,
          out_dtype=torch.bfloat16, alpha: float = 1.0, cta_group: Optional[int] = None,
-         dyn_m: Optional[torch.Tensor] = None, dyn_k: Optional[torch.Tensor] = None) -> torch.Tensor:
+         dyn_m: Optional[torch.Tensor] = None, dyn_k: Optional[torch.Tensor] = None,
+         streamk: bool = False) -> torch.Tensor:
     """D[m][n] = alpha * sum_k A[m][k] B[n][k] on the tcgen05 kernel.
 
     a is stored [m][k] (a_mn=False) or [k][m] (a_mn=True); b likewise with n.
@@ -114,7 +123,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, m: int, n: int, k: int, *, a_mn: bool
     out = torch.empty(m, n, dtype=out_dtype, device=a.device)
     _lib.call("p2t_gemm_bf16", _ptr(a), a.stride(0), int(a_mn), _ptr(b), b.stride(0), int(b_mn), _ptr(out),
               out.stride(0), int(out_dtype == torch.float32), m, n, k, float(alpha), _ptr(dyn_m), _ptr(dyn_k),
-              cta_group or default_cta_group(), _stream())
+              _ptr(gemm_workspace(a.device) if streamk else None), cta_group or default_cta_group(), _stream())
     return out
 
 
@@ -170,7 +179,8 @@ def adapter_backward(acts: AdapterActs, dz2: torch.Tensor, w1, w2, need_dx: bool
     ws = torch.empty((acts.rows_cap + 63) // 64, max(d_mid, d_out) if need_db2 else d_mid, dtype=torch.float32, device=dev)
     _lib.call("p2t_adapter_bwd", _ptr(acts.x), acts.x_rows, _ptr(w1), _ptr(w2), _ptr(acts.h1), _ptr(acts.g1),
               _ptr(dz2), d_in, d_mid, d_out, acts.rows_cap, _ptr(acts.n_rows), _ptr(dz1), _ptr(dw1), _ptr(db1),
-              _ptr(dw2), _ptr(db2), _ptr(dx), _ptr(ws), cta_group or default_cta_group(), _stream())
+              _ptr(dw2), _ptr(db2), _ptr(dx), _ptr(ws), _ptr(gemm_workspace(dev)), cta_group or default_cta_group(),
+              _stream())
     return dw1, db1, dw2, db2, dx
 
 

@@ -15,7 +15,7 @@ _vp, _i, _ll, _f, _ull = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulong
 
 # name -> argument ctypes, in header order (include/p2t_b200.h)
 SIGNATURES = {
-    "p2t_gemm_bf16": [_vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp],
+    "p2t_gemm_bf16": [_vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _vp],
     "p2t_rows_plan": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "p2t_row_inv_norm": [_vp, _i, _vp, _i, _vp, _vp],
     "p2t_gather_rows": [_vp, _ll, _vp, _vp, _i, _i, _vp, _vp],
@@ -29,7 +29,7 @@ SIGNATURES = {
     "p2t_readout_bwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "p2t_adapter_tail_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "p2t_adapter_tail_bwd_dy": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp],
-    "p2t_adapter_bwd": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+    "p2t_adapter_bwd": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "p2t_similarity": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i, _vp],
     "p2t_infonce_col_stats": [_vp, _i, _i, _vp, _vp, _vp, _i, _vp],
     "p2t_infonce_ce": [_vp, _vp, _i, _i, _f, _f, _f, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp],
@@ -39,11 +39,11 @@ SIGNATURES = {
     "p2t_bf16_to_f32": [_vp, _ll, _vp, _vp],
     "p2t_colsum": [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp],
     "p2t_dropout_mask": [_i, _i, _f, _ull, _i, _vp, _vp],
-    "p2t_gemm_timing_collect": [C.POINTER(C.c_double), C.POINTER(C.c_int)],
+    "p2t_gemm_timing_collect": [C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_double), _i],
 }
 NON_STATUS = {"p2t_abi_version": (_i, []), "p2t_last_error": (C.c_char_p, []),
               "p2t_launch_count": (_ull, []), "p2t_reset_launch_count": (None, []),
-              "p2t_gemm_timing_enable": (None, [_i])}
+              "p2t_gemm_timing_enable": (None, [_i]), "p2t_gemm_workspace_bytes": (_ull, [])}
 
 _lib = None
 
@@ -95,8 +95,9 @@ def gemm_timing_enable(on: bool) -> None:
     load().p2t_gemm_timing_enable(int(on))
 
 
-def gemm_timing_collect():
-    """(total GEMM-kernel milliseconds, number of GEMM launches) since enable; synchronise first."""
+def gemm_timing_collect(cap: int = 4096):
+    """(total GEMM-kernel milliseconds, number of GEMM launches, per-launch ms list) since enable; synchronise first."""
     ms, n = C.c_double(0.0), C.c_int(0)
-    call("p2t_gemm_timing_collect", C.byref(ms), C.byref(n))
-    return ms.value, n.value
+    each = (C.c_double * cap)()
+    call("p2t_gemm_timing_collect", C.byref(ms), C.byref(n), each, cap)
+    return ms.value, n.value, list(each[:min(n.value, cap)])

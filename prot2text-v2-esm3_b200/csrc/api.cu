@@ -58,17 +58,19 @@ const char* p2t_last_error(void) { return last_error(); }
 unsigned long long p2t_launch_count(void) { return launches(); }
 void p2t_reset_launch_count(void) { reset_launches(); }
 void p2t_gemm_timing_enable(int on) { gemm_timing_enable(on != 0); }
-int p2t_gemm_timing_collect(double* total_ms, int* launches) {
+int p2t_gemm_timing_collect(double* total_ms, int* launches, double* each_ms, int each_cap) {
   if (!total_ms || !launches) return set_error(-1, "p2t_gemm_timing_collect: null pointer");
-  return gemm_timing_collect(total_ms, launches);
+  return gemm_timing_collect(total_ms, launches, each_ms, each_cap);
 }
+
+unsigned long long p2t_gemm_workspace_bytes(void) { return (unsigned long long)gemm_streamk_workspace_bytes(); }
 
 int p2t_gemm_bf16(const void* a, long long lda, int a_mn_major, const void* b, long long ldb, int b_mn_major,
                   void* d, long long ldd, int d_is_f32, int m, int n, int k, float alpha, const int* dyn_m,
-                  const int* dyn_k, int cta_group, void* stream) {
+                  const int* dyn_k, void* gemm_ws, int cta_group, void* stream) {
   if (!a || !b || !d) return set_error(-1, "p2t_gemm_bf16: null pointer");
   GemmParams p = base_params(m, n, k);
-  p.dyn_m = dyn_m; p.dyn_k = dyn_k;
+  p.dyn_m = dyn_m; p.dyn_k = dyn_k; p.sk_ws = gemm_ws;
   p.d0 = d; p.ldd0 = ldd; p.alpha = alpha;
   return launch_gemm(a, lda, a_mn_major != 0, b, ldb, b_mn_major != 0, d_is_f32 ? EPI_STORE_F32 : EPI_STORE_BF16, p,
                      cta_group, S(stream));
@@ -176,7 +178,8 @@ int p2t_adapter_tail_bwd_dy(const void* a, const void* g2, const float* inv_norm
 
 int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, const void* h1, const void* g1, const void* dz2,
                     int d_in, int d_mid, int d_out, int rows_cap, const int* n_rows_dev, void* dz1, void* dw1,
-                    void* db1, void* dw2, void* db2, void* dx, float* colsum_ws, int cta_group, void* stream) {
+                    void* db1, void* dw2, void* db2, void* dx, float* colsum_ws, void* gemm_ws, int cta_group,
+                    void* stream) {
   if (!x || !w2 || !h1 || !g1 || !dz2 || !dz1 || !dw1 || !dw2 || !colsum_ws)
     return set_error(-1, "p2t_adapter_bwd: null pointer");
   cudaStream_t st = S(stream);
@@ -192,6 +195,7 @@ int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, c
   {
     GemmParams p = base_params(d_out, d_mid, rows_cap);
     p.dyn_k = n_rows_dev;
+    p.sk_ws = gemm_ws;
     p.d0 = dw2; p.ldd0 = d_mid;
     if (int rc = launch_gemm(dz2, d_out, true, h1, d_mid, true, EPI_STORE_BF16, p, cta_group, st)) return rc;
   }
@@ -199,6 +203,7 @@ int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, c
   {
     GemmParams p = base_params(d_mid, d_in, rows_cap);
     p.dyn_k = n_rows_dev;
+    p.sk_ws = gemm_ws;
     p.d0 = dw1; p.ldd0 = d_in;
     p.b_extent = x_rows;
     if (int rc = launch_gemm(dz1, d_mid, true, x, d_in, true, EPI_STORE_BF16, p, cta_group, st)) return rc;

@@ -45,7 +45,7 @@ void gemm_timing_record(cudaStream_t st, bool begin) {
 }
 void gemm_timing_enable(bool on) { g_timing = on; g_ev_used = 0; }
 // sum of (end - begin) over recorded pairs, in ms; caller must have synchronised the stream
-int gemm_timing_collect(double* total_ms, int* pairs) {
+int gemm_timing_collect(double* total_ms, int* pairs, double* each_ms, int each_cap) {
   double t = 0.0;
   int n = 0;
   for (size_t i = 0; i + 1 < g_ev_used; i += 2) {
@@ -53,6 +53,7 @@ int gemm_timing_collect(double* total_ms, int* pairs) {
     cudaError_t e = cudaEventElapsedTime(&ms, g_ev[i], g_ev[i + 1]);
     if (e != cudaSuccess) return set_error((int)e, "cudaEventElapsedTime: %s", cudaGetErrorString(e));
     t += ms;
+    if (each_ms != nullptr && n < each_cap) each_ms[n] = ms;
     ++n;
   }
   *total_ms = t;

@@ -1,6 +1,7 @@
 // Library-internal helpers: error reporting and launch accounting behind the C ABI (include/p2t_b200.h).
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 namespace p2t {

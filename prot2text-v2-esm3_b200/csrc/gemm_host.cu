@@ -39,6 +39,10 @@ static int make_tmap_bf16(CUtensorMap* map, const void* ptr, long long inner, lo
   return 0;
 }
 
+size_t gemm_streamk_workspace_bytes() {
+  return (size_t)GEMM_SK_FLAG_BYTES + (size_t)GEMM_SK_SLOTS_PER_SM * sm_count() * GEMM_SK_SLOT_FLOATS * sizeof(float);
+}
+
 int sm_count() {
   static int n = 0;
   if (!n) {
@@ -62,8 +66,31 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   const int tile_m = GEMM_BLOCK_M * CTA_GROUP;
   const long long tiles = (long long)((p.m + tile_m - 1) / tile_m) * ((p.n + GEMM_BLOCK_N - 1) / GEMM_BLOCK_N);
   if (tiles == 0) return 0;
-  int workers = sm_count() / CTA_GROUP;
+  const int all_workers = sm_count() / CTA_GROUP;
+  int workers = all_workers;
   if (tiles < workers) workers = (int)tiles;
+  GemmParams q = p;
+  q.sk_splits = 1;
+  const int tail = (int)(tiles % all_workers);  // tiles of the incomplete last wave
+  if (p.sk_ws != nullptr && p.dyn_m == nullptr && tail != 0) {
+    // split-K tail (M is static here, so the tile count is known on the host): cut the last wave's tiles into S
+    // K ranges so that tail*S pieces fill the machine; cost model = rounds of pieces / S + a small per-dump charge
+    const int kb = (p.k + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+    double best = 1.0;
+    int best_s = 1;
+    for (int sp = 2; sp <= GEMM_SK_MAX_SPLITS; ++sp) {
+      if ((long long)tail * sp > (long long)GEMM_SK_SLOTS_PER_SM * all_workers || kb / sp < 4) break;
+      const long long rounds = ((long long)tail * sp + all_workers - 1) / all_workers;
+      const double cost = (double)rounds / sp + 0.004 * (sp - 1);
+      if (cost < best - 1e-9) { best = cost; best_s = sp; }
+    }
+    if (best_s > 1 && best <= 0.92) {
+      q.sk_splits = best_s;
+      workers = all_workers;
+      cudaError_t me = cudaMemsetAsync(p.sk_ws, 0, GEMM_SK_FLAG_BYTES, stream);
+      if (me != cudaSuccess) return set_error((int)me, "split-K flag reset failed: %s", cudaGetErrorString(me));
+    }
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(workers * CTA_GROUP);
   cfg.blockDim = dim3(GEMM_THREADS);
@@ -78,7 +105,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   cfg.numAttrs = 1;
   const bool timed = gemm_timing_enabled();
   if (timed) gemm_timing_record(stream, true);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, q);
   if (timed) gemm_timing_record(stream, false);
   if (e != cudaSuccess) return set_error((int)e, "GEMM launch failed: %s", cudaGetErrorString(e));
   count_launch();

@@ -7,10 +7,22 @@
 //   the weight-gradient GEMMs need (dW = dZ^T H with the long residue axis as K)
 // * one elected thread issues tcgen05.mma (UMMA 128x256x16, or 256x256x16 across a CTA pair with
 //   cta_group::2, each CTA loading half of B)
-// * two 256-column fp32 accumulators live in TMEM so the epilogue of tile i overlaps the MMAs of
-//   tile i+1; 16 epilogue warps (four per SM sub-partition) read TMEM with tcgen05.ld, one row per thread
+// * two 256-column fp32 accumulators live in TMEM so the epilogue of one piece of work overlaps the
+//   MMAs of the next; 16 epilogue warps (four per SM sub-partition) read TMEM with tcgen05.ld, one
+//   row per thread
 // * M and/or K may be read from device memory (ragged batches: the residue-row count is produced
 //   on the device by the packing kernel, no host sync)
+// * work distribution: whole output tiles round-robin over the persistent workers.  When the last wave
+//   would leave SMs idle (the weight gradients: 80 resp. 128 tiles of 256x256 for 74 CTA pairs) the
+//   launcher asks for a split-K tail: the tiles of the incomplete last wave are cut into S K-ranges
+//   each, so that R*S pieces fill the machine.  Pieces of one tile run side by side on neighbouring
+//   workers over the same K range as their row/column neighbours (L2 sharing of operand slabs is kept,
+//   which a free-running stream-K cut destroyed: measured slower).  A piece that does not hold a
+//   tile's first K range dumps its raw fp32 accumulator to a workspace slot and bumps the tile's flag;
+//   the piece that holds the first range owns the tile, adds the dumps in a fixed order
+//   (deterministic) and runs the epilogue.  Every worker executes ALL its dump pieces first (they never
+//   wait) and its owning pieces and whole tiles afterwards, so a wait can only target work that
+//   needs nothing but an SM to run.
 //
 // Epilogues (reference sites in models/modeling_esm2llama_instruct.py:60-68 and its autograd):
 //   EPI_STORE_BF16 / EPI_STORE_F32 : D = alpha * acc
@@ -39,6 +51,10 @@ constexpr int GEMM_UMMA_K = 16;
 constexpr int GEMM_EPI_WARPS = 16;
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;  // warp0 TMA, warp1 MMA + TMEM alloc, warps 2.. epilogue
 constexpr int GEMM_TMEM_COLS = 512;
+constexpr int GEMM_SK_SLOT_FLOATS = GEMM_BLOCK_M * GEMM_BLOCK_N;  // one CTA's raw accumulator (128 KB)
+constexpr int GEMM_SK_FLAG_BYTES = 4096;                           // flags live in front of the slots
+constexpr int GEMM_SK_SLOTS_PER_SM = 3;                            // R*S <= 3 * workers
+constexpr int GEMM_SK_MAX_SPLITS = 16;
 
 struct GemmParams {
   int m, n, k;          // problem size (upper bounds when dyn_* are set)
@@ -58,6 +74,9 @@ struct GemmParams {
   int ld_rowsq;
   float alpha;
   DropoutParams drop;         // p == 0 -> disabled
+  // split-K tail (see header comment); sk_ws == nullptr -> whole tiles only
+  void* sk_ws;                // [GEMM_SK_FLAG_BYTES of int flags][GEMM_SK_SLOTS_PER_SM * #SM slots of 128x256 fp32]
+  int sk_splits;              // S, set by the launcher (1 = whole tiles only)
 };
 
 template <int CTA_GROUP>
@@ -73,23 +92,71 @@ struct GemmSmem {
 };
 
 // ------------------------------------------------------------------------------------------------
-// Epilogue math for 32 consecutive columns of one accumulator row (one thread), in 8-column groups
-// (= one 16-byte store per output, one Philox block of dropout decisions).
+// work distribution: identical sequence of pieces (tile, kb0, kb1) in every role of a worker.
+//   tiles [0, t_full)           whole, round-robin (t_full = complete waves; = num_tiles when S == 1)
+//   tiles [t_full, num_tiles)   cut into S K-ranges each: tail piece idx = r*S + s on worker idx % W
+// order per worker: its dump pieces (s > 0), then its owning pieces (s == 0), then its whole tiles.
+// ------------------------------------------------------------------------------------------------
+struct PieceIter {
+  int num_tiles, num_kb, worker, W, S, t_full, n_tail;
+  int phase, idx;
+  __device__ __forceinline__ PieceIter(int tiles, int kb, int w, int nw, int splits)
+      : num_tiles(tiles), num_kb(kb), worker(w), W(nw), S(splits) {
+    t_full = (S > 1) ? (tiles / nw) * nw : tiles;
+    n_tail = (tiles - t_full) * S;
+    phase = (S > 1) ? 0 : 2;
+    idx = (S > 1) ? w : first_whole();
+  }
+  __device__ __forceinline__ int first_whole() const { return ((worker - n_tail) % W + W) % W; }
+  // tail_r: index of the tile among the tail tiles (flag / slot addressing), -1 for a whole tile; s: K-range index
+  __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1, int& tail_r, int& s) {
+    while (phase < 2) {
+      while (idx < n_tail) {
+        const int r = idx / S, ss = idx - r * S;
+        idx += W;
+        if ((ss != 0) == (phase == 0)) {
+          tile = t_full + r; tail_r = r; s = ss;
+          kb0 = (int)((long long)num_kb * ss / S);
+          kb1 = (int)((long long)num_kb * (ss + 1) / S);
+          return true;
+        }
+      }
+      ++phase;
+      idx = (phase == 1) ? worker : first_whole();
+    }
+    if (idx >= t_full) return false;
+    tile = idx; tail_r = -1; s = 0; kb0 = 0; kb1 = num_kb;
+    idx += W;
+    return true;
+  }
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue math, 8-column groups (= one 16-byte store per output, one Philox block of dropout bits)
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__device__ __forceinline__ void store8(T* dst, const float (&f)[8], int n_ok) {
-  if (n_ok == 8 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-    uint4 u;
-    if constexpr (sizeof(T) == 2 && std::is_same<T, __half>::value) {
-      u = make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]), pack_f16x2(f[6], f[7]));
-      *reinterpret_cast<uint4*>(dst) = u;
-    } else if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-      u = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-      *reinterpret_cast<uint4*>(dst) = u;
-    } else {
-      reinterpret_cast<float4*>(dst)[0] = make_float4(f[0], f[1], f[2], f[3]);
-      reinterpret_cast<float4*>(dst)[1] = make_float4(f[4], f[5], f[6], f[7]);
-    }
+__device__ __forceinline__ void store8_vec(T* dst, const float (&f)[8]) {
+  if constexpr (std::is_same<T, __half>::value) {
+    *reinterpret_cast<uint4*>(dst) =
+        make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]), pack_f16x2(f[6], f[7]));
+  } else if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    *reinterpret_cast<uint4*>(dst) =
+        make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  } else {
+    reinterpret_cast<float4*>(dst)[0] = make_float4(f[0], f[1], f[2], f[3]);
+    reinterpret_cast<float4*>(dst)[1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* dst, const float (&f)[8], int n_ok, bool vec_ok) {
+  if (n_ok == 8 && vec_ok) {  // vec_ok: every row of the tensor starts 16-byte aligned
+    store8_vec(dst, f);
   } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -120,73 +187,103 @@ __device__ __forceinline__ void load8(const T* src, float (&f)[8], int n_ok) {
   }
 }
 
+// what the epilogue warps need from GemmParams, read once into registers (the parameter bank costs
+// an LDC round trip per use inside the loop otherwise)
+struct EpiArgs {
+  char* d0;
+  char* d1;
+  long long ldd0, ldd1, ldaux;
+  const __half* aux;
+  float alpha, scale;
+  uint32_t threshold, layer;
+  uint2 key;
+};
+
+// One 32-column chunk of one accumulator row.  `ncols` < 32 only in the last chunk of a ragged N; columns
+// beyond N hold zero accumulators (TMA zero fill) and zero bias, so the math may run on them and only the
+// stores are clipped.  Rows in [M, rows_cap) are the zero padding of the packed buffers.
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const GemmParams& p, const float* bias_s, int row,
-                                               int col, int ncols, bool row_valid, bool row_in_buf, float& sumsq) {
-  // dropout decisions for the whole 32-column chunk first: four independent Philox blocks in flight
-  uint4 rnd[4];
-  if constexpr (EPI == EPI_FC1 || EPI == EPI_FC2) {
-    if (p.drop.threshold != 0) {
-      const uint2 key = make_uint2(static_cast<uint32_t>(p.drop.seed), static_cast<uint32_t>(p.drop.seed >> 32));
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const EpiArgs& e, const uint4 (&rnd)[4],
+                                               uint32_t bias_addr, int row, int col, int ncols, bool row_valid,
+                                               bool row_in_buf, bool vec_ok, float& sumsq) {
+  using T0 = typename std::conditional<EPI == EPI_STORE_F32, float,
+             typename std::conditional<EPI == EPI_FC2, __half, __nv_bfloat16>::type>::type;
+  T0* dst0 = reinterpret_cast<T0*>(e.d0) + (long long)row * e.ldd0 + col;
+  __half* dst1 = reinterpret_cast<__half*>(e.d1) + (long long)row * e.ldd1 + col;
+  const bool want_der = (EPI == EPI_FC1 || EPI == EPI_FC2) && e.d1 != nullptr;
+  if (!row_valid) {
+    if constexpr (EPI == EPI_FC1 || EPI == EPI_FC2 || EPI == EPI_MUL_AUX) {
+      if (row_in_buf) {
+        const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        rnd[j] = philox4x32_10(make_uint4(static_cast<uint32_t>(row), static_cast<uint32_t>((col >> 3) + j), p.drop.layer, 0u), key);
+        for (int j = 0; j < 4; ++j) {
+          const int n_ok = min(8, ncols - 8 * j);
+          if (n_ok <= 0) break;
+          store8(dst0 + 8 * j, zero, n_ok, vec_ok);
+          if (want_der) store8(dst1 + 8 * j, zero, n_ok, vec_ok);
+        }
+      }
+    }
+    return;
+  }
+  uint4 g4[4];
+  if constexpr (EPI == EPI_MUL_AUX) {
+    // all 16-byte loads of the multiplier first (the only long-latency operation of this epilogue)
+    const __half* ap = e.aux + (long long)row * e.ldaux + col;
+    if (vec_ok && ncols == 32) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g4[j] = __ldg(reinterpret_cast<const uint4*>(ap) + j);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float g[8];
+        load8(ap + 8 * j, g, max(0, min(8, ncols - 8 * j)));
+        g4[j] = make_uint4(pack_f16x2(g[0], g[1]), pack_f16x2(g[2], g[3]), pack_f16x2(g[4], g[5]), pack_f16x2(g[6], g[7]));
+      }
     }
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const int c8 = col + 8 * j;
     const int n_ok = min(8, ncols - 8 * j);
     if (n_ok <= 0) break;
-    float acc[8];
+    float val[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = __uint_as_float(v[8 * j + i]);
-    if constexpr (EPI == EPI_STORE_BF16) {
-      if (row_valid) {
+    for (int i = 0; i < 8; ++i) val[i] = __uint_as_float(v[8 * j + i]);
+    if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_STORE_F32) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] *= p.alpha;
-        store8(reinterpret_cast<__nv_bfloat16*>(p.d0) + (long long)row * p.ldd0 + c8, acc, n_ok);
-      }
-    } else if constexpr (EPI == EPI_STORE_F32) {
-      if (row_valid) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] *= p.alpha;
-        store8(reinterpret_cast<float*>(p.d0) + (long long)row * p.ldd0 + c8, acc, n_ok);
-      }
-    } else if constexpr (EPI == EPI_FC1 || EPI == EPI_FC2) {
-      if (row_in_buf) {
-        float keep[8], val[8], der[8];
-        if (p.drop.threshold != 0) dropout_keep8_from(p.drop, rnd[j], keep);
-        else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) keep[i] = 1.f;
-        }
-        const float4 bz0 = *reinterpret_cast<const float4*>(bias_s + 8 * j);
-        const float4 bz1 = *reinterpret_cast<const float4*>(bias_s + 8 * j + 4);
-        const float bias[8] = {bz0.x, bz0.y, bz0.z, bz0.w, bz1.x, bz1.y, bz1.z, bz1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float gl, gd;
-          gelu_erf_both_fast(acc[i] + bias[i], gl, gd);
-          const float kp = (row_valid && i < n_ok) ? keep[i] : 0.f;
-          val[i] = gl * kp;
-          der[i] = gd * kp;
-          if constexpr (EPI == EPI_FC2) sumsq = fmaf(val[i], val[i], sumsq);
-        }
-        if constexpr (EPI == EPI_FC1)  // h1 feeds the next GEMM: bf16
-          store8(reinterpret_cast<__nv_bfloat16*>(p.d0) + (long long)row * p.ldd0 + c8, val, n_ok);
-        else                           // a is read only by our own streaming kernels: fp16
-          store8(reinterpret_cast<__half*>(p.d0) + (long long)row * p.ldd0 + c8, val, n_ok);
-        if (p.d1 != nullptr) store8(reinterpret_cast<__half*>(p.d1) + (long long)row * p.ldd1 + c8, der, n_ok);
-      }
+      for (int i = 0; i < 8; ++i) val[i] *= e.alpha;
+      store8(dst0 + 8 * j, val, n_ok, vec_ok);
     } else if constexpr (EPI == EPI_MUL_AUX) {
-      if (row_in_buf) {
-        float g[8];
-        if (row_valid) load8(p.aux + (long long)row * p.ldaux + c8, g, n_ok);
+      const uint32_t w[4] = {g4[j].x, g4[j].y, g4[j].z, g4[j].w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = row_valid ? acc[i] * p.alpha * g[i] : 0.f;
-        store8(reinterpret_cast<__nv_bfloat16*>(p.d0) + (long long)row * p.ldd0 + c8, acc, n_ok);
+      for (int i = 0; i < 4; ++i) {
+        const float2 g = unpack_f16x2(w[i]);
+        val[2 * i] *= e.alpha * g.x;
+        val[2 * i + 1] *= e.alpha * g.y;
       }
+      store8(dst0 + 8 * j, val, n_ok, vec_ok);
+    } else {
+      float bias[8], der[8];
+      lds_f32x4(bias_addr + 32 * j, bias[0], bias[1], bias[2], bias[3]);
+      lds_f32x4(bias_addr + 32 * j + 16, bias[4], bias[5], bias[6], bias[7]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) gelu_erf_both_fast(val[i] + bias[i], val[i], der[i]);
+      if (e.threshold != 0) {
+        const uint32_t w[4] = {rnd[j].x, rnd[j].y, rnd[j].z, rnd[j].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float k0 = ((w[i] & 0xFFFFu) >= e.threshold) ? e.scale : 0.f;
+          const float k1 = ((w[i] >> 16) >= e.threshold) ? e.scale : 0.f;
+          val[2 * i] *= k0; der[2 * i] *= k0;
+          val[2 * i + 1] *= k1; der[2 * i + 1] *= k1;
+        }
+      }
+      if constexpr (EPI == EPI_FC2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sumsq = fmaf(val[i], val[i], sumsq);
+      }
+      store8(dst0 + 8 * j, val, n_ok, vec_ok);
+      if (want_der) store8(dst1 + 8 * j, der, n_ok, vec_ok);
     }
   }
 }
@@ -198,7 +295,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                          const GemmParams p) {
   using S = GemmSmem<CTA_GROUP>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align inside the shared window with pointer arithmetic (keeps the address space known to the compiler)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + S::STAGES * S::A_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
@@ -217,7 +315,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int M = p.dyn_m ? min(*p.dyn_m, p.m) : p.m;
   const int K = p.dyn_k ? min(*p.dyn_k, p.k) : p.k;
   const int N = p.n;
-  const int num_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  // K == 0 (an empty batch) gives pieces with an empty K range: no MMA is issued and the epilogue runs on a
+  // zero accumulator
+  const int num_kb = (max(K, 0) + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
   const int tile_m = GEMM_BLOCK_M * CTA_GROUP;
   const int num_m_blk = (M + tile_m - 1) / tile_m;
   const int num_n_blk = (N + GEMM_BLOCK_N - 1) / GEMM_BLOCK_N;
@@ -251,14 +351,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0 && num_kb > 0) {
+    if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = worker; t < num_tiles; t += num_workers) {
+      PieceIter pieces(num_tiles, num_kb, worker, num_workers, p.sk_splits);
+      int t, kb0, kb1, tail_r, split;
+      while (pieces.next(t, kb0, kb1, tail_r, split)) {
         const int m_blk = t / num_n_blk, n_blk = t % num_n_blk;
         const int m_base = (m_blk * CTA_GROUP + (int)cta_rank) * GEMM_BLOCK_M;
         const int n_base = n_blk * GEMM_BLOCK_N + (int)cta_rank * S::B_ROWS;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem_a + stage * S::A_BYTES;
           uint8_t* sb = smem_b + stage * S::B_BYTES;
@@ -288,18 +390,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else if (warp == 1) {
     // =============================== MMA issuer (leader CTA) ===============================
-    if (is_leader && lane == 0 && num_kb > 0) {
+    if (is_leader && lane == 0) {
       // (fp16 x bf16 mixed operands are rejected by the hardware: 'illegal instruction' on sm_100a, tried in round 1)
       constexpr uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M * CTA_GROUP, GEMM_BLOCK_N, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = worker; t < num_tiles; t += num_workers) {
+      PieceIter pieces(num_tiles, num_kb, worker, num_workers, p.sk_splits);
+      int t, kb0, kb1, tail_r, split;
+      while (pieces.next(t, kb0, kb1, tail_r, split)) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * GEMM_BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem_a + stage * S::A_BYTES);
@@ -313,7 +417,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                                         : make_smem_desc_sw128(sa + k * (GEMM_UMMA_K * 2), 16, 1024);
             const uint64_t bdesc = B_MN ? make_smem_desc_sw128(sb + k * (GEMM_UMMA_K * 128), GEMM_BLOCK_K * 128, 1024)
                                         : make_smem_desc_sw128(sb + k * (GEMM_UMMA_K * 2), 16, 1024);
-            umma_bf16<CTA_GROUP>(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16<CTA_GROUP>(tmem_d, adesc, bdesc, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
           if constexpr (CTA_GROUP == 2) umma_commit_pair(&empty_bar[stage], 0x3);
           else umma_commit_1cta(&empty_bar[stage]);
@@ -326,23 +430,46 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else {
     // =============================== epilogue warps ===============================
-    // 16 warps (four per SM sub-partition, enough thread-level parallelism to hide the MUFU / Philox
-    // dependency chains): warp w may read TMEM lanes [32*(w%4), +32); the four warps of a lane quarter
-    // split the tile's 256 columns into 64-column parts.  The chunk loop is NOT unrolled: the epilogue
-    // body is ~1000 instructions and must stay inside the instruction cache.
+    // 16 warps (four per SM sub-partition): warp w may read TMEM lanes [32*(w%4), +32); the four warps of a
+    // lane quarter split the tile's 256 columns into 64-column parts.  Per 32-column chunk: issue the TMEM
+    // load, generate the chunk's dropout bits (4 Philox blocks, independent of the data) while it is in
+    // flight, then wait and run the math.  The chunk loop is NOT unrolled: the body is ~1000 instructions
+    // and must stay inside the instruction cache.
     const int quarter = warp & 3;
     const int part = (warp - 2) >> 2;
     constexpr int COLS_PER_WARP = GEMM_BLOCK_N / (GEMM_EPI_WARPS / 4);
     constexpr int CHUNKS = COLS_PER_WARP / 32;
     float* bias_s = bias_smem + (warp - 2) * COLS_PER_WARP;  // this warp's private slice
+    const uint32_t bias_addr0 = smem_u32(bias_s);
+    EpiArgs e;
+    e.d0 = reinterpret_cast<char*>(p.d0); e.d1 = reinterpret_cast<char*>(p.d1);
+    e.ldd0 = p.ldd0; e.ldd1 = p.ldd1; e.ldaux = p.ldaux; e.aux = p.aux;
+    e.alpha = p.alpha; e.scale = p.drop.scale; e.threshold = p.drop.threshold; e.layer = p.drop.layer;
+    e.key = make_uint2(static_cast<uint32_t>(p.drop.seed), static_cast<uint32_t>(p.drop.seed >> 32));
+    const int rows_cap = p.rows_cap;
+    // the interior path moves 16-byte vectors: every row of every output/aux tensor must start 16-byte aligned
+    auto rows_aligned = [](const void* ptr, long long ld, int elem_bytes) {
+      return ptr == nullptr || (((reinterpret_cast<uintptr_t>(ptr) | (uintptr_t)(ld * elem_bytes)) & 15) == 0);
+    };
+    const bool vec_ok = rows_aligned(p.d0, p.ldd0, EPI == EPI_STORE_F32 ? 4 : 2) && rows_aligned(p.d1, p.ldd1, 2) &&
+                        rows_aligned(p.aux, p.ldaux, 2);
+    int* sk_flags = reinterpret_cast<int*>(p.sk_ws);
+    float* sk_slots = reinterpret_cast<float*>(reinterpret_cast<char*>(p.sk_ws) + GEMM_SK_FLAG_BYTES);
+    const int row_in_cta = quarter * 32 + lane;
+    const int S_ = p.sk_splits;
     int acc = 0;
     uint32_t acc_phase = 0;
-    if (num_kb > 0) {
-      for (int t = worker; t < num_tiles; t += num_workers) {
-        const int m_blk = t / num_n_blk, n_blk = t % num_n_blk;
-        const int row = (m_blk * CTA_GROUP + (int)cta_rank) * GEMM_BLOCK_M + quarter * 32 + lane;
-        const int col0 = n_blk * GEMM_BLOCK_N + part * COLS_PER_WARP;
-        if constexpr (EPI == EPI_FC1 || EPI == EPI_FC2) {
+    PieceIter pieces(num_tiles, num_kb, worker, num_workers, S_);
+    int t, kb0, kb1, tail_r, split;
+    while (pieces.next(t, kb0, kb1, tail_r, split)) {
+      const int m_blk = t / num_n_blk, n_blk = t % num_n_blk;
+      const int row = (m_blk * CTA_GROUP + (int)cta_rank) * GEMM_BLOCK_M + row_in_cta;
+      const int col0 = n_blk * GEMM_BLOCK_N + part * COLS_PER_WARP;
+      const bool is_head = split == 0;             // owns the tile: runs the epilogue
+      const bool has_peers = is_head && tail_r >= 0;  // ... after adding the S-1 dumped K ranges
+      const bool empty_k = kb1 <= kb0;
+      if constexpr (EPI == EPI_FC1 || EPI == EPI_FC2) {
+        if (is_head) {
           // stage this warp's bias slice once per tile (read back as shared-memory broadcasts)
           __syncwarp();
 #pragma unroll
@@ -350,32 +477,73 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             bias_s[i] = (p.bias != nullptr && col0 + i < N) ? __bfloat162float(p.bias[col0 + i]) : 0.f;
           __syncwarp();
         }
-        mbar_wait(&tmem_full_bar[acc], acc_phase);
-        tcgen05_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * GEMM_BLOCK_N +
-                               part * COLS_PER_WARP;
-        const bool row_valid = row < M;
-        const bool row_in_buf = row < p.rows_cap;
-        float sumsq = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < CHUNKS; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(taddr + c * 32, v);
-          tmem_ld_wait();
-          const int col = col0 + c * 32;
-          if (col < N) epilogue_chunk<EPI>(v, p, bias_s + c * 32, row, col, min(32, N - col), row_valid, row_in_buf, sumsq);
-        }
-        if constexpr (EPI == EPI_FC2) {
-          if (row_in_buf) p.rowsq[(long long)row * p.ld_rowsq + n_blk * (GEMM_EPI_WARPS / 4) + part] = sumsq;
-        }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if constexpr (CTA_GROUP == 2) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
-          else mbar_arrive(&tmem_empty_bar[acc]);
-        }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      if (has_peers) {
+        if (lane == 0)
+          while (ld_acquire_gpu(sk_flags + tail_r) < (S_ - 1) * GEMM_EPI_WARPS * CTA_GROUP) __nanosleep(100);
+        __syncwarp();
+      }
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * GEMM_BLOCK_N +
+                             part * COLS_PER_WARP;
+      const bool row_valid = row < M;
+      const bool row_in_buf = row < rows_cap;
+      float sumsq = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < CHUNKS; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, v);
+        const int col = col0 + c * 32;
+        uint4 rnd[4];
+        if constexpr (EPI == EPI_FC1 || EPI == EPI_FC2) {
+          if (e.threshold != 0 && is_head) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              rnd[j] = philox4x32_10(make_uint4(static_cast<uint32_t>(row), static_cast<uint32_t>((col >> 3) + j), e.layer, 0u), e.key);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rnd[j] = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+        tmem_ld_wait();
+        if (empty_k) {  // no MMA wrote this accumulator
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+        }
+        if (!is_head) {
+          // raw partial accumulator -> the piece's slot, column-major so that the 32 rows of a warp coalesce
+          float* slot = sk_slots + ((size_t)((tail_r * S_ + split) * CTA_GROUP + (int)cta_rank)) * GEMM_SK_SLOT_FLOATS +
+                        (size_t)(part * COLS_PER_WARP + c * 32) * GEMM_BLOCK_M + row_in_cta;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) slot[(size_t)i * GEMM_BLOCK_M] = __uint_as_float(v[i]);
+          continue;
+        }
+        if (has_peers) {
+          for (int s2 = 1; s2 < S_; ++s2) {
+            const float* slot = sk_slots + ((size_t)((tail_r * S_ + s2) * CTA_GROUP + (int)cta_rank)) * GEMM_SK_SLOT_FLOATS +
+                                (size_t)(part * COLS_PER_WARP + c * 32) * GEMM_BLOCK_M + row_in_cta;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __ldcg(slot + (size_t)i * GEMM_BLOCK_M));
+          }
+        }
+        if (col < N) {
+          const uint32_t bias_addr = bias_addr0 + c * 32 * 4;
+          epilogue_chunk<EPI>(v, e, rnd, bias_addr, row, col, min(32, N - col), row_valid, row_in_buf, vec_ok, sumsq);
+        }
+      }
+      if constexpr (EPI == EPI_FC2) {
+        if (row_in_buf && is_head) p.rowsq[(long long)row * p.ld_rowsq + n_blk * (GEMM_EPI_WARPS / 4) + part] = sumsq;
+      }
+      tcgen05_fence_before();
+      if (!is_head) __threadfence();  // the dumped piece must be visible before the flag
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CTA_GROUP == 2) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+        else mbar_arrive(&tmem_empty_bar[acc]);
+        if (!is_head) atomicAdd(sk_flags + tail_r, 1);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 

@@ -105,6 +105,16 @@ __device__ __forceinline__ void dropout_keep8_from(const DropoutParams& d, const
   }
 }
 
+// same, from plain (threshold, scale) values held in registers; threshold 0 -> dropout disabled
+__device__ __forceinline__ void dropout_keep8_raw(uint32_t threshold, float scale, const uint4& r, float (&keep)[8]) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    keep[2 * i] = (threshold == 0 || (w[i] & 0xFFFFu) >= threshold) ? scale : 0.0f;
+    keep[2 * i + 1] = (threshold == 0 || (w[i] >> 16) >= threshold) ? scale : 0.0f;
+  }
+}
+
 // keep multipliers for 32 consecutive columns starting at `col` (col % 8 == 0)
 struct DropoutRow {
   float k[32];

@@ -21,6 +21,11 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// 16-byte shared-memory load through a 32-bit shared address (never a generic LD)
+__device__ __forceinline__ void lds_f32x4(uint32_t addr, float& a, float& b, float& c, float& d) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr));
+}
+
 // ------------------------------------------------------------------------------------------
 // cluster
 // ------------------------------------------------------------------------------------------

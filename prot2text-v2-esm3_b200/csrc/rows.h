@@ -47,10 +47,11 @@ int convert_bf16_to_f32(const void* in, long long n, float* out, cudaStream_t st
 int launch_gemm(const void* a, long long lda, bool a_mn, const void* b, long long ldb, bool b_mn, int epi,
                 GemmParams p, int cta_group, cudaStream_t stream);
 
+size_t gemm_streamk_workspace_bytes();
 const char* last_error();
 unsigned long long launches();
 void reset_launches();
 void gemm_timing_enable(bool on);
-int gemm_timing_collect(double* total_ms, int* pairs);
+int gemm_timing_collect(double* total_ms, int* pairs, double* each_ms, int each_cap);
 
 }  // namespace p2t

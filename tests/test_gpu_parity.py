@@ -145,6 +145,29 @@ def test_gemm_matches_fp64_matmul(core, dev, cta_group, m, n, k, a_mn, b_mn, f32
     assert err <= (2e-5 if f32 else 4.5e-3) * scale, f"max err {err:.3e} vs scale {scale:.3e}"
 
 
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("m,n,k,a_mn,b_mn,f32", [
+    (2048, 2560, 18143 // 8 * 8, 1, 1, 0),   # dW1 at config 2: 80 tiles of 256x256 for 74 CTA pairs
+    (4096, 2048, 4000, 1, 1, 0),             # dW2 shape, shorter K
+    (512, 512, 8192, 0, 0, 1),               # 4 tiles: every tile is cut 16 ways
+    (300, 704, 2048, 0, 1, 1),               # ragged M and N
+])
+def test_gemm_split_k_tail_matches_fp64_matmul_and_is_deterministic(core, dev, cta_group, m, n, k, a_mn, b_mn, f32):
+    g = torch.Generator(device="cpu").manual_seed(m + n + k)
+    A = bf(torch.randn(m, k, generator=g)).to(dev)
+    B = bf(torch.randn(n, k, generator=g)).to(dev)
+    a_store = A.t().contiguous() if a_mn else A
+    b_store = B.t().contiguous() if b_mn else B
+    kw = dict(a_mn=bool(a_mn), b_mn=bool(b_mn), out_dtype=torch.float32 if f32 else torch.bfloat16, cta_group=cta_group)
+    out = core.gemm(a_store, b_store, m, n, k, streamk=True, **kw)
+    again = core.gemm(a_store, b_store, m, n, k, streamk=True, **kw)
+    ref = A.double() @ B.double().t()
+    scale = ref.abs().max().item()
+    err = (out.double() - ref).abs().max().item()
+    assert err <= (2e-5 if f32 else 4.5e-3) * scale, f"max err {err:.3e} vs scale {scale:.3e}"
+    assert torch.equal(out, again)  # fixed summation order of the partial tiles
+
+
 def test_gemm_device_side_extents(core, dev):
     """dyn_m / dyn_k are read from device memory: rows >= dyn_m are not written, the K loop stops at dyn_k."""
     m, n, k = 700, 256, 512
@@ -153,7 +176,7 @@ def test_gemm_device_side_extents(core, dev):
     dyn_m = torch.tensor([333], dtype=torch.int32, device=dev)
     out = torch.full((m, n), 7.0, dtype=torch.bfloat16, device=dev)
     core._lib.call("p2t_gemm_bf16", A.data_ptr(), k, 0, B.data_ptr(), k, 0, out.data_ptr(), n, 0, m, n, k, 1.0,
-                   dyn_m.data_ptr(), None, 2, torch.cuda.current_stream().cuda_stream)
+                   dyn_m.data_ptr(), None, None, 2, torch.cuda.current_stream().cuda_stream)
     ref = A[:333].double() @ B.double().t()
     assert maxrel(out[:333], ref) < 4.5e-3 and bool((out[333:] == 7.0).all())
     # K from the device: operands are [K][rows] (the weight-gradient layout), rows >= dyn_k zero up to the 64-block
