@@ -2,6 +2,8 @@
 // time, so the library links without libcuda) and template dispatch.
 #include "common.h"
 #include "gemm_sm100.cuh"
+#include <cstdlib>
+#include <cstring>
 
 namespace p2t {
 
@@ -21,22 +23,27 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// bf16 row-major matrix [outer][inner] with leading dimension `ld` elements; box = {64 inner, box_outer}
-static int make_tmap_bf16(CUtensorMap* map, const void* ptr, long long inner, long long outer, long long ld,
-                          int box_outer) {
+// 16-bit row-major matrix [outer][inner] with leading dimension `ld` elements; box = {box_inner, box_outer}
+// (operands: 64-element = 128-byte inner box, 128-byte swizzle; staged outputs: 32-element inner box, 64-byte swizzle)
+static int make_tmap_16bit(CUtensorMap* map, const void* ptr, long long inner, long long outer, long long ld,
+                           int box_inner, int box_outer, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return set_error(-10, "cuTensorMapEncodeTiled entry point not available");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * 2) % 16)
     return set_error(-11, "GEMM operand must be 16-byte aligned with a leading dimension multiple of 8");
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_outer)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer)};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(-12, "cuTensorMapEncodeTiled failed (code %d)", (int)r);
   return 0;
+}
+static int make_tmap_bf16(CUtensorMap* map, const void* ptr, long long inner, long long outer, long long ld,
+                          int box_outer) {
+  return make_tmap_16bit(map, ptr, inner, outer, ld, 64, box_outer, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 size_t gemm_streamk_workspace_bytes() {
@@ -55,7 +62,7 @@ int sm_count() {
 
 template <int CTA_GROUP, bool A_MN, bool B_MN, int EPI>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-  using S = GemmSmem<CTA_GROUP>;
+  using S = GemmSmem<CTA_GROUP, EPI>;
   auto kern = gemm_bf16_tcgen05_kernel<CTA_GROUP, A_MN, B_MN, EPI>;
   static bool configured = false;
   if (!configured) {
@@ -71,6 +78,8 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   if (tiles < workers) workers = (int)tiles;
   GemmParams q = p;
   q.sk_splits = 1;
+  static const int nostore = getenv("P2T_DEBUG_NOSTORE") ? atoi(getenv("P2T_DEBUG_NOSTORE")) : 0;
+  q.debug_nostore = nostore;
   const int tail = (int)(tiles % all_workers);  // tiles of the incomplete last wave
   if (p.sk_ws != nullptr && p.dyn_m == nullptr && tail != 0) {
     // split-K tail (M is static here, so the tile count is known on the host): cut the last wave's tiles into S
@@ -105,7 +114,22 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   cfg.numAttrs = 1;
   const bool timed = gemm_timing_enabled();
   if (timed) gemm_timing_record(stream, true);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, q);
+  // FC epilogues write their 16-bit outputs with TMA stores when the output rows are 16-byte aligned
+  CUtensorMap td0, td1;
+  memset(&td0, 0, sizeof(td0));
+  memset(&td1, 0, sizeof(td1));
+  q.tma_store = 0;
+  if (S::TMA_STORE && !nostore) {
+    const bool ok0 = !((reinterpret_cast<uintptr_t>(p.d0) & 15) || (p.ldd0 * 2) % 16);
+    const bool ok1 = p.d1 == nullptr || !((reinterpret_cast<uintptr_t>(p.d1) & 15) || (p.ldd1 * 2) % 16);
+    if (ok0 && ok1) {
+      if (int rc = make_tmap_16bit(&td0, p.d0, p.n, p.rows_cap, p.ldd0, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+      if (p.d1)
+        if (int rc = make_tmap_16bit(&td1, p.d1, p.n, p.rows_cap, p.ldd1, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+      q.tma_store = 1;
+    }
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, td0, td1, q);
   if (timed) gemm_timing_record(stream, false);
   if (e != cudaSuccess) return set_error((int)e, "GEMM launch failed: %s", cudaGetErrorString(e));
   count_launch();

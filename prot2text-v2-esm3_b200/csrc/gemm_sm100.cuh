@@ -77,18 +77,25 @@ struct GemmParams {
   // split-K tail (see header comment); sk_ws == nullptr -> whole tiles only
   void* sk_ws;                // [GEMM_SK_FLAG_BYTES of int flags][GEMM_SK_SLOTS_PER_SM * #SM slots of 128x256 fp32]
   int sk_splits;              // S, set by the launcher (1 = whole tiles only)
+  int tma_store;              // FC epilogues: tmap_d0/tmap_d1 are valid, write outputs through shared memory + TMA
+  int debug_nostore;          // bring-up aid (P2T_DEBUG_NOSTORE=1): run the epilogue math, skip its global stores
 };
 
-template <int CTA_GROUP>
+// The FC epilogues stage their two 16-bit outputs in shared memory (one 32-row x 32-column box per output and
+// epilogue warp, 64-byte swizzle) and write them with TMA stores; they give up pipeline stages for it.
+template <int CTA_GROUP, int EPI>
 struct GemmSmem {
+  static constexpr bool TMA_STORE = (EPI == EPI_FC1 || EPI == EPI_FC2);
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;                 // 16 KB
   static constexpr int B_ROWS = GEMM_BLOCK_N / CTA_GROUP;                         // rows of B this CTA loads
   static constexpr int B_BYTES = B_ROWS * GEMM_BLOCK_K * 2;                       // 32 / 16 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (CTA_GROUP == 1) ? 4 : 6;
+  static constexpr int STAGES = TMA_STORE ? ((CTA_GROUP == 1) ? 3 : 4) : ((CTA_GROUP == 1) ? 4 : 6);
   static constexpr int BAR_BYTES = 1024;
   static constexpr int BIAS_BYTES = GEMM_BLOCK_N * 4 * 4;  // per-epilogue-warp bias slices (16 warps x 64 floats)
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + 1024;  // + slack for 1024-B alignment
+  static constexpr int OUT_BOX_BYTES = 32 * 32 * 2;        // one staged output box
+  static constexpr int OUT_BYTES = TMA_STORE ? GEMM_EPI_WARPS * 2 * OUT_BOX_BYTES : 0;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + OUT_BYTES + 1024;  // + slack for 1024-B alignment
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -197,6 +204,7 @@ struct EpiArgs {
   float alpha, scale;
   uint32_t threshold, layer;
   uint2 key;
+  int nostore;
 };
 
 // One 32-column chunk of one accumulator row.  `ncols` < 32 only in the last chunk of a ragged N; columns
@@ -282,9 +290,60 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ep
 #pragma unroll
         for (int i = 0; i < 8; ++i) sumsq = fmaf(val[i], val[i], sumsq);
       }
+      if (e.nostore && val[0] != 12345.678f) continue;
       store8(dst0 + 8 * j, val, n_ok, vec_ok);
       if (want_der) store8(dst1 + 8 * j, der, n_ok, vec_ok);
     }
+  }
+}
+
+// FC epilogues, TMA-store flavour: the chunk's 32 rows x 32 columns of each output go to this warp's staging boxes
+// (row = lane, 64-byte rows, 64-byte swizzle: the 16-byte unit u of row r sits at unit u ^ ((r >> 1) & 3), which is
+// also what makes the 32 lanes' 16-byte stores bank-conflict free).  d0 box at `stage_addr`, d1 box 2 KB behind it.
+// Rows past M are staged as zeros (the zero padding of the packed buffers); TMA clips rows/columns outside the tensor.
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk_staged(const uint32_t (&v)[32], const EpiArgs& e, const uint4 (&rnd)[4],
+                                                      uint32_t bias_addr, uint32_t stage_addr, int lane, bool row_valid,
+                                                      bool want_der, float& sumsq) {
+  const uint32_t row_addr = stage_addr + lane * 64;
+  const uint32_t sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float val[8], der[8];
+    if (row_valid) {
+      float bias[8];
+      lds_f32x4(bias_addr + 32 * j, bias[0], bias[1], bias[2], bias[3]);
+      lds_f32x4(bias_addr + 32 * j + 16, bias[4], bias[5], bias[6], bias[7]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) gelu_erf_both_fast(__uint_as_float(v[8 * j + i]) + bias[i], val[i], der[i]);
+      if (e.threshold != 0) {
+        const uint32_t w[4] = {rnd[j].x, rnd[j].y, rnd[j].z, rnd[j].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float k0 = ((w[i] & 0xFFFFu) >= e.threshold) ? e.scale : 0.f;
+          const float k1 = ((w[i] >> 16) >= e.threshold) ? e.scale : 0.f;
+          val[2 * i] *= k0; der[2 * i] *= k0;
+          val[2 * i + 1] *= k1; der[2 * i + 1] *= k1;
+        }
+      }
+      if constexpr (EPI == EPI_FC2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sumsq = fmaf(val[i], val[i], sumsq);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { val[i] = 0.f; der[i] = 0.f; }
+    }
+    const uint32_t unit = ((static_cast<uint32_t>(j) ^ sw) << 4);
+    if constexpr (EPI == EPI_FC1)  // h1 feeds the next GEMM: bf16
+      sts_b32x4(row_addr + unit, pack_bf16x2(val[0], val[1]), pack_bf16x2(val[2], val[3]), pack_bf16x2(val[4], val[5]),
+                pack_bf16x2(val[6], val[7]));
+    else                           // a is read only by our own streaming kernels: fp16
+      sts_b32x4(row_addr + unit, pack_f16x2(val[0], val[1]), pack_f16x2(val[2], val[3]), pack_f16x2(val[4], val[5]),
+                pack_f16x2(val[6], val[7]));
+    if (want_der)
+      sts_b32x4(row_addr + 2048 + unit, pack_f16x2(der[0], der[1]), pack_f16x2(der[2], der[3]), pack_f16x2(der[4], der[5]),
+                pack_f16x2(der[6], der[7]));
   }
 }
 
@@ -292,8 +351,9 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ep
 template <int CTA_GROUP, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ CUtensorMap tmap_d0, const __grid_constant__ CUtensorMap tmap_d1,
                          const GemmParams p) {
-  using S = GemmSmem<CTA_GROUP>;
+  using S = GemmSmem<CTA_GROUP, EPI>;
   extern __shared__ uint8_t smem_raw[];
   // align inside the shared window with pointer arithmetic (keeps the address space known to the compiler)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -306,6 +366,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint64_t* tmem_empty_bar = bars + 2 * S::STAGES + 2; // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::STAGES + 4);
   float* bias_smem = reinterpret_cast<float*>(smem + S::STAGES * S::STAGE_BYTES + S::BAR_BYTES);
+  uint8_t* out_smem = smem + S::STAGES * S::STAGE_BYTES + S::BAR_BYTES + S::BIAS_BYTES;  // 1024-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -441,11 +502,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     constexpr int CHUNKS = COLS_PER_WARP / 32;
     float* bias_s = bias_smem + (warp - 2) * COLS_PER_WARP;  // this warp's private slice
     const uint32_t bias_addr0 = smem_u32(bias_s);
+    uint8_t* out_stage = out_smem + (warp - 2) * 2 * S::OUT_BOX_BYTES;  // this warp's two staging boxes (FC epilogues)
+    const uint32_t stage_addr = smem_u32(out_stage);
     EpiArgs e;
     e.d0 = reinterpret_cast<char*>(p.d0); e.d1 = reinterpret_cast<char*>(p.d1);
     e.ldd0 = p.ldd0; e.ldd1 = p.ldd1; e.ldaux = p.ldaux; e.aux = p.aux;
     e.alpha = p.alpha; e.scale = p.drop.scale; e.threshold = p.drop.threshold; e.layer = p.drop.layer;
     e.key = make_uint2(static_cast<uint32_t>(p.drop.seed), static_cast<uint32_t>(p.drop.seed >> 32));
+    e.nostore = p.debug_nostore;
     const int rows_cap = p.rows_cap;
     // the interior path moves 16-byte vectors: every row of every output/aux tensor must start 16-byte aligned
     auto rows_aligned = [](const void* ptr, long long ld, int elem_bytes) {
@@ -500,7 +564,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           if (e.threshold != 0 && is_head) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              rnd[j] = philox4x32_10(make_uint4(static_cast<uint32_t>(row), static_cast<uint32_t>((col >> 3) + j), e.layer, 0u), e.key);
+              rnd[j] = philox4x32<kDropoutPhiloxRounds>(make_uint4(static_cast<uint32_t>(row), static_cast<uint32_t>((col >> 3) + j), e.layer, 0u), e.key);
           } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) rnd[j] = make_uint4(0u, 0u, 0u, 0u);
@@ -529,6 +593,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
         if (col < N) {
           const uint32_t bias_addr = bias_addr0 + c * 32 * 4;
+          if constexpr (S::TMA_STORE) {
+            if (p.tma_store) {
+              const bool want_der = p.d1 != nullptr;
+              if (lane == 0) tma_store_wait_read();  // the previous chunk's boxes have been read out
+              __syncwarp();
+              epilogue_chunk_staged<EPI>(v, e, rnd, bias_addr, stage_addr, lane, row_valid, want_der, sumsq);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                const int row0 = row - lane;
+                tma_store_2d(&tmap_d0, out_stage, col, row0);
+                if (want_der) tma_store_2d(&tmap_d1, out_stage + S::OUT_BOX_BYTES, col, row0);
+                tma_store_commit();
+              }
+              continue;
+            }
+          }
           epilogue_chunk<EPI>(v, e, rnd, bias_addr, row, col, min(32, N - col), row_valid, row_in_buf, vec_ok, sumsq);
         }
       }
@@ -544,6 +625,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (!is_head) atomicAdd(sk_flags + tail_r, 1);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if constexpr (S::TMA_STORE) {
+      if (lane == 0) tma_store_wait_all();  // staged outputs are in global memory before the CTA retires
     }
   }
 

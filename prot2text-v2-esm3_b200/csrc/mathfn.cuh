@@ -56,7 +56,7 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 
 // ------------------------------------------------------------------------------------------------
 // dropout: keep multiplier for element (row, col) of layer `layer`
-//   one Philox4x32-10 block = 8 x 16-bit lanes = columns [8g, 8g+8) of a row
+//   one Philox4x32-7 block = 8 x 16-bit lanes = columns [8g, 8g+8) of a row
 //   counter = (row, g, layer, 0), key = seed; keep iff u16 >= threshold (threshold = round(p*65536))
 // ------------------------------------------------------------------------------------------------
 struct DropoutParams {
@@ -66,6 +66,21 @@ struct DropoutParams {
   uint32_t layer;      // 1 = after fc1 GELU, 2 = after fc2 GELU
 };
 
+// Philox4x32 with R rounds (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3": 7 rounds is the
+// shortest variant that passes BigCrush; 10 is the library default).  The dropout masks use 7.
+constexpr int kDropoutPhiloxRounds = 7;
+template <int ROUNDS>
+__device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
@@ -85,8 +100,8 @@ __device__ __forceinline__ void dropout_keep8(const DropoutParams& d, uint32_t r
     for (int i = 0; i < 8; ++i) keep[i] = 1.0f;
     return;
   }
-  const uint4 r = philox4x32_10(make_uint4(row, g, d.layer, 0u),
-                                make_uint2(static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32)));
+  const uint4 r = philox4x32<kDropoutPhiloxRounds>(make_uint4(row, g, d.layer, 0u),
+                                                  make_uint2(static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32)));
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
