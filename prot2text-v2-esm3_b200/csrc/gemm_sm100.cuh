@@ -92,7 +92,9 @@ struct GemmSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = TMA_STORE ? ((CTA_GROUP == 1) ? 3 : 4) : ((CTA_GROUP == 1) ? 4 : 6);
   static constexpr int BAR_BYTES = 1024;
-  static constexpr int BIAS_BYTES = GEMM_BLOCK_N * 4 * 4;  // per-epilogue-warp bias slices (16 warps x 64 floats)
+  // FC epilogues keep the whole bias vector (fp32) resident when N <= BIAS_ALL_N, else per-warp slices staged per tile
+  static constexpr int BIAS_ALL_N = TMA_STORE ? 4096 : 0;
+  static constexpr int BIAS_BYTES = TMA_STORE ? BIAS_ALL_N * 4 : GEMM_BLOCK_N * 4 * 4;  // (16 warps x 64 floats)
   static constexpr int OUT_BOX_BYTES = 32 * 32 * 2;        // one staged output box
   static constexpr int OUT_BYTES = TMA_STORE ? GEMM_EPI_WARPS * 2 * OUT_BOX_BYTES : 0;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + OUT_BYTES + 1024;  // + slack for 1024-B alignment
@@ -501,7 +503,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     constexpr int COLS_PER_WARP = GEMM_BLOCK_N / (GEMM_EPI_WARPS / 4);
     constexpr int CHUNKS = COLS_PER_WARP / 32;
     float* bias_s = bias_smem + (warp - 2) * COLS_PER_WARP;  // this warp's private slice
-    const uint32_t bias_addr0 = smem_u32(bias_s);
+    const uint32_t bias_slice_addr = smem_u32(bias_s);
+    // whole bias vector resident in shared memory (no per-tile global load on the critical path)
+    const bool bias_resident = (EPI == EPI_FC1 || EPI == EPI_FC2) && N <= S::BIAS_ALL_N;
+    if constexpr (EPI == EPI_FC1 || EPI == EPI_FC2) {
+      if (bias_resident) {
+        const int n_pad = (N + 31) & ~31;
+        for (int i = threadIdx.x - 64; i < n_pad; i += 32 * GEMM_EPI_WARPS)
+          bias_smem[i] = (p.bias != nullptr && i < N) ? __bfloat162float(p.bias[i]) : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * GEMM_EPI_WARPS) : "memory");
+      }
+    }
     uint8_t* out_stage = out_smem + (warp - 2) * 2 * S::OUT_BOX_BYTES;  // this warp's two staging boxes (FC epilogues)
     const uint32_t stage_addr = smem_u32(out_stage);
     EpiArgs e;
@@ -533,7 +545,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const bool has_peers = is_head && tail_r >= 0;  // ... after adding the S-1 dumped K ranges
       const bool empty_k = kb1 <= kb0;
       if constexpr (EPI == EPI_FC1 || EPI == EPI_FC2) {
-        if (is_head) {
+        if (is_head && !bias_resident) {
           // stage this warp's bias slice once per tile (read back as shared-memory broadcasts)
           __syncwarp();
 #pragma unroll
@@ -592,7 +604,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
         }
         if (col < N) {
-          const uint32_t bias_addr = bias_addr0 + c * 32 * 4;
+          const uint32_t bias_addr = bias_resident ? smem_u32(bias_smem) + col * 4 : bias_slice_addr + c * 32 * 4;
           if constexpr (S::TMA_STORE) {
             if (p.tma_store) {
               const bool want_der = p.d1 != nullptr;
