@@ -75,6 +75,18 @@ int p2t_gemm_bf16(const void* a, long long lda, int a_mn_major, const void* b, l
 int p2t_rows_plan(const void* mask, int mask_bytes, int B, int L, int chunk_rows, int* counts, int* seq_off,
                   int* chunk_off, int* n_rows_dev, int* row_src, int* chunk_seq, void* stream);
 
+/* The same plan for rows that are already packed (the ragged hand-over format of SURVEY.md §8f-3: the encoder or
+ * the host stager delivers [sum L_b][D] rows plus per-sequence counts): counts[B] int32 on the device. */
+int p2t_rows_plan_counts(const int* counts, int B, int chunk_rows, int* seq_off, int* chunk_off, int* n_rows_dev,
+                         int* chunk_seq, void* stream);
+
+/* Host -> device staging of a padded host batch [B][L][row_bytes] (pinned memory) as PACKED rows: sequence b
+ * contributes rows [starts[b], starts[b] + counts[b]) (HOST int arrays; contiguous valid ranges, i.e. right or
+ * left padding), written back to back at dev_dst.  Only valid rows cross PCIe; one cudaMemcpyAsync per sequence
+ * on `stream`.  Replaces `tensor.to(rank)` of the padded batch (scripts/train_contrast.py:329-330). */
+int p2t_stage_rows_h2d(const void* host_src, long long seq_stride_bytes, long long row_bytes, const int* starts,
+                       const int* counts, int B, void* dev_dst, void* stream);
+
 /* out[i] = src[row_src[i]] (bf16 rows of D elements), zero rows from n_rows up to the next multiple
  * of 256 (<= rows_cap).  Packs the padded (B, L, D_in) residue states that
  * models/esmc_qwen_arc.py:84-86 hands to the adapter. */

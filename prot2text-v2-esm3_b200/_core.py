@@ -84,6 +84,22 @@ def plan_rows(mask: torch.Tensor, want_row_src: bool = True) -> RowPlan:
                    chunk_seq=chunk_seq, rows_cap=_round_up(B * L, ROW_ALIGN), max_chunks=max_chunks)
 
 
+def plan_packed(counts: torch.Tensor, total_rows: int) -> RowPlan:
+    """Plan for rows that are already packed back to back: `counts` (B,) valid rows per sequence (any integer
+    dtype, CPU or CUDA), `total_rows` = the packed buffer's row count (a host integer >= sum(counts))."""
+    dev_counts = counts.to(device="cuda" if not counts.is_cuda else counts.device, dtype=torch.int32, non_blocking=True).contiguous()
+    B = dev_counts.shape[0]
+    dev = dev_counts.device
+    ints = torch.empty(2 * (B + 1) + 1, dtype=torch.int32, device=dev)
+    seq_off, chunk_off, n_rows = ints[:B + 1], ints[B + 1:2 * B + 2], ints[2 * B + 2:]
+    max_chunks = (total_rows + CHUNK_ROWS - 1) // CHUNK_ROWS + B
+    chunk_seq = torch.empty(max_chunks, dtype=torch.int32, device=dev)
+    _lib.call("p2t_rows_plan_counts", _ptr(dev_counts), B, CHUNK_ROWS, _ptr(seq_off), _ptr(chunk_off), _ptr(n_rows),
+              _ptr(chunk_seq), _stream())
+    return RowPlan(B=B, L=0, counts=dev_counts, seq_off=seq_off, chunk_off=chunk_off, n_rows=n_rows, row_src=None,
+                   chunk_seq=chunk_seq, rows_cap=_round_up(max(total_rows, 1), ROW_ALIGN), max_chunks=max_chunks)
+
+
 def dense_plan(B: int, L: int, device) -> RowPlan:
     """Plan for an all-ones mask (every row valid) without reading a mask."""
     ones = torch.ones(B, L, dtype=torch.uint8, device=device)

@@ -84,6 +84,33 @@ int p2t_rows_plan(const void* mask, int mask_bytes, int B, int L, int chunk_rows
   return rows_plan(mask, mask_bytes, B, L, chunk_rows, counts, seq_off, chunk_off, n_rows_dev, row_src, chunk_seq, S(stream));
 }
 
+int p2t_rows_plan_counts(const int* counts, int B, int chunk_rows, int* seq_off, int* chunk_off, int* n_rows_dev,
+                         int* chunk_seq, void* stream) {
+  if (!counts || !seq_off || !chunk_off || !n_rows_dev) return set_error(-1, "p2t_rows_plan_counts: null pointer");
+  if (chunk_rows <= 0) return set_error(-1, "p2t_rows_plan_counts: chunk_rows must be positive");
+  return rows_plan_counts(counts, B, chunk_rows, seq_off, chunk_off, n_rows_dev, chunk_seq, S(stream));
+}
+
+int p2t_stage_rows_h2d(const void* host_src, long long seq_stride_bytes, long long row_bytes, const int* starts,
+                       const int* counts, int B, void* dev_dst, void* stream) {
+  if (!host_src || !starts || !counts || !dev_dst) return set_error(-1, "p2t_stage_rows_h2d: null pointer");
+  if (row_bytes <= 0 || seq_stride_bytes < 0) return set_error(-1, "p2t_stage_rows_h2d: bad strides");
+  // one plain cudaMemcpyAsync per sequence (the batched-memcpy entry points are not used on purpose)
+  char* dst = reinterpret_cast<char*>(dev_dst);
+  const char* src = reinterpret_cast<const char*>(host_src);
+  for (int b = 0; b < B; ++b) {
+    if (counts[b] < 0 || starts[b] < 0) return set_error(-1, "p2t_stage_rows_h2d: negative start/count");
+    const size_t bytes = (size_t)counts[b] * (size_t)row_bytes;
+    if (bytes) {
+      cudaError_t e = cudaMemcpyAsync(dst, src + (size_t)b * seq_stride_bytes + (size_t)starts[b] * row_bytes, bytes,
+                                      cudaMemcpyHostToDevice, S(stream));
+      if (e != cudaSuccess) return set_error((int)e, "cudaMemcpyAsync: %s", cudaGetErrorString(e));
+    }
+    dst += bytes;
+  }
+  return 0;
+}
+
 int p2t_gather_rows(const void* src, long long ld_src, const int* row_src, const int* n_rows_dev, int rows_cap,
                     int D, void* out, void* stream) {
   if (!src || !row_src || !n_rows_dev || !out) return set_error(-1, "p2t_gather_rows: null pointer");

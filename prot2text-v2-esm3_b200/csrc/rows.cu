@@ -703,6 +703,14 @@ int rows_plan(const void* mask, int mask_bytes, int B, int L, int rc, int* count
   return check_launch("plan_fill_kernel");
 }
 
+// plan for rows that are ALREADY packed: only the per-sequence counts are given
+int rows_plan_counts(const int* counts, int B, int rc, int* seq_off, int* chunk_off, int* n_rows, int* chunk_seq,
+                     cudaStream_t st) {
+  if (B <= 0) return set_error(-1, "rows_plan_counts: empty batch");
+  plan_fill_kernel<<<B, 256, 0, st>>>(nullptr, 0, B, 0, counts, rc, seq_off, chunk_off, n_rows, nullptr, chunk_seq);
+  return check_launch("plan_fill_kernel");
+}
+
 int gather_rows(const void* src, long long ld_src, const int* row_src, const int* n_rows, int cap, int D, void* out,
                 cudaStream_t st) {
   if (D % 8) return set_error(-1, "gather_rows: D must be a multiple of 8");

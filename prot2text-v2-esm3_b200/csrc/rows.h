@@ -9,6 +9,8 @@ struct GemmParams;
 
 int rows_plan(const void* mask, int mask_bytes, int B, int L, int rc, int* counts, int* seq_off, int* chunk_off,
               int* n_rows, int* row_src, int* chunk_seq, cudaStream_t st);
+int rows_plan_counts(const int* counts, int B, int rc, int* seq_off, int* chunk_off, int* n_rows, int* chunk_seq,
+                     cudaStream_t st);
 int row_inv_norm(const float* rowsq, int nblk, const int* n_rows, int cap, float* inv_norm, cudaStream_t st);
 int gather_rows(const void* src, long long ld_src, const int* row_src, const int* n_rows, int cap, int D, void* out,
                 cudaStream_t st);

@@ -53,15 +53,18 @@ def reduce_scatter_text_grad(dt_full: torch.Tensor, group=None) -> torch.Tensor:
 
 
 def distributed_contrastive_step(residue_states, protein_mask, adapter, text_hidden, text_mask, *,
+                                 residue_lengths=None, text_lengths=None,
                                  temperature: float = 0.05, symmetric: bool = False, group=None,
                                  aux: Optional[_step.StepAux] = None) -> torch.Tensor:
-    """Sharded-batch contrastive step with all-gathered negatives; returns the local mean loss."""
+    """Sharded-batch contrastive step with all-gathered negatives; returns the local mean loss.
+    Accepts the padded (mask) or the packed (lengths) input form of `contrastive_step`."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    t_local = _step.text_embeddings(text_hidden, text_mask, dtype=torch.float32)
+    t_local = _step.text_embeddings(text_hidden, text_mask, dtype=torch.float32, text_lengths=text_lengths)
     t_global = all_gather_embeddings(t_local, group) if world > 1 else t_local
-    B = residue_states.shape[0]
+    B = residue_lengths.shape[0] if residue_lengths is not None else residue_states.shape[0]
     labels = torch.arange(rank * B, (rank + 1) * B, device=residue_states.device, dtype=torch.int32)
     hook = (lambda m, s: merge_column_stats(m, s, group)) if (symmetric and world > 1) else None
     return _step.contrastive_step(residue_states, protein_mask, adapter, text_embeds=t_global,
+                                  residue_lengths=residue_lengths,
                                   temperature=temperature, symmetric=symmetric, labels=labels, aux=aux,
                                   col_stats_hook=hook, all_cols_labelled=symmetric and world > 1)

@@ -1,0 +1,96 @@
+"""Host -> device staging of a padded batch as packed rows (the ragged hand-over format).
+
+The reference moves whole padded tensors with `.to(rank)` (scripts/train_contrast.py:329-330).  When the
+batch starts in host memory (data loader, CPU-side trunk, benchmark harness) only the VALID rows need to
+cross PCIe: `HostStager` copies each sequence's valid range straight into a packed device buffer on a
+dedicated copy stream, so the copy of batch i+1 overlaps the kernels of batch i, and the device-side
+pack (gather) kernel disappears.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+@dataclass
+class StagedBatch:
+    """Packed device tensors of one batch; feed to `contrastive_step(..., residue_lengths=, text_lengths=)`."""
+    residue_rows: torch.Tensor     # (sum L_b, D_in) bf16
+    residue_lengths: torch.Tensor  # (B,) int32, device
+    text_rows: torch.Tensor        # (sum T_b, H) bf16
+    text_lengths: torch.Tensor     # (B,) int32, device
+    h2d_bytes: int
+    _event: Optional[torch.cuda.Event] = None
+
+
+def _valid_ranges(mask: torch.Tensor):
+    """(starts, counts) as int32 CPU tensors if every row's valid positions are contiguous, else None."""
+    m = mask != 0
+    counts = m.sum(dim=1)
+    starts = torch.argmax(m.to(torch.uint8), dim=1)
+    L = mask.shape[1]
+    ar = torch.arange(L)[None, :]
+    expect = (ar >= starts[:, None]) & (ar < (starts + counts)[:, None])
+    if not torch.equal(expect, m):
+        return None
+    return starts.to(torch.int32).contiguous(), counts.to(torch.int32).contiguous()
+
+
+class HostStager:
+    """Stages padded HOST batches (ideally pinned) as packed device rows on a private copy stream.
+
+        stager = HostStager(device)
+        stager.submit(x, mask, text, text_mask)        # asynchronous
+        batch = stager.take()                          # current stream now waits for the copies
+        loss = contrastive_step(batch.residue_rows, None, adapter, batch.text_rows, None,
+                                residue_lengths=batch.residue_lengths, text_lengths=batch.text_lengths)
+    """
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.P2TError("HostStager needs a CUDA device: this package has no CPU path")
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._pending = []
+
+    def _stage(self, src: torch.Tensor, mask: torch.Tensor):
+        if src.is_cuda or mask.is_cuda:
+            raise _lib.P2TError("HostStager takes host tensors")
+        if src.dtype != torch.bfloat16:
+            raise _lib.P2TError(f"host states must be bfloat16 (got {src.dtype})")
+        src = src.contiguous()
+        B, L, D = src.shape
+        ranges = _valid_ranges(mask)
+        if ranges is None:
+            raise _lib.P2TError("HostStager needs contiguous valid ranges (right or left padding); move masks with "
+                                "holes to the device and use the mask form of contrastive_step")
+        starts, counts = ranges
+        total = int(counts.sum())
+        rows = torch.empty(max(total, 1), D, dtype=torch.bfloat16, device=self.device)
+        _lib.call("p2t_stage_rows_h2d", src.data_ptr(), L * D * 2, D * 2, starts.data_ptr(), counts.data_ptr(), B,
+                  rows.data_ptr(), self.stream.cuda_stream)
+        lens = counts.pin_memory().to(self.device, non_blocking=True)
+        return rows[:total] if total else rows[:0], lens, total * D * 2 + B * 4
+
+    def submit(self, x: torch.Tensor, mask: torch.Tensor, text: torch.Tensor, text_mask: torch.Tensor) -> None:
+        with torch.cuda.stream(self.stream):
+            xr, xl, b0 = self._stage(x, mask)
+            tr, tl, b1 = self._stage(text, text_mask)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self._pending.append(StagedBatch(xr, xl, tr, tl, b0 + b1, ev))
+
+    def take(self) -> StagedBatch:
+        if not self._pending:
+            raise _lib.P2TError("HostStager.take() without a submitted batch")
+        batch = self._pending.pop(0)
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(batch._event)
+        for t in (batch.residue_rows, batch.residue_lengths, batch.text_rows, batch.text_lengths):
+            t.record_stream(cur)  # allocated on the copy stream, consumed on the compute stream
+        return batch

@@ -35,16 +35,25 @@ class StepAux:
 
 
 @torch.no_grad()
-def text_embeddings(text_hidden: torch.Tensor, text_mask: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
+def text_embeddings(text_hidden: torch.Tensor, text_mask: Optional[torch.Tensor] = None, dtype=torch.bfloat16, *,
+                    text_lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
     """readout 'mix' + L2 normalise of the frozen LLM's hidden states (reference :284-310, :354).
 
-    Returns (B, 2H) unit-norm embeddings in `dtype`: bfloat16 like the reference, or float32 — the
-    fused step keeps the fp32 copy for the loss gradient (see csrc/infonce.cu)."""
+    text_hidden is (B, T, H) with a (B, T) mask, or — ragged hand-over — packed rows (sum T_b, H) with
+    `text_lengths` (B,).  Returns (B, 2H) unit-norm embeddings in `dtype`: bfloat16 like the reference, or
+    float32 — the fused step keeps the fp32 copy for the loss gradient (see csrc/infonce.cu)."""
     _core.require_cuda_bf16(text_hidden, "text_hidden")
-    B, T, H = text_hidden.shape
     th = text_hidden.contiguous()
-    plan = _core.plan_rows(text_mask)
-    stats = _core.pool_forward(th.view(B * T, H), plan, H, row_src=plan.row_src)
+    if text_lengths is not None:
+        if th.dim() != 2:
+            raise ValueError("with text_lengths, text_hidden must be packed rows (sum T_b, H)")
+        H = th.shape[1]
+        plan = _core.plan_packed(text_lengths, th.shape[0])
+        stats = _core.pool_forward(th, plan, H, row_src=None)
+    else:
+        B, T, H = th.shape
+        plan = _core.plan_rows(text_mask)
+        stats = _core.pool_forward(th.view(B * T, H), plan, H, row_src=plan.row_src)
     t_bf, t_f32, _ = _core.l2norm_forward(stats, want_f32=(dtype == torch.float32))
     return t_f32 if dtype == torch.float32 else t_bf
 
@@ -54,13 +63,19 @@ class _ContrastiveStepFunction(torch.autograd.Function):
     def forward(ctx, x, prot_mask, w1, b1, w2, b2, t_in, labels, cfg: dict, aux: StepAux):
         for t, name in ((x, "residue states"), (w1, "fc1.weight"), (b1, "fc1.bias"), (w2, "fc2.weight"), (b2, "fc2.bias")):
             _core.require_cuda_bf16(t, name)
-        B, L, d_in = x.shape
         d_out = w2.shape[0]
         need_grad = any(ctx.needs_input_grad[2:6])
         w1c, b1c, w2c, b2c = w1.contiguous(), b1.contiguous(), w2.contiguous(), b2.contiguous()
-        plan = _core.plan_rows(prot_mask)
-        xp = _core.gather_rows(x.contiguous().view(B * L, d_in), plan)
-        acts = _core.adapter_forward(xp, plan.rows_cap, plan.rows_cap, plan.n_rows, w1c, b1c, w2c, b2c,
+        if cfg["packed"]:  # residue rows already packed, prot_mask holds the per-sequence lengths
+            xp = x.contiguous()
+            plan = _core.plan_packed(prot_mask, xp.shape[0])
+            x_rows = xp.shape[0]
+        else:
+            B, L, d_in = x.shape
+            plan = _core.plan_rows(prot_mask)
+            xp = _core.gather_rows(x.contiguous().view(B * L, d_in), plan)
+            x_rows = plan.rows_cap
+        acts = _core.adapter_forward(xp, x_rows, plan.rows_cap, plan.n_rows, w1c, b1c, w2c, b2c,
                                      cfg["dropout_p"], cfg["seed"], need_grad)
         inv_norm = _core.row_inv_norm(acts)
         stats = _core.pool_forward(acts.a, plan, d_out, row_src=None, inv_norm=inv_norm)
@@ -105,8 +120,9 @@ class _ContrastiveStepFunction(torch.autograd.Function):
         return None, None, dw1, db1, dw2, db2, None, None, None, None
 
 
-def contrastive_step(residue_states: torch.Tensor, protein_mask: torch.Tensor, adapter: ModalityAdapter,
+def contrastive_step(residue_states: torch.Tensor, protein_mask: Optional[torch.Tensor], adapter: ModalityAdapter,
                      text_hidden: Optional[torch.Tensor] = None, text_mask: Optional[torch.Tensor] = None, *,
+                     residue_lengths: Optional[torch.Tensor] = None, text_lengths: Optional[torch.Tensor] = None,
                      text_embeds: Optional[torch.Tensor] = None, temperature: float = 0.05,
                      contrastive_num_segments: int = 1, symmetric: bool = False,
                      labels: Optional[torch.Tensor] = None, aux: Optional[StepAux] = None,
@@ -118,15 +134,22 @@ def contrastive_step(residue_states: torch.Tensor, protein_mask: torch.Tensor, a
     (models/esmc_qwen_arc.py:84-86); text_hidden (B_t, T, H) bf16 is hidden_states[16] of the frozen
     LLM with its attention mask (scripts/train_contrast.py:304), or pass already normalised
     `text_embeds` (B_t, 2H), float32 (preferred) or bfloat16 — e.g. the all-gathered global negatives.  `labels[i]` is the text row
-    paired with protein i (default: i).  `contrastive_num_segments` reproduces the reference's
+    paired with protein i (default: i).  Ragged hand-over: with `residue_lengths` (B,),
+    `residue_states` is the PACKED (sum L_b, D_in) row buffer and `protein_mask` is ignored; likewise
+    `text_lengths` with packed `text_hidden` (see host_io.HostStager).  `contrastive_num_segments` reproduces the reference's
     segment averaging including its dropping of the remainder rows; `symmetric` adds the
     text->protein term.
     """
     if text_embeds is None:
-        if text_hidden is None or text_mask is None:
-            raise ValueError("pass either text_hidden + text_mask or text_embeds")
-        text_embeds = text_embeddings(text_hidden, text_mask, dtype=torch.float32)
-    B = residue_states.shape[0]
+        if text_hidden is None or (text_mask is None and text_lengths is None):
+            raise ValueError("pass either text_hidden + text_mask (or text_lengths) or text_embeds")
+        text_embeds = text_embeddings(text_hidden, text_mask, dtype=torch.float32, text_lengths=text_lengths)
+    packed = residue_lengths is not None
+    if packed and residue_states.dim() != 2:
+        raise ValueError("with residue_lengths, residue_states must be packed rows (sum L_b, D_in)")
+    if not packed and protein_mask is None:
+        raise ValueError("pass protein_mask, or residue_lengths with packed rows")
+    B = residue_lengths.shape[0] if packed else residue_states.shape[0]
     seg = B // contrastive_num_segments
     if seg * contrastive_num_segments != B:
         print("WARNING: Given batch size is not divisible by the number of segments for contrastive learning.")
@@ -134,8 +157,9 @@ def contrastive_step(residue_states: torch.Tensor, protein_mask: torch.Tensor, a
         labels = torch.arange(B, device=residue_states.device, dtype=torch.int32)
     p = adapter.dropout_p()
     cfg = dict(tau=float(temperature), w_row=0.5 if symmetric else 1.0, w_col=0.5 if symmetric else 0.0,
-               dropout_p=p, seed=_draw_seed() if p > 0 else 0, rows_used=seg * contrastive_num_segments,
+               dropout_p=p, seed=_draw_seed() if p > 0 else 0, rows_used=seg * contrastive_num_segments, packed=packed,
                col_stats_hook=col_stats_hook, loss_scale=loss_scale, all_cols_labelled=all_cols_labelled)
     aux = aux if aux is not None else StepAux()
-    return _ContrastiveStepFunction.apply(residue_states, protein_mask, adapter.fc1.weight, adapter.fc1.bias,
+    return _ContrastiveStepFunction.apply(residue_states, residue_lengths if packed else protein_mask,
+                                          adapter.fc1.weight, adapter.fc1.bias,
                                           adapter.fc2.weight, adapter.fc2.bias, text_embeds, labels, cfg, aux)

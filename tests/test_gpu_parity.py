@@ -564,3 +564,47 @@ def test_step_scales_with_upstream_gradient_and_accumulates_like_the_reference(p
     (acc / 4).backward()
     for k in PARAMS:
         assert maxrel(adapter_grads(ad)[k], 0.5 * g1[k]) <= 1e-2
+
+
+# --------------------------------------------------------------------------------------------------
+# ragged hand-over format: packed rows + lengths, and the host stager
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("left_pad", [False, True])
+def test_packed_input_step_is_bit_identical_to_the_padded_step(p2t, synth, dev, left_pad):
+    sb = synth.make_config_batch("cfg1_esm2_t6_llama1b", weight_gain=2.5, left_pad=left_pad)
+    ad = make_adapter(p2t, dev, sb.w1, sb.b1, sb.w2, sb.b2)
+    loss = p2t.contrastive_step(sb.x.to(dev), sb.prot_mask.to(dev), ad, sb.text.to(dev), sb.text_mask.to(dev))
+    loss.backward()
+    g_ref = {k: v.clone() for k, v in adapter_grads(ad).items()}
+    ad.zero_grad(set_to_none=True)
+    # (a) packed by hand on the host
+    xr = sb.x[sb.prot_mask.bool()].to(dev)
+    tr = sb.text[sb.text_mask.bool()].to(dev)
+    l2 = p2t.contrastive_step(xr, None, ad, tr, None, residue_lengths=sb.prot_mask.sum(1), text_lengths=sb.text_mask.sum(1).to(dev))
+    l2.backward()
+    assert torch.equal(loss, l2) and all(torch.equal(g_ref[k], adapter_grads(ad)[k]) for k in PARAMS)
+    ad.zero_grad(set_to_none=True)
+    # (b) through the host stager: pinned padded host batch -> packed device rows on a copy stream
+    stager = p2t.HostStager(dev)
+    stager.submit(sb.x.pin_memory(), sb.prot_mask.pin_memory(), sb.text.pin_memory(), sb.text_mask.pin_memory())
+    batch = stager.take()
+    assert torch.equal(batch.residue_rows, xr) and torch.equal(batch.text_rows, tr)  # byte moves: exact
+    assert torch.equal(batch.residue_lengths.cpu().long(), sb.prot_mask.sum(1))
+    assert batch.h2d_bytes == xr.numel() * 2 + tr.numel() * 2 + 2 * 4 * sb.x.shape[0]
+    l3 = p2t.contrastive_step(batch.residue_rows, None, ad, batch.text_rows, None,
+                              residue_lengths=batch.residue_lengths, text_lengths=batch.text_lengths)
+    l3.backward()
+    assert torch.equal(loss, l3) and all(torch.equal(g_ref[k], adapter_grads(ad)[k]) for k in PARAMS)
+
+
+def test_host_stager_rejects_masks_with_holes_and_device_tensors(p2t, dev):
+    stager = p2t.HostStager(dev)
+    x = bf(torch.randn(2, 6, 16))
+    holes = torch.tensor([[1, 0, 1, 1, 0, 0], [1, 1, 1, 0, 0, 0]])
+    ok = torch.tensor([[1, 1, 1, 1, 0, 0], [0, 0, 0, 1, 1, 1]])
+    with pytest.raises(p2t.P2TError, match="contiguous"):
+        stager.submit(x, holes, x, ok)
+    with pytest.raises(p2t.P2TError, match="host tensors"):
+        stager.submit(x.to(dev), ok.to(dev), x, ok)
+    with pytest.raises(p2t.P2TError, match="without a submitted"):
+        stager.take()
