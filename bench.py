@@ -37,8 +37,8 @@ CPU_SAMPLE_PAIRS = 4
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -108,23 +108,71 @@ def run_reference_arm(args, rank, world):
 # clocks
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """Samples SM clock, power and clock-event reasons of one GPU DURING the timed region: an NVML polling thread
+    (every ~10 ms, cheap enough not to disturb the launching thread; `nvidia-smi -lms` is too coarse for a ~0.1 s region), with
+    `nvidia-smi` as the fallback when NVML cannot be loaded."""
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.proc = None
         self.gpu_index = gpu_index
+        self.proc = None
+        self.thread = None
+        self.stop_flag = False
+        self.sm, self.power, self.reasons = [], [], set()
+        self.sm_max = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.gpu_index < len(ids) and ids[self.gpu_index].isdigit():
+                return int(ids[self.gpu_index])
+        return self.gpu_index
+
+    def _poll(self, nv, handle):
+        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksEventReasonHwPowerBrakeSlowdown: "hw_power_brake_slowdown"}
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(handle) / 1e3)
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                for bit, nm in names.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception:  # noqa: BLE001 - sampling must never break the benchmark
+                pass
+            time.sleep(0.01)
 
     def start(self):
         try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            handle = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001
+            self.thread = None
+        try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.sm_max,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml",
+                    "power_w_max": max(self.power) if self.power else None}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -147,7 +195,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -234,8 +282,10 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
+    t_host0 = time.perf_counter()
     for i in range(args.steps):
         loss = step(resident[i % nbatches])
+    host_issue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps  # CPU time to enqueue one step (no sync inside)
     ev1.record()
     barrier()
     launches = lib.launch_count()
@@ -338,7 +388,7 @@ def main():
                        "valid_rows_per_step": valid_rows[0], "dropout_p": 0.0 if args.eval_mode else 0.3,
                        "parallelism": f"dp{world}", "l2": "inputs+activations per step exceed the 126 MB L2; 2 batches alternate",
                        "cta_group": int(os.environ.get("P2T_CTA_GROUP", "2"))},
-            "loss": last_loss, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline,
+            "loss": last_loss, "gpu_launches": int(launches), "host_issue_ms_per_step": host_issue_ms, "clocks": clocks, "e2e": e2e, "roofline": roofline,
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)

@@ -70,7 +70,8 @@ int p2t_gemm_bf16(const void* a, long long lda, int a_mn_major, const void* b, l
  * pattern is accepted (right padded, left padded, holes).
  *   counts[B], seq_off[B+1], chunk_off[B+1] (pooling chunks of `chunk_rows` rows), n_rows_dev[1],
  *   row_src[>= sum(mask)] = flat source row b*L + r of each packed row (may be NULL),
- *   chunk_seq[>= ceil(B*L/chunk_rows)+B] = sequence owning each pooling chunk (may be NULL).
+ *   chunk_seq[4 * (ceil(B*L/chunk_rows)+B)] = one int4 descriptor per pooling chunk
+ *       {first packed row, end row, owning sequence, 0} (may be NULL).
  * ------------------------------------------------------------------------------------------- */
 int p2t_rows_plan(const void* mask, int mask_bytes, int B, int L, int chunk_rows, int* counts, int* seq_off,
                   int* chunk_off, int* n_rows_dev, int* row_src, int* chunk_seq, void* stream);
@@ -101,7 +102,7 @@ int p2t_gather_rows(const void* src, long long ld_src, const int* row_src, const
  *   g2 = keep * GELU'(h1 W2^T + b2)         [rows_cap][d_out] fp16   (NULL when no backward)
  *   (a, g1, g2 are read only by this library's streaming kernels; fp16 keeps 3 more mantissa bits
  *    than bf16 at the same bytes.  h1 and every GEMM operand are bf16.)
- *   rowsq[row][nblk] = partial sums of a^2, nblk = 4*ceil(d_out/256) — the per-residue L2 norm (:67)
+ *   rowsq[nblk][rows_cap] = partial sums of a^2, nblk = 4*ceil(d_out/256) — the per-residue L2 norm (:67)
  * x has x_rows rows allocated (TMA zero-fills beyond); outputs have rows_cap rows.
  * Weights in nn.Linear layout (out, in), bf16.  dropout_p = 0 is eval mode; otherwise a Philox
  * mask keyed by (seed, layer, row, column) with multiplier 1/(1-p) (nn.Dropout, :63,:66).
@@ -112,8 +113,8 @@ int p2t_adapter_fwd(const void* x, int x_rows, const void* w1, const void* b1, c
 
 /* y[row] = a[row] / max(|a[row]|, 1e-12) for the first n rows: the (B, L, d_out) tensor that
  * ModalityAdapter.forward returns (:67-68).  inv_norm[row] is saved for backward (may be NULL). */
-int p2t_adapter_scale_rows(const void* a, const float* rowsq, int nblk, int n, int d_out, void* y, float* inv_norm,
-                           void* stream);
+int p2t_adapter_scale_rows(const void* a, const float* rowsq, int nblk, int rows_cap, int n, int d_out, void* y,
+                           float* inv_norm, void* stream);
 
 /* inv_norm[row] = 1 / max(sqrt(sum_j rowsq[row][j]), 1e-12) for row < n_rows: the per-residue
  * F.normalize denominator of models/modeling_esm2llama_instruct.py:67 */
@@ -121,12 +122,13 @@ int p2t_row_inv_norm(const float* rowsq, int nblk, const int* n_rows_dev, int ro
 
 /* ---------------------------------------------------------------------------------------------
  * readout_embeddings(..., "mean"|"std"|"mix") — scripts/train_contrast.py:217-248 — over the rows
- * listed by a plan.  `src` is bf16 (or fp16 when src_is_f16: the adapter's own `a`) [*][ld_src];
+ * listed by a plan.  `src` is bf16 (or fp16 when src_is_f16: the adapter's own `a`) [src_rows][ld_src], 16-byte
+ * aligned rows (read by TMA);
  * row_src == NULL means rows are already packed.  With inv_norm != NULL every row is first scaled
  * by inv_norm[row] (adapter output: normalise fused into the pooling pass).
  * partial_ws: float2 [max_chunks][D]; out: fp32 [B][ld_out] (mean | std for mix).
  * ------------------------------------------------------------------------------------------- */
-int p2t_pool_fwd(const void* src, int src_is_f16, long long ld_src, const int* row_src, const float* inv_norm,
+int p2t_pool_fwd(const void* src, int src_is_f16, long long ld_src, int src_rows, const int* row_src, const float* inv_norm,
                  const int* seq_off, const int* chunk_off, const int* chunk_seq, int B, int D, int chunk_rows,
                  int max_chunks, int mode, void* partial_ws, float* out, long long ld_out, void* stream);
 

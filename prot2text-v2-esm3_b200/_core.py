@@ -55,7 +55,7 @@ class RowPlan:
     chunk_off: torch.Tensor   # int32 [B+1]
     n_rows: torch.Tensor      # int32 [1] (device)
     row_src: Optional[torch.Tensor]  # int32 [B*L]
-    chunk_seq: torch.Tensor   # int32 [max_chunks] sequence owning each pooling chunk
+    chunk_seq: torch.Tensor   # int32 [max_chunks, 4] per pooling chunk: first row, end row, sequence, 0
     rows_cap: int             # allocation size for packed buffers
     max_chunks: int           # upper bound on pooling chunks
 
@@ -77,7 +77,7 @@ def plan_rows(mask: torch.Tensor, want_row_src: bool = True) -> RowPlan:
     counts, seq_off, chunk_off, n_rows = ints[:B], ints[B + 1:2 * B + 2], ints[2 * B + 2:3 * B + 3], ints[3 * B + 3:]
     row_src = torch.empty(B * L, dtype=torch.int32, device=dev) if want_row_src else None
     max_chunks = (B * L + CHUNK_ROWS - 1) // CHUNK_ROWS + B
-    chunk_seq = torch.empty(max_chunks, dtype=torch.int32, device=dev)
+    chunk_seq = torch.empty(max_chunks, 4, dtype=torch.int32, device=dev)
     _lib.call("p2t_rows_plan", _ptr(mask), nbytes, B, L, CHUNK_ROWS, _ptr(counts), _ptr(seq_off), _ptr(chunk_off),
               _ptr(n_rows), _ptr(row_src), _ptr(chunk_seq), _stream())
     return RowPlan(B=B, L=L, counts=counts, seq_off=seq_off, chunk_off=chunk_off, n_rows=n_rows, row_src=row_src,
@@ -93,7 +93,7 @@ def plan_packed(counts: torch.Tensor, total_rows: int) -> RowPlan:
     ints = torch.empty(2 * (B + 1) + 1, dtype=torch.int32, device=dev)
     seq_off, chunk_off, n_rows = ints[:B + 1], ints[B + 1:2 * B + 2], ints[2 * B + 2:]
     max_chunks = (total_rows + CHUNK_ROWS - 1) // CHUNK_ROWS + B
-    chunk_seq = torch.empty(max_chunks, dtype=torch.int32, device=dev)
+    chunk_seq = torch.empty(max_chunks, 4, dtype=torch.int32, device=dev)
     _lib.call("p2t_rows_plan_counts", _ptr(dev_counts), B, CHUNK_ROWS, _ptr(seq_off), _ptr(chunk_off), _ptr(n_rows),
               _ptr(chunk_seq), _stream())
     return RowPlan(B=B, L=0, counts=dev_counts, seq_off=seq_off, chunk_off=chunk_off, n_rows=n_rows, row_src=None,
@@ -154,7 +154,7 @@ class AdapterActs:
     g1: Optional[torch.Tensor]
     a: torch.Tensor           # [rows_cap, d_out]
     g2: Optional[torch.Tensor]
-    rowsq: torch.Tensor       # fp32 [rows_cap, nblk]
+    rowsq: torch.Tensor       # fp32 [nblk, rows_cap]
     nblk: int
     rows_cap: int
     n_rows: torch.Tensor      # int32 [1] device
@@ -171,7 +171,7 @@ def adapter_forward(x: torch.Tensor, x_rows: int, rows_cap: int, n_rows: torch.T
     g1 = torch.empty(rows_cap, d_mid, dtype=torch.float16, device=dev) if need_grad else None
     g2 = torch.empty(rows_cap, d_out, dtype=torch.float16, device=dev) if need_grad else None
     nblk = 4 * ((d_out + 255) // 256)
-    rowsq = torch.empty(rows_cap, nblk, dtype=torch.float32, device=dev)
+    rowsq = torch.empty(nblk, rows_cap, dtype=torch.float32, device=dev)
     _lib.call("p2t_adapter_fwd", _ptr(x), x_rows, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), d_in, d_mid, d_out,
               rows_cap, _ptr(n_rows), _ptr(h1), _ptr(g1), _ptr(a), _ptr(g2), _ptr(rowsq), float(dropout_p),
               int(seed) & 0xFFFFFFFFFFFFFFFF, cta_group or default_cta_group(), _stream())
@@ -217,7 +217,7 @@ def pool_forward(src: torch.Tensor, plan: RowPlan, D: int, *, row_src: Optional[
     dev = src.device
     partial = torch.empty(plan.max_chunks, D, 2, dtype=torch.float32, device=dev)
     stats = torch.empty(plan.B, 2 * D, dtype=torch.float32, device=dev)
-    _lib.call("p2t_pool_fwd", _ptr(src), int(src.dtype == torch.float16), src.stride(0), _ptr(row_src), _ptr(inv_norm),
+    _lib.call("p2t_pool_fwd", _ptr(src), int(src.dtype == torch.float16), src.stride(0), src.shape[0], _ptr(row_src), _ptr(inv_norm),
               _ptr(plan.seq_off), _ptr(plan.chunk_off), _ptr(plan.chunk_seq), plan.B, D, CHUNK_ROWS, plan.max_chunks,
               READOUT_MODES["mix"], _ptr(partial), _ptr(stats), 2 * D, _stream())
     return stats

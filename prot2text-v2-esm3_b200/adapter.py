@@ -52,7 +52,7 @@ class _AdapterFunction(torch.autograd.Function):
                                      b2.contiguous(), dropout_p, seed, need_grad)
         y = torch.empty(n, d_out, dtype=torch.bfloat16, device=x.device)
         inv_norm = torch.empty(rows_cap, dtype=torch.float32, device=x.device) if need_grad else None
-        _lib.call("p2t_adapter_scale_rows", _core._ptr(acts.a), _core._ptr(acts.rowsq), acts.nblk, n, d_out,
+        _lib.call("p2t_adapter_scale_rows", _core._ptr(acts.a), _core._ptr(acts.rowsq), acts.nblk, rows_cap, n, d_out,
                   _core._ptr(y), _core._ptr(inv_norm), _core._stream())
         if need_grad:
             ctx.acts, ctx.inv_norm, ctx.n = acts, inv_norm, n

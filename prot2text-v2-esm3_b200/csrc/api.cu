@@ -134,16 +134,16 @@ int p2t_adapter_fwd(const void* x, int x_rows, const void* w1, const void* b1, c
   q.dyn_m = n_rows_dev;
   q.d0 = a; q.ldd0 = d_out; q.d1 = g2; q.ldd1 = d_out;
   q.bias = reinterpret_cast<const __nv_bfloat16*>(b2);
-  q.rowsq = rowsq; q.ld_rowsq = (GEMM_EPI_WARPS / 4) * ((d_out + GEMM_BLOCK_N - 1) / GEMM_BLOCK_N);
+  q.rowsq = rowsq; q.ld_rowsq = rows_cap;
   q.drop = make_dropout(dropout_p, seed, 2);
   return launch_gemm(h1, d_mid, false, w2, d_mid, false, EPI_FC2, q, cta_group, S(stream));
 }
 
-int p2t_adapter_scale_rows(const void* a, const float* rowsq, int nblk, int n, int d_out, void* y, float* inv_norm,
-                           void* stream) {
+int p2t_adapter_scale_rows(const void* a, const float* rowsq, int nblk, int rows_cap, int n, int d_out, void* y,
+                           float* inv_norm, void* stream) {
   if (!a || !rowsq || !y) return set_error(-1, "p2t_adapter_scale_rows: null pointer");
   if (d_out % 8) return set_error(-1, "p2t_adapter_scale_rows: d_out must be a multiple of 8");
-  return scale_rows(a, rowsq, nblk, n, d_out, y, inv_norm, S(stream));
+  return scale_rows(a, rowsq, nblk, rows_cap, n, d_out, y, inv_norm, S(stream));
 }
 
 int p2t_row_inv_norm(const float* rowsq, int nblk, const int* n_rows_dev, int rows_cap, float* inv_norm, void* stream) {
@@ -151,13 +151,13 @@ int p2t_row_inv_norm(const float* rowsq, int nblk, const int* n_rows_dev, int ro
   return row_inv_norm(rowsq, nblk, n_rows_dev, rows_cap, inv_norm, S(stream));
 }
 
-int p2t_pool_fwd(const void* src, int src_is_f16, long long ld_src, const int* row_src, const float* inv_norm,
+int p2t_pool_fwd(const void* src, int src_is_f16, long long ld_src, int src_rows, const int* row_src, const float* inv_norm,
                  const int* seq_off, const int* chunk_off, const int* chunk_seq, int B, int D, int chunk_rows,
                  int max_chunks, int mode, void* partial_ws, float* out, long long ld_out, void* stream) {
   if (!src || !seq_off || !chunk_off || !chunk_seq || !partial_ws || !out) return set_error(-1, "p2t_pool_fwd: null pointer");
   if (mode < 1 || mode > 3) return set_error(-1, "p2t_pool_fwd: mode must be MEAN, STD or MIX");
   if (max_chunks <= 0) return 0;
-  return pool_forward(src, src_is_f16 != 0, ld_src, row_src, inv_norm, seq_off, chunk_off, chunk_seq, B, D, chunk_rows,
+  return pool_forward(src, src_is_f16 != 0, ld_src, src_rows, row_src, inv_norm, seq_off, chunk_off, chunk_seq, B, D, chunk_rows,
                       max_chunks, mode, reinterpret_cast<float2*>(partial_ws), out, ld_out, S(stream));
 }
 

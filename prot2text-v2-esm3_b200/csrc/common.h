@@ -1,5 +1,6 @@
 // Library-internal helpers: error reporting and launch accounting behind the C ABI (include/p2t_b200.h).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -14,6 +15,10 @@ void count_launch();
 int check_launch(const char* what);
 
 int sm_count();
+
+// TMA descriptor of a 16-bit row-major matrix [outer][inner] (leading dimension `ld` elements), box {box_inner, box_outer}
+int make_tmap_16bit(CUtensorMap* map, const void* ptr, long long inner, long long outer, long long ld, int box_inner,
+                    int box_outer, CUtensorMapSwizzle swizzle);
 
 // Optional per-launch timing of the GEMM kernel with CUDA events on the launching stream (bench.py's roofline).
 bool gemm_timing_enabled();

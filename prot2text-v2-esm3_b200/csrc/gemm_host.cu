@@ -25,8 +25,8 @@ static EncodeTiledFn encode_tiled_fn() {
 
 // 16-bit row-major matrix [outer][inner] with leading dimension `ld` elements; box = {box_inner, box_outer}
 // (operands: 64-element = 128-byte inner box, 128-byte swizzle; staged outputs: 32-element inner box, 64-byte swizzle)
-static int make_tmap_16bit(CUtensorMap* map, const void* ptr, long long inner, long long outer, long long ld,
-                           int box_inner, int box_outer, CUtensorMapSwizzle swizzle) {
+int make_tmap_16bit(CUtensorMap* map, const void* ptr, long long inner, long long outer, long long ld,
+                    int box_inner, int box_outer, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return set_error(-10, "cuTensorMapEncodeTiled entry point not available");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * 2) % 16)

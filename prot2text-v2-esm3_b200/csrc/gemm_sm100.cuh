@@ -28,7 +28,7 @@
 //   EPI_STORE_BF16 / EPI_STORE_F32 : D = alpha * acc
 //   EPI_FC1    : z1 = acc + b1;  D0 = h1 = keep*GELU(z1) (bf16);  D1 = g1 = keep*GELU'(z1) (fp16)   (:62-63)
 //   EPI_FC2    : z2 = acc + b2;  D0 = a  = keep*GELU(z2) (fp16);  D1 = g2 = keep*GELU'(z2) (fp16);
-//                rowsq[row][4*n_blk + part] = sum over 64 columns of a^2                         (:65-67)
+//                rowsq[4*n_blk + part][row] = sum over 64 columns of a^2                         (:65-67)
 //   (fp16 for tensors only our own streaming kernels read: bf16's 8-bit mantissa adds rounding noise
 //    of 2^-9*|a| to every residue, which inflates the pooled std and its 1/std backward)
 //   EPI_MUL_AUX: D0 = alpha * acc * aux   (fc2 dgrad chained into GELU'(z1): aux = g1)
@@ -70,7 +70,7 @@ struct GemmParams {
   const __nv_bfloat16* bias;  // [n]
   const __half* aux;          // EPI_MUL_AUX: fp16 multiplier [rows][ldaux]
   long long ldaux;
-  float* rowsq;               // EPI_FC2: [rows][ld_rowsq] partial sums of squares, four per 256-column N block
+  float* rowsq;               // EPI_FC2: [4 * n_blocks][ld_rowsq = rows_cap] partial sums of squares (four per 256-column N block)
   int ld_rowsq;
   float alpha;
   DropoutParams drop;         // p == 0 -> disabled
@@ -626,7 +626,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
       }
       if constexpr (EPI == EPI_FC2) {
-        if (row_in_buf && is_head) p.rowsq[(long long)row * p.ld_rowsq + n_blk * (GEMM_EPI_WARPS / 4) + part] = sumsq;
+        if (row_in_buf && is_head) p.rowsq[(long long)(n_blk * (GEMM_EPI_WARPS / 4) + part) * p.ld_rowsq + row] = sumsq;
       }
       tcgen05_fence_before();
       if (!is_head) __threadfence();  // the dumped piece must be visible before the flag

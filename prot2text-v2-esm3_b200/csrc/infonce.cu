@@ -21,71 +21,69 @@ namespace p2t {
 // fp32-embedding flavour: random-init / early-training embeddings are nearly parallel (loss ~ ln B), so the
 // informative part of S and of dp = dS t is a small difference of large common components; rounding p and t
 // to bf16 costs ~1 % of that difference.  The fused step therefore keeps p and t in fp32 on this path.
+// one CTA per (row i, 4 consecutive columns j): its 8 warps split E, partial dot products meet in shared memory
+template <bool F32>
 __global__ void __launch_bounds__(256)
-sim_small_f32_kernel(const float* __restrict__ p, const float* __restrict__ t, int R, int C, int E, float alpha,
-                     float* __restrict__ S) {
-  const int lane = threadIdx.x & 31;
-  const int cgroups = (C + 3) / 4;
-  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (warp_id >= (long long)R * cgroups) return;
-  const int i = (int)(warp_id / cgroups), j0 = (int)(warp_id % cgroups) * 4;
-  const float4* pr = reinterpret_cast<const float4*>(p + (long long)i * E);
-  const float4* tr[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) tr[q] = reinterpret_cast<const float4*>(t + (long long)min(j0 + q, C - 1) * E);
+sim_small_kernel(const void* __restrict__ pv, const void* __restrict__ tv, int R, int C, int E, float alpha,
+                 float* __restrict__ S) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x, j0 = blockIdx.y * 4;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  const int nvec = E >> 2;
-  for (int v = lane; v < nvec; v += 32) {
-    const float4 a = __ldg(pr + v);
+  if constexpr (F32) {
+    const float* p = reinterpret_cast<const float*>(pv);
+    const float* t = reinterpret_cast<const float*>(tv);
+    const float4* pr = reinterpret_cast<const float4*>(p + (long long)i * E);
+    const float4* tr[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 b = __ldg(tr[q] + v);
-      acc[q] = fmaf(a.x, b.x, acc[q]);
-      acc[q] = fmaf(a.y, b.y, acc[q]);
-      acc[q] = fmaf(a.z, b.z, acc[q]);
-      acc[q] = fmaf(a.w, b.w, acc[q]);
-    }
-  }
+    for (int q = 0; q < 4; ++q) tr[q] = reinterpret_cast<const float4*>(t + (long long)min(j0 + q, C - 1) * E);
+    const int nvec = E >> 2;
+    for (int v = threadIdx.x; v < nvec; v += 256) {
+      const float4 a = __ldg(pr + v);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float s = warp_sum(acc[q]);
-    if (lane == 0 && j0 + q < C) S[(long long)i * C + j0 + q] = s * alpha;
-  }
-}
-
-__global__ void __launch_bounds__(256)
-sim_small_kernel(const __nv_bfloat16* __restrict__ p, const __nv_bfloat16* __restrict__ t, int R, int C, int E,
-                 float alpha, float* __restrict__ S) {
-  const int lane = threadIdx.x & 31;
-  const int cgroups = (C + 3) / 4;
-  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (warp_id >= (long long)R * cgroups) return;
-  const int i = (int)(warp_id / cgroups), j0 = (int)(warp_id % cgroups) * 4;
-  const uint4* pr = reinterpret_cast<const uint4*>(p + (long long)i * E);
-  const uint4* tr[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) tr[q] = reinterpret_cast<const uint4*>(t + (long long)min(j0 + q, C - 1) * E);
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  const int nvec = E >> 3;
-  for (int v = lane; v < nvec; v += 32) {
-    const uint4 pu = __ldg(pr + v);
-    const uint32_t pw[4] = {pu.x, pu.y, pu.z, pu.w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint4 tu = __ldg(tr[q] + v);
-      const uint32_t tw[4] = {tu.x, tu.y, tu.z, tu.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 a = unpack_bf16x2(pw[k]), b = unpack_bf16x2(tw[k]);
+      for (int q = 0; q < 4; ++q) {
+        const float4 b = __ldg(tr[q] + v);
         acc[q] = fmaf(a.x, b.x, acc[q]);
         acc[q] = fmaf(a.y, b.y, acc[q]);
+        acc[q] = fmaf(a.z, b.z, acc[q]);
+        acc[q] = fmaf(a.w, b.w, acc[q]);
+      }
+    }
+  } else {
+    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(pv);
+    const __nv_bfloat16* t = reinterpret_cast<const __nv_bfloat16*>(tv);
+    const uint4* pr = reinterpret_cast<const uint4*>(p + (long long)i * E);
+    const uint4* tr[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tr[q] = reinterpret_cast<const uint4*>(t + (long long)min(j0 + q, C - 1) * E);
+    const int nvec = E >> 3;
+    for (int v = threadIdx.x; v < nvec; v += 256) {
+      const uint4 pu = __ldg(pr + v);
+      const uint32_t pw[4] = {pu.x, pu.y, pu.z, pu.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 tu = __ldg(tr[q] + v);
+        const uint32_t tw[4] = {tu.x, tu.y, tu.z, tu.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 a = unpack_bf16x2(pw[k]), b = unpack_bf16x2(tw[k]);
+          acc[q] = fmaf(a.x, b.x, acc[q]);
+          acc[q] = fmaf(a.y, b.y, acc[q]);
+        }
       }
     }
   }
+  __shared__ float red[8][4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const float s = warp_sum(acc[q]);
-    if (lane == 0 && j0 + q < C) S[(long long)i * C + j0 + q] = s * alpha;
+    if (lane == 0) red[warp][q] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4 && j0 + threadIdx.x < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];  // fixed order: deterministic
+    S[(long long)i * C + j0 + threadIdx.x] = s * alpha;
   }
 }
 
@@ -263,14 +261,9 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, long lo
 // ================================================================================================
 int sim_small(const void* p, const void* t, bool in_f32, int R, int C, int E, float alpha, float* S, cudaStream_t st) {
   if (E % 8) return set_error(-1, "similarity: E must be a multiple of 8");
-  const long long warps = (long long)R * ((C + 3) / 4);
-  const int blocks = (int)((warps + 7) / 8);
-  if (in_f32)
-    sim_small_f32_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(p), reinterpret_cast<const float*>(t), R,
-                                                 C, E, alpha, S);
-  else
-    sim_small_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(p),
-                                             reinterpret_cast<const __nv_bfloat16*>(t), R, C, E, alpha, S);
+  const dim3 grid(R, (C + 3) / 4);
+  if (in_f32) sim_small_kernel<true><<<grid, 256, 0, st>>>(p, t, R, C, E, alpha, S);
+  else sim_small_kernel<false><<<grid, 256, 0, st>>>(p, t, R, C, E, alpha, S);
   return check_launch("sim_small_kernel");
 }
 

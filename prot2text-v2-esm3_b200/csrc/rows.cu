@@ -11,7 +11,9 @@
 // and reduces in a fixed order (no floating-point atomics), so results are run-to-run identical.
 #include "common.h"
 #include "mathfn.cuh"
+#include "ptx.cuh"
 #include "rows.h"
+#include <cuda.h>
 #include <algorithm>
 
 namespace p2t {
@@ -91,9 +93,12 @@ __global__ void plan_fill_kernel(const void* mask, int mask_bytes, int B, int L,
     s_cbase = t1;
   }
   __syncthreads();
-  if (chunk_seq != nullptr) {
-    const int nchunks = (counts[b] + rc - 1) / rc;
-    for (int j = threadIdx.x; j < nchunks; j += blockDim.x) chunk_seq[s_cbase + j] = b;
+  if (chunk_seq != nullptr) {  // one descriptor per pooling chunk: {first packed row, end row, sequence, 0}
+    const int cnt = counts[b];
+    const int nchunks = (cnt + rc - 1) / rc;
+    int4* desc = reinterpret_cast<int4*>(chunk_seq);
+    for (int j = threadIdx.x; j < nchunks; j += blockDim.x)
+      desc[s_cbase + j] = make_int4(s_base + j * rc, s_base + min(cnt, (j + 1) * rc), b, 0);
   }
   if (row_src == nullptr) return;
   // ordered compaction of the valid positions of this sequence
@@ -152,12 +157,13 @@ __device__ __forceinline__ int find_segment(const int* __restrict__ off, int n, 
 }
 
 // inverse L2 norm of each adapter output row from the fc2 epilogue's partial sums of squares
+// rowsq is [nblk][cap] (partial index major): consecutive threads read consecutive rows
 __global__ void row_inv_norm_kernel(const float* __restrict__ rowsq, int nblk, const int* __restrict__ n_rows, int cap,
                                     float* __restrict__ inv_norm) {
   const int n = min(*n_rows, cap);
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
     float s = 0.f;
-    for (int j = 0; j < nblk; ++j) s += rowsq[(long long)r * nblk + j];
+    for (int j = 0; j < nblk; ++j) s += rowsq[(long long)j * cap + r];
     inv_norm[r] = 1.f / fmaxf(sqrtf(s), kEpsNorm);
   }
 }
@@ -168,93 +174,171 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 
-// grid (max_chunks, ceil(D/256)), block 256 = 64 column groups (4 columns = one 8-byte load each) x 4 row
-// subsets.  A chunk has <= 64 rows, so a thread owns <= 16 rows: it issues ALL 16 loads at once (a single level
-// of memory latency after the chunk lookup), then does an exact two-pass mean / M2 in registers; the 4 subsets
-// are merged with Chan's formula through shared memory.  Small per-thread state (~50 registers) keeps 4+ CTAs
-// resident per SM, i.e. >100 KB of loads in flight per SM.
+// Persistent TMA-fed streaming kernel.  grid (ctas_per_slab, ceil(D/256)), at most one CTA per SM; block = 8 consumer
+// warps + 1 producer warp.  A CTA owns one 256-column slab and strides over the pooling chunks (<= 64 rows of ONE
+// sequence each, described by an int4 {first row, end row, sequence, 0}).  The rows of a chunk are contiguous in the
+// source (packed activations; padded tensors with contiguous masks), so the producer brings a chunk in with one 2D TMA
+// box (64 rows x 256 columns = 32 KB) into a 5-deep shared-memory ring, together with the rows' scale factors:
+// ~128 KB of loads stay in flight per SM independent of register pressure, which is what an HBM latency of ~2 us under
+// load needs.  Chunks whose source rows are not contiguous (masks with holes) are read straight from global memory.
+// Consumer thread = 8 columns (one 16-byte shared-memory load per row) x the rows {sub, sub+8, ...}; it accumulates
+// sums shifted by the chunk's first row, s1 = sum(v - K), s2 = sum((v - K)^2), which merge across the 8 row subsets
+// by plain addition (fixed order) and stay well conditioned; thread (sub, group) then finishes column 8*group + sub.
+constexpr int POOL_NSUB = 8, POOL_RPT = 8, POOL_CONSUMERS = 32 * POOL_NSUB, POOL_THREADS = POOL_CONSUMERS + 32;
+constexpr int POOL_STAGES = 5, POOL_BOX_ROWS = 64, POOL_BOX_COLS = 256, POOL_STAGE_BYTES = POOL_BOX_ROWS * POOL_BOX_COLS * 2;
+struct PoolSmem {
+  uint8_t stage[POOL_STAGES][POOL_STAGE_BYTES];  // 1024-byte aligned
+  float comb[2][POOL_NSUB][32][17];              // [buffer][row subset][column group][s1[8] | s2[8]] (+1 pad)
+  float sc[POOL_STAGES][POOL_BOX_ROWS];          // per-row scale of the chunk held by each stage (0 beyond its rows)
+  uint64_t full[POOL_STAGES], empty[POOL_STAGES];
+  int4 desc[POOL_STAGES];   // descriptor of the chunk held by each stage
+  int src_row[POOL_STAGES]; // first source row of that chunk, or -1: not contiguous, read from global memory
+};
 template <bool F16>
-__global__ void __launch_bounds__(256, 2)
-pool_partial_kernel(const __nv_bfloat16* __restrict__ src, long long ld_src, const int* __restrict__ row_src,
-                    const float* __restrict__ inv_norm, const int* __restrict__ seq_off,
-                    const int* __restrict__ chunk_off, const int* __restrict__ chunk_seq, int B, int D, int rc,
+__global__ void __launch_bounds__(POOL_THREADS, 1)
+pool_partial_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16* __restrict__ src, long long ld_src,
+                    const int* __restrict__ row_src, const float* __restrict__ inv_norm,
+                    const int* __restrict__ chunk_off, const int4* __restrict__ chunk_desc, int B, int D,
                     float2* __restrict__ partial) {
-  const int chunk = blockIdx.x;
-  if (chunk >= chunk_off[B]) return;
-  const int b = chunk_seq[chunk];
-  const int r0 = seq_off[b] + (chunk - chunk_off[b]) * rc;
-  const int r1 = min(r0 + rc, seq_off[b + 1]);
-  const int cgl = threadIdx.x & 63, sub = threadIdx.x >> 6;  // sub in [0, 4)
-  const int g = blockIdx.y * 64 + cgl;                       // 4-column group
-  const bool active = g * 4 < D;
-  constexpr int RPT = 16, NSUB = 4;
-  __shared__ float comb[NSUB - 1][64][9];
-  __shared__ float comb_n[NSUB - 1];
-  float mean[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f};
-  int cnt = 0;
-  for (int r = r0 + sub; r < r1; r += NSUB) ++cnt;
-  if (active && cnt > 0) {
-    uint2 u[RPT];
-    float sc[RPT];
-#pragma unroll
-    for (int k = 0; k < RPT; ++k) {
-      const int r = r0 + sub + NSUB * k;
-      if (r < r1) {
-        const long long sr = row_src ? (long long)row_src[r] : (long long)r;
-        u[k] = __ldg(reinterpret_cast<const uint2*>(src + sr * ld_src) + g);
-        sc[k] = inv_norm ? __ldg(inv_norm + r) : 1.f;
-      } else {
-        u[k] = make_uint2(0, 0);
-        sc[k] = 0.f;
-      }
+  extern __shared__ uint8_t pool_smem_raw[];
+  PoolSmem& sm = *reinterpret_cast<PoolSmem*>(pool_smem_raw + ((1024u - (smem_u32(pool_smem_raw) & 1023u)) & 1023u));
+  const int total = chunk_off[B];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int stride = gridDim.x;
+  const int col0 = blockIdx.y * POOL_BOX_COLS;
+  if (tid == 0) {
+    tma_prefetch_desc(&tmap);
+    for (int s = 0; s < POOL_STAGES; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], POOL_NSUB);  // one arrive per consumer warp
     }
-#pragma unroll
-    for (int k = 0; k < RPT; ++k) {
-      const float2 lo = unpack_h2<F16>(u[k].x), hi = unpack_h2<F16>(u[k].y);
-      mean[0] = fmaf(lo.x, sc[k], mean[0]);  // absent rows: sc == 0, exact zeros
-      mean[1] = fmaf(lo.y, sc[k], mean[1]);
-      mean[2] = fmaf(hi.x, sc[k], mean[2]);
-      mean[3] = fmaf(hi.y, sc[k], mean[3]);
-    }
-    const float inv_cnt = 1.f / (float)cnt;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) mean[i] *= inv_cnt;
-#pragma unroll
-    for (int k = 0; k < RPT; ++k) {
-      if (k < cnt) {
-        const float2 lo = unpack_h2<F16>(u[k].x), hi = unpack_h2<F16>(u[k].y);
-        const float d0 = fmaf(lo.x, sc[k], -mean[0]), d1 = fmaf(lo.y, sc[k], -mean[1]);
-        const float d2 = fmaf(hi.x, sc[k], -mean[2]), d3 = fmaf(hi.y, sc[k], -mean[3]);
-        m2[0] = fmaf(d0, d0, m2[0]); m2[1] = fmaf(d1, d1, m2[1]); m2[2] = fmaf(d2, d2, m2[2]); m2[3] = fmaf(d3, d3, m2[3]);
-      }
-    }
-  }
-  if (sub > 0) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { comb[sub - 1][cgl][i] = mean[i]; comb[sub - 1][cgl][4 + i] = m2[i]; }
-    if (cgl == 0) comb_n[sub - 1] = (float)cnt;
+    fence_barrier_init();
   }
   __syncthreads();
-  if (sub == 0 && active) {
-    float n = (float)cnt;
-#pragma unroll
-    for (int k = 0; k < NSUB - 1; ++k) {
-      const float nk = comb_n[k];
-      if (nk > 0.f) {
-        const float tot = n + nk;
-        const float w = nk / tot, w2 = n * nk / tot;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float delta = comb[k][cgl][i] - mean[i];
-          mean[i] = fmaf(delta, w, mean[i]);
-          m2[i] += comb[k][cgl][4 + i] + delta * delta * w2;
-        }
-        n = tot;
+  if (warp == POOL_NSUB) {
+    // ------------------------------- producer warp -------------------------------
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int c = blockIdx.x; c < total; c += stride) {
+      mbar_wait(&sm.empty[stage], phase ^ 1);
+      const int4 d = __ldg(chunk_desc + c);
+      int first = d.x;
+      if (row_src != nullptr) {
+        first = __ldg(row_src + d.x);
+        if (__ldg(row_src + d.y - 1) - first != d.y - 1 - d.x) first = -1;  // row_src is increasing: holes inside
       }
+#pragma unroll
+      for (int h = 0; h < POOL_BOX_ROWS / 32; ++h) {
+        const int r = d.x + lane + 32 * h;
+        sm.sc[stage][lane + 32 * h] = (r < d.y) ? (inv_norm ? __ldg(inv_norm + r) : 1.f) : 0.f;
+      }
+      if (lane == 0) {
+        sm.desc[stage] = d;
+        sm.src_row[stage] = first;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        if (first >= 0) {
+          mbar_arrive_expect_tx(&sm.full[stage], POOL_STAGE_BYTES);
+          tma_load_2d(sm.stage[stage], &tmap, &sm.full[stage], col0, first);
+        } else {
+          mbar_arrive(&sm.full[stage]);
+        }
+      }
+      if (++stage == POOL_STAGES) { stage = 0; phase ^= 1; }
     }
-    float4* out = reinterpret_cast<float4*>(partial + (long long)chunk * D + g * 4);
-    out[0] = make_float4(mean[0], m2[0], mean[1], m2[1]);
-    out[1] = make_float4(mean[2], m2[2], mean[3], m2[3]);
+    return;
+  }
+  // ------------------------------- consumer warps -------------------------------
+  const int grp = lane, sub = warp;                 // 8-column group inside the slab, row subset
+  const int colb = col0 + grp * 8;                  // first of this thread's 8 columns
+  const bool active = colb < D;
+  int stage = 0, buf = 0;
+  uint32_t phase = 0;
+  for (int c = blockIdx.x; c < total; c += stride) {
+    mbar_wait(&sm.full[stage], phase);  // also orders the producer's desc / sc / src_row writes before these reads
+    const int4 d = sm.desc[stage];
+    const int first = sm.src_row[stage];
+    float s1[8], s2[8], K[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+    if (first >= 0) {
+      const uint8_t* base = sm.stage[stage] + grp * 16;
+      {
+        float f[8];
+        unpack8<F16>(*reinterpret_cast<const uint4*>(base), f);
+        const float sc0 = sm.sc[stage][0];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) K[i] = f[i] * sc0;
+      }
+      uint4 u[POOL_RPT];
+      float sc[POOL_RPT];
+#pragma unroll
+      for (int k = 0; k < POOL_RPT; ++k) {
+        const int rr = sub + POOL_NSUB * k;
+        u[k] = *reinterpret_cast<const uint4*>(base + rr * (POOL_BOX_COLS * 2));  // rows past the chunk: ignored below
+        sc[k] = sm.sc[stage][rr];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.empty[stage]);  // this warp holds its part of the stage in registers
+      const int nrows = d.y - d.x;
+#pragma unroll
+      for (int k = 0; k < POOL_RPT; ++k) {
+        if (sub + POOL_NSUB * k < nrows) {  // warp-uniform
+          float f[8];
+          unpack8<F16>(u[k], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float v = fmaf(f[i], sc[k], -K[i]);
+            s1[i] += v;
+            s2[i] = fmaf(v, v, s2[i]);
+          }
+        }
+      }
+    } else {
+      // rows scattered in the source: straight from global memory (rare; correctness path)
+      if (active) {
+        float f[8];
+        unpack8<F16>(__ldg(reinterpret_cast<const uint4*>(src + (long long)__ldg(row_src + d.x) * ld_src + colb)), f);
+        const float sc0 = sm.sc[stage][0];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) K[i] = f[i] * sc0;
+        for (int r = d.x + sub; r < d.y; r += POOL_NSUB) {
+          unpack8<F16>(__ldg(reinterpret_cast<const uint4*>(src + (long long)__ldg(row_src + r) * ld_src + colb)), f);
+          const float scr = sm.sc[stage][r - d.x];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float v = fmaf(f[i], scr, -K[i]);
+            s1[i] += v;
+            s2[i] = fmaf(v, v, s2[i]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) K[i] = 0.f;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.empty[stage]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sm.comb[buf][sub][grp][i] = s1[i]; sm.comb[buf][sub][grp][8 + i] = s2[i]; }
+    asm volatile("bar.sync 1, %0;" ::"n"(POOL_CONSUMERS) : "memory");  // consumers only; `buf` alternates
+    {
+      // thread (sub, grp) finishes column 8*grp + sub: add the 8 row subsets in a fixed order
+      float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < POOL_NSUB; ++k) {
+        t1 += sm.comb[buf][k][grp][sub];
+        t2 += sm.comb[buf][k][grp][8 + sub];
+      }
+      float kk = K[0];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) kk = (sub == i) ? K[i] : kk;
+      const float n = (float)(d.y - d.x);
+      if (colb + sub < D) partial[(long long)c * D + colb + sub] = make_float2(kk + t1 / n, fmaxf(t2 - t1 * t1 / n, 0.f));
+    }
+    buf ^= 1;
+    if (++stage == POOL_STAGES) { stage = 0; phase ^= 1; }
   }
 }
 
@@ -385,9 +469,8 @@ adapter_tail_bwd_kernel(const __half* __restrict__ a, const __half* __restrict__
       if (tid < nvec) reinterpret_cast<uint4*>(dz2 + (long long)row * D)[tid] = make_uint4(0, 0, 0, 0);
     return;
   }
-  const int b = chunk_seq[chunk];
-  const int r0 = seq_off[b] + (chunk - chunk_off[b]) * rc;
-  const int r1 = min(r0 + rc, seq_off[b + 1]);
+  const int4 desc = __ldg(reinterpret_cast<const int4*>(chunk_seq) + chunk);
+  const int b = desc.z, r0 = desc.x, r1 = desc.y;
   const bool active = tid < nvec;
   const int warp = tid >> 5, lane = tid & 31;
   constexpr int NWARPS = THREADS / 32;
@@ -479,19 +562,20 @@ adapter_tail_bwd_kernel(const __half* __restrict__ a, const __half* __restrict__
   }
 }
 
-// sum `nparts` partial rows: out[col] = sum_k partial[k][col].  grid ceil(D/32), block (32, 8): thread (x, y)
-// adds parts y, y+8, ... of column 32*blockIdx.x + x, then the 8 lanes are merged in shared memory (fixed order).
+// sum `nparts` partial rows: out[col] = sum_k partial[k][col].  grid ceil(D/32), block (32, 32): thread (x, y)
+// adds parts y, y+32, ... of column 32*blockIdx.x + x, then the 32 rows are merged in shared memory (fixed order).
+constexpr int PARTS_Y = 32;
 __device__ __forceinline__ float sum_parts(const float* __restrict__ partial, int nparts, int D, int col) {
   float s0 = 0.f, s1 = 0.f;
   int k = threadIdx.y;
-  for (; k + 8 < nparts; k += 16) {
+  for (; k + PARTS_Y < nparts; k += 2 * PARTS_Y) {
     s0 += partial[(long long)k * D + col];
-    s1 += partial[(long long)(k + 8) * D + col];
+    s1 += partial[(long long)(k + PARTS_Y) * D + col];
   }
   if (k < nparts) s0 += partial[(long long)k * D + col];
   return s0 + s1;
 }
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * PARTS_Y)
 parts_colsum_final_kernel(const float* __restrict__ partial, const int* __restrict__ chunk_off, int B,
                           const int* __restrict__ n_rows, int n_static, int D, __nv_bfloat16* __restrict__ out_bf16,
                           float* __restrict__ out_f32) {
@@ -500,13 +584,13 @@ parts_colsum_final_kernel(const float* __restrict__ partial, const int* __restri
   if (chunk_off != nullptr) nparts = chunk_off[B];
   else nparts = ((n_rows ? min(*n_rows, n_static) : n_static) + 63) / 64;
   const int col = blockIdx.x * 32 + threadIdx.x;
-  __shared__ float sm[8][33];
+  __shared__ float sm[PARTS_Y][33];
   sm[threadIdx.y][threadIdx.x] = (col < D) ? sum_parts(partial, nparts, D, col) : 0.f;
   __syncthreads();
   if (threadIdx.y == 0 && col < D) {
     float s = 0.f;
 #pragma unroll
-    for (int y = 0; y < 8; ++y) s += sm[y][threadIdx.x];
+    for (int y = 0; y < PARTS_Y; ++y) s += sm[y][threadIdx.x];
     if (out_bf16) out_bf16[col] = __float2bfloat16_rn(s);
     if (out_f32) out_f32[col] = s;
   }
@@ -577,14 +661,14 @@ adapter_tail_bwd_dy_kernel(const __half* __restrict__ a, const __half* __restric
 
 // y[row] = a[row] * inv_norm[row]  (module API forward tail).  inv from rowsq partials.
 __global__ void __launch_bounds__(256)
-scale_rows_kernel(const __half* __restrict__ a, const float* __restrict__ rowsq, int nblk, int n, int D,
+scale_rows_kernel(const __half* __restrict__ a, const float* __restrict__ rowsq, int nblk, int cap, int n, int D,
                   __nv_bfloat16* __restrict__ y, float* __restrict__ inv_norm_out) {
   const int lane = threadIdx.x & 31;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
   const int nvec = D >> 3;
   for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps_total) {
     float s = 0.f;
-    for (int j = lane; j < nblk; j += 32) s += rowsq[(long long)row * nblk + j];
+    for (int j = lane; j < nblk; j += 32) s += rowsq[(long long)j * cap + row];
     s = warp_sum(s);
     const float inv = 1.f / fmaxf(sqrtf(s), kEpsNorm);
     if (lane == 0 && inv_norm_out) inv_norm_out[row] = inv;
@@ -727,16 +811,31 @@ int row_inv_norm(const float* rowsq, int nblk, const int* n_rows, int cap, float
   return check_launch("row_inv_norm_kernel");
 }
 
-int pool_forward(const void* src, bool src_is_f16, long long ld_src, const int* row_src, const float* inv_norm,
+int pool_forward(const void* src, bool src_is_f16, long long ld_src, int src_rows, const int* row_src, const float* inv_norm,
                  const int* seq_off, const int* chunk_off, const int* chunk_seq, int B, int D, int rc, int max_chunks,
                  int mode, float2* partial, float* out, long long ld_out, cudaStream_t st) {
   if (D % 8) return set_error(-1, "pool_forward: D must be a multiple of 8");
-  dim3 grid(max_chunks, (D / 4 + 63) / 64);
+  if (rc != POOL_BOX_ROWS) return set_error(-1, "pool_forward: chunk_rows must be 64");
+  if (src_rows <= 0) return set_error(-1, "pool_forward: source row count required");
+  const int slabs = (D + POOL_BOX_COLS - 1) / POOL_BOX_COLS;
+  const int per_slab = std::max(1, std::min(max_chunks, sm_count() / slabs));  // at most one CTA per SM: a single wave
+  dim3 grid(per_slab, slabs);
   const __nv_bfloat16* sp = reinterpret_cast<const __nv_bfloat16*>(src);
+  const int4* desc = reinterpret_cast<const int4*>(chunk_seq);
+  CUtensorMap tmap;
+  if (int r = make_tmap_16bit(&tmap, src, D, src_rows, ld_src, POOL_BOX_COLS, POOL_BOX_ROWS, CU_TENSOR_MAP_SWIZZLE_NONE)) return r;
+  const int smem = (int)sizeof(PoolSmem) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e1 = cudaFuncSetAttribute(pool_partial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e2 = cudaFuncSetAttribute(pool_partial_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) return set_error((int)(e1 != cudaSuccess ? e1 : e2), "pool_forward: cannot reserve %d bytes of shared memory", smem);
+    configured = true;
+  }
   if (src_is_f16)
-    pool_partial_kernel<true><<<grid, 256, 0, st>>>(sp, ld_src, row_src, inv_norm, seq_off, chunk_off, chunk_seq, B, D, rc, partial);
+    pool_partial_kernel<true><<<grid, POOL_THREADS, smem, st>>>(tmap, sp, ld_src, row_src, inv_norm, chunk_off, desc, B, D, partial);
   else
-    pool_partial_kernel<false><<<grid, 256, 0, st>>>(sp, ld_src, row_src, inv_norm, seq_off, chunk_off, chunk_seq, B, D, rc, partial);
+    pool_partial_kernel<false><<<grid, POOL_THREADS, smem, st>>>(tmap, sp, ld_src, row_src, inv_norm, chunk_off, desc, B, D, partial);
   if (int r = check_launch("pool_partial_kernel")) return r;
   dim3 g2(B, (D + 255) / 256);
   pool_finalize_kernel<<<g2, 256, 0, st>>>(partial, seq_off, chunk_off, B, D, rc, mode, out, ld_out);
@@ -775,7 +874,7 @@ int adapter_tail_backward(const void* a, const void* g, const float* inv_norm, c
   if (int r = check_launch("adapter_tail_bwd_kernel")) return r;
   if (db2 != nullptr) {
     if (!colsum_partial) return set_error(-1, "adapter_tail_backward: db2 needs the partial workspace");
-    parts_colsum_final_kernel<<<(D + 31) / 32, dim3(32, 8), 0, st>>>(colsum_partial, chunk_off, B, nullptr, 0, D,
+    parts_colsum_final_kernel<<<(D + 31) / 32, dim3(32, PARTS_Y), 0, st>>>(colsum_partial, chunk_off, B, nullptr, 0, D,
                                                                      reinterpret_cast<__nv_bfloat16*>(db2), nullptr);
     return check_launch("parts_colsum_final_kernel");
   }
@@ -798,10 +897,11 @@ int adapter_tail_backward_dy(const void* a, const void* g, const float* inv_norm
   return tail_bwd_dy_launch<16>(a, g, inv_norm, dy, n, cap, D, dz2, st);
 }
 
-int scale_rows(const void* a, const float* rowsq, int nblk, int n, int D, void* y, float* inv_norm_out, cudaStream_t st) {
+int scale_rows(const void* a, const float* rowsq, int nblk, int cap, int n, int D, void* y, float* inv_norm_out,
+               cudaStream_t st) {
   if (n <= 0) return 0;
   const int blocks = min((n + 7) / 8, sm_count() * 8);
-  scale_rows_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __half*>(a), rowsq, nblk, n, D,
+  scale_rows_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __half*>(a), rowsq, nblk, cap, n, D,
                                             reinterpret_cast<__nv_bfloat16*>(y), inv_norm_out);
   return check_launch("scale_rows_kernel");
 }
@@ -822,7 +922,7 @@ int colsum(const void* x, const int* n_rows, int n_static, int D, float* partial
   dim3 g((n_static + 63) / 64, (D / 8 + 63) / 64);
   colsum_partial_kernel<<<g, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), n_rows, n_static, D, partial);
   if (int r = check_launch("colsum_partial_kernel")) return r;
-  parts_colsum_final_kernel<<<(D + 31) / 32, dim3(32, 8), 0, st>>>(partial, nullptr, 0, n_rows, n_static, D,
+  parts_colsum_final_kernel<<<(D + 31) / 32, dim3(32, PARTS_Y), 0, st>>>(partial, nullptr, 0, n_rows, n_static, D,
                                                                    reinterpret_cast<__nv_bfloat16*>(out_bf16), out_f32);
   return check_launch("parts_colsum_final_kernel");
 }

@@ -14,7 +14,7 @@ int rows_plan_counts(const int* counts, int B, int rc, int* seq_off, int* chunk_
 int row_inv_norm(const float* rowsq, int nblk, const int* n_rows, int cap, float* inv_norm, cudaStream_t st);
 int gather_rows(const void* src, long long ld_src, const int* row_src, const int* n_rows, int cap, int D, void* out,
                 cudaStream_t st);
-int pool_forward(const void* src, bool src_is_f16, long long ld_src, const int* row_src, const float* inv_norm,
+int pool_forward(const void* src, bool src_is_f16, long long ld_src, int src_rows, const int* row_src, const float* inv_norm,
                  const int* seq_off, const int* chunk_off, const int* chunk_seq, int B, int D, int rc, int max_chunks,
                  int mode, float2* partial, float* out, long long ld_out, cudaStream_t st);
 int l2norm_forward(const float* e, int B, int E, void* p_bf16, float* p_f32, float* norm, cudaStream_t st);
@@ -26,7 +26,8 @@ int adapter_tail_backward(const void* a, const void* g, const float* inv_norm, c
                           int rc, int max_chunks, void* dz2, float* colsum_partial, void* db2, cudaStream_t st);
 int adapter_tail_backward_dy(const void* a, const void* g, const float* inv_norm, const void* dy, int n, int cap, int D,
                              void* dz2, cudaStream_t st);
-int scale_rows(const void* a, const float* rowsq, int nblk, int n, int D, void* y, float* inv_norm_out, cudaStream_t st);
+int scale_rows(const void* a, const float* rowsq, int nblk, int cap, int n, int D, void* y, float* inv_norm_out,
+               cudaStream_t st);
 int readout_backward(const void* x, const void* mask, int mask_bytes, int B, int S, int D, const float* c1,
                      const float* c2, void* dx, cudaStream_t st);
 int colsum(const void* x, const int* n_rows, int n_static, int D, float* partial, void* out_bf16, float* out_f32,

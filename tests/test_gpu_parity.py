@@ -220,7 +220,12 @@ def test_row_plan_and_gather_are_bit_exact(core, dev, kind, dtype):
     assert n == int(mask.sum())
     flat = mask.flatten().nonzero().flatten()
     assert torch.equal(plan.row_src[:n].cpu().long(), flat)
-    assert torch.equal(plan.chunk_seq[:int(chunks.sum())].cpu().long(), torch.repeat_interleave(torch.arange(B), chunks))
+    nch = int(chunks.sum())
+    desc = plan.chunk_seq[:nch].cpu().long()  # {first packed row, end row, sequence, 0} per 64-row pooling chunk
+    seq = torch.repeat_interleave(torch.arange(B), chunks)
+    first = torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)])[seq] + 64 * (torch.arange(nch) - torch.cat([torch.zeros(1, dtype=torch.long), chunks.cumsum(0)])[seq])
+    end = torch.minimum(first + 64, counts.cumsum(0)[seq])
+    assert torch.equal(desc[:, 2], seq) and torch.equal(desc[:, 0], first) and torch.equal(desc[:, 1], end)
     x = bf(torch.randn(B * L, D)).to(dev)
     xp = core.gather_rows(x, plan)
     assert torch.equal(xp[:n].cpu(), x.cpu()[flat])

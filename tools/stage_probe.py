@@ -57,7 +57,7 @@ def main():
     torch.cuda.synchronize()
     print(f"fc1: h1 rel={rel(acts.h1[:n], tr.h1[valid]):.3e}  g1 rel={rel(acts.g1[:n], R.gelu_erf_grad(tr.z1[valid])):.3e}")
     print(f"fc2: a rel={rel(acts.a[:n], tr.a[valid]):.3e}  g2 rel={rel(acts.g2[:n], R.gelu_erf_grad(tr.z2[valid])):.3e}")
-    print(f"rowsq: rel={rel(acts.rowsq[:n].sum(1), tr.a[valid].pow(2).sum(-1)):.3e}")
+    print(f"rowsq: rel={rel(acts.rowsq[:, :n].sum(0), tr.a[valid].pow(2).sum(-1)):.3e}")
 
     # 3/4. pool + normalise
     inv_norm = core.row_inv_norm(acts)
