@@ -1,0 +1,96 @@
+"""Multi-GPU parity check of the sharded contrastive step (run under torchrun, one rank per GPU).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
+        tools/dist_check.py [workload] [weight_gain]
+
+Every rank runs `dist.distributed_contrastive_step` on its own shard (all-gathered text negatives over NCCL, with
+and without the symmetric column term); gradients are averaged across ranks the way DDP does.  Rank 0 rebuilds the
+GLOBAL batch on the CPU and runs the oracle on it in one process: the mean of the local losses must
+equal the global-batch loss, the averaged gradients the global-batch gradients.  Exit code 0 = parity.
+"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import __graft_entry__ as entry
+from oracle import restatement as R
+
+PARAMS = ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias")
+
+
+def main():
+    name = sys.argv[1] if len(sys.argv) > 1 else "cfg1_esm2_t6_llama1b"
+    gain = float(sys.argv[2]) if len(sys.argv) > 2 else 2.5
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    pkg = entry.load_package()
+    import importlib
+    synth = importlib.import_module("p2t_b200.synth")
+    pdist = importlib.import_module("p2t_b200.dist")
+    shards = [synth.make_config_batch(name, weight_gain=gain, rank=r) for r in range(world)]
+    sb = shards[rank]
+    cfg = pkg.ModalityAdapterConfig(input_dim=sb.w1.shape[1], intermediate_dim=sb.w1.shape[0], output_dim=sb.w2.shape[0])
+    ad = pkg.ModalityAdapter(cfg).to(dev).to(torch.bfloat16).eval()
+    with torch.no_grad():
+        ad.fc1.weight.copy_(sb.w1); ad.fc1.bias.copy_(sb.b1); ad.fc2.weight.copy_(sb.w2); ad.fc2.bias.copy_(sb.b2)
+    ok = True
+    for sym in (False, True):
+        ad.zero_grad(set_to_none=True)
+        aux = pkg.StepAux()
+        loss = pdist.distributed_contrastive_step(sb.x.to(dev), sb.prot_mask.to(dev), ad, sb.text.to(dev),
+                                                  sb.text_mask.to(dev), symmetric=sym, aux=aux)
+        loss.backward()
+        lt = loss.detach().clone()
+        dist.all_reduce(lt)
+        grads = {}
+        for k, prm in zip(PARAMS, (ad.fc1.weight, ad.fc1.bias, ad.fc2.weight, ad.fc2.bias)):
+            g = prm.grad.float().clone()
+            dist.all_reduce(g)
+            grads[k] = (g / world).cpu()
+        am_row = [torch.empty_like(aux.argmax_row) for _ in range(world)]
+        dist.all_gather(am_row, aux.argmax_row)
+        if rank == 0:
+            f = torch.float32
+            B = sb.x.shape[0]
+            Lmax = max(s.x.shape[1] for s in shards)
+            Tmax = max(s.text.shape[1] for s in shards)
+            X = torch.zeros(world * B, Lmax, sb.x.shape[2])
+            PM = torch.zeros(world * B, Lmax, dtype=torch.long)
+            TX = torch.zeros(world * B, Tmax, sb.text.shape[2])
+            TM = torch.zeros(world * B, Tmax, dtype=torch.long)
+            for r, s in enumerate(shards):
+                X[r * B:(r + 1) * B, :s.x.shape[1]] = s.x.to(f)
+                PM[r * B:(r + 1) * B, :s.x.shape[1]] = s.prot_mask
+                TX[r * B:(r + 1) * B, :s.text.shape[1]] = s.text.to(f)
+                TM[r * B:(r + 1) * B, :s.text.shape[1]] = s.text_mask
+            st = R.step_forward(X, PM, sb.w1.to(f), sb.b1.to(f), sb.w2.to(f), sb.b2.to(f), TX, TM, 0.05, 1, sym)
+            ref = R.step_backward(st, X, PM, sb.w1.to(f), sb.w2.to(f), 0.05, 1, sym)
+            lrel = abs(lt.item() / world - st.loss.item()) / abs(st.loss.item())
+            line = f"world={world} {name} symmetric={sym}: loss {lt.item() / world:.6f} vs global oracle {st.loss.item():.6f} rel={lrel:.2e}"
+            ok &= lrel <= 1e-3
+            for k in PARAMS:
+                a, b = grads[k].double().flatten(), ref[k].double().flatten()
+                c = torch.nn.functional.cosine_similarity(a, b, dim=0).item()
+                m = ((a - b).abs().max() / b.abs().max()).item()
+                line += f" | {k} cos={c:.6f} maxrel={m:.2e}"
+                # reference semantics (row term): north_star's 1e-2; the symmetric extension has no reference
+                # counterpart and sits at the bf16 noise floor of this near-degenerate random-init problem
+                # (an fp32 oracle whose h1 alone is rounded to bf16 already differs by 3e-3 .. 4e-3): 2e-2
+                ok &= c >= 0.999 and m <= (2e-2 if sym else 1e-2)
+            am_ref, _ = R.retrieval_argmax(st.p, st.t)
+            am = torch.cat([a.cpu().long() for a in am_row])
+            line += f" | argmax_row exact={torch.equal(am, am_ref)}"
+            print(line, flush=True)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
