@@ -127,10 +127,13 @@ int p2t_row_inv_norm(const float* rowsq, int nblk, const int* n_rows_dev, int ro
  * row_src == NULL means rows are already packed.  With inv_norm != NULL every row is first scaled
  * by inv_norm[row] (adapter output: normalise fused into the pooling pass).
  * partial_ws: float2 [max_chunks][D]; out: fp32 [B][ld_out] (mean | std for mix).
+ * With p_bf16 and/or p_f32 given (mode MIX, ld_out == 2*D) the following F.normalize (:354/:365) is fused into
+ * the final pass: p = out / max(|out|, 1e-12) [B][2*D], norm[B] = |out| (unclamped).
  * ------------------------------------------------------------------------------------------- */
 int p2t_pool_fwd(const void* src, int src_is_f16, long long ld_src, int src_rows, const int* row_src, const float* inv_norm,
                  const int* seq_off, const int* chunk_off, const int* chunk_seq, int B, int D, int chunk_rows,
-                 int max_chunks, int mode, void* partial_ws, float* out, long long ld_out, void* stream);
+                 int max_chunks, int mode, void* partial_ws, float* out, long long ld_out, void* p_bf16, float* p_f32,
+                 float* norm, void* stream);
 
 /* readout_embeddings(..., "last") — :207-215 — out fp32 [B][D] from padded x [B][S][D] */
 int p2t_readout_last(const void* x, const int* counts, int B, int S, int D, float* out, void* stream);
@@ -143,6 +146,13 @@ int p2t_l2norm_bwd(const float* dp, const float* p_f32, const float* norm, int B
 /* backward of the readout: coefficient vectors with dy_r = c1[b] + c2[b] * y_r (fp32 [B][D]) */
 int p2t_pool_bwd_coef(const float* de, long long ld_de, const float* stats, long long ld_stats, const int* seq_off,
                       int B, int D, int mode, float* c1, float* c2, void* stream);
+/* The same coefficients straight from dLogits in one kernel, for small similarity blocks (autograd of
+ * :108-113 -> :365 -> :277-281): dp = dloss/tau * dS t (rows >= R get 0), F.normalize backward, 'mix' coefficients.
+ * dS fp32 [R][C] (as left by p2t_infonce_ce), t_f32 [C][2D], p_f32 [B][2D], pnorm[B], stats [B][2D], dloss: device
+ * scalar or NULL (= 1). */
+int p2t_loss_bwd_coef(const float* dS, const float* t_f32, const float* p_f32, const float* pnorm, const float* stats,
+                      const int* seq_off, const float* dloss, int R, int B, int C, int D, float tau, float* c1,
+                      float* c2, void* stream);
 /* dx[b,r] = mask[b,r] * (c1[b] + c2[b] * x[b,r]) on a padded bf16 (B, S, D) tensor */
 int p2t_readout_bwd(const void* x, const void* mask, int mask_bytes, int B, int S, int D, const float* c1,
                     const float* c2, void* dx, void* stream);

@@ -211,16 +211,35 @@ def row_inv_norm(acts: "AdapterActs") -> torch.Tensor:
 
 
 def pool_forward(src: torch.Tensor, plan: RowPlan, D: int, *, row_src: Optional[torch.Tensor],
-                 inv_norm: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 inv_norm: Optional[torch.Tensor] = None, normalize: bool = False, want_f32: bool = True):
     """(mean | std) statistics fp32 [B, 2D] of the plan's rows of `src` (bf16 or fp16, row stride src.stride(0)),
-    each row optionally scaled by inv_norm[row] first."""
+    each row optionally scaled by inv_norm[row] first.  With `normalize` the following F.normalize is fused in and
+    (stats, p_bf16, p_f32 or None, norm) is returned."""
     dev = src.device
     partial = torch.empty(plan.max_chunks, D, 2, dtype=torch.float32, device=dev)
     stats = torch.empty(plan.B, 2 * D, dtype=torch.float32, device=dev)
+    p_bf = p_f32 = norm = None
+    if normalize:
+        p_bf = torch.empty(plan.B, 2 * D, dtype=torch.bfloat16, device=dev)
+        p_f32 = torch.empty(plan.B, 2 * D, dtype=torch.float32, device=dev) if want_f32 else None
+        norm = torch.empty(plan.B, dtype=torch.float32, device=dev)
     _lib.call("p2t_pool_fwd", _ptr(src), int(src.dtype == torch.float16), src.stride(0), src.shape[0], _ptr(row_src), _ptr(inv_norm),
               _ptr(plan.seq_off), _ptr(plan.chunk_off), _ptr(plan.chunk_seq), plan.B, D, CHUNK_ROWS, plan.max_chunks,
-              READOUT_MODES["mix"], _ptr(partial), _ptr(stats), 2 * D, _stream())
+              READOUT_MODES["mix"], _ptr(partial), _ptr(stats), 2 * D, _ptr(p_bf), _ptr(p_f32), _ptr(norm), _stream())
+    if normalize:
+        return stats, p_bf, p_f32, norm
     return stats
+
+
+def loss_backward_coef(res: "InfoNCEResult", t_f32: torch.Tensor, p_f32: torch.Tensor, pnorm: torch.Tensor,
+                       stats: torch.Tensor, plan: RowPlan, D: int, tau: float, dloss: Optional[torch.Tensor]):
+    """dLogits -> pooling coefficients (c1, c2) in one kernel (small similarity blocks, fp32 embeddings)."""
+    R, C = res.dS.shape
+    c1 = torch.empty(plan.B, D, dtype=torch.float32, device=p_f32.device)
+    c2 = torch.empty(plan.B, D, dtype=torch.float32, device=p_f32.device)
+    _lib.call("p2t_loss_bwd_coef", _ptr(res.dS), _ptr(t_f32), _ptr(p_f32), _ptr(pnorm), _ptr(stats), _ptr(plan.seq_off),
+              _ptr(dloss), R, plan.B, C, D, float(tau), _ptr(c1), _ptr(c2), _stream())
+    return c1, c2
 
 
 def l2norm_forward(e: torch.Tensor, want_f32: bool = True):

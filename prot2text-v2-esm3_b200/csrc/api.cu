@@ -153,12 +153,13 @@ int p2t_row_inv_norm(const float* rowsq, int nblk, const int* n_rows_dev, int ro
 
 int p2t_pool_fwd(const void* src, int src_is_f16, long long ld_src, int src_rows, const int* row_src, const float* inv_norm,
                  const int* seq_off, const int* chunk_off, const int* chunk_seq, int B, int D, int chunk_rows,
-                 int max_chunks, int mode, void* partial_ws, float* out, long long ld_out, void* stream) {
+                 int max_chunks, int mode, void* partial_ws, float* out, long long ld_out, void* p_bf16, float* p_f32,
+                 float* norm, void* stream) {
   if (!src || !seq_off || !chunk_off || !chunk_seq || !partial_ws || !out) return set_error(-1, "p2t_pool_fwd: null pointer");
   if (mode < 1 || mode > 3) return set_error(-1, "p2t_pool_fwd: mode must be MEAN, STD or MIX");
   if (max_chunks <= 0) return 0;
   return pool_forward(src, src_is_f16 != 0, ld_src, src_rows, row_src, inv_norm, seq_off, chunk_off, chunk_seq, B, D, chunk_rows,
-                      max_chunks, mode, reinterpret_cast<float2*>(partial_ws), out, ld_out, S(stream));
+                      max_chunks, mode, reinterpret_cast<float2*>(partial_ws), out, ld_out, p_bf16, p_f32, norm, S(stream));
 }
 
 int p2t_readout_last(const void* x, const int* counts, int B, int S_, int D, float* out, void* stream) {
@@ -181,6 +182,14 @@ int p2t_pool_bwd_coef(const float* de, long long ld_de, const float* stats, long
   if (mode != P2T_READOUT_MEAN && !stats) return set_error(-1, "p2t_pool_bwd_coef: stats required for std/mix");
   return pool_bwd_coef(de, ld_de, stats, ld_stats, seq_off, B, D, mode, c1, c2, S(stream));
 }
+int p2t_loss_bwd_coef(const float* dS, const float* t_f32, const float* p_f32, const float* pnorm, const float* stats,
+                      const int* seq_off, const float* dloss, int R, int B, int C, int D, float tau, float* c1,
+                      float* c2, void* stream) {
+  if (!dS || !t_f32 || !p_f32 || !pnorm || !stats || !seq_off || !c1 || !c2) return set_error(-1, "p2t_loss_bwd_coef: null pointer");
+  if (R > B || tau <= 0.f) return set_error(-1, "p2t_loss_bwd_coef: bad sizes");
+  return loss_bwd_coef(dS, t_f32, p_f32, pnorm, stats, seq_off, dloss, R, B, C, D, tau, c1, c2, S(stream));
+}
+
 int p2t_readout_bwd(const void* x, const void* mask, int mask_bytes, int B, int S_, int D, const float* c1,
                     const float* c2, void* dx, void* stream) {
   if (!x || !mask || !c1 || !c2 || !dx) return set_error(-1, "p2t_readout_bwd: null pointer");

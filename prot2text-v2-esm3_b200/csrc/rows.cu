@@ -162,8 +162,17 @@ __global__ void row_inv_norm_kernel(const float* __restrict__ rowsq, int nblk, c
                                     float* __restrict__ inv_norm) {
   const int n = min(*n_rows, cap);
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int j = 0; j < nblk; ++j) s += rowsq[(long long)j * cap + r];
+    // fixed summation order (four interleaved partial sums), all loads of a trip in flight together
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int j = 0;
+    for (; j + 4 <= nblk; j += 4) {
+      s0 += rowsq[(long long)j * cap + r];
+      s1 += rowsq[(long long)(j + 1) * cap + r];
+      s2 += rowsq[(long long)(j + 2) * cap + r];
+      s3 += rowsq[(long long)(j + 3) * cap + r];
+    }
+    for (; j < nblk; ++j) s0 += rowsq[(long long)j * cap + r];
+    const float s = (s0 + s1) + (s2 + s3);
     inv_norm[r] = 1.f / fmaxf(sqrtf(s), kEpsNorm);
   }
 }
@@ -372,6 +381,47 @@ __global__ void pool_finalize_kernel(const float2* __restrict__ partial, const i
   else { o[col] = mu; o[D + col] = sd; }
 }
 
+// phase 2 of the fused step ('mix' readout followed by F.normalize, scripts/train_contrast.py:277-281 + :354/:365):
+// combine the chunks, write stats = (mean | std), then p = stats / max(|stats|, eps).  grid B, block 1024.
+__global__ void __launch_bounds__(1024)
+pool_finalize_normalize_kernel(const float2* __restrict__ partial, const int* __restrict__ seq_off,
+                               const int* __restrict__ chunk_off, int D, int rc, float* __restrict__ stats,
+                               __nv_bfloat16* __restrict__ p_bf16, float* __restrict__ p_f32, float* __restrict__ norm_out) {
+  const int b = blockIdx.x;
+  const int c0 = chunk_off[b], c1 = chunk_off[b + 1];
+  const int n_total = seq_off[b + 1] - seq_off[b];
+  float* st = stats + (long long)b * 2 * D;
+  __shared__ float sh[32];
+  float sq = 0.f;
+  for (int col = threadIdx.x; col < D; col += 1024) {
+    float n = 0.f, mean = 0.f, m2 = 0.f;
+    for (int c = c0; c < c1; ++c) {
+      const float nc = (float)min(rc, n_total - (c - c0) * rc);
+      const float2 pc = partial[(long long)c * D + col];
+      const float tot = n + nc;
+      const float delta = pc.x - mean;
+      mean += delta * (nc / tot);
+      m2 += pc.y + delta * delta * (n * nc / tot);
+      n = tot;
+    }
+    float mu, sd;
+    if (n_total > 0) { mu = mean; sd = sqrtf(m2 / n); }
+    else { mu = __int_as_float(0x7fc00000); sd = mu; }  // 0/0 in the reference
+    st[col] = mu;
+    st[D + col] = sd;
+    sq = fmaf(mu, mu, fmaf(sd, sd, sq));
+  }
+  sq = block_sum<1024>(sq, sh);  // (its barriers also make the stats written above visible to the whole block)
+  const float nrm = sqrtf(sq);
+  const float inv = 1.f / fmaxf(nrm, kEpsNorm);
+  if (threadIdx.x == 0 && norm_out) norm_out[b] = nrm;
+  for (int i = threadIdx.x; i < 2 * D; i += 1024) {
+    const float v = st[i] * inv;
+    if (p_f32) p_f32[(long long)b * 2 * D + i] = v;
+    if (p_bf16) p_bf16[(long long)b * 2 * D + i] = __float2bfloat16_rn(v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // L2 normalisation of pooled embeddings: p = e / max(|e|, eps).  grid B, block 256.
 // ------------------------------------------------------------------------------------------------
@@ -438,6 +488,56 @@ __global__ void pool_bwd_coef_kernel(const float* __restrict__ de, long long ld_
   }
   c1[(long long)b * D + col] = k1;
   c2[(long long)b * D + col] = k2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward from dLogits to the pooling coefficients in ONE kernel (small similarity blocks), grid B, block 1024:
+//   dp_i = (dloss / tau) * sum_j dS_ij t_j          (rows i >= R were dropped by the segment split: dp = 0)
+//   de_i = (dp_i - p_i (p_i . dp_i)) / |e_i|        (autograd of F.normalize, eps clamp as in l2norm_bwd_kernel)
+//   c2 = dsd / (n sd),  c1 = dmu / n - c2 mu        ('mix': de = (dmu | dsd)), so that dy_r = c1 + c2 * y_r
+// de lives in shared memory (E floats).  t is fp32 [C][E]; dS fp32 [R][C] already carries the 1/R of the mean.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+loss_bwd_coef_kernel(const float* __restrict__ dS, const float* __restrict__ t, const float* __restrict__ p,
+                     const float* __restrict__ pnorm, const float* __restrict__ stats, const int* __restrict__ seq_off,
+                     const float* __restrict__ dloss, int R, int C, int D, float inv_tau, float* __restrict__ c1,
+                     float* __restrict__ c2) {
+  extern __shared__ float de_s[];  // [2 * D]
+  __shared__ float sh[32];
+  const int i = blockIdx.x;
+  const int E = 2 * D;
+  const float scale = inv_tau * (dloss ? dloss[0] : 1.f);
+  const float* pr = p + (long long)i * E;
+  float dot = 0.f;
+  for (int e0 = threadIdx.x * 4; e0 < E; e0 += 4096) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < R) {
+      const float* ds = dS + (long long)i * C;
+      for (int j = 0; j < C; ++j) {
+        const float w = ds[j];
+        const float4 tv = __ldg(reinterpret_cast<const float4*>(t + (long long)j * E + e0));
+        acc.x = fmaf(w, tv.x, acc.x); acc.y = fmaf(w, tv.y, acc.y); acc.z = fmaf(w, tv.z, acc.z); acc.w = fmaf(w, tv.w, acc.w);
+      }
+    }
+    acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale;
+    const float4 pv = *reinterpret_cast<const float4*>(pr + e0);
+    dot = fmaf(acc.x, pv.x, fmaf(acc.y, pv.y, fmaf(acc.z, pv.z, fmaf(acc.w, pv.w, dot))));
+    *reinterpret_cast<float4*>(de_s + e0) = acc;
+  }
+  dot = block_sum<1024>(dot, sh);
+  const float nrm = pnorm[i];
+  const bool clamped = nrm < kEpsNorm;
+  const float inv = 1.f / fmaxf(nrm, kEpsNorm);
+  const float n = (float)(seq_off[i + 1] - seq_off[i]);
+  const float* st = stats + (long long)i * E;
+  for (int col = threadIdx.x; col < D; col += 1024) {
+    const float dmu = clamped ? de_s[col] * inv : (de_s[col] - pr[col] * dot) * inv;
+    const float dsd = clamped ? de_s[D + col] * inv : (de_s[D + col] - pr[D + col] * dot) * inv;
+    const float mu = st[col], sd = st[D + col];
+    const float k2 = dsd / (n * sd);  // inf/NaN when sd == 0, as autograd on the reference
+    c1[(long long)i * D + col] = dmu / n - k2 * mu;
+    c2[(long long)i * D + col] = k2;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -668,7 +768,7 @@ scale_rows_kernel(const __half* __restrict__ a, const float* __restrict__ rowsq,
   const int nvec = D >> 3;
   for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps_total) {
     float s = 0.f;
-    for (int j = lane; j < nblk; j += 32) s += rowsq[(long long)j * cap + row];
+    for (int j = lane; j < nblk; j += 32) s += rowsq[(long long)j * cap + row];  // (order differs from row_inv_norm: module API only)
     s = warp_sum(s);
     const float inv = 1.f / fmaxf(sqrtf(s), kEpsNorm);
     if (lane == 0 && inv_norm_out) inv_norm_out[row] = inv;
@@ -813,7 +913,8 @@ int row_inv_norm(const float* rowsq, int nblk, const int* n_rows, int cap, float
 
 int pool_forward(const void* src, bool src_is_f16, long long ld_src, int src_rows, const int* row_src, const float* inv_norm,
                  const int* seq_off, const int* chunk_off, const int* chunk_seq, int B, int D, int rc, int max_chunks,
-                 int mode, float2* partial, float* out, long long ld_out, cudaStream_t st) {
+                 int mode, float2* partial, float* out, long long ld_out, void* norm_p_bf16, float* norm_p_f32,
+                 float* norm_out, cudaStream_t st) {
   if (D % 8) return set_error(-1, "pool_forward: D must be a multiple of 8");
   if (rc != POOL_BOX_ROWS) return set_error(-1, "pool_forward: chunk_rows must be 64");
   if (src_rows <= 0) return set_error(-1, "pool_forward: source row count required");
@@ -837,6 +938,12 @@ int pool_forward(const void* src, bool src_is_f16, long long ld_src, int src_row
   else
     pool_partial_kernel<false><<<grid, POOL_THREADS, smem, st>>>(tmap, sp, ld_src, row_src, inv_norm, chunk_off, desc, B, D, partial);
   if (int r = check_launch("pool_partial_kernel")) return r;
+  if (norm_p_bf16 != nullptr || norm_p_f32 != nullptr) {
+    if (mode != 3 || ld_out != 2LL * D) return set_error(-1, "pool_forward: fused normalise needs the dense 'mix' layout");
+    pool_finalize_normalize_kernel<<<B, 1024, 0, st>>>(partial, seq_off, chunk_off, D, rc, out,
+                                                       reinterpret_cast<__nv_bfloat16*>(norm_p_bf16), norm_p_f32, norm_out);
+    return check_launch("pool_finalize_normalize_kernel");
+  }
   dim3 g2(B, (D + 255) / 256);
   pool_finalize_kernel<<<g2, 256, 0, st>>>(partial, seq_off, chunk_off, B, D, rc, mode, out, ld_out);
   return check_launch("pool_finalize_kernel");
@@ -855,6 +962,22 @@ int pool_bwd_coef(const float* de, long long ld_de, const float* stats, long lon
   dim3 g(B, (D + 255) / 256);
   pool_bwd_coef_kernel<<<g, 256, 0, st>>>(de, ld_de, stats, ld_stats, seq_off, D, mode, c1, c2);
   return check_launch("pool_bwd_coef_kernel");
+}
+
+int loss_bwd_coef(const float* dS, const float* t, const float* p, const float* pnorm, const float* stats,
+                  const int* seq_off, const float* dloss, int R, int B, int C, int D, float tau, float* c1, float* c2,
+                  cudaStream_t st) {
+  if (D % 4) return set_error(-1, "loss_bwd_coef: D must be a multiple of 4");
+  const int smem = 2 * D * (int)sizeof(float);
+  if (smem > 200 * 1024) return set_error(-1, "loss_bwd_coef: embedding too wide for shared memory");
+  static int configured_for = 0;
+  if (smem > 48 * 1024 && smem > configured_for) {
+    cudaError_t e = cudaFuncSetAttribute(loss_bwd_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_error((int)e, "loss_bwd_coef: cannot reserve %d bytes of shared memory", smem);
+    configured_for = smem;
+  }
+  loss_bwd_coef_kernel<<<B, 1024, smem, st>>>(dS, t, p, pnorm, stats, seq_off, dloss, R, C, D, 1.f / tau, c1, c2);
+  return check_launch("loss_bwd_coef_kernel");
 }
 
 int adapter_tail_backward(const void* a, const void* g, const float* inv_norm, const int* seq_off, const int* chunk_off,

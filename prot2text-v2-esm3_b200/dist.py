@@ -23,12 +23,20 @@ import torch.distributed as dist
 from . import step as _step
 
 
-def all_gather_embeddings(t_local: torch.Tensor, group=None) -> torch.Tensor:
-    """(B, E) per rank -> (W*B, E), rank-major.  One NCCL all-gather (B*E*2 bytes per rank)."""
+def all_gather_embeddings(t_local: torch.Tensor, group=None, async_op: bool = False):
+    """(B, E) per rank -> (W*B, E), rank-major.  One NCCL all-gather (B*E*elem bytes per rank).
+    With async_op the collective stays on NCCL's stream and a zero-argument callable is returned that waits
+    for it (on the then-current stream) and hands out the gathered tensor."""
     world = dist.get_world_size(group)
     out = torch.empty(world * t_local.shape[0], t_local.shape[1], dtype=t_local.dtype, device=t_local.device)
-    dist.all_gather_into_tensor(out, t_local.contiguous(), group=group)
-    return out
+    work = dist.all_gather_into_tensor(out, t_local.contiguous(), group=group, async_op=async_op)
+    if not async_op:
+        return out
+
+    def wait():
+        work.wait()
+        return out
+    return wait
 
 
 def merge_column_stats(col_max: torch.Tensor, col_sum: torch.Tensor, group=None):
@@ -60,7 +68,8 @@ def distributed_contrastive_step(residue_states, protein_mask, adapter, text_hid
     Accepts the padded (mask) or the packed (lengths) input form of `contrastive_step`."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     t_local = _step.text_embeddings(text_hidden, text_mask, dtype=torch.float32, text_lengths=text_lengths)
-    t_global = all_gather_embeddings(t_local, group) if world > 1 else t_local
+    # the gather runs on NCCL's stream behind the adapter GEMMs; it is waited for right before the similarity
+    t_global = all_gather_embeddings(t_local, group, async_op=True) if world > 1 else t_local
     B = residue_lengths.shape[0] if residue_lengths is not None else residue_states.shape[0]
     labels = torch.arange(rank * B, (rank + 1) * B, device=residue_states.device, dtype=torch.int32)
     hook = (lambda m, s: merge_column_stats(m, s, group)) if (symmetric and world > 1) else None

@@ -49,13 +49,14 @@ def text_embeddings(text_hidden: torch.Tensor, text_mask: Optional[torch.Tensor]
             raise ValueError("with text_lengths, text_hidden must be packed rows (sum T_b, H)")
         H = th.shape[1]
         plan = _core.plan_packed(text_lengths, th.shape[0])
-        stats = _core.pool_forward(th, plan, H, row_src=None)
+        src, row_src = th, None
     else:
         B, T, H = th.shape
         plan = _core.plan_rows(text_mask)
-        stats = _core.pool_forward(th.view(B * T, H), plan, H, row_src=plan.row_src)
-    t_bf, t_f32, _ = _core.l2norm_forward(stats, want_f32=(dtype == torch.float32))
-    return t_f32 if dtype == torch.float32 else t_bf
+        src, row_src = th.view(B * T, H), plan.row_src
+    want_f32 = dtype == torch.float32
+    _, t_bf, t_f32, _ = _core.pool_forward(src, plan, H, row_src=row_src, normalize=True, want_f32=want_f32)
+    return t_f32 if want_f32 else t_bf
 
 
 class _ContrastiveStepFunction(torch.autograd.Function):
@@ -78,8 +79,9 @@ class _ContrastiveStepFunction(torch.autograd.Function):
         acts = _core.adapter_forward(xp, x_rows, plan.rows_cap, plan.n_rows, w1c, b1c, w2c, b2c,
                                      cfg["dropout_p"], cfg["seed"], need_grad)
         inv_norm = _core.row_inv_norm(acts)
-        stats = _core.pool_forward(acts.a, plan, d_out, row_src=None, inv_norm=inv_norm)
-        p_bf, p_f32, pnorm = _core.l2norm_forward(stats)
+        stats, p_bf, p_f32, pnorm = _core.pool_forward(acts.a, plan, d_out, row_src=None, inv_norm=inv_norm, normalize=True)
+        if callable(t_in):  # deferred text embeddings (e.g. an all-gather still in flight behind the adapter GEMMs)
+            t_in = t_in()
         if t_in.dtype == torch.float32:
             t_f32 = t_in.contiguous()
             t_bf = _core.to_bf16(t_f32)
@@ -105,16 +107,21 @@ class _ContrastiveStepFunction(torch.autograd.Function):
         ctx.state = None
         used = cfg["rows_used"]
         d_out = w2c.shape[0]
-        dp_used, _ = _core.infonce_backward(res, p_bf[:used], t_bf, cfg["tau"], need_dp=True, need_dt=False,
-                                            p_f32=p_f32[:used] if t_f32 is not None else None, t_f32=t_f32)
-        if used == p_bf.shape[0]:
-            dp = dp_used
-        else:  # rows dropped by the segment split get no gradient (reference :337, :357-359)
-            dp = torch.zeros_like(p_f32)
-            dp[:used] = dp_used
-        dp.mul_(dloss.to(torch.float32))
-        de = _core.l2norm_backward(dp, p_f32, pnorm)
-        c1, c2 = _core.pool_backward_coef(de, stats, plan, d_out, "mix")
+        if t_f32 is not None and res.dS_bf16 is None:
+            # small similarity block with fp32 embeddings: dLogits -> (c1, c2) in one kernel
+            c1, c2 = _core.loss_backward_coef(res, t_f32, p_f32, pnorm, stats, plan, d_out, cfg["tau"],
+                                              dloss.to(torch.float32).contiguous())
+        else:
+            dp_used, _ = _core.infonce_backward(res, p_bf[:used], t_bf, cfg["tau"], need_dp=True, need_dt=False,
+                                                p_f32=p_f32[:used] if t_f32 is not None else None, t_f32=t_f32)
+            if used == p_bf.shape[0]:
+                dp = dp_used
+            else:  # rows dropped by the segment split get no gradient (reference :337, :357-359)
+                dp = torch.zeros_like(p_f32)
+                dp[:used] = dp_used
+            dp.mul_(dloss.to(torch.float32))
+            de = _core.l2norm_backward(dp, p_f32, pnorm)
+            c1, c2 = _core.pool_backward_coef(de, stats, plan, d_out, "mix")
         dz2, db2 = _core.adapter_tail_backward(acts, inv_norm, plan, c1, c2)
         dw1, db1, dw2, _, _ = _core.adapter_backward(acts, dz2, w1c, w2c, need_db2=False)
         return None, None, dw1, db1, dw2, db2, None, None, None, None
@@ -133,7 +140,9 @@ def contrastive_step(residue_states: torch.Tensor, protein_mask: Optional[torch.
     residue_states (B, L, D_in) bf16 and protein_mask (B, L) come from the frozen protein encoder
     (models/esmc_qwen_arc.py:84-86); text_hidden (B_t, T, H) bf16 is hidden_states[16] of the frozen
     LLM with its attention mask (scripts/train_contrast.py:304), or pass already normalised
-    `text_embeds` (B_t, 2H), float32 (preferred) or bfloat16 — e.g. the all-gathered global negatives.  `labels[i]` is the text row
+    `text_embeds` (B_t, 2H), float32 (preferred) or bfloat16 — e.g. the all-gathered global negatives — or a
+    zero-argument callable returning them, which is invoked only when the loss needs them (so a collective
+    can run behind the adapter GEMMs).  `labels[i]` is the text row
     paired with protein i (default: i).  Ragged hand-over: with `residue_lengths` (B,),
     `residue_states` is the PACKED (sum L_b, D_in) row buffer and `protein_mask` is ignored; likewise
     `text_lengths` with packed `text_hidden` (see host_io.HostStager).  `contrastive_num_segments` reproduces the reference's
