@@ -106,10 +106,13 @@ int p2t_gather_rows(const void* src, long long ld_src, const int* row_src, const
  * x has x_rows rows allocated (TMA zero-fills beyond); outputs have rows_cap rows.
  * Weights in nn.Linear layout (out, in), bf16.  dropout_p = 0 is eval mode; otherwise a Philox
  * mask keyed by (seed, layer, row, column) with multiplier 1/(1-p) (nn.Dropout, :63,:66).
+ * seed_dev (optional, device): its value is added to `seed` on the device — a CUDA-graph replay freezes
+ * kernel arguments, so the replaying host bumps this word instead.
  * ------------------------------------------------------------------------------------------- */
 int p2t_adapter_fwd(const void* x, int x_rows, const void* w1, const void* b1, const void* w2, const void* b2, int d_in,
                     int d_mid, int d_out, int rows_cap, const int* n_rows_dev, void* h1, void* g1, void* a,
-                    void* g2, float* rowsq, float dropout_p, unsigned long long seed, int cta_group, void* stream);
+                    void* g2, float* rowsq, float dropout_p, unsigned long long seed, const unsigned long long* seed_dev,
+                    int cta_group, void* stream);
 
 /* y[row] = a[row] / max(|a[row]|, 1e-12) for the first n rows: the (B, L, d_out) tensor that
  * ModalityAdapter.forward returns (:67-68).  inv_norm[row] is saved for backward (may be NULL). */

@@ -13,12 +13,13 @@ from ._lib import P2TError
 from .adapter import ModalityAdapter, ModalityAdapterConfig
 from .losses import BatchInfoNCELoss, SegmentedBatchInfoNCELoss, SymmetricInfoNCELoss
 from .readout import readout_embeddings
+from .graph import GraphedContrastiveStep
 from .host_io import HostStager, StagedBatch
 from .step import StepAux, contrastive_step, text_embeddings
 
 __all__ = [
     "ModalityAdapter", "ModalityAdapterConfig", "readout_embeddings", "BatchInfoNCELoss",
     "SegmentedBatchInfoNCELoss", "SymmetricInfoNCELoss", "contrastive_step", "text_embeddings", "StepAux",
-    "HostStager", "StagedBatch",
+    "HostStager", "StagedBatch", "GraphedContrastiveStep",
     "P2TError",
 ]

@@ -161,7 +161,8 @@ class AdapterActs:
 
 
 def adapter_forward(x: torch.Tensor, x_rows: int, rows_cap: int, n_rows: torch.Tensor, w1, b1, w2, b2,
-                    dropout_p: float, seed: int, need_grad: bool, cta_group: Optional[int] = None) -> AdapterActs:
+                    dropout_p: float, seed: int, need_grad: bool, cta_group: Optional[int] = None,
+                    seed_dev: Optional[torch.Tensor] = None) -> AdapterActs:
     d_mid, d_in = w1.shape
     d_out = w2.shape[0]
     dev = x.device
@@ -174,7 +175,7 @@ def adapter_forward(x: torch.Tensor, x_rows: int, rows_cap: int, n_rows: torch.T
     rowsq = torch.empty(nblk, rows_cap, dtype=torch.float32, device=dev)
     _lib.call("p2t_adapter_fwd", _ptr(x), x_rows, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), d_in, d_mid, d_out,
               rows_cap, _ptr(n_rows), _ptr(h1), _ptr(g1), _ptr(a), _ptr(g2), _ptr(rowsq), float(dropout_p),
-              int(seed) & 0xFFFFFFFFFFFFFFFF, cta_group or default_cta_group(), _stream())
+              int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(seed_dev), cta_group or default_cta_group(), _stream())
     return AdapterActs(x=x, x_rows=x_rows, h1=h1, g1=g1, a=a, g2=g2, rowsq=rowsq, nblk=nblk, rows_cap=rows_cap,
                        n_rows=n_rows)
 

@@ -520,7 +520,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     e.d0 = reinterpret_cast<char*>(p.d0); e.d1 = reinterpret_cast<char*>(p.d1);
     e.ldd0 = p.ldd0; e.ldd1 = p.ldd1; e.ldaux = p.ldaux; e.aux = p.aux;
     e.alpha = p.alpha; e.scale = p.drop.scale; e.threshold = p.drop.threshold; e.layer = p.drop.layer;
-    e.key = make_uint2(static_cast<uint32_t>(p.drop.seed), static_cast<uint32_t>(p.drop.seed >> 32));
+    const unsigned long long seed = p.drop.seed + (p.drop.seed_dev ? *p.drop.seed_dev : 0ull);
+    e.key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
     e.nostore = p.debug_nostore;
     const int rows_cap = p.rows_cap;
     // the interior path moves 16-byte vectors: every row of every output/aux tensor must start 16-byte aligned

@@ -61,6 +61,8 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 // ------------------------------------------------------------------------------------------------
 struct DropoutParams {
   unsigned long long seed;
+  const unsigned long long* seed_dev;  // optional: the seed is read from device memory and ADDED to `seed`
+                                       // (CUDA-graph replays bump it on the device; kernel parameters are frozen)
   float scale;         // 1/(1-p)
   uint32_t threshold;  // 0 -> dropout disabled
   uint32_t layer;      // 1 = after fc1 GELU, 2 = after fc2 GELU

@@ -59,71 +59,84 @@ def text_embeddings(text_hidden: torch.Tensor, text_mask: Optional[torch.Tensor]
     return t_f32 if want_f32 else t_bf
 
 
+def step_forward(x, prot_mask, w1, b1, w2, b2, t_in, labels, cfg: dict, aux: StepAux, need_grad: bool):
+    """Forward of the fused step on raw tensors (no autograd): returns (loss, state for step_backward or None)."""
+    for t, name in ((x, "residue states"), (w1, "fc1.weight"), (b1, "fc1.bias"), (w2, "fc2.weight"), (b2, "fc2.bias")):
+        _core.require_cuda_bf16(t, name)
+    d_out = w2.shape[0]
+    w1c, b1c, w2c, b2c = w1.contiguous(), b1.contiguous(), w2.contiguous(), b2.contiguous()
+    if cfg["packed"]:  # residue rows already packed, prot_mask holds the per-sequence lengths
+        xp = x.contiguous()
+        plan = _core.plan_packed(prot_mask, xp.shape[0])
+        x_rows = xp.shape[0]
+    else:
+        B, L, d_in = x.shape
+        plan = _core.plan_rows(prot_mask)
+        xp = _core.gather_rows(x.contiguous().view(B * L, d_in), plan)
+        x_rows = plan.rows_cap
+    acts = _core.adapter_forward(xp, x_rows, plan.rows_cap, plan.n_rows, w1c, b1c, w2c, b2c,
+                                 cfg["dropout_p"], cfg["seed"], need_grad, seed_dev=cfg.get("seed_dev"))
+    inv_norm = _core.row_inv_norm(acts)
+    stats, p_bf, p_f32, pnorm = _core.pool_forward(acts.a, plan, d_out, row_src=None, inv_norm=inv_norm, normalize=True)
+    if callable(t_in):  # deferred text embeddings (e.g. an all-gather still in flight behind the adapter GEMMs)
+        t_in = t_in()
+    if t_in.dtype == torch.float32:
+        t_f32 = t_in.contiguous()
+        t_bf = _core.to_bf16(t_f32)
+    else:
+        _core.require_cuda_bf16(t_in, "text_embeds")
+        t_f32, t_bf = None, t_in.contiguous()
+    used = cfg["rows_used"]
+    hook = cfg.get("col_stats_hook")
+    res = _core.infonce_forward(p_bf[:used], t_bf, labels[:used], cfg["tau"], w_row=cfg["w_row"], w_col=cfg["w_col"],
+                                need_grad=need_grad, want_col_argmax=True, col_stats_hook=hook,
+                                p_f32=p_f32[:used] if t_f32 is not None else None, t_f32=t_f32,
+                                loss_scale=cfg.get("loss_scale"),
+                                all_cols_labelled=cfg.get("all_cols_labelled", False))
+    aux.protein_embeddings, aux.text_embeddings = p_bf, t_bf
+    aux.argmax_row, aux.argmax_col, aux.n_rows = res.argmax_row, res.argmax_col, plan.n_rows
+    state = (plan, acts, stats, inv_norm, p_bf, p_f32, pnorm, res, t_bf, t_f32, w1c, w2c, cfg) if need_grad else None
+    return res.loss, state
+
+
+def step_backward(state, dloss: Optional[torch.Tensor]):
+    """Backward of the fused step: (dW1, db1, dW2, db2) in bf16 for the upstream gradient `dloss` (device scalar;
+    None = 1)."""
+    plan, acts, stats, inv_norm, p_bf, p_f32, pnorm, res, t_bf, t_f32, w1c, w2c, cfg = state
+    used = cfg["rows_used"]
+    d_out = w2c.shape[0]
+    dl = None if dloss is None else dloss.to(torch.float32).contiguous()
+    if t_f32 is not None and res.dS_bf16 is None:
+        # small similarity block with fp32 embeddings: dLogits -> (c1, c2) in one kernel
+        c1, c2 = _core.loss_backward_coef(res, t_f32, p_f32, pnorm, stats, plan, d_out, cfg["tau"], dl)
+    else:
+        dp_used, _ = _core.infonce_backward(res, p_bf[:used], t_bf, cfg["tau"], need_dp=True, need_dt=False,
+                                            p_f32=p_f32[:used] if t_f32 is not None else None, t_f32=t_f32)
+        if used == p_bf.shape[0]:
+            dp = dp_used
+        else:  # rows dropped by the segment split get no gradient (reference :337, :357-359)
+            dp = torch.zeros_like(p_f32)
+            dp[:used] = dp_used
+        if dl is not None:
+            dp.mul_(dl)
+        de = _core.l2norm_backward(dp, p_f32, pnorm)
+        c1, c2 = _core.pool_backward_coef(de, stats, plan, d_out, "mix")
+    dz2, db2 = _core.adapter_tail_backward(acts, inv_norm, plan, c1, c2)
+    dw1, db1, dw2, _, _ = _core.adapter_backward(acts, dz2, w1c, w2c, need_db2=False)
+    return dw1, db1, dw2, db2
+
+
 class _ContrastiveStepFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, prot_mask, w1, b1, w2, b2, t_in, labels, cfg: dict, aux: StepAux):
-        for t, name in ((x, "residue states"), (w1, "fc1.weight"), (b1, "fc1.bias"), (w2, "fc2.weight"), (b2, "fc2.bias")):
-            _core.require_cuda_bf16(t, name)
-        d_out = w2.shape[0]
-        need_grad = any(ctx.needs_input_grad[2:6])
-        w1c, b1c, w2c, b2c = w1.contiguous(), b1.contiguous(), w2.contiguous(), b2.contiguous()
-        if cfg["packed"]:  # residue rows already packed, prot_mask holds the per-sequence lengths
-            xp = x.contiguous()
-            plan = _core.plan_packed(prot_mask, xp.shape[0])
-            x_rows = xp.shape[0]
-        else:
-            B, L, d_in = x.shape
-            plan = _core.plan_rows(prot_mask)
-            xp = _core.gather_rows(x.contiguous().view(B * L, d_in), plan)
-            x_rows = plan.rows_cap
-        acts = _core.adapter_forward(xp, x_rows, plan.rows_cap, plan.n_rows, w1c, b1c, w2c, b2c,
-                                     cfg["dropout_p"], cfg["seed"], need_grad)
-        inv_norm = _core.row_inv_norm(acts)
-        stats, p_bf, p_f32, pnorm = _core.pool_forward(acts.a, plan, d_out, row_src=None, inv_norm=inv_norm, normalize=True)
-        if callable(t_in):  # deferred text embeddings (e.g. an all-gather still in flight behind the adapter GEMMs)
-            t_in = t_in()
-        if t_in.dtype == torch.float32:
-            t_f32 = t_in.contiguous()
-            t_bf = _core.to_bf16(t_f32)
-        else:
-            _core.require_cuda_bf16(t_in, "text_embeds")
-            t_f32, t_bf = None, t_in.contiguous()
-        used = cfg["rows_used"]
-        hook = cfg.get("col_stats_hook")
-        res = _core.infonce_forward(p_bf[:used], t_bf, labels[:used], cfg["tau"], w_row=cfg["w_row"], w_col=cfg["w_col"],
-                                    need_grad=need_grad, want_col_argmax=True, col_stats_hook=hook,
-                                    p_f32=p_f32[:used] if t_f32 is not None else None, t_f32=t_f32,
-                                    loss_scale=cfg.get("loss_scale"),
-                                    all_cols_labelled=cfg.get("all_cols_labelled", False))
-        aux.protein_embeddings, aux.text_embeddings = p_bf, t_bf
-        aux.argmax_row, aux.argmax_col, aux.n_rows = res.argmax_row, res.argmax_col, plan.n_rows
-        if need_grad:
-            ctx.state = (plan, acts, stats, inv_norm, p_bf, p_f32, pnorm, res, t_bf, t_f32, w1c, w2c, cfg)
-        return res.loss
+        loss, ctx.state = step_forward(x, prot_mask, w1, b1, w2, b2, t_in, labels, cfg, aux,
+                                       need_grad=any(ctx.needs_input_grad[2:6]))
+        return loss
 
     @staticmethod
     def backward(ctx, dloss):
-        plan, acts, stats, inv_norm, p_bf, p_f32, pnorm, res, t_bf, t_f32, w1c, w2c, cfg = ctx.state
-        ctx.state = None
-        used = cfg["rows_used"]
-        d_out = w2c.shape[0]
-        if t_f32 is not None and res.dS_bf16 is None:
-            # small similarity block with fp32 embeddings: dLogits -> (c1, c2) in one kernel
-            c1, c2 = _core.loss_backward_coef(res, t_f32, p_f32, pnorm, stats, plan, d_out, cfg["tau"],
-                                              dloss.to(torch.float32).contiguous())
-        else:
-            dp_used, _ = _core.infonce_backward(res, p_bf[:used], t_bf, cfg["tau"], need_dp=True, need_dt=False,
-                                                p_f32=p_f32[:used] if t_f32 is not None else None, t_f32=t_f32)
-            if used == p_bf.shape[0]:
-                dp = dp_used
-            else:  # rows dropped by the segment split get no gradient (reference :337, :357-359)
-                dp = torch.zeros_like(p_f32)
-                dp[:used] = dp_used
-            dp.mul_(dloss.to(torch.float32))
-            de = _core.l2norm_backward(dp, p_f32, pnorm)
-            c1, c2 = _core.pool_backward_coef(de, stats, plan, d_out, "mix")
-        dz2, db2 = _core.adapter_tail_backward(acts, inv_norm, plan, c1, c2)
-        dw1, db1, dw2, _, _ = _core.adapter_backward(acts, dz2, w1c, w2c, need_db2=False)
+        state, ctx.state = ctx.state, None
+        dw1, db1, dw2, db2 = step_backward(state, dloss)
         return None, None, dw1, db1, dw2, db2, None, None, None, None
 
 
@@ -134,7 +147,8 @@ def contrastive_step(residue_states: torch.Tensor, protein_mask: Optional[torch.
                      contrastive_num_segments: int = 1, symmetric: bool = False,
                      labels: Optional[torch.Tensor] = None, aux: Optional[StepAux] = None,
                      col_stats_hook=None, loss_scale: Optional[float] = None,
-                     all_cols_labelled: bool = False) -> torch.Tensor:
+                     all_cols_labelled: bool = False, seed_dev: Optional[torch.Tensor] = None,
+                     _raw: bool = False) -> torch.Tensor:
     """One Stage-1 step from trunk outputs to the (differentiable) fp32 loss.
 
     residue_states (B, L, D_in) bf16 and protein_mask (B, L) come from the frozen protein encoder
@@ -147,7 +161,8 @@ def contrastive_step(residue_states: torch.Tensor, protein_mask: Optional[torch.
     `residue_states` is the PACKED (sum L_b, D_in) row buffer and `protein_mask` is ignored; likewise
     `text_lengths` with packed `text_hidden` (see host_io.HostStager).  `contrastive_num_segments` reproduces the reference's
     segment averaging including its dropping of the remainder rows; `symmetric` adds the
-    text->protein term.
+    text->protein term.  `seed_dev` (int64 device tensor, 1 element): dropout seed read on the device instead
+    of drawn from torch's CPU generator (CUDA-graph replays, see graph.GraphedContrastiveStep).
     """
     if text_embeds is None:
         if text_hidden is None or (text_mask is None and text_lengths is None):
@@ -166,9 +181,14 @@ def contrastive_step(residue_states: torch.Tensor, protein_mask: Optional[torch.
         labels = torch.arange(B, device=residue_states.device, dtype=torch.int32)
     p = adapter.dropout_p()
     cfg = dict(tau=float(temperature), w_row=0.5 if symmetric else 1.0, w_col=0.5 if symmetric else 0.0,
-               dropout_p=p, seed=_draw_seed() if p > 0 else 0, rows_used=seg * contrastive_num_segments, packed=packed,
+               dropout_p=p, seed=_draw_seed() if (p > 0 and seed_dev is None) else 0, seed_dev=seed_dev,
+               rows_used=seg * contrastive_num_segments, packed=packed,
                col_stats_hook=col_stats_hook, loss_scale=loss_scale, all_cols_labelled=all_cols_labelled)
     aux = aux if aux is not None else StepAux()
+    if _raw:  # graph capture: no autograd, the caller runs step_backward itself
+        return step_forward(residue_states, residue_lengths if packed else protein_mask, adapter.fc1.weight.detach(),
+                            adapter.fc1.bias.detach(), adapter.fc2.weight.detach(), adapter.fc2.bias.detach(),
+                            text_embeds, labels, cfg, aux, need_grad=True)
     return _ContrastiveStepFunction.apply(residue_states, residue_lengths if packed else protein_mask,
                                           adapter.fc1.weight, adapter.fc1.bias,
                                           adapter.fc2.weight, adapter.fc2.bias, text_embeds, labels, cfg, aux)

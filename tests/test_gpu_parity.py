@@ -613,3 +613,46 @@ def test_host_stager_rejects_masks_with_holes_and_device_tensors(p2t, dev):
         stager.submit(x.to(dev), ok.to(dev), x, ok)
     with pytest.raises(p2t.P2TError, match="without a submitted"):
         stager.take()
+
+
+# --------------------------------------------------------------------------------------------------
+# CUDA-graph replay of the step
+# --------------------------------------------------------------------------------------------------
+def test_graphed_step_replays_bit_identically_to_the_eager_step(p2t, synth, dev):
+    sb = synth.make_config_batch("cfg1_esm2_t6_llama1b", weight_gain=2.5)
+    ad = make_adapter(p2t, dev, sb.w1, sb.b1, sb.w2, sb.b2)  # eval mode: no dropout, results comparable bit for bit
+    x, pm, text, tm = sb.x.to(dev), sb.prot_mask.to(dev), sb.text.to(dev), sb.text_mask.to(dev)
+    loss = p2t.contrastive_step(x, pm, ad, text, tm)
+    loss.backward()
+    g_ref = {k: v.clone() for k, v in adapter_grads(ad).items()}
+    l_ref = loss.detach().clone()
+    ad.zero_grad(set_to_none=True)
+    step = p2t.GraphedContrastiveStep(ad, x, pm, text, tm)
+    assert step.launches_per_replay >= 20
+    for _ in range(3):
+        out = step.replay()
+    assert torch.equal(out, l_ref) and all(torch.equal(g_ref[k], adapter_grads(ad)[k]) for k in PARAMS)
+    # new data in the SAME input buffers (shorter sequences: the ragged extents are read on the device)
+    sb2 = synth.make_config_batch("cfg1_esm2_t6_llama1b", weight_gain=2.5, seed=77)
+    L2, T2 = min(sb2.x.shape[1], x.shape[1]), min(sb2.text.shape[1], text.shape[1])
+    x.zero_(); pm.zero_(); text.zero_(); tm.zero_()
+    x[:, :L2] = sb2.x[:, :L2].to(dev); pm[:, :L2] = sb2.prot_mask[:, :L2].to(dev)
+    text[:, :T2] = sb2.text[:, :T2].to(dev); tm[:, :T2] = sb2.text_mask[:, :T2].to(dev)
+    x.mul_(pm[..., None].to(x.dtype))
+    out2 = step.replay().clone()
+    g2 = {k: v.clone() for k, v in adapter_grads(ad).items()}
+    ad.zero_grad(set_to_none=True)
+    l_eager = p2t.contrastive_step(x, pm, ad, text, tm)
+    l_eager.backward()
+    assert torch.equal(out2, l_eager) and all(torch.equal(g2[k], adapter_grads(ad)[k]) for k in PARAMS)
+
+
+def test_graphed_step_draws_a_new_dropout_mask_every_replay(p2t, synth, dev):
+    sb = synth.make_config_batch("tiny", weight_gain=6.0)
+    ad = make_adapter(p2t, dev, sb.w1, sb.b1, sb.w2, sb.b2, train=True, p=0.3)
+    step = p2t.GraphedContrastiveStep(ad, sb.x.to(dev), sb.prot_mask.to(dev), sb.text.to(dev), sb.text_mask.to(dev), seed=5)
+    a = step.replay().item()
+    b = step.replay().item()
+    assert a != b and math.isfinite(a) and math.isfinite(b)
+    again = p2t.GraphedContrastiveStep(ad, sb.x.to(dev), sb.prot_mask.to(dev), sb.text.to(dev), sb.text_mask.to(dev), seed=5)
+    assert again.replay().item() == a  # same seed, same replay index: same mask
