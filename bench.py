@@ -273,7 +273,8 @@ def main():
 
     # ------------------------------ device-resident timing ------------------------------
     # Pass A (eager launches): the library brackets every GEMM launch with CUDA events on its stream -> roofline.
-    # Pass B (CUDA-graph replay of the same step through GraphedContrastiveStep, single GPU): the headline `value`.
+    # Pass B (CUDA-graph replay of the same step through GraphedContrastiveStep, single GPU; the sharded step with its
+    # NCCL all-gather stays eager): the headline `value`.
     for i in range(args.warmup):
         step(resident[i % nbatches])
     barrier()

@@ -149,13 +149,13 @@ int p2t_l2norm_bwd(const float* dp, const float* p_f32, const float* norm, int B
 /* backward of the readout: coefficient vectors with dy_r = c1[b] + c2[b] * y_r (fp32 [B][D]) */
 int p2t_pool_bwd_coef(const float* de, long long ld_de, const float* stats, long long ld_stats, const int* seq_off,
                       int B, int D, int mode, float* c1, float* c2, void* stream);
-/* The same coefficients straight from dLogits in one kernel, for small similarity blocks (autograd of
+/* The same coefficients straight from dLogits, for small / medium similarity blocks with fp32 embeddings (autograd of
  * :108-113 -> :365 -> :277-281): dp = dloss/tau * dS t (rows >= R get 0), F.normalize backward, 'mix' coefficients.
  * dS fp32 [R][C] (as left by p2t_infonce_ce), t_f32 [C][2D], p_f32 [B][2D], pnorm[B], stats [B][2D], dloss: device
- * scalar or NULL (= 1). */
+ * scalar or NULL (= 1); dp_ws: fp32 scratch [B][2D + ceil(2D/64)]. */
 int p2t_loss_bwd_coef(const float* dS, const float* t_f32, const float* p_f32, const float* pnorm, const float* stats,
-                      const int* seq_off, const float* dloss, int R, int B, int C, int D, float tau, float* c1,
-                      float* c2, void* stream);
+                      const int* seq_off, const float* dloss, int R, int B, int C, int D, float tau, float* dp_ws,
+                      float* c1, float* c2, void* stream);
 /* dx[b,r] = mask[b,r] * (c1[b] + c2[b] * x[b,r]) on a padded bf16 (B, S, D) tensor */
 int p2t_readout_bwd(const void* x, const void* mask, int mask_bytes, int B, int S, int D, const float* c1,
                     const float* c2, void* dx, void* stream);

@@ -238,8 +238,9 @@ def loss_backward_coef(res: "InfoNCEResult", t_f32: torch.Tensor, p_f32: torch.T
     R, C = res.dS.shape
     c1 = torch.empty(plan.B, D, dtype=torch.float32, device=p_f32.device)
     c2 = torch.empty(plan.B, D, dtype=torch.float32, device=p_f32.device)
+    ws = torch.empty(plan.B, 2 * D + (2 * D + 63) // 64, dtype=torch.float32, device=p_f32.device)
     _lib.call("p2t_loss_bwd_coef", _ptr(res.dS), _ptr(t_f32), _ptr(p_f32), _ptr(pnorm), _ptr(stats), _ptr(plan.seq_off),
-              _ptr(dloss), R, plan.B, C, D, float(tau), _ptr(c1), _ptr(c2), _stream())
+              _ptr(dloss), R, plan.B, C, D, float(tau), _ptr(ws), _ptr(c1), _ptr(c2), _stream())
     return c1, c2
 
 

@@ -24,7 +24,7 @@ SIGNATURES = {
     "p2t_adapter_fwd": [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _ull, _vp, _i, _vp],
     "p2t_adapter_scale_rows": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "p2t_pool_fwd": [_vp, _i, _ll, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _ll, _vp, _vp, _vp, _vp],
-    "p2t_loss_bwd_coef": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp],
+    "p2t_loss_bwd_coef": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp],
     "p2t_readout_last": [_vp, _vp, _i, _i, _i, _vp, _vp],
     "p2t_l2norm_fwd": [_vp, _i, _i, _vp, _vp, _vp, _vp],
     "p2t_l2norm_bwd": [_vp, _vp, _vp, _i, _i, _vp, _vp],

@@ -185,11 +185,11 @@ int p2t_pool_bwd_coef(const float* de, long long ld_de, const float* stats, long
   return pool_bwd_coef(de, ld_de, stats, ld_stats, seq_off, B, D, mode, c1, c2, S(stream));
 }
 int p2t_loss_bwd_coef(const float* dS, const float* t_f32, const float* p_f32, const float* pnorm, const float* stats,
-                      const int* seq_off, const float* dloss, int R, int B, int C, int D, float tau, float* c1,
-                      float* c2, void* stream) {
-  if (!dS || !t_f32 || !p_f32 || !pnorm || !stats || !seq_off || !c1 || !c2) return set_error(-1, "p2t_loss_bwd_coef: null pointer");
+                      const int* seq_off, const float* dloss, int R, int B, int C, int D, float tau, float* dp_ws,
+                      float* c1, float* c2, void* stream) {
+  if (!dS || !t_f32 || !p_f32 || !pnorm || !stats || !seq_off || !dp_ws || !c1 || !c2) return set_error(-1, "p2t_loss_bwd_coef: null pointer");
   if (R > B || tau <= 0.f) return set_error(-1, "p2t_loss_bwd_coef: bad sizes");
-  return loss_bwd_coef(dS, t_f32, p_f32, pnorm, stats, seq_off, dloss, R, B, C, D, tau, c1, c2, S(stream));
+  return loss_bwd_coef(dS, t_f32, p_f32, pnorm, stats, seq_off, dloss, R, B, C, D, tau, dp_ws, c1, c2, S(stream));
 }
 
 int p2t_readout_bwd(const void* x, const void* mask, int mask_bytes, int B, int S_, int D, const float* c1,

@@ -491,48 +491,80 @@ __global__ void pool_bwd_coef_kernel(const float* __restrict__ de, long long ld_
 }
 
 // ------------------------------------------------------------------------------------------------
-// Backward from dLogits to the pooling coefficients in ONE kernel (small similarity blocks), grid B, block 1024:
-//   dp_i = (dloss / tau) * sum_j dS_ij t_j          (rows i >= R were dropped by the segment split: dp = 0)
-//   de_i = (dp_i - p_i (p_i . dp_i)) / |e_i|        (autograd of F.normalize, eps clamp as in l2norm_bwd_kernel)
-//   c2 = dsd / (n sd),  c1 = dmu / n - c2 mu        ('mix': de = (dmu | dsd)), so that dy_r = c1 + c2 * y_r
-// de lives in shared memory (E floats).  t is fp32 [C][E]; dS fp32 [R][C] already carries the 1/R of the mean.
+// Backward from dLogits to the pooling coefficients (small / medium similarity blocks, fp32 embeddings), two kernels:
+//   (1) loss_bwd_dp_kernel, grid E/64, block 256: dp[:, slice] = (dloss / tau) * dS t[:, slice] for ALL rows
+//       (t's 64-column slab is read once by one CTA and shared by every row: the work scales with R*C*E / #SM,
+//       not with C per row) + per-slice partial dot products  dotp[i][slice] = sum_e dp_ie p_ie
+//   (2) loss_bwd_coef_kernel, grid B, block 1024: de_i = (dp_i - p_i (p_i . dp_i)) / |e_i| (autograd of
+//       F.normalize, eps clamp as in l2norm_bwd_kernel), then the 'mix' coefficients
+//       c2 = dsd / (n sd),  c1 = dmu / n - c2 mu   (de = (dmu | dsd)), so that dy_r = c1 + c2 * y_r
+// Rows i >= R were dropped by the segment split: dp = 0.  dS fp32 [R][C] already carries the 1/R of the mean.
 // ------------------------------------------------------------------------------------------------
+constexpr int LBW_SLICE = 64;
+__global__ void __launch_bounds__(256)
+loss_bwd_dp_kernel(const float* __restrict__ dS, const float* __restrict__ t, const float* __restrict__ p,
+                   const float* __restrict__ dloss, int R, int B, int C, int E, float inv_tau, float* __restrict__ dp,
+                   float* __restrict__ dotp) {
+  // thread = (row group rg of 8 -> rows rg, rg+8, ...; column quad cq -> 4 columns), 16 column quads x 16 row groups
+  const int e0 = blockIdx.x * LBW_SLICE;
+  const int cq = threadIdx.x & 15, rg = threadIdx.x >> 4;
+  const int col = e0 + cq * 4;
+  const float scale = inv_tau * (dloss ? dloss[0] : 1.f);
+  const int nslice = gridDim.x;
+  for (int i0 = 0; i0 < B; i0 += 64) {  // 64 rows per pass: 4 rows per thread
+    float4 acc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < E) {
+      for (int j = 0; j < C; ++j) {
+        const float4 tv = __ldg(reinterpret_cast<const float4*>(t + (long long)j * E + col));
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = i0 + rg + 16 * q;
+          const float w = (i < R) ? __ldg(dS + (long long)i * C + j) : 0.f;
+          acc[q].x = fmaf(w, tv.x, acc[q].x); acc[q].y = fmaf(w, tv.y, acc[q].y);
+          acc[q].z = fmaf(w, tv.z, acc[q].z); acc[q].w = fmaf(w, tv.w, acc[q].w);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = i0 + rg + 16 * q;
+      float d = 0.f;
+      if (i < B && col < E) {
+        const float4 v = make_float4(acc[q].x * scale, acc[q].y * scale, acc[q].z * scale, acc[q].w * scale);
+        *reinterpret_cast<float4*>(dp + (long long)i * E + col) = v;
+        const float4 pv = *reinterpret_cast<const float4*>(p + (long long)i * E + col);
+        d = fmaf(v.x, pv.x, fmaf(v.y, pv.y, fmaf(v.z, pv.z, v.w * pv.w)));
+      }
+      // the 16 column quads of a row sit in 16 consecutive lanes: fixed-order shuffle reduction
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      if (cq == 0 && i < B) dotp[(long long)i * nslice + blockIdx.x] = d;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(1024)
-loss_bwd_coef_kernel(const float* __restrict__ dS, const float* __restrict__ t, const float* __restrict__ p,
+loss_bwd_coef_kernel(const float* __restrict__ dp, const float* __restrict__ dotp, int nslice, const float* __restrict__ p,
                      const float* __restrict__ pnorm, const float* __restrict__ stats, const int* __restrict__ seq_off,
-                     const float* __restrict__ dloss, int R, int C, int D, float inv_tau, float* __restrict__ c1,
-                     float* __restrict__ c2) {
-  extern __shared__ float de_s[];  // [2 * D]
+                     int D, float* __restrict__ c1, float* __restrict__ c2) {
   __shared__ float sh[32];
   const int i = blockIdx.x;
   const int E = 2 * D;
-  const float scale = inv_tau * (dloss ? dloss[0] : 1.f);
-  const float* pr = p + (long long)i * E;
   float dot = 0.f;
-  for (int e0 = threadIdx.x * 4; e0 < E; e0 += 4096) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < R) {
-      const float* ds = dS + (long long)i * C;
-      for (int j = 0; j < C; ++j) {
-        const float w = ds[j];
-        const float4 tv = __ldg(reinterpret_cast<const float4*>(t + (long long)j * E + e0));
-        acc.x = fmaf(w, tv.x, acc.x); acc.y = fmaf(w, tv.y, acc.y); acc.z = fmaf(w, tv.z, acc.z); acc.w = fmaf(w, tv.w, acc.w);
-      }
-    }
-    acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale;
-    const float4 pv = *reinterpret_cast<const float4*>(pr + e0);
-    dot = fmaf(acc.x, pv.x, fmaf(acc.y, pv.y, fmaf(acc.z, pv.z, fmaf(acc.w, pv.w, dot))));
-    *reinterpret_cast<float4*>(de_s + e0) = acc;
-  }
+  for (int k = threadIdx.x; k < nslice; k += 1024) dot += dotp[(long long)i * nslice + k];
   dot = block_sum<1024>(dot, sh);
   const float nrm = pnorm[i];
   const bool clamped = nrm < kEpsNorm;
   const float inv = 1.f / fmaxf(nrm, kEpsNorm);
   const float n = (float)(seq_off[i + 1] - seq_off[i]);
   const float* st = stats + (long long)i * E;
+  const float* pr = p + (long long)i * E;
+  const float* dr = dp + (long long)i * E;
   for (int col = threadIdx.x; col < D; col += 1024) {
-    const float dmu = clamped ? de_s[col] * inv : (de_s[col] - pr[col] * dot) * inv;
-    const float dsd = clamped ? de_s[D + col] * inv : (de_s[D + col] - pr[D + col] * dot) * inv;
+    const float dmu = clamped ? dr[col] * inv : (dr[col] - pr[col] * dot) * inv;
+    const float dsd = clamped ? dr[D + col] * inv : (dr[D + col] - pr[D + col] * dot) * inv;
     const float mu = st[col], sd = st[D + col];
     const float k2 = dsd / (n * sd);  // inf/NaN when sd == 0, as autograd on the reference
     c1[(long long)i * D + col] = dmu / n - k2 * mu;
@@ -965,18 +997,16 @@ int pool_bwd_coef(const float* de, long long ld_de, const float* stats, long lon
 }
 
 int loss_bwd_coef(const float* dS, const float* t, const float* p, const float* pnorm, const float* stats,
-                  const int* seq_off, const float* dloss, int R, int B, int C, int D, float tau, float* c1, float* c2,
-                  cudaStream_t st) {
+                  const int* seq_off, const float* dloss, int R, int B, int C, int D, float tau, float* dp_ws,
+                  float* c1, float* c2, cudaStream_t st) {
   if (D % 4) return set_error(-1, "loss_bwd_coef: D must be a multiple of 4");
-  const int smem = 2 * D * (int)sizeof(float);
-  if (smem > 200 * 1024) return set_error(-1, "loss_bwd_coef: embedding too wide for shared memory");
-  static int configured_for = 0;
-  if (smem > 48 * 1024 && smem > configured_for) {
-    cudaError_t e = cudaFuncSetAttribute(loss_bwd_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return set_error((int)e, "loss_bwd_coef: cannot reserve %d bytes of shared memory", smem);
-    configured_for = smem;
-  }
-  loss_bwd_coef_kernel<<<B, 1024, smem, st>>>(dS, t, p, pnorm, stats, seq_off, dloss, R, C, D, 1.f / tau, c1, c2);
+  const int E = 2 * D;
+  const int nslice = (E + LBW_SLICE - 1) / LBW_SLICE;
+  float* dp = dp_ws;                         // [B][E]
+  float* dotp = dp_ws + (size_t)B * E;       // [B][nslice]
+  loss_bwd_dp_kernel<<<nslice, 256, 0, st>>>(dS, t, p, dloss, R, B, C, E, 1.f / tau, dp, dotp);
+  if (int r = check_launch("loss_bwd_dp_kernel")) return r;
+  loss_bwd_coef_kernel<<<B, 1024, 0, st>>>(dp, dotp, nslice, p, pnorm, stats, seq_off, D, c1, c2);
   return check_launch("loss_bwd_coef_kernel");
 }
 

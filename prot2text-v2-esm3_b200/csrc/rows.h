@@ -19,8 +19,8 @@ int pool_forward(const void* src, bool src_is_f16, long long ld_src, int src_row
                  int mode, float2* partial, float* out, long long ld_out, void* norm_p_bf16, float* norm_p_f32,
                  float* norm_out, cudaStream_t st);
 int loss_bwd_coef(const float* dS, const float* t, const float* p, const float* pnorm, const float* stats,
-                  const int* seq_off, const float* dloss, int R, int B, int C, int D, float tau, float* c1, float* c2,
-                  cudaStream_t st);
+                  const int* seq_off, const float* dloss, int R, int B, int C, int D, float tau, float* dp_ws,
+                  float* c1, float* c2, cudaStream_t st);
 int l2norm_forward(const float* e, int B, int E, void* p_bf16, float* p_f32, float* norm, cudaStream_t st);
 int l2norm_backward(const float* dp, const float* p, const float* norm, int B, int E, float* de, cudaStream_t st);
 int pool_bwd_coef(const float* de, long long ld_de, const float* stats, long long ld_stats, const int* seq_off, int B,

@@ -63,7 +63,7 @@ def reduce_scatter_text_grad(dt_full: torch.Tensor, group=None) -> torch.Tensor:
 def distributed_contrastive_step(residue_states, protein_mask, adapter, text_hidden, text_mask, *,
                                  residue_lengths=None, text_lengths=None,
                                  temperature: float = 0.05, symmetric: bool = False, group=None,
-                                 aux: Optional[_step.StepAux] = None) -> torch.Tensor:
+                                 aux: Optional[_step.StepAux] = None, **step_kw) -> torch.Tensor:
     """Sharded-batch contrastive step with all-gathered negatives; returns the local mean loss.
     Accepts the padded (mask) or the packed (lengths) input form of `contrastive_step`."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -76,4 +76,4 @@ def distributed_contrastive_step(residue_states, protein_mask, adapter, text_hid
     return _step.contrastive_step(residue_states, protein_mask, adapter, text_embeds=t_global,
                                   residue_lengths=residue_lengths,
                                   temperature=temperature, symmetric=symmetric, labels=labels, aux=aux,
-                                  col_stats_hook=hook, all_cols_labelled=symmetric and world > 1)
+                                  col_stats_hook=hook, all_cols_labelled=symmetric and world > 1, **step_kw)

@@ -32,6 +32,8 @@ class GraphedContrastiveStep:
             raise _lib.P2TError("GraphedContrastiveStep needs CUDA tensors: this package has no CPU path")
         self.adapter = adapter
         self.inputs = (residue_states, protein_mask, text_hidden, text_mask)
+        # (single-process step only: capturing the sharded step's NCCL all-gather hung on this stack — torch 2.11,
+        #  NCCL 2.28.9, async_op + wait inside capture — so the multi-GPU step stays on eager launches)
         self.kw = dict(temperature=temperature, contrastive_num_segments=contrastive_num_segments, symmetric=symmetric)
         self.params = [adapter.fc1.weight, adapter.fc1.bias, adapter.fc2.weight, adapter.fc2.bias]
         dev = residue_states.device
