@@ -90,14 +90,13 @@ struct GemmSmem {
   static constexpr int B_ROWS = GEMM_BLOCK_N / CTA_GROUP;                         // rows of B this CTA loads
   static constexpr int B_BYTES = B_ROWS * GEMM_BLOCK_K * 2;                       // 32 / 16 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = TMA_STORE ? ((CTA_GROUP == 1) ? 3 : 4) : ((CTA_GROUP == 1) ? 4 : 6);
+  // (5 x 32 KB of operands in flight per SM is what keeps the MMA fed from L2: with 4 stages ncu showed the epilogue
+  //  warps waiting for the accumulator 29 % of the time while the tensor pipe was 63 % active)
+  static constexpr int STAGES = TMA_STORE ? ((CTA_GROUP == 1) ? 3 : 5) : ((CTA_GROUP == 1) ? 4 : 6);
   static constexpr int BAR_BYTES = 1024;
-  // FC epilogues keep the whole bias vector (fp32) resident when N <= BIAS_ALL_N, else per-warp slices staged per tile
-  static constexpr int BIAS_ALL_N = TMA_STORE ? 4096 : 0;
-  static constexpr int BIAS_BYTES = TMA_STORE ? BIAS_ALL_N * 4 : GEMM_BLOCK_N * 4 * 4;  // (16 warps x 64 floats)
   static constexpr int OUT_BOX_BYTES = 32 * 32 * 2;        // one staged output box
   static constexpr int OUT_BYTES = TMA_STORE ? GEMM_EPI_WARPS * 2 * OUT_BOX_BYTES : 0;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + OUT_BYTES + 1024;  // + slack for 1024-B alignment
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + OUT_BYTES + 1024;  // + slack for 1024-B alignment
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -196,9 +195,27 @@ __device__ __forceinline__ void load8(const T* src, float (&f)[8], int n_ok) {
   }
 }
 
+// bias[col .. col+8) as fp32: one 16-byte load when the eight bf16 values are in range and aligned (every lane of
+// the warp reads the same address: a broadcast served by L1), element-wise at the ragged end of N
+__device__ __forceinline__ void load_bias8(const __nv_bfloat16* __restrict__ bias, int col, int n, float (&b)[8]) {
+  if (bias == nullptr) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = 0.f;
+  } else if (col + 8 <= n && ((reinterpret_cast<uintptr_t>(bias + col) & 15) == 0)) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(bias + col));
+    const float2 a = unpack_bf16x2(u.x), c = unpack_bf16x2(u.y), d = unpack_bf16x2(u.z), e = unpack_bf16x2(u.w);
+    b[0] = a.x; b[1] = a.y; b[2] = c.x; b[3] = c.y; b[4] = d.x; b[5] = d.y; b[6] = e.x; b[7] = e.y;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = (col + i < n) ? __bfloat162float(bias[col + i]) : 0.f;
+  }
+}
+
 // what the epilogue warps need from GemmParams, read once into registers (the parameter bank costs
 // an LDC round trip per use inside the loop otherwise)
 struct EpiArgs {
+  const __nv_bfloat16* bias;
+  int n;
   char* d0;
   char* d1;
   long long ldd0, ldd1, ldaux;
@@ -214,7 +231,7 @@ struct EpiArgs {
 // stores are clipped.  Rows in [M, rows_cap) are the zero padding of the packed buffers.
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const EpiArgs& e, const uint4 (&rnd)[4],
-                                               uint32_t bias_addr, int row, int col, int ncols, bool row_valid,
+                                               int row, int col, int ncols, bool row_valid,
                                                bool row_in_buf, bool vec_ok, float& sumsq) {
   using T0 = typename std::conditional<EPI == EPI_STORE_F32, float,
              typename std::conditional<EPI == EPI_FC2, __half, __nv_bfloat16>::type>::type;
@@ -274,8 +291,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ep
       store8(dst0 + 8 * j, val, n_ok, vec_ok);
     } else {
       float bias[8], der[8];
-      lds_f32x4(bias_addr + 32 * j, bias[0], bias[1], bias[2], bias[3]);
-      lds_f32x4(bias_addr + 32 * j + 16, bias[4], bias[5], bias[6], bias[7]);
+      load_bias8(e.bias, col + 8 * j, e.n, bias);
 #pragma unroll
       for (int i = 0; i < 8; ++i) gelu_erf_both_fast(val[i] + bias[i], val[i], der[i]);
       if (e.threshold != 0) {
@@ -305,7 +321,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ep
 // Rows past M are staged as zeros (the zero padding of the packed buffers); TMA clips rows/columns outside the tensor.
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk_staged(const uint32_t (&v)[32], const EpiArgs& e, const uint4 (&rnd)[4],
-                                                      uint32_t bias_addr, uint32_t stage_addr, int lane, bool row_valid,
+                                                      int col, uint32_t stage_addr, int lane, bool row_valid,
                                                       bool want_der, float& sumsq) {
   const uint32_t row_addr = stage_addr + lane * 64;
   const uint32_t sw = (lane >> 1) & 3;
@@ -314,8 +330,7 @@ __device__ __forceinline__ void epilogue_chunk_staged(const uint32_t (&v)[32], c
     float val[8], der[8];
     if (row_valid) {
       float bias[8];
-      lds_f32x4(bias_addr + 32 * j, bias[0], bias[1], bias[2], bias[3]);
-      lds_f32x4(bias_addr + 32 * j + 16, bias[4], bias[5], bias[6], bias[7]);
+      load_bias8(e.bias, col + 8 * j, e.n, bias);
 #pragma unroll
       for (int i = 0; i < 8; ++i) gelu_erf_both_fast(__uint_as_float(v[8 * j + i]) + bias[i], val[i], der[i]);
       if (e.threshold != 0) {
@@ -367,8 +382,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint64_t* tmem_full_bar = bars + 2 * S::STAGES;      // [2]
   uint64_t* tmem_empty_bar = bars + 2 * S::STAGES + 2; // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::STAGES + 4);
-  float* bias_smem = reinterpret_cast<float*>(smem + S::STAGES * S::STAGE_BYTES + S::BAR_BYTES);
-  uint8_t* out_smem = smem + S::STAGES * S::STAGE_BYTES + S::BAR_BYTES + S::BIAS_BYTES;  // 1024-byte aligned
+  uint8_t* out_smem = smem + S::STAGES * S::STAGE_BYTES + S::BAR_BYTES;  // 1024-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -453,9 +467,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else if (warp == 1) {
     // =============================== MMA issuer (leader CTA) ===============================
-    if (is_leader && lane == 0) {
+    // The whole warp runs the loop converged and only the tcgen05 instructions are issued by one elected lane:
+    // all addresses and descriptors are then warp-uniform values (uniform datapath, no per-MMA vector->uniform
+    // register moves).  That matters: with the epilogue warps busy, a ~110-instruction issue sequence per K block
+    // could not keep up with the 512 cycles its four MMAs take (ncu: tensor pipe 63 % active while the epilogue
+    // warps waited 45 % of their time for the accumulator and the MMA warp never waited for operands).
+    if (is_leader) {
       // (fp16 x bf16 mixed operands are rejected by the hardware: 'illegal instruction' on sm_100a, tried in round 1)
       constexpr uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M * CTA_GROUP, GEMM_BLOCK_N, A_MN, B_MN);
+      // shared-memory descriptors: high word constant, low word = (address >> 4) | (LBO >> 4) << 16
+      //   K-major SW128: rows are 128 B, 8-row groups 1024 B apart (SBO); k-step = 32 B inside the row (LBO unused: 1).
+      //   MN-major SW128: each 64-element slab is [64 k][128 B]; k-step = 16 rows = 2048 B,
+      //                   8-k groups 1024 B apart (SBO), slabs BLOCK_K*128 B apart (LBO).
+      constexpr uint32_t desc_hi = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);  // SBO | version 1 | SW128
+      constexpr uint32_t a_lbo = A_MN ? (uint32_t)(GEMM_BLOCK_K * 128) : 16u;
+      constexpr uint32_t b_lbo = B_MN ? (uint32_t)(GEMM_BLOCK_K * 128) : 16u;
+      constexpr uint32_t a_kstep = (A_MN ? GEMM_UMMA_K * 128 : GEMM_UMMA_K * 2) >> 4;
+      constexpr uint32_t b_kstep = (B_MN ? GEMM_UMMA_K * 128 : GEMM_UMMA_K * 2) >> 4;
+      const uint32_t a_lo0 = ((smem_u32(smem_a) & 0x3FFFFu) >> 4) | (((a_lbo >> 4) & 0x3FFFu) << 16);
+      const uint32_t b_lo0 = ((smem_u32(smem_b) & 0x3FFFFu) >> 4) | (((b_lbo >> 4) & 0x3FFFu) << 16);
+      const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -469,25 +500,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem_a + stage * S::A_BYTES);
-          const uint32_t sb = smem_u32(smem_b + stage * S::B_BYTES);
+          const uint32_t a_lo = a_lo0 + stage * (S::A_BYTES >> 4);
+          const uint32_t b_lo = b_lo0 + stage * (S::B_BYTES >> 4);
+          if (issuer) {
 #pragma unroll
-          for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
-            // K-major SW128: rows are 128 B, 8-row groups 1024 B apart (SBO); k-step = 32 B inside the row.
-            // MN-major SW128: each 64-element slab is [64 k][128 B]; k-step = 16 rows = 2048 B,
-            //                 8-k groups 1024 B apart (SBO), slabs BLOCK_K*128 B apart (LBO).
-            const uint64_t adesc = A_MN ? make_smem_desc_sw128(sa + k * (GEMM_UMMA_K * 128), GEMM_BLOCK_K * 128, 1024)
-                                        : make_smem_desc_sw128(sa + k * (GEMM_UMMA_K * 2), 16, 1024);
-            const uint64_t bdesc = B_MN ? make_smem_desc_sw128(sb + k * (GEMM_UMMA_K * 128), GEMM_BLOCK_K * 128, 1024)
-                                        : make_smem_desc_sw128(sb + k * (GEMM_UMMA_K * 2), 16, 1024);
-            umma_bf16<CTA_GROUP>(tmem_d, adesc, bdesc, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
+              const uint64_t adesc = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + k * a_kstep);
+              const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + k * b_kstep);
+              umma_bf16<CTA_GROUP>(tmem_d, adesc, bdesc, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+            }
+            if constexpr (CTA_GROUP == 2) umma_commit_pair(&empty_bar[stage], 0x3);
+            else umma_commit_1cta(&empty_bar[stage]);
           }
-          if constexpr (CTA_GROUP == 2) umma_commit_pair(&empty_bar[stage], 0x3);
-          else umma_commit_1cta(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
         }
-        if constexpr (CTA_GROUP == 2) umma_commit_pair(&tmem_full_bar[acc], 0x3);
-        else umma_commit_1cta(&tmem_full_bar[acc]);
+        if (issuer) {
+          if constexpr (CTA_GROUP == 2) umma_commit_pair(&tmem_full_bar[acc], 0x3);
+          else umma_commit_1cta(&tmem_full_bar[acc]);
+        }
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -502,21 +534,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int part = (warp - 2) >> 2;
     constexpr int COLS_PER_WARP = GEMM_BLOCK_N / (GEMM_EPI_WARPS / 4);
     constexpr int CHUNKS = COLS_PER_WARP / 32;
-    float* bias_s = bias_smem + (warp - 2) * COLS_PER_WARP;  // this warp's private slice
-    const uint32_t bias_slice_addr = smem_u32(bias_s);
-    // whole bias vector resident in shared memory (no per-tile global load on the critical path)
-    const bool bias_resident = (EPI == EPI_FC1 || EPI == EPI_FC2) && N <= S::BIAS_ALL_N;
-    if constexpr (EPI == EPI_FC1 || EPI == EPI_FC2) {
-      if (bias_resident) {
-        const int n_pad = (N + 31) & ~31;
-        for (int i = threadIdx.x - 64; i < n_pad; i += 32 * GEMM_EPI_WARPS)
-          bias_smem[i] = (p.bias != nullptr && i < N) ? __bfloat162float(p.bias[i]) : 0.f;
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * GEMM_EPI_WARPS) : "memory");
-      }
-    }
     uint8_t* out_stage = out_smem + (warp - 2) * 2 * S::OUT_BOX_BYTES;  // this warp's two staging boxes (FC epilogues)
     const uint32_t stage_addr = smem_u32(out_stage);
     EpiArgs e;
+    e.bias = p.bias; e.n = N;
     e.d0 = reinterpret_cast<char*>(p.d0); e.d1 = reinterpret_cast<char*>(p.d1);
     e.ldd0 = p.ldd0; e.ldd1 = p.ldd1; e.ldaux = p.ldaux; e.aux = p.aux;
     e.alpha = p.alpha; e.scale = p.drop.scale; e.threshold = p.drop.threshold; e.layer = p.drop.layer;
@@ -545,16 +566,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const bool is_head = split == 0;             // owns the tile: runs the epilogue
       const bool has_peers = is_head && tail_r >= 0;  // ... after adding the S-1 dumped K ranges
       const bool empty_k = kb1 <= kb0;
-      if constexpr (EPI == EPI_FC1 || EPI == EPI_FC2) {
-        if (is_head && !bias_resident) {
-          // stage this warp's bias slice once per tile (read back as shared-memory broadcasts)
-          __syncwarp();
-#pragma unroll
-          for (int i = lane; i < COLS_PER_WARP; i += 32)
-            bias_s[i] = (p.bias != nullptr && col0 + i < N) ? __bfloat162float(p.bias[col0 + i]) : 0.f;
-          __syncwarp();
-        }
-      }
       if (has_peers) {
         if (lane == 0)
           while (ld_acquire_gpu(sk_flags + tail_r) < (S_ - 1) * GEMM_EPI_WARPS * CTA_GROUP) __nanosleep(100);
@@ -605,13 +616,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
         }
         if (col < N) {
-          const uint32_t bias_addr = bias_resident ? smem_u32(bias_smem) + col * 4 : bias_slice_addr + c * 32 * 4;
           if constexpr (S::TMA_STORE) {
             if (p.tma_store) {
               const bool want_der = p.d1 != nullptr;
               if (lane == 0) tma_store_wait_read();  // the previous chunk's boxes have been read out
               __syncwarp();
-              epilogue_chunk_staged<EPI>(v, e, rnd, bias_addr, stage_addr, lane, row_valid, want_der, sumsq);
+              epilogue_chunk_staged<EPI>(v, e, rnd, col, stage_addr, lane, row_valid, want_der, sumsq);
               fence_proxy_async_smem();
               __syncwarp();
               if (lane == 0) {
@@ -623,7 +633,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               continue;
             }
           }
-          epilogue_chunk<EPI>(v, e, rnd, bias_addr, row, col, min(32, N - col), row_valid, row_in_buf, vec_ok, sumsq);
+          epilogue_chunk<EPI>(v, e, rnd, row, col, min(32, N - col), row_valid, row_in_buf, vec_ok, sumsq);
         }
       }
       if constexpr (EPI == EPI_FC2) {
