@@ -29,6 +29,13 @@ int make_tmap_16bit(CUtensorMap* map, const void* ptr, long long inner, long lon
                     int box_inner, int box_outer, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return set_error(-10, "cuTensorMapEncodeTiled entry point not available");
+  // the encoder is a driver-API call and needs the primary context current on THIS host thread; a thread whose
+  // first CUDA call is this one (e.g. autograd's backward worker) has none yet: one runtime call binds it
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * 2) % 16)
     return set_error(-11, "GEMM operand must be 16-byte aligned with a leading dimension multiple of 8");
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};

@@ -656,3 +656,31 @@ def test_graphed_step_draws_a_new_dropout_mask_every_replay(p2t, synth, dev):
     assert a != b and math.isfinite(a) and math.isfinite(b)
     again = p2t.GraphedContrastiveStep(ad, sb.x.to(dev), sb.prot_mask.to(dev), sb.text.to(dev), sb.text_mask.to(dev), seed=5)
     assert again.replay().item() == a  # same seed, same replay index: same mask
+
+
+def test_step_with_many_negatives_uses_the_tensor_core_loss_path(p2t, synth, dev):
+    """B = 160 pairs against 2048 text embeddings of width 2*256: R*C*E > 2^26, so the similarity, dLogits (bf16) and
+    dp = dS t run on the tcgen05 GEMM — the first CUDA call of autograd's backward thread is then a TMA descriptor."""
+    sb = synth.make_batch(d_in=64, d_mid=128, d_out=256, batch=160, lmin=3, lmax=24, tmin=2, tmax=8, weight_gain=8.0)
+    f = torch.float32
+    w1, b1, w2, b2 = (t.to(f).requires_grad_() for t in (sb.w1, sb.b1, sb.w2, sb.b2))
+    tr = R.adapter_rows(sb.x.to(f), w1, b1, w2, b2)
+    p, _ = R.l2_normalize(R.readout(tr.y, sb.prot_mask, "mix"))
+    g = torch.Generator().manual_seed(11)
+    t_all = torch.nn.functional.normalize(torch.randn(2048, 512, generator=g), dim=-1)
+    labels = torch.randperm(2048, generator=g)[:160]
+    # plant the partners (retrieval margins far above the bf16 noise of the tensor-core similarity)
+    t_all[labels] = torch.nn.functional.normalize(p.detach() + 0.5 * torch.randn(160, 512, generator=g) / math.sqrt(512), dim=-1)
+    ref = R.infonce_rows(p, t_all, labels, 0.05)
+    gs = torch.autograd.grad(ref, (w1, b1, w2, b2))
+    ad = make_adapter(p2t, dev, sb.w1, sb.b1, sb.w2, sb.b2)
+    aux = p2t.StepAux()
+    loss = p2t.contrastive_step(sb.x.to(dev), sb.prot_mask.to(dev), ad, text_embeds=t_all.to(dev),
+                                labels=labels.to(torch.int32).to(dev), aux=aux)
+    loss.backward()
+    assert abs(loss.item() - ref.item()) <= 5 * LOSS_RTOL * abs(ref.item()) + 1e-4  # bf16 p and t in the similarity
+    for k, gref in zip(PARAMS, gs):
+        c, m = cosine(adapter_grads(ad)[k], gref), maxrel(adapter_grads(ad)[k], gref)
+        assert c >= GRAD_COS and m <= 2e-2, f"{k}: cosine {c:.6f} maxrel {m:.3e}"  # bf16 dS and bf16 p/t operands
+    am = torch.argmax(p.detach() @ t_all.t(), dim=1)
+    assert torch.equal(am, labels) and torch.equal(aux.argmax_row.cpu().long(), am)
