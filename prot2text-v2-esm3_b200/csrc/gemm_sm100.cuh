@@ -428,7 +428,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
+    // (whole warp converged, one elected lane issues: see the MMA warp below for why)
+    {
+      const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       PieceIter pieces(num_tiles, num_kb, worker, num_workers, p.sk_splits);
@@ -439,28 +441,31 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int n_base = n_blk * GEMM_BLOCK_N + (int)cta_rank * S::B_ROWS;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem_a + stage * S::A_BYTES;
-          uint8_t* sb = smem_b + stage * S::B_BYTES;
-          const int k0 = kb * GEMM_BLOCK_K;
-          if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES * CTA_GROUP);
-          auto load = [&](void* dst, const CUtensorMap* tm, int c0, int c1) {
-            if constexpr (CTA_GROUP == 2) tma_load_2d_pair(dst, tm, &full_bar[stage], c0, c1);
-            else tma_load_2d(dst, tm, &full_bar[stage], c0, c1);
-          };
-          if constexpr (!A_MN) {
-            load(sa, &tmap_a, k0, m_base);  // box {64 k, 128 rows}
-          } else {
+          if (issuer) {
+            uint8_t* sa = smem_a + stage * S::A_BYTES;
+            uint8_t* sb = smem_b + stage * S::B_BYTES;
+            const int k0 = kb * GEMM_BLOCK_K;
+            if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES * CTA_GROUP);
+            auto load = [&](void* dst, const CUtensorMap* tm, int c0, int c1) {
+              if constexpr (CTA_GROUP == 2) tma_load_2d_pair(dst, tm, &full_bar[stage], c0, c1);
+              else tma_load_2d(dst, tm, &full_bar[stage], c0, c1);
+            };
+            if constexpr (!A_MN) {
+              load(sa, &tmap_a, k0, m_base);  // box {64 k, 128 rows}
+            } else {
 #pragma unroll
-            for (int j = 0; j < GEMM_BLOCK_M / 64; ++j)  // box {64 m, 64 k}: one 128-B-wide slab each
-              load(sa + j * (GEMM_BLOCK_K * 128), &tmap_a, m_base + j * 64, k0);
-          }
-          if constexpr (!B_MN) {
-            load(sb, &tmap_b, k0, n_base);  // box {64 k, B_ROWS rows}
-          } else {
+              for (int j = 0; j < GEMM_BLOCK_M / 64; ++j)  // box {64 m, 64 k}: one 128-B-wide slab each
+                load(sa + j * (GEMM_BLOCK_K * 128), &tmap_a, m_base + j * 64, k0);
+            }
+            if constexpr (!B_MN) {
+              load(sb, &tmap_b, k0, n_base);  // box {64 k, B_ROWS rows}
+            } else {
 #pragma unroll
-            for (int j = 0; j < S::B_ROWS / 64; ++j)
-              load(sb + j * (GEMM_BLOCK_K * 128), &tmap_b, n_base + j * 64, k0);
+              for (int j = 0; j < S::B_ROWS / 64; ++j)
+                load(sb + j * (GEMM_BLOCK_K * 128), &tmap_b, n_base + j * 64, k0);
+            }
           }
+          __syncwarp();
           if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
         }
       }
