@@ -318,9 +318,14 @@ def infonce_forward(p_bf: torch.Tensor, t_bf: torch.Tensor, labels: torch.Tensor
     p/t the dominant gradient error).
     """
     require_cuda_bf16(p_bf, "p")
-    require_cuda_bf16(t_bf, "t")
+    if t_bf.dtype == torch.float32:  # small blocks with fp32 embeddings never touch a bf16 copy of t
+        if t_f32 is None or p_f32 is None or p_bf.shape[0] * t_bf.shape[0] * t_bf.shape[1] > (1 << 26):
+            raise _lib.P2TError("fp32 text embeddings need the fp32 protein embeddings and a small similarity block")
+        t_bf = None
+    else:
+        require_cuda_bf16(t_bf, "t")
     R, E = p_bf.shape
-    C = t_bf.shape[0]
+    C = (t_bf if t_bf is not None else t_f32).shape[0]
     dev = p_bf.device
     cg = cta_group or default_cta_group()
     labels32 = labels.to(device=dev, dtype=torch.int32).contiguous()
@@ -355,7 +360,7 @@ def infonce_backward(res: InfoNCEResult, p_bf, t_bf, tau: float, need_dp: bool =
                      p_f32: Optional[torch.Tensor] = None, t_f32: Optional[torch.Tensor] = None,
                      cta_group: Optional[int] = None):
     R, E = p_bf.shape
-    C = t_bf.shape[0]
+    C = (t_bf if t_bf is not None else t_f32).shape[0]
     dev = p_bf.device
     dp = torch.empty(R, E, dtype=torch.float32, device=dev) if need_dp else None
     dt = torch.empty(C, E, dtype=torch.float32, device=dev) if need_dt else None

@@ -28,7 +28,7 @@ from .adapter import ModalityAdapter, _draw_seed
 class StepAux:
     """Side outputs of the last contrastive step (no gradient)."""
     protein_embeddings: Optional[torch.Tensor] = None   # (B, 2*D_out) bf16, unit norm
-    text_embeddings: Optional[torch.Tensor] = None      # (B_global, 2*H) bf16, unit norm
+    text_embeddings: Optional[torch.Tensor] = None      # (B_global, 2*H) unit norm (fp32, or bf16 on the tensor-core path)
     argmax_row: Optional[torch.Tensor] = None           # int32 (B,)  protein -> text retrieval
     argmax_col: Optional[torch.Tensor] = None           # int32 (B_global,) text -> protein retrieval (local rows)
     n_rows: Optional[torch.Tensor] = None               # int32 (1,) valid residue rows
@@ -82,18 +82,21 @@ def step_forward(x, prot_mask, w1, b1, w2, b2, t_in, labels, cfg: dict, aux: Ste
         t_in = t_in()
     if t_in.dtype == torch.float32:
         t_f32 = t_in.contiguous()
-        t_bf = _core.to_bf16(t_f32)
+        # the bf16 copy is an operand of the tensor-core loss path only (large similarity blocks)
+        big = cfg["rows_used"] * t_f32.shape[0] * t_f32.shape[1] > (1 << 26)
+        t_bf = _core.to_bf16(t_f32) if big else None
     else:
         _core.require_cuda_bf16(t_in, "text_embeds")
         t_f32, t_bf = None, t_in.contiguous()
     used = cfg["rows_used"]
     hook = cfg.get("col_stats_hook")
-    res = _core.infonce_forward(p_bf[:used], t_bf, labels[:used], cfg["tau"], w_row=cfg["w_row"], w_col=cfg["w_col"],
+    res = _core.infonce_forward(p_bf[:used], t_bf if t_bf is not None else t_f32, labels[:used], cfg["tau"],
+                                w_row=cfg["w_row"], w_col=cfg["w_col"],
                                 need_grad=need_grad, want_col_argmax=True, col_stats_hook=hook,
                                 p_f32=p_f32[:used] if t_f32 is not None else None, t_f32=t_f32,
                                 loss_scale=cfg.get("loss_scale"),
                                 all_cols_labelled=cfg.get("all_cols_labelled", False))
-    aux.protein_embeddings, aux.text_embeddings = p_bf, t_bf
+    aux.protein_embeddings, aux.text_embeddings = p_bf, (t_bf if t_bf is not None else t_f32)
     aux.argmax_row, aux.argmax_col, aux.n_rows = res.argmax_row, res.argmax_col, plan.n_rows
     state = (plan, acts, stats, inv_norm, p_bf, p_f32, pnorm, res, t_bf, t_f32, w1c, w2c, cfg) if need_grad else None
     return res.loss, state
@@ -140,6 +143,18 @@ class _ContrastiveStepFunction(torch.autograd.Function):
         return None, None, dw1, db1, dw2, db2, None, None, None, None
 
 
+_LABELS = {}
+
+
+def _default_labels(n: int, device) -> torch.Tensor:
+    """arange(n) int32 on `device`, created once per (n, device): the diagonal pairing of the reference (:88-89)."""
+    key = (n, str(device))
+    t = _LABELS.get(key)
+    if t is None:
+        t = _LABELS[key] = torch.arange(n, device=device, dtype=torch.int32)
+    return t
+
+
 def contrastive_step(residue_states: torch.Tensor, protein_mask: Optional[torch.Tensor], adapter: ModalityAdapter,
                      text_hidden: Optional[torch.Tensor] = None, text_mask: Optional[torch.Tensor] = None, *,
                      residue_lengths: Optional[torch.Tensor] = None, text_lengths: Optional[torch.Tensor] = None,
@@ -178,7 +193,7 @@ def contrastive_step(residue_states: torch.Tensor, protein_mask: Optional[torch.
     if seg * contrastive_num_segments != B:
         print("WARNING: Given batch size is not divisible by the number of segments for contrastive learning.")
     if labels is None:
-        labels = torch.arange(B, device=residue_states.device, dtype=torch.int32)
+        labels = _default_labels(B, residue_states.device)
     p = adapter.dropout_p()
     cfg = dict(tau=float(temperature), w_row=0.5 if symmetric else 1.0, w_col=0.5 if symmetric else 0.0,
                dropout_p=p, seed=_draw_seed() if (p > 0 and seed_dev is None) else 0, seed_dev=seed_dev,
