@@ -68,7 +68,8 @@ def distributed_contrastive_step(residue_states, protein_mask, adapter, text_hid
     Accepts the padded (mask) or the packed (lengths) input form of `contrastive_step`."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     t_local = _step.text_embeddings(text_hidden, text_mask, dtype=torch.float32, text_lengths=text_lengths)
-    # the gather runs on NCCL's stream behind the adapter GEMMs; it is waited for right before the similarity
+    # the gather runs on NCCL's stream behind the plan/pack kernels of the protein side and is waited for right
+    # before the (persistent, one-CTA-per-SM) adapter GEMMs
     t_global = all_gather_embeddings(t_local, group, async_op=True) if world > 1 else t_local
     B = residue_lengths.shape[0] if residue_lengths is not None else residue_states.shape[0]
     labels = torch.arange(rank * B, (rank + 1) * B, device=residue_states.device, dtype=torch.int32)

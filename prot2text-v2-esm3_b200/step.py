@@ -74,12 +74,15 @@ def step_forward(x, prot_mask, w1, b1, w2, b2, t_in, labels, cfg: dict, aux: Ste
         plan = _core.plan_rows(prot_mask)
         xp = _core.gather_rows(x.contiguous().view(B * L, d_in), plan)
         x_rows = plan.rows_cap
+    if callable(t_in):
+        # deferred text embeddings (the all-gather of the sharded step): the collective has been running behind the
+        # plan/pack kernels above; it must be OVER before the persistent GEMMs start — they assume one CTA per SM, and
+        # a communication kernel still holding SMs delays a whole tile share (measured: fc1 163 -> 250 us)
+        t_in = t_in()
     acts = _core.adapter_forward(xp, x_rows, plan.rows_cap, plan.n_rows, w1c, b1c, w2c, b2c,
                                  cfg["dropout_p"], cfg["seed"], need_grad, seed_dev=cfg.get("seed_dev"))
     inv_norm = _core.row_inv_norm(acts)
     stats, p_bf, p_f32, pnorm = _core.pool_forward(acts.a, plan, d_out, row_src=None, inv_norm=inv_norm, normalize=True)
-    if callable(t_in):  # deferred text embeddings (e.g. an all-gather still in flight behind the adapter GEMMs)
-        t_in = t_in()
     if t_in.dtype == torch.float32:
         t_f32 = t_in.contiguous()
         # the bf16 copy is an operand of the tensor-core loss path only (large similarity blocks)
@@ -170,8 +173,9 @@ def contrastive_step(residue_states: torch.Tensor, protein_mask: Optional[torch.
     (models/esmc_qwen_arc.py:84-86); text_hidden (B_t, T, H) bf16 is hidden_states[16] of the frozen
     LLM with its attention mask (scripts/train_contrast.py:304), or pass already normalised
     `text_embeds` (B_t, 2H), float32 (preferred) or bfloat16 — e.g. the all-gathered global negatives — or a
-    zero-argument callable returning them, which is invoked only when the loss needs them (so a collective
-    can run behind the adapter GEMMs).  `labels[i]` is the text row
+    zero-argument callable returning them, which is invoked after the residue rows have been packed and before
+    the adapter GEMMs (so a collective overlaps the plan/pack kernels but never shares SMs with the persistent
+    GEMMs).  `labels[i]` is the text row
     paired with protein i (default: i).  Ragged hand-over: with `residue_lengths` (B,),
     `residue_states` is the PACKED (sum L_b, D_in) row buffer and `protein_mask` is ignored; likewise
     `text_lengths` with packed `text_hidden` (see host_io.HostStager).  `contrastive_num_segments` reproduces the reference's
