@@ -165,6 +165,7 @@ __global__ void row_inv_norm_kernel(const float* __restrict__ rowsq, int nblk, c
     // fixed summation order (four interleaved partial sums), all loads of a trip in flight together
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     int j = 0;
+#pragma unroll 4
     for (; j + 4 <= nblk; j += 4) {
       s0 += rowsq[(long long)j * cap + r];
       s1 += rowsq[(long long)(j + 1) * cap + r];
@@ -382,19 +383,27 @@ __global__ void pool_finalize_kernel(const float2* __restrict__ partial, const i
 }
 
 // phase 2 of the fused step ('mix' readout followed by F.normalize, scripts/train_contrast.py:277-281 + :354/:365):
-// combine the chunks, write stats = (mean | std), then p = stats / max(|stats|, eps).  grid B, block 1024.
-__global__ void __launch_bounds__(1024)
+// combine the chunks, write stats = (mean | std), then p = stats / max(|stats|, eps).
+// grid (FIN_CLUSTER, B) launched as thread-block clusters of FIN_CLUSTER CTAs along x: the CTAs of a cluster share
+// one sequence, each finalises a column slice, and the slices' sums of squares meet through distributed shared
+// memory (fixed order), so the whole embedding is normalised without a second kernel and with 8x more CTAs in flight
+// than one CTA per sequence would give.
+constexpr int FIN_CLUSTER = 8, FIN_THREADS = 256;
+__global__ void __launch_bounds__(FIN_THREADS)
 pool_finalize_normalize_kernel(const float2* __restrict__ partial, const int* __restrict__ seq_off,
                                const int* __restrict__ chunk_off, int D, int rc, float* __restrict__ stats,
                                __nv_bfloat16* __restrict__ p_bf16, float* __restrict__ p_f32, float* __restrict__ norm_out) {
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;
+  const uint32_t rank = cluster_ctarank();
   const int c0 = chunk_off[b], c1 = chunk_off[b + 1];
   const int n_total = seq_off[b + 1] - seq_off[b];
   float* st = stats + (long long)b * 2 * D;
-  __shared__ float sh[32];
+  __shared__ float sh[FIN_THREADS / 32];
+  __shared__ float cluster_sq[FIN_CLUSTER];  // slot r of EVERY CTA receives CTA r's partial sum of squares
   float sq = 0.f;
-  for (int col = threadIdx.x; col < D; col += 1024) {
+  for (int col = rank * FIN_THREADS + threadIdx.x; col < D; col += FIN_CLUSTER * FIN_THREADS) {
     float n = 0.f, mean = 0.f, m2 = 0.f;
+#pragma unroll 4
     for (int c = c0; c < c1; ++c) {
       const float nc = (float)min(rc, n_total - (c - c0) * rc);
       const float2 pc = partial[(long long)c * D + col];
@@ -411,14 +420,23 @@ pool_finalize_normalize_kernel(const float2* __restrict__ partial, const int* __
     st[D + col] = sd;
     sq = fmaf(mu, mu, fmaf(sd, sd, sq));
   }
-  sq = block_sum<1024>(sq, sh);  // (its barriers also make the stats written above visible to the whole block)
-  const float nrm = sqrtf(sq);
+  sq = block_sum<FIN_THREADS>(sq, sh);
+  if (threadIdx.x < FIN_CLUSTER) {  // broadcast this CTA's partial into slot `rank` of every CTA of the cluster
+    const uint32_t remote = mapa_shared(smem_u32(&cluster_sq[rank]), threadIdx.x);
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(sq) : "memory");
+  }
+  cluster_sync_all();  // release/acquire: the remote stores above are visible after the barrier
+  float total = 0.f;
+#pragma unroll
+  for (int r = 0; r < FIN_CLUSTER; ++r) total += cluster_sq[r];  // same order in every CTA: identical norm
+  const float nrm = sqrtf(total);
   const float inv = 1.f / fmaxf(nrm, kEpsNorm);
-  if (threadIdx.x == 0 && norm_out) norm_out[b] = nrm;
-  for (int i = threadIdx.x; i < 2 * D; i += 1024) {
-    const float v = st[i] * inv;
-    if (p_f32) p_f32[(long long)b * 2 * D + i] = v;
-    if (p_bf16) p_bf16[(long long)b * 2 * D + i] = __float2bfloat16_rn(v);
+  if (rank == 0 && threadIdx.x == 0 && norm_out) norm_out[b] = nrm;
+  for (int col = rank * FIN_THREADS + threadIdx.x; col < D; col += FIN_CLUSTER * FIN_THREADS) {
+    const float mu = st[col] * inv, sd = st[D + col] * inv;  // written by this very thread above
+    const long long o = (long long)b * 2 * D;
+    if (p_f32) { p_f32[o + col] = mu; p_f32[o + D + col] = sd; }
+    if (p_bf16) { p_bf16[o + col] = __float2bfloat16_rn(mu); p_bf16[o + D + col] = __float2bfloat16_rn(sd); }
   }
 }
 
@@ -516,6 +534,7 @@ loss_bwd_dp_kernel(const float* __restrict__ dS, const float* __restrict__ t, co
 #pragma unroll
     for (int q = 0; q < 4; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (col < E) {
+#pragma unroll 8
       for (int j = 0; j < C; ++j) {
         const float4 tv = __ldg(reinterpret_cast<const float4*>(t + (long long)j * E + col));
 #pragma unroll
@@ -972,9 +991,22 @@ int pool_forward(const void* src, bool src_is_f16, long long ld_src, int src_row
   if (int r = check_launch("pool_partial_kernel")) return r;
   if (norm_p_bf16 != nullptr || norm_p_f32 != nullptr) {
     if (mode != 3 || ld_out != 2LL * D) return set_error(-1, "pool_forward: fused normalise needs the dense 'mix' layout");
-    pool_finalize_normalize_kernel<<<B, 1024, 0, st>>>(partial, seq_off, chunk_off, D, rc, out,
-                                                       reinterpret_cast<__nv_bfloat16*>(norm_p_bf16), norm_p_f32, norm_out);
-    return check_launch("pool_finalize_normalize_kernel");
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(FIN_CLUSTER, B);
+    cfg.blockDim = dim3(FIN_THREADS);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = FIN_CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, pool_finalize_normalize_kernel, (const float2*)partial, seq_off, chunk_off, D, rc,
+                                        out, reinterpret_cast<__nv_bfloat16*>(norm_p_bf16), norm_p_f32, norm_out);
+    if (le != cudaSuccess) return set_error((int)le, "pool_finalize_normalize_kernel: %s", cudaGetErrorString(le));
+    count_launch();
+    return 0;
   }
   dim3 g2(B, (D + 255) / 256);
   pool_finalize_kernel<<<g2, 256, 0, st>>>(partial, seq_off, chunk_off, B, D, rc, mode, out, ld_out);
