@@ -7,8 +7,9 @@ One "step" = one fused contrastive step, forward AND backward, over one syntheti
 BASELINE config: residue states -> ModalityAdapter (fc1/GELU/dropout/fc2/GELU/dropout/L2-norm) ->
 'mix' readout -> L2 normalise; text hidden states -> 'mix' readout -> normalise; similarity / tau;
 InfoNCE; gradients of fc1/fc2 weights and biases.  Training mode (dropout p = 0.3) as in the
-reference's train_epoch.  N > 1 (under torchrun): every rank holds B pairs (weak scaling), text
-embeddings are all-gathered over NCCL to form global negatives.
+reference's train_epoch.  N > 1 (under torchrun): every rank holds B pairs (weak scaling: each rank gets rank 0's
+multiset of sequence lengths with its own data); the unit-norm text embeddings are all-gathered by peer-memory
+kernels over NVLink (csrc/peer.cu) to form global negatives, inside the same CUDA graph as the rest of the step.
 
 Prints ONE JSON line (rank 0).  `value` = pairs/s with inputs resident in HBM; `e2e` = the same
 through the public API with inputs in pinned host memory (H2D of the step's inputs and D2H of the
@@ -43,6 +44,7 @@ def parse_args():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-optimizer", action="store_true", help="skip the (separately reported) optimizer leg")
     ap.add_argument("--eval-mode", action="store_true", help="dropout off (parity runs); default is training mode")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     return ap.parse_args()
@@ -233,7 +235,8 @@ def main():
 
     cfg = synth.CONFIGS[args.workload]
     nbatches = 2
-    batches = [synth.make_config_batch(args.workload, seed=1234 + 17 * i, rank=rank) for i in range(nbatches)]
+    batches = [synth.make_config_batch(args.workload, seed=1234 + 17 * i, rank=rank, same_lengths_as_rank0=True)
+               for i in range(nbatches)]
     B = cfg["batch"]
     acfg = pkg.ModalityAdapterConfig(input_dim=cfg["d_in"], intermediate_dim=cfg["d_mid"], output_dim=cfg["d_out"], dropout_rate=0.3)
     adapter = pkg.ModalityAdapter(acfg).to(dev).to(torch.bfloat16)
@@ -249,11 +252,14 @@ def main():
     resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
     valid_rows = [int(b.prot_lens.sum()) for b in batches]
 
+    # N > 1: the exchange step of the sharded batch runs as peer-memory kernels (no NCCL on the data path)
+    exchange = pdist.ShardedExchange(B, 2 * cfg["d_out"]) if world > 1 else None
+
     def step(inp):
         for p in params:
             p.grad = None
         if world > 1:
-            loss = pdist.distributed_contrastive_step(inp["x"], inp["pm"], adapter, inp["text"], inp["tm"])
+            loss = pdist.distributed_contrastive_step(inp["x"], inp["pm"], adapter, inp["text"], inp["tm"], exchange=exchange)
         else:
             loss = pkg.contrastive_step(inp["x"], inp["pm"], adapter, inp["text"], inp["tm"])
         loss.backward()
@@ -273,8 +279,8 @@ def main():
 
     # ------------------------------ device-resident timing ------------------------------
     # Pass A (eager launches): the library brackets every GEMM launch with CUDA events on its stream -> roofline.
-    # Pass B (CUDA-graph replay of the same step through GraphedContrastiveStep, single GPU; the sharded step with its
-    # NCCL all-gather stays eager): the headline `value`.
+    # Pass B (CUDA-graph replay of the same step through GraphedContrastiveStep; for N > 1 the sharded step including
+    # its peer-memory exchange): the headline `value`.
     for i in range(args.warmup):
         step(resident[i % nbatches])
     barrier()
@@ -294,10 +300,11 @@ def main():
     lib.gemm_timing_enable(False)
     eager_ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     last_loss = float(loss.item())
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = not args.no_graph
     sampler = ClockSampler(local_rank)
     if use_graph:
-        graphs = [pkg.GraphedContrastiveStep(adapter, r["x"], r["pm"], r["text"], r["tm"], seed=1000 * (i + 1))
+        graphs = [pkg.GraphedContrastiveStep(adapter, r["x"], r["pm"], r["text"], r["tm"], seed=1000 * (i + 1),
+                                             exchange=exchange)
                   for i, r in enumerate(resident)]
         for i in range(args.warmup):
             graphs[i % nbatches].replay()
@@ -350,7 +357,8 @@ def main():
                 p.grad = None
             kw = dict(residue_lengths=batch.residue_lengths, text_lengths=batch.text_lengths)
             if world > 1:
-                l = pdist.distributed_contrastive_step(batch.residue_rows, None, adapter, batch.text_rows, None, **kw)
+                l = pdist.distributed_contrastive_step(batch.residue_rows, None, adapter, batch.text_rows, None,
+                                                       exchange=exchange, **kw)
             else:
                 l = pkg.contrastive_step(batch.residue_rows, None, adapter, batch.text_rows, None, **kw)
             l.backward()
@@ -376,6 +384,44 @@ def main():
                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
                "how": "pinned host batch -> HostStager (valid rows only, copy stream, next step's copy overlaps this "
                       "step's kernels) -> contrastive_step(packed rows + lengths) -> backward -> loss.item()"}
+
+    # ------------------------------ outside the metric: gradient exchange + optimizer ------------------------------
+    # (the DDP weight-gradient all-reduce and the optimizer step are reported separately.)
+    # mean all-reduce of the four weight gradients over peer memory (N > 1) + clip_grad_norm_ + AdamW in 3 launches
+    optim_leg = None
+    if not args.no_optimizer:
+        peer = importlib.import_module("p2t_b200.peer")
+        if exchange is not None:
+            exchange.check()
+        opt = pkg.FusedAdamW(params, lr=1e-4, eps=1e-6, betas=(0.9, 0.999), max_grad_norm=1.0)
+        reducer = peer.PeerGradAllReduce(params) if world > 1 else None
+        step(resident[0])
+        grads = [p.grad for p in params]
+
+        def opt_step():
+            if reducer is not None:
+                reducer.reduce_(grads)
+            opt.step()
+
+        for _ in range(3):
+            opt_step()
+        barrier()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_opt = 20
+        o0.record()
+        for _ in range(n_opt):
+            opt_step()
+        o1.record()
+        barrier()
+        opt_ms = max_over_ranks(o0.elapsed_time(o1)) / n_opt
+        n_el = sum(p.numel() for p in params)
+        opt_bytes = n_el * (2 + 2 + 4 * 3 * 2 + 2)  # norm pass reads g; update reads g, m, v, master and writes m, v, master, p
+        optim_leg = {"ms_per_step": opt_ms, "parameters": n_el, "algorithmic_bytes": opt_bytes,
+                     "gb_per_s": (opt_bytes / 1e9) / (opt_ms / 1e3) if reducer is None else None,
+                     "includes": ("peer-memory mean all-reduce of the weight gradients + " if reducer is not None else "") +
+                                 "clip_grad_norm_ + AdamW (FusedAdamW, 3 launches); outside `value`"}
+        if reducer is not None:
+            reducer.buffer.check()
 
     # ------------------------------ roofline of the dominant kernel ------------------------------
     d_in, d_mid, d_out = cfg["d_in"], cfg["d_mid"], cfg["d_out"]
@@ -420,13 +466,21 @@ def main():
             "config": {"workload": args.workload, "d_in": d_in, "d_mid": d_mid, "d_out": d_out, "pairs_per_gpu": B,
                        "global_pairs": world * B, "residue_len": [cfg["lmin"], cfg["lmax"]],
                        "valid_rows_per_step": valid_rows[0], "dropout_p": 0.0 if args.eval_mode else 0.3,
-                       "parallelism": f"dp{world}", "l2": "inputs+activations per step exceed the 126 MB L2; 2 batches alternate",
+                       "parallelism": f"dp{world}",
+                       "exchange": None if world == 1 else "text embeddings all-gathered by peer-memory kernels over NVLink "
+                                                           "(csrc/peer.cu), inside the step's CUDA graph; no NCCL on the data path",
+                       "rank_lengths": "rank 0's multiset of sequence lengths on every rank, own data (fixed per-GPU work)",
+                       "l2": "inputs+activations per step exceed the 126 MB L2; 2 batches alternate",
                        "cta_group": int(os.environ.get("P2T_CTA_GROUP", "2"))},
             "loss": last_loss, "gpu_launches": int(launches), "cuda_graph": bool(use_graph),
             "eager_ms_per_step": eager_ms_total / args.steps, "host_issue_ms_per_step_eager": host_issue_ms, "clocks": clocks, "e2e": e2e, "roofline": roofline,
-            "cpu_baseline": cpu_baseline,
+            "cpu_baseline": cpu_baseline, "optimizer": optim_leg,
         }
         print(json.dumps(line), flush=True)
+    if exchange is not None:
+        exchange.check()
+        torch.cuda.synchronize()
+        dist.barrier()
     if world > 1:
         dist.destroy_process_group()
 

@@ -168,8 +168,10 @@ int p2t_adapter_tail_bwd(const void* a, const void* g2, const float* inv_norm, c
                          const int* chunk_seq, int B, const float* c1, const float* c2, const int* n_rows_dev,
                          int rows_cap, int d_out, int chunk_rows, int max_chunks, void* dz2, float* colsum_ws, void* db2,
                          void* stream);
+/* (_dy form: rows < min(n, *n_rows_dev) are computed — n_rows_dev may be NULL —, rows up to the next multiple of 256
+ * are zeroed) */
 int p2t_adapter_tail_bwd_dy(const void* a, const void* g2, const float* inv_norm, const void* dy, int n,
-                            int rows_cap, int d_out, void* dz2, void* stream);
+                            const int* n_rows_dev, int rows_cap, int d_out, void* dz2, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * backward GEMMs of the adapter (autograd of :62-65; scripts/train_contrast.py:448):
@@ -217,6 +219,74 @@ int p2t_colsum(const void* x, const int* n_rows_dev, int n_static, int D, float*
 /* debug/test aid: the dropout keep-multipliers the kernels use, as fp32 [rows][cols] */
 int p2t_dropout_mask(int rows, int cols, float dropout_p, unsigned long long seed, int layer, float* out,
                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage-2 hand-off — replaces `inputs_embeds[placeholder_mask] = encoder_hidden_states[encoder_mask]`
+ * (models/esmc_qwen_arc.py:127-144, models/modeling_esm2llama_instruct.py:134-138): the adapter's k-th valid output
+ * row y_k = a_k / max(|a_k|, 1e-12) is written to row row_dst[k] of dst (bf16, row stride ld_dst elements) — i.e. into
+ * the k-th placeholder slot of the LLM's input embeddings — without materialising (B, L, d_out).  Rows k < min(n,
+ * *n_rows_dev, *n_dst_dev) are written (either device count may be NULL).  inv_norm[k] is saved when non-NULL.
+ * ------------------------------------------------------------------------------------------- */
+int p2t_adapter_scatter_rows(const void* a, const float* rowsq, int nblk, int rows_cap, int n, int d_out, void* dst,
+                             long long ld_dst, const int* row_dst, const int* n_rows_dev, const int* n_dst_dev,
+                             float* inv_norm, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Exchange steps of the sharded step over NVLink peer memory (the reference has none: D6) and of the
+ * adapter weight gradients (DistributedDataParallel in the reference, scripts/train_contrast.py:611-614).
+ * Kernels on the caller's stream, epochs in device memory: capturable in a CUDA graph, no NCCL on the data path.
+ *
+ * Peer buffers: p2t_peer_alloc = cudaMalloc + zero fill + cudaIpcGetMemHandle (64-byte handle, HOST pointer);
+ * a peer process maps it with p2t_peer_open (cudaIpcOpenMemHandle, peer access enabled lazily) and unmaps with
+ * p2t_peer_close; the owner releases with p2t_peer_free.  These four are the only entries that allocate or
+ * synchronise.  Every channel buffer starts with p2t_peer_ctrl_bytes() of control words (zero = fresh).
+ *
+ * `peers` is a HOST array of `world` device pointers: this process's mapping of every rank's channel buffer
+ * (peers[rank] = own buffer).  world <= 16.
+ *
+ * p2t_peer_allgather: buffer size ctrl + 2 * world * bytes_per_rank.  phases bit 0 (push): store `src`
+ * (bytes_per_rank, multiple of 16) into slot `rank` of every peer and raise the arrival flags; bit 1 (arrive): wait
+ * for all ranks' blocks of this round and copy the world * bytes_per_rank gathered bytes, rank-major, to `dst`.
+ * Kernels between the two halves overlap the transfer.  Rounds are double-buffered: a rank may run one round ahead.
+ *
+ * p2t_peer_allreduce_mean_bf16: buffer size ctrl + 2 * n_bytes; the caller has written its contribution
+ * (bf16, n_bytes multiple of 16) at offset ctrl.  phases bit 0: announce; bit 1: sum slice `rank` over all peers in
+ * rank order in fp32, store mean (bf16) to every peer at offset ctrl + n_bytes; bit 2: wait for all slices and copy
+ * the result to `dst` (may be NULL: read it in place).  Every rank obtains bit-identical results.
+ *
+ * A rank that waits more than 20 s for a peer stores 1 + that peer's rank in control word 4 and carries on.
+ * ------------------------------------------------------------------------------------------- */
+unsigned long long p2t_peer_ctrl_bytes(void);
+int p2t_peer_alloc(unsigned long long bytes, void** dptr, unsigned char* handle64);
+int p2t_peer_open(const unsigned char* handle64, void** dptr);
+int p2t_peer_close(void* dptr);
+int p2t_peer_free(void* dptr);
+int p2t_peer_allgather(void* const* peers, int world, int rank, const void* src, long long bytes_per_rank, void* dst,
+                       int phases, void* stream);
+int p2t_peer_allreduce_mean_bf16(void* const* peers, int world, int rank, long long n_bytes, void* dst, int phases,
+                                 void* stream);
+/* cudaMemcpyAsync device -> device on `stream` (moving contributions into / results out of a channel buffer, which
+ * torch cannot address as a tensor) */
+int p2t_copy_d2d(void* dst, const void* src, unsigned long long bytes, void* stream);
+/* control word 4 of this rank's channel buffer -> *status_host (synchronous; 0 = no time-out so far) */
+int p2t_peer_status(const void* channel_base, unsigned int* status_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW.step + zero_grad for up to 8 bf16 tensors per call
+ * (scripts/train_contrast.py:455-465, optimizer built at :621-626 with eps=1e-6, betas=(0.9, 0.999)).
+ * HOST arrays of `count` DEVICE pointers: params/grads bf16 (16-byte aligned), exp_avg/exp_avg_sq fp32,
+ * master fp32 or NULL entries / NULL array (then the bf16 parameter is the state, as in the reference).
+ *   partial_ws: fp32 [p2t_adamw_workspace_floats(count, numel)];  scal: fp32 [4] = {|g|, clip coefficient,
+ *   lr / (1 - beta1^t), 1 / sqrt(1 - beta2^t)} written each call;  lr_dev: device float;  step_dev: device int64 step
+ *   counter, incremented by the call.  max_norm <= 0 or inf: no clipping (|g| is still reported).
+ *   g' = g * min(1, max_norm / (|g| + 1e-6));  p *= 1 - lr*wd;  m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2;
+ *   p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).   zero_grad != 0 also clears the gradients.
+ * ------------------------------------------------------------------------------------------- */
+int p2t_adamw_workspace_floats(int count, const long long* numel);
+int p2t_adamw_step(int count, void* const* params, void* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                   float* const* master, const long long* numel, float* partial_ws, float* scal, const float* lr_dev,
+                   long long* step_dev, float beta1, float beta2, float eps, float weight_decay, float max_norm,
+                   int zero_grad, void* stream);
 
 #ifdef __cplusplus
 }

@@ -25,6 +25,14 @@ Reference sites restated (paths relative to /root/reference):
   scripts/train_contrast.py:100-114             SegmentedBatchInfoNCELoss     -> infonce_rows
   scripts/train_contrast.py:345-379             segment loop / averaging      -> step_forward
   scripts/train_contrast.py:448                 loss.backward()               -> step_backward
+SURVEY.md §8f rows (callers either side of the path):
+  scripts/train_contrast.py:455-465,621-626     clip_grad_norm_ + AdamW.step  -> clip_grad_norm, adamw_step
+                                                (third-party: torch.nn.utils.clip_grad_norm_, torch.optim.AdamW of
+                                                 torch==2.3.0 per the reference README; pinned against the installed
+                                                 torch 2.11 in tests/test_oracle_next.py and tests/golden/next_adamw.npz)
+  scripts/train_contrast.py:611-614             DDP gradient averaging        -> mean_allreduce_bf16
+  models/modeling_esm2llama_instruct.py:134-138 placeholder replacement       -> placeholder_scatter
+  models/esmc_qwen_arc.py:127-144               (same, with the count check)
 """
 from __future__ import annotations
 
@@ -302,3 +310,53 @@ def step_backward(st: StepTrace, x, prot_mask, w1, w2, tau: float = 0.05, num_se
     grads["dp"] = dp
     grads["de"] = de
     return grads
+
+
+# ----------------------------------------------------------------------------------------------
+# SURVEY.md §8f rows
+# ----------------------------------------------------------------------------------------------
+def clip_grad_norm(grads, max_norm: float):
+    """torch.nn.utils.clip_grad_norm_ (L2): returns (total_norm, clipped grads).  coefficient =
+    clamp(max_norm / (total_norm + 1e-6), max=1); max_norm = inf leaves the gradients untouched
+    (scripts/train_contrast.py:456-463)."""
+    total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads))
+    if max_norm is None or math.isinf(max_norm):
+        return total, [g.clone() for g in grads]
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    return total, [g * coef.to(g.dtype) for g in grads]
+
+
+def adamw_step(params, grads, exp_avg, exp_avg_sq, step: int, lr: float, betas=(0.9, 0.999), eps: float = 1e-6,
+               weight_decay: float = 1e-2):
+    """One torch.optim.AdamW step (decoupled weight decay, `step` counts from 1), out of place:
+    returns (params, exp_avg, exp_avg_sq).  Reference optimizer: AdamW(lr, eps=1e-6, betas=(0.9, 0.999)),
+    scripts/train_contrast.py:621-626 (weight_decay at torch's default 1e-2)."""
+    b1, b2 = betas
+    bc1, bc2 = 1.0 - b1 ** step, 1.0 - b2 ** step
+    out_p, out_m, out_v = [], [], []
+    for p, g, m, v in zip(params, grads, exp_avg, exp_avg_sq):
+        p = p * (1.0 - lr * weight_decay)
+        m = b1 * m + (1.0 - b1) * g
+        v = b2 * v + (1.0 - b2) * g * g
+        denom = v.sqrt() / math.sqrt(bc2) + eps
+        p = p - (lr / bc1) * m / denom
+        out_p.append(p); out_m.append(m); out_v.append(v)
+    return out_p, out_m, out_v
+
+
+def mean_allreduce_bf16(per_rank):
+    """What DDP's gradient averaging yields for bf16 gradients, evaluated the way csrc/peer.cu does: fp32 sum in rank
+    order, times 1/W, rounded to bf16 once."""
+    acc = torch.zeros_like(per_rank[0], dtype=torch.float32)
+    for g in per_rank:
+        acc = acc + g.to(torch.float32)
+    return (acc * (1.0 / len(per_rank))).to(torch.bfloat16)
+
+
+def placeholder_scatter(inputs_embeds, placeholder_mask, encoder_hidden_states, encoder_mask):
+    """inputs_embeds[placeholder_mask] = encoder_hidden_states[encoder_mask]
+    (models/modeling_esm2llama_instruct.py:134-138): the k-th valid encoder row, batch-major, goes to the k-th
+    placeholder slot, batch-major."""
+    out = inputs_embeds.clone()
+    out[placeholder_mask.bool()] = encoder_hidden_states[encoder_mask.bool()].to(out.dtype)
+    return out

@@ -31,7 +31,7 @@ SIGNATURES = {
     "p2t_pool_bwd_coef": [_vp, _ll, _vp, _ll, _vp, _i, _i, _i, _vp, _vp, _vp],
     "p2t_readout_bwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "p2t_adapter_tail_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
-    "p2t_adapter_tail_bwd_dy": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp],
+    "p2t_adapter_tail_bwd_dy": [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp],
     "p2t_adapter_bwd": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "p2t_similarity": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i, _vp],
     "p2t_infonce_col_stats": [_vp, _i, _i, _vp, _vp, _vp, _i, _vp],
@@ -42,11 +42,23 @@ SIGNATURES = {
     "p2t_bf16_to_f32": [_vp, _ll, _vp, _vp],
     "p2t_colsum": [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp],
     "p2t_dropout_mask": [_i, _i, _f, _ull, _i, _vp, _vp],
+    "p2t_adapter_scatter_rows": [_vp, _vp, _i, _i, _i, _i, _vp, _ll, _vp, _vp, _vp, _vp, _vp],
+    "p2t_peer_alloc": [_ull, C.POINTER(_vp), C.c_char_p],
+    "p2t_peer_open": [C.c_char_p, C.POINTER(_vp)],
+    "p2t_peer_close": [_vp],
+    "p2t_peer_free": [_vp],
+    "p2t_peer_allgather": [C.POINTER(_vp), _i, _i, _vp, _ll, _vp, _i, _vp],
+    "p2t_peer_allreduce_mean_bf16": [C.POINTER(_vp), _i, _i, _ll, _vp, _i, _vp],
+    "p2t_copy_d2d": [_vp, _vp, _ull, _vp],
+    "p2t_peer_status": [_vp, C.POINTER(C.c_uint)],
+    "p2t_adamw_step": [_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
+                       C.POINTER(_ll), _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _i, _vp],
     "p2t_gemm_timing_collect": [C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_double), _i],
 }
 NON_STATUS = {"p2t_abi_version": (_i, []), "p2t_last_error": (C.c_char_p, []),
               "p2t_launch_count": (_ull, []), "p2t_reset_launch_count": (None, []),
-              "p2t_gemm_timing_enable": (None, [_i]), "p2t_gemm_workspace_bytes": (_ull, [])}
+              "p2t_gemm_timing_enable": (None, [_i]), "p2t_gemm_workspace_bytes": (_ull, []),
+              "p2t_peer_ctrl_bytes": (_ull, []), "p2t_adamw_workspace_floats": (_i, [_i, C.POINTER(_ll)])}
 
 _lib = None
 

@@ -68,7 +68,7 @@ class _AdapterFunction(torch.autograd.Function):
         dy2d = dy.reshape(-1, d_out).to(torch.bfloat16).contiguous()
         dz2 = torch.empty(acts.rows_cap, d_out, dtype=torch.bfloat16, device=dy.device)
         _lib.call("p2t_adapter_tail_bwd_dy", _core._ptr(acts.a), _core._ptr(acts.g2), _core._ptr(ctx.inv_norm),
-                  _core._ptr(dy2d), n, acts.rows_cap, d_out, _core._ptr(dz2), _core._stream())
+                  _core._ptr(dy2d), n, None, acts.rows_cap, d_out, _core._ptr(dz2), _core._stream())
         need_dx = ctx.needs_input_grad[0]
         dw1, db1, dw2, db2, dx = _core.adapter_backward(acts, dz2, w1.contiguous(), w2.contiguous(), need_dx=need_dx)
         if dx is not None:

@@ -209,9 +209,9 @@ int p2t_adapter_tail_bwd(const void* a, const void* g2, const float* inv_norm, c
                                chunk_rows, max_chunks, dz2, colsum_ws, db2, S(stream));
 }
 int p2t_adapter_tail_bwd_dy(const void* a, const void* g2, const float* inv_norm, const void* dy, int n,
-                            int rows_cap, int d_out, void* dz2, void* stream) {
+                            const int* n_rows_dev, int rows_cap, int d_out, void* dz2, void* stream) {
   if (!a || !g2 || !inv_norm || !dy || !dz2) return set_error(-1, "p2t_adapter_tail_bwd_dy: null pointer");
-  return adapter_tail_backward_dy(a, g2, inv_norm, dy, n, rows_cap, d_out, dz2, S(stream));
+  return adapter_tail_backward_dy(a, g2, inv_norm, dy, n, n_rows_dev, rows_cap, d_out, dz2, S(stream));
 }
 
 int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, const void* h1, const void* g1, const void* dz2,
@@ -351,6 +351,67 @@ int p2t_dropout_mask(int rows, int cols, float dropout_p, unsigned long long see
   DropoutParams d = make_dropout(dropout_p, seed, layer);
   dropout_mask_kernel<<<256, 256, 0, S(stream)>>>(rows, cols, d, out);
   return check_launch("dropout_mask_kernel");
+}
+
+/* ---- Stage-2 hand-off: adapter rows straight into the LLM's inputs_embeds slots ---- */
+int p2t_adapter_scatter_rows(const void* a, const float* rowsq, int nblk, int rows_cap, int n, int d_out, void* dst,
+                             long long ld_dst, const int* row_dst, const int* n_rows_dev, const int* n_dst_dev,
+                             float* inv_norm, void* stream) {
+  if (!a || !rowsq || !dst || !row_dst) return set_error(-1, "p2t_adapter_scatter_rows: null pointer");
+  if (n > rows_cap) return set_error(-1, "p2t_adapter_scatter_rows: n > rows_cap");
+  return scatter_scaled_rows(a, rowsq, nblk, rows_cap, n, d_out, dst, ld_dst, row_dst, n_rows_dev, n_dst_dev, inv_norm, S(stream));
+}
+
+/* ---- exchange steps over NVLink peer memory ---- */
+unsigned long long p2t_peer_ctrl_bytes(void) { return (unsigned long long)peer_ctrl_bytes(); }
+int p2t_peer_alloc(unsigned long long bytes, void** dptr, unsigned char* handle64) { return peer_alloc((size_t)bytes, dptr, handle64); }
+int p2t_peer_open(const unsigned char* handle64, void** dptr) { return peer_open(handle64, dptr); }
+int p2t_peer_close(void* dptr) { return dptr ? peer_close(dptr) : set_error(-1, "p2t_peer_close: null pointer"); }
+int p2t_peer_free(void* dptr) { return dptr ? peer_free(dptr) : set_error(-1, "p2t_peer_free: null pointer"); }
+int p2t_peer_allgather(void* const* peers, int world, int rank, const void* src, long long bytes_per_rank, void* dst,
+                       int phases, void* stream) {
+  return peer_allgather(peers, world, rank, src, bytes_per_rank, dst, phases, S(stream));
+}
+int p2t_peer_allreduce_mean_bf16(void* const* peers, int world, int rank, long long n_bytes, void* dst, int phases,
+                                 void* stream) {
+  return peer_allreduce_mean(peers, world, rank, n_bytes, dst, phases, S(stream));
+}
+
+int p2t_copy_d2d(void* dst, const void* src, unsigned long long bytes, void* stream) {
+  if (!dst || !src) return set_error(-1, "p2t_copy_d2d: null pointer");
+  cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, S(stream));
+  if (e != cudaSuccess) return set_error((int)e, "p2t_copy_d2d: %s", cudaGetErrorString(e));
+  return 0;
+}
+int p2t_peer_status(const void* channel_base, unsigned int* status_host) {
+  if (!channel_base || !status_host) return set_error(-1, "p2t_peer_status: null pointer");
+  cudaError_t e = cudaMemcpy(status_host, static_cast<const unsigned*>(channel_base) + 4, sizeof(unsigned), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return set_error((int)e, "p2t_peer_status: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+/* ---- clip_grad_norm_ + AdamW ---- */
+int p2t_adamw_workspace_floats(int count, const long long* numel) {
+  if (!numel || count < 1) return 0;
+  int blocks = 0;
+  for (int i = 0; i < count; ++i) blocks += adamw_blocks(numel[i]);
+  return blocks;
+}
+int p2t_adamw_step(int count, void* const* params, void* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                   float* const* master, const long long* numel, float* partial_ws, float* scal, const float* lr_dev,
+                   long long* step_dev, float beta1, float beta2, float eps, float weight_decay, float max_norm,
+                   int zero_grad, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !numel || !partial_ws || !scal || !lr_dev || !step_dev)
+    return set_error(-1, "p2t_adamw_step: null pointer");
+  if (count < 1 || count > kAdamMaxTensors) return set_error(-1, "p2t_adamw_step: 1..%d tensors per call", kAdamMaxTensors);
+  AdamTable t{};
+  t.count = count;
+  for (int i = 0; i < count; ++i) {
+    t.param[i] = params[i]; t.grad[i] = grads[i]; t.exp_avg[i] = exp_avg[i]; t.exp_avg_sq[i] = exp_avg_sq[i];
+    t.master[i] = master ? master[i] : nullptr;
+    t.numel[i] = numel[i];
+  }
+  return adamw_step(t, partial_ws, scal, lr_dev, step_dev, beta1, beta2, eps, weight_decay, max_norm, zero_grad, S(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,287 @@
+// Exchange steps of the sharded contrastive step over NVLink peer memory (no NCCL on the data path):
+//   * all-gather of the unit-norm text embeddings (global negatives), push model: every rank stores
+//     its block straight into every peer's gather buffer and raises a per-source flag there;
+//   * mean all-reduce of the adapter weight gradients (what DDP does in the reference, scripts/train_contrast.py:611-614),
+//     two-shot: rank k sums slice k out of every peer's buffer (P2P loads, fixed rank order = identical bits on all
+//     ranks) and stores the mean back into every peer's result buffer.
+// Everything is plain kernels on the caller's stream with device-resident epochs, so the whole sharded step
+// (exchange included) can be captured in one CUDA graph.  Peer buffers are cudaMalloc'ed here (they must be
+// exportable with cudaIpcGetMemHandle, which torch's caching allocator does not guarantee) and mapped by the peers
+// with cudaIpcOpenMemHandle; the handles travel through torch.distributed on the host side (peer.py).
+//
+// Flag protocol.  A channel owns, in its peer buffer, `world` arrival words per phase; a writer publishes with
+// data stores -> __threadfence_system() -> (last CTA) st.release.sys flag := epoch; a reader spins with
+// ld.acquire.sys until flag - epoch >= 0 and then reads the data with L1-bypassing loads.  The epoch lives in device
+// memory and is advanced by the channel's last kernel of a round, so graph replays need no host-side argument.
+// A reader that waits longer than `timeout_ns` gives up, records it in `status` and lets the stream drain (the host
+// raises on the next status check) instead of hanging the GPU.
+#include "common.h"
+#include "mathfn.cuh"
+#include "rows.h"
+
+namespace p2t {
+namespace {
+
+constexpr int kPeerMaxWorld = 16;
+constexpr unsigned long long kTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;  // 20 s
+
+struct PeerTable {
+  void* base[kPeerMaxWorld];  // base[r] = this process's mapping of rank r's peer buffer (base[rank] = own)
+};
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ld_sys_v4(const uint4* p) {  // relaxed system-scope load: never served from a stale L1 line
+  uint4 v;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Threads [0, world) of the CTA wait for flags[t] to reach `epoch`; returns after a CTA-wide barrier.
+__device__ __forceinline__ void wait_flags(const unsigned* flags, int world, unsigned epoch, unsigned* status) {
+  if ((int)threadIdx.x < world) {
+    const unsigned long long t0 = global_ns();
+    while ((int)(ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) {
+      if (global_ns() - t0 > kTimeoutNs) {
+        atomicExch(status, 1u + threadIdx.x);
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+}
+
+// Every thread has fenced its stores; the last CTA of the grid to get here publishes `epoch` in slot `rank` of the
+// flag row at byte offset `flag_off` of every peer buffer (and, optionally, advances the local epoch word).
+__device__ __forceinline__ void publish_when_grid_done(const PeerTable& peers, int world, int rank, size_t flag_off,
+                                                       unsigned epoch, unsigned* grid_counter, unsigned* epoch_word) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(grid_counter, 1u);
+    if (done == gridDim.x - 1) {
+      __threadfence_system();
+      if (flag_off != (size_t)-1)
+        for (int r = 0; r < world; ++r)
+          st_release_sys(reinterpret_cast<unsigned*>(static_cast<char*>(peers.base[r]) + flag_off) + rank, epoch);
+      *grid_counter = 0;
+      if (epoch_word) *epoch_word = epoch;
+    }
+  }
+}
+
+// ---- control block at the start of every channel buffer ----
+//   u32 [0]            epoch of the last completed round
+//   u32 [1], [2], [3]  grid counters of the channel's kernels
+//   u32 [4]            status (0 = ok, 1 + r = timed out waiting for rank r)
+//   u32 [64 + ph*16 + r]  arrival flag of phase ph (0, 1) from rank r
+constexpr size_t kCtrlBytes = 1024;
+__host__ __device__ constexpr size_t flag_row_off(int phase) { return (64 + phase * 16) * sizeof(unsigned); }
+
+// ------------------------------------------------------------------------------------------------
+// all-gather, push half: slot (epoch parity, rank) of every peer's buffer := src
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+peer_allgather_push_kernel(PeerTable peers, int world, int rank, const uint4* __restrict__ src, long long vecs_per_rank) {
+  unsigned* ctrl = static_cast<unsigned*>(peers.base[rank]);
+  const unsigned epoch = ctrl[0] + 1;
+  const size_t slot_off = kCtrlBytes + ((size_t)(epoch & 1) * world + rank) * (size_t)vecs_per_rank * sizeof(uint4);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < vecs_per_rank; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(src + i);
+    for (int r = 0; r < world; ++r) {
+      const int dst = (rank + r) % world;  // ranks start on different links
+      reinterpret_cast<uint4*>(static_cast<char*>(peers.base[dst]) + slot_off)[i] = v;
+    }
+  }
+  publish_when_grid_done(peers, world, rank, flag_row_off(0), epoch, ctrl + 1, nullptr);
+}
+
+// all-gather, arrival half: wait for every rank's block of this epoch, copy the gathered rows out, close the round
+__global__ void __launch_bounds__(256)
+peer_allgather_wait_kernel(PeerTable peers, int world, int rank, uint4* __restrict__ dst, long long vecs_per_rank) {
+  unsigned* ctrl = static_cast<unsigned*>(peers.base[rank]);
+  const unsigned epoch = ctrl[0] + 1;
+  wait_flags(reinterpret_cast<const unsigned*>(static_cast<char*>(peers.base[rank]) + flag_row_off(0)), world, epoch, ctrl + 4);
+  const uint4* slots = reinterpret_cast<const uint4*>(static_cast<char*>(peers.base[rank]) + kCtrlBytes +
+                                                      (size_t)(epoch & 1) * world * (size_t)vecs_per_rank * sizeof(uint4));
+  const long long total = vecs_per_rank * world;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = ld_sys_v4(slots + i);
+  publish_when_grid_done(peers, world, rank, (size_t)-1, epoch, ctrl + 2, ctrl);
+}
+
+// ------------------------------------------------------------------------------------------------
+// mean all-reduce of a flat bf16 vector (adapter weight gradients), two-shot over peer memory
+//   buffer layout after the control block: in[n_vec] (this rank's contribution), out[n_vec] (reduced result)
+// ------------------------------------------------------------------------------------------------
+// phase 0: this rank's contribution is in place (stream order) -> tell everybody
+__global__ void peer_allreduce_ready_kernel(PeerTable peers, int world, int rank) {
+  unsigned* ctrl = static_cast<unsigned*>(peers.base[rank]);
+  const unsigned epoch = ctrl[0] + 1;
+  publish_when_grid_done(peers, world, rank, flag_row_off(0), epoch, ctrl + 1, nullptr);
+}
+
+// phase 1: reduce my slice out of every peer's `in`, store the mean into every peer's `out`
+__global__ void __launch_bounds__(256)
+peer_allreduce_reduce_kernel(PeerTable peers, int world, int rank, long long n_vec, float scale) {
+  unsigned* ctrl = static_cast<unsigned*>(peers.base[rank]);
+  const unsigned epoch = ctrl[0] + 1;
+  wait_flags(reinterpret_cast<const unsigned*>(static_cast<char*>(peers.base[rank]) + flag_row_off(0)), world, epoch, ctrl + 4);
+  const long long per = (n_vec + world - 1) / world;
+  const long long lo = per * rank, hi = min(n_vec, lo + per);
+  const size_t in_off = kCtrlBytes, out_off = kCtrlBytes + (size_t)n_vec * sizeof(uint4);
+  for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r0 = 0; r0 < world; r0 += 8) {  // fixed rank order: every rank computes bit-identical sums
+      uint4 u[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)  // all loads of a batch are in flight together (NVLink latency ~2 us)
+        if (r0 + j < world) u[j] = ld_sys_v4(reinterpret_cast<const uint4*>(static_cast<char*>(peers.base[r0 + j]) + in_off) + i);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (r0 + j < world) {
+          const float2 a = unpack_bf16x2(u[j].x), b = unpack_bf16x2(u[j].y), c = unpack_bf16x2(u[j].z), d = unpack_bf16x2(u[j].w);
+          acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+          acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+        }
+    }
+    const uint4 o = make_uint4(pack_bf16x2(acc[0] * scale, acc[1] * scale), pack_bf16x2(acc[2] * scale, acc[3] * scale),
+                               pack_bf16x2(acc[4] * scale, acc[5] * scale), pack_bf16x2(acc[6] * scale, acc[7] * scale));
+    for (int r = 0; r < world; ++r) {
+      const int dst = (rank + r) % world;
+      reinterpret_cast<uint4*>(static_cast<char*>(peers.base[dst]) + out_off)[i] = o;
+    }
+  }
+  publish_when_grid_done(peers, world, rank, flag_row_off(1), epoch, ctrl + 2, nullptr);
+}
+
+// phase 2: every slice of `out` has arrived -> (optionally) copy it to the caller's flat buffer, close the round
+__global__ void __launch_bounds__(256)
+peer_allreduce_wait_kernel(PeerTable peers, int world, int rank, long long n_vec, uint4* __restrict__ dst) {
+  unsigned* ctrl = static_cast<unsigned*>(peers.base[rank]);
+  const unsigned epoch = ctrl[0] + 1;
+  wait_flags(reinterpret_cast<const unsigned*>(static_cast<char*>(peers.base[rank]) + flag_row_off(1)), world, epoch, ctrl + 4);
+  if (dst != nullptr) {
+    const uint4* out = reinterpret_cast<const uint4*>(static_cast<char*>(peers.base[rank]) + kCtrlBytes) + n_vec;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x)
+      dst[i] = ld_sys_v4(out + i);
+  }
+  publish_when_grid_done(peers, world, rank, (size_t)-1, epoch, ctrl + 3, ctrl);
+}
+
+int fill_table(PeerTable& t, void* const* peers, int world, int rank, const char* what) {
+  if (!peers) return set_error(-1, "%s: null peer table", what);
+  if (world < 1 || world > kPeerMaxWorld) return set_error(-1, "%s: world %d outside [1, %d]", what, world, kPeerMaxWorld);
+  if (rank < 0 || rank >= world) return set_error(-1, "%s: rank %d outside [0, %d)", what, rank, world);
+  for (int r = 0; r < world; ++r) {
+    if (!peers[r]) return set_error(-1, "%s: peer %d not mapped", what, r);
+    t.base[r] = peers[r];
+  }
+  return 0;
+}
+
+int grid_for(long long vecs) {
+  const long long want = (vecs + 255) / 256;
+  const long long cap = sm_count() / 2 > 0 ? sm_count() / 2 : 1;  // all CTAs of a waiting kernel must be co-resident
+  return (int)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+}  // namespace
+
+size_t peer_ctrl_bytes() { return kCtrlBytes; }
+
+int peer_alloc(size_t bytes, void** dptr, unsigned char* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!dptr || !handle64 || bytes == 0) return set_error(-1, "p2t_peer_alloc: bad argument");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return set_error((int)e, "p2t_peer_alloc: cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+  e = cudaMemset(p, 0, bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return set_error((int)e, "p2t_peer_alloc: %s", cudaGetErrorString(e));
+  }
+  memcpy(handle64, &h, 64);
+  *dptr = p;
+  return 0;
+}
+
+int peer_open(const unsigned char* handle64, void** dptr) {
+  if (!dptr || !handle64) return set_error(-1, "p2t_peer_open: bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return set_error((int)e, "p2t_peer_open: cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+  *dptr = p;
+  return 0;
+}
+
+int peer_close(void* dptr) {
+  cudaError_t e = cudaIpcCloseMemHandle(dptr);
+  if (e != cudaSuccess) return set_error((int)e, "p2t_peer_close: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int peer_free(void* dptr) {
+  cudaError_t e = cudaFree(dptr);
+  if (e != cudaSuccess) return set_error((int)e, "p2t_peer_free: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int peer_allgather(void* const* peers, int world, int rank, const void* src, long long bytes_per_rank, void* dst,
+                   int phases, cudaStream_t st) {
+  PeerTable t{};
+  if (int r = fill_table(t, peers, world, rank, "p2t_peer_allgather")) return r;
+  if (bytes_per_rank <= 0 || bytes_per_rank % 16) return set_error(-1, "p2t_peer_allgather: bytes_per_rank must be a positive multiple of 16");
+  const long long vecs = bytes_per_rank / 16;
+  if (phases & 1) {
+    if (!src) return set_error(-1, "p2t_peer_allgather: null src");
+    peer_allgather_push_kernel<<<grid_for(vecs), 256, 0, st>>>(t, world, rank, static_cast<const uint4*>(src), vecs);
+    if (int r = check_launch("peer_allgather_push_kernel")) return r;
+  }
+  if (phases & 2) {
+    if (!dst) return set_error(-1, "p2t_peer_allgather: null dst");
+    peer_allgather_wait_kernel<<<grid_for(vecs * world), 256, 0, st>>>(t, world, rank, static_cast<uint4*>(dst), vecs);
+    if (int r = check_launch("peer_allgather_wait_kernel")) return r;
+  }
+  return 0;
+}
+
+int peer_allreduce_mean(void* const* peers, int world, int rank, long long n_bytes, void* dst, int phases, cudaStream_t st) {
+  PeerTable t{};
+  if (int r = fill_table(t, peers, world, rank, "p2t_peer_allreduce_mean_bf16")) return r;
+  if (n_bytes <= 0 || n_bytes % 16) return set_error(-1, "p2t_peer_allreduce_mean_bf16: n_bytes must be a positive multiple of 16");
+  const long long n_vec = n_bytes / 16;
+  if (phases & 1) {
+    peer_allreduce_ready_kernel<<<1, 32, 0, st>>>(t, world, rank);
+    if (int r = check_launch("peer_allreduce_ready_kernel")) return r;
+  }
+  if (phases & 2) {
+    peer_allreduce_reduce_kernel<<<grid_for((n_vec + world - 1) / world), 256, 0, st>>>(t, world, rank, n_vec, 1.f / (float)world);
+    if (int r = check_launch("peer_allreduce_reduce_kernel")) return r;
+  }
+  if (phases & 4) {
+    peer_allreduce_wait_kernel<<<grid_for(n_vec), 256, 0, st>>>(t, world, rank, n_vec, static_cast<uint4*>(dst));
+    if (int r = check_launch("peer_allreduce_wait_kernel")) return r;
+  }
+  return 0;
+}
+
+}  // namespace p2t

@@ -751,8 +751,9 @@ parts_colsum_final_kernel(const float* __restrict__ partial, const int* __restri
 template <int NV>
 __global__ void __launch_bounds__(256)
 adapter_tail_bwd_dy_kernel(const __half* __restrict__ a, const __half* __restrict__ g,
-                           const float* __restrict__ inv_norm, const __nv_bfloat16* __restrict__ dy, int n, int cap,
-                           int D, __nv_bfloat16* __restrict__ dz2) {
+                           const float* __restrict__ inv_norm, const __nv_bfloat16* __restrict__ dy, int n,
+                           const int* __restrict__ n_dev, int cap, int D, __nv_bfloat16* __restrict__ dz2) {
+  if (n_dev) n = min(n, *n_dev);
   const int n_pad = min(cap, (n + 255) & ~255);
   const int lane = threadIdx.x & 31;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
@@ -810,13 +811,19 @@ adapter_tail_bwd_dy_kernel(const __half* __restrict__ a, const __half* __restric
   }
 }
 
-// y[row] = a[row] * inv_norm[row]  (module API forward tail).  inv from rowsq partials.
+// y[dst(row)] = a[row] * inv_norm[row]  (module API forward tail).  inv from rowsq partials.  dst(row) = row, or
+// row_dst[row] when the rows go straight into another tensor's slots (Stage-2 placeholder replacement,
+// models/esmc_qwen_arc.py:142: inputs_embeds[placeholder_mask] = encoder_hidden_states[encoder_mask]).
+// n_dev / n_dst_dev (optional, device) bound the row count from both sides without a host sync.
 __global__ void __launch_bounds__(256)
 scale_rows_kernel(const __half* __restrict__ a, const float* __restrict__ rowsq, int nblk, int cap, int n, int D,
-                  __nv_bfloat16* __restrict__ y, float* __restrict__ inv_norm_out) {
+                  __nv_bfloat16* __restrict__ y, long long ld_y, const int* __restrict__ row_dst,
+                  const int* __restrict__ n_dev, const int* __restrict__ n_dst_dev, float* __restrict__ inv_norm_out) {
   const int lane = threadIdx.x & 31;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
   const int nvec = D >> 3;
+  if (n_dev) n = min(n, *n_dev);
+  if (n_dst_dev) n = min(n, *n_dst_dev);
   for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps_total) {
     float s = 0.f;
     for (int j = lane; j < nblk; j += 32) s += rowsq[(long long)j * cap + row];  // (order differs from row_inv_norm: module API only)
@@ -824,7 +831,7 @@ scale_rows_kernel(const __half* __restrict__ a, const float* __restrict__ rowsq,
     const float inv = 1.f / fmaxf(sqrtf(s), kEpsNorm);
     if (lane == 0 && inv_norm_out) inv_norm_out[row] = inv;
     const uint4* ar = reinterpret_cast<const uint4*>(a + (long long)row * D);
-    uint4* yr = reinterpret_cast<uint4*>(y + (long long)row * D);
+    uint4* yr = reinterpret_cast<uint4*>(y + (long long)(row_dst ? row_dst[row] : row) * ld_y);
     for (int v = lane; v < nvec; v += 32) {
       const uint4 u = __ldg(ar + v);
       const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -1067,27 +1074,33 @@ int adapter_tail_backward(const void* a, const void* g, const float* inv_norm, c
 }
 
 template <int NV>
-static int tail_bwd_dy_launch(const void* a, const void* g, const float* inv_norm, const void* dy, int n, int cap, int D,
-                              void* dz2, cudaStream_t st) {
+static int tail_bwd_dy_launch(const void* a, const void* g, const float* inv_norm, const void* dy, int n,
+                              const int* n_dev, int cap, int D, void* dz2, cudaStream_t st) {
   const int blocks = min((cap + 7) / 8, sm_count() * 8);
   adapter_tail_bwd_dy_kernel<NV><<<blocks, 256, 0, st>>>(
       reinterpret_cast<const __half*>(a), reinterpret_cast<const __half*>(g), inv_norm,
-      reinterpret_cast<const __nv_bfloat16*>(dy), n, cap, D, reinterpret_cast<__nv_bfloat16*>(dz2));
+      reinterpret_cast<const __nv_bfloat16*>(dy), n, n_dev, cap, D, reinterpret_cast<__nv_bfloat16*>(dz2));
   return check_launch("adapter_tail_bwd_dy_kernel");
 }
-int adapter_tail_backward_dy(const void* a, const void* g, const float* inv_norm, const void* dy, int n, int cap, int D,
-                             void* dz2, cudaStream_t st) {
+int adapter_tail_backward_dy(const void* a, const void* g, const float* inv_norm, const void* dy, int n,
+                             const int* n_dev, int cap, int D, void* dz2, cudaStream_t st) {
   if (D % 8 || D > 4096) return set_error(-1, "adapter_tail_backward_dy: D must be a multiple of 8 and <= 4096");
-  if (D <= 2048) return tail_bwd_dy_launch<8>(a, g, inv_norm, dy, n, cap, D, dz2, st);
-  return tail_bwd_dy_launch<16>(a, g, inv_norm, dy, n, cap, D, dz2, st);
+  if (D <= 2048) return tail_bwd_dy_launch<8>(a, g, inv_norm, dy, n, n_dev, cap, D, dz2, st);
+  return tail_bwd_dy_launch<16>(a, g, inv_norm, dy, n, n_dev, cap, D, dz2, st);
 }
 
 int scale_rows(const void* a, const float* rowsq, int nblk, int cap, int n, int D, void* y, float* inv_norm_out,
                cudaStream_t st) {
+  return scatter_scaled_rows(a, rowsq, nblk, cap, n, D, y, D, nullptr, nullptr, nullptr, inv_norm_out, st);
+}
+
+int scatter_scaled_rows(const void* a, const float* rowsq, int nblk, int cap, int n, int D, void* y, long long ld_y,
+                        const int* row_dst, const int* n_dev, const int* n_dst_dev, float* inv_norm_out, cudaStream_t st) {
   if (n <= 0) return 0;
+  if (D % 8 || ld_y % 8) return set_error(-1, "scale_rows: D and the destination row stride must be multiples of 8");
   const int blocks = min((n + 7) / 8, sm_count() * 8);
   scale_rows_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __half*>(a), rowsq, nblk, cap, n, D,
-                                            reinterpret_cast<__nv_bfloat16*>(y), inv_norm_out);
+                                            reinterpret_cast<__nv_bfloat16*>(y), ld_y, row_dst, n_dev, n_dst_dev, inv_norm_out);
   return check_launch("scale_rows_kernel");
 }
 

@@ -28,10 +28,12 @@ int pool_bwd_coef(const float* de, long long ld_de, const float* stats, long lon
 int adapter_tail_backward(const void* a, const void* g, const float* inv_norm, const int* seq_off, const int* chunk_off,
                           const int* chunk_seq, int B, const float* c1, const float* c2, const int* n_rows, int cap, int D,
                           int rc, int max_chunks, void* dz2, float* colsum_partial, void* db2, cudaStream_t st);
-int adapter_tail_backward_dy(const void* a, const void* g, const float* inv_norm, const void* dy, int n, int cap, int D,
-                             void* dz2, cudaStream_t st);
+int adapter_tail_backward_dy(const void* a, const void* g, const float* inv_norm, const void* dy, int n,
+                             const int* n_dev, int cap, int D, void* dz2, cudaStream_t st);
 int scale_rows(const void* a, const float* rowsq, int nblk, int cap, int n, int D, void* y, float* inv_norm_out,
                cudaStream_t st);
+int scatter_scaled_rows(const void* a, const float* rowsq, int nblk, int cap, int n, int D, void* y, long long ld_y,
+                        const int* row_dst, const int* n_dev, const int* n_dst_dev, float* inv_norm_out, cudaStream_t st);
 int readout_backward(const void* x, const void* mask, int mask_bytes, int B, int S, int D, const float* c1,
                      const float* c2, void* dx, cudaStream_t st);
 int colsum(const void* x, const int* n_rows, int n_static, int D, float* partial, void* out_bf16, float* out_f32,
@@ -53,6 +55,32 @@ int convert_bf16_to_f32(const void* in, long long n, float* out, cudaStream_t st
 
 int launch_gemm(const void* a, long long lda, bool a_mn, const void* b, long long ldb, bool b_mn, int epi,
                 GemmParams p, int cta_group, cudaStream_t stream);
+
+// peer.cu: exchange steps over NVLink peer memory
+size_t peer_ctrl_bytes();
+int peer_alloc(size_t bytes, void** dptr, unsigned char* handle64);
+int peer_open(const unsigned char* handle64, void** dptr);
+int peer_close(void* dptr);
+int peer_free(void* dptr);
+int peer_allgather(void* const* peers, int world, int rank, const void* src, long long bytes_per_rank, void* dst,
+                   int phases, cudaStream_t st);
+int peer_allreduce_mean(void* const* peers, int world, int rank, long long n_bytes, void* dst, int phases, cudaStream_t st);
+
+// optim.cu: clip_grad_norm_ + AdamW over a table of tensors
+constexpr int kAdamMaxTensors = 8;
+struct AdamTable {
+  int count;
+  int block_start[kAdamMaxTensors];
+  long long numel[kAdamMaxTensors];
+  void* param[kAdamMaxTensors];       // bf16
+  void* grad[kAdamMaxTensors];        // bf16
+  float* exp_avg[kAdamMaxTensors];
+  float* exp_avg_sq[kAdamMaxTensors];
+  float* master[kAdamMaxTensors];     // fp32 master weights or nullptr
+};
+int adamw_blocks(long long numel);
+int adamw_step(AdamTable t, float* partial_ws, float* scal, const float* lr_dev, long long* step_dev, float beta1,
+               float beta2, float eps, float weight_decay, float max_norm, int zero_grad, cudaStream_t st);
 
 size_t gemm_streamk_workspace_bytes();
 const char* last_error();

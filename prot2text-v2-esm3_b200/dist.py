@@ -21,6 +21,66 @@ import torch
 import torch.distributed as dist
 
 from . import step as _step
+from .peer import PeerAllGather
+
+
+class ShardedExchange:
+    """The exchange channels of the sharded step over NVLink peer memory (csrc/peer.cu), built once per
+    (pairs per rank, embedding width): `text` all-gathers the (B, E) fp32 unit-norm text embeddings, `stats` the
+    (2, W*B) per-column (max, sum-exp) statistics of the symmetric loss.  With an exchange no NCCL call is on the data
+    path and the sharded step is capturable in a CUDA graph (`graph.GraphedContrastiveStep(exchange=...)`)."""
+
+    def __init__(self, pairs_per_rank: int, embed_dim: int, group=None, symmetric: bool = False):
+        self.group = group
+        self.text = PeerAllGather(pairs_per_rank, embed_dim, torch.float32, group)
+        self.rank, self.world = self.text.rank, self.text.world
+        self.stats = PeerAllGather(2, self.world * pairs_per_rank, torch.float32, group) if symmetric else None
+
+    def merge_column_stats(self, col_max: torch.Tensor, col_sum: torch.Tensor):
+        if self.stats is None:
+            raise ValueError("build the exchange with symmetric=True to merge column statistics")
+        gathered = self.stats(torch.stack([col_max, col_sum])).view(self.world, 2, -1)
+        return _merge(gathered[:, 0], gathered[:, 1])
+
+    def check(self) -> None:
+        """Raise if a peer-memory wait timed out since the last check (synchronises the device)."""
+        self.text.buffer.check()
+        if self.stats is not None:
+            self.stats.buffer.check()
+
+    def close(self) -> None:
+        self.text.close()
+        if self.stats is not None:
+            self.stats.close()
+
+
+def balanced_shards(lengths, world: int):
+    """Assign the pairs of a global batch to `world` ranks, the same number of pairs each, so that the ranks' residue
+    row totals are as equal as a greedy longest-first pass gets them.  The step time of a rank is proportional to its
+    valid residue rows (the adapter GEMMs), and every rank waits for the slowest at the exchange; the reference's
+    DistributedSampler (scripts/train_contrast.py:551-556) shards at random, which at 32 pairs of 50..1024 residues
+    leaves the heaviest of 8 ranks ~13 % above the mean.  The loss is invariant under the permutation (labels follow
+    the pairs).  Returns a list of `world` index lists into `lengths`."""
+    lengths = [int(v) for v in lengths]
+    n = len(lengths)
+    if world < 1 or n % world:
+        raise ValueError("the global batch must split into equal shards")
+    per = n // world
+    order = sorted(range(n), key=lambda i: (-lengths[i], i))
+    shards, totals = [[] for _ in range(world)], [0] * world
+    for i in order:
+        open_ranks = [r for r in range(world) if len(shards[r]) < per]
+        r = min(open_ranks, key=lambda k: (totals[k], k))
+        shards[r].append(i)
+        totals[r] += lengths[i]
+    return shards
+
+
+def _merge(m_all: torch.Tensor, s_all: torch.Tensor):
+    """M = max_k m_k, S = sum_k s_k exp(m_k - M) over the leading (rank) axis."""
+    m = m_all.max(dim=0).values
+    s = (s_all * torch.exp(m_all - m)).sum(dim=0)
+    return m, s
 
 
 def all_gather_embeddings(t_local: torch.Tensor, group=None, async_op: bool = False):
@@ -46,10 +106,7 @@ def merge_column_stats(col_max: torch.Tensor, col_sum: torch.Tensor, group=None)
     gathered = torch.empty(world * 2, col_max.shape[0], dtype=packed.dtype, device=packed.device)
     dist.all_gather_into_tensor(gathered, packed, group=group)
     gathered = gathered.view(world, 2, -1)
-    m_all, s_all = gathered[:, 0], gathered[:, 1]
-    m = m_all.max(dim=0).values
-    s = (s_all * torch.exp(m_all - m)).sum(dim=0)
-    return m, s
+    return _merge(gathered[:, 0], gathered[:, 1])
 
 
 def reduce_scatter_text_grad(dt_full: torch.Tensor, group=None) -> torch.Tensor:
@@ -63,17 +120,31 @@ def reduce_scatter_text_grad(dt_full: torch.Tensor, group=None) -> torch.Tensor:
 def distributed_contrastive_step(residue_states, protein_mask, adapter, text_hidden, text_mask, *,
                                  residue_lengths=None, text_lengths=None,
                                  temperature: float = 0.05, symmetric: bool = False, group=None,
-                                 aux: Optional[_step.StepAux] = None, **step_kw) -> torch.Tensor:
+                                 aux: Optional[_step.StepAux] = None, exchange: Optional[ShardedExchange] = None,
+                                 **step_kw) -> torch.Tensor:
     """Sharded-batch contrastive step with all-gathered negatives; returns the local mean loss.
-    Accepts the padded (mask) or the packed (lengths) input form of `contrastive_step`."""
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    Accepts the padded (mask) or the packed (lengths) input form of `contrastive_step`.
+    `exchange`: a ShardedExchange — the gather (and the column-statistics merge) then run as peer-memory kernels on
+    the current stream instead of NCCL collectives."""
+    if exchange is not None:
+        rank, world = exchange.rank, exchange.world
+    else:
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
     t_local = _step.text_embeddings(text_hidden, text_mask, dtype=torch.float32, text_lengths=text_lengths)
-    # the gather runs on NCCL's stream behind the plan/pack kernels of the protein side and is waited for right
-    # before the (persistent, one-CTA-per-SM) adapter GEMMs
-    t_global = all_gather_embeddings(t_local, group, async_op=True) if world > 1 else t_local
+    # the gather travels behind the plan/pack kernels of the protein side and is waited for right before the
+    # (persistent, one-CTA-per-SM) adapter GEMMs
+    if exchange is not None:
+        exchange.text.push(t_local)
+        t_global = exchange.text.arrive
+    else:
+        t_global = all_gather_embeddings(t_local, group, async_op=True) if world > 1 else t_local
     B = residue_lengths.shape[0] if residue_lengths is not None else residue_states.shape[0]
-    labels = torch.arange(rank * B, (rank + 1) * B, device=residue_states.device, dtype=torch.int32)
-    hook = (lambda m, s: merge_column_stats(m, s, group)) if (symmetric and world > 1) else None
+    labels = _step._rank_labels(rank, B, residue_states.device)
+    if symmetric and world > 1:
+        hook = exchange.merge_column_stats if (exchange is not None and exchange.stats is not None) \
+            else (lambda m, s: merge_column_stats(m, s, group))
+    else:
+        hook = None
     return _step.contrastive_step(residue_states, protein_mask, adapter, text_embeds=t_global,
                                   residue_lengths=residue_lengths,
                                   temperature=temperature, symmetric=symmetric, labels=labels, aux=aux,

@@ -27,13 +27,19 @@ from .step import StepAux, contrastive_step, step_backward
 class GraphedContrastiveStep:
     def __init__(self, adapter: ModalityAdapter, residue_states: torch.Tensor, protein_mask: torch.Tensor,
                  text_hidden: torch.Tensor, text_mask: torch.Tensor, *, temperature: float = 0.05,
-                 contrastive_num_segments: int = 1, symmetric: bool = False, seed: int = 0, warmup: int = 2):
+                 contrastive_num_segments: int = 1, symmetric: bool = False, seed: int = 0, warmup: int = 2,
+                 exchange=None, grad_reducer=None):
         if not residue_states.is_cuda:
             raise _lib.P2TError("GraphedContrastiveStep needs CUDA tensors: this package has no CPU path")
         self.adapter = adapter
         self.inputs = (residue_states, protein_mask, text_hidden, text_mask)
-        # (single-process step only: capturing the sharded step's NCCL all-gather hung on this stack — torch 2.11,
-        #  NCCL 2.28.9, async_op + wait inside capture — so the multi-GPU step stays on eager launches)
+        # Sharded step: pass `exchange` (dist.ShardedExchange).  Its gather is a pair of peer-memory kernels, so the
+        # exchange is captured with everything else.  (Capturing the NCCL all-gather instead hung on this stack —
+        # torch 2.11, NCCL 2.28.9, async_op + wait inside capture.)  `grad_reducer` (peer.PeerGradAllReduce) appends
+        # the mean all-reduce of the four weight gradients, DDP's job in the reference (scripts/train_contrast.py:611-614).
+        self.exchange, self.grad_reducer = exchange, grad_reducer
+        if exchange is not None and contrastive_num_segments != 1:
+            raise ValueError("the sharded step averages over the whole local batch: contrastive_num_segments must be 1")
         self.kw = dict(temperature=temperature, contrastive_num_segments=contrastive_num_segments, symmetric=symmetric)
         self.params = [adapter.fc1.weight, adapter.fc1.bias, adapter.fc2.weight, adapter.fc2.bias]
         dev = residue_states.device
@@ -61,8 +67,17 @@ class GraphedContrastiveStep:
         with stream capture): forward, then the explicit backward for an upstream gradient of 1."""
         self.seed.add_(1)  # captured: each replay draws a fresh dropout mask
         x, pm, th, tm = self.inputs
-        loss, state = contrastive_step(x, pm, self.adapter, th, tm, aux=self.aux, seed_dev=self.seed, _raw=True, **self.kw)
-        return loss, list(step_backward(state, None))
+        if self.exchange is None:
+            loss, state = contrastive_step(x, pm, self.adapter, th, tm, aux=self.aux, seed_dev=self.seed, _raw=True, **self.kw)
+        else:
+            from .dist import distributed_contrastive_step
+            loss, state = distributed_contrastive_step(x, pm, self.adapter, th, tm, aux=self.aux, seed_dev=self.seed,
+                                                       _raw=True, exchange=self.exchange, temperature=self.kw["temperature"],
+                                                       symmetric=self.kw["symmetric"])
+        grads = list(step_backward(state, None))
+        if self.grad_reducer is not None:
+            self.grad_reducer.reduce_(grads)
+        return loss, grads
 
     def replay(self) -> torch.Tensor:
         """Run the captured step on the current contents of the input tensors; returns the (static) loss tensor."""

@@ -1,0 +1,217 @@
+"""Exchange steps of the sharded contrastive step over NVLink peer memory (csrc/peer.cu).
+
+The sharded step has ONE data-path exchange: the all-gather of the unit-norm text embeddings that
+form the global negatives; the training loop around it has a second one, the mean all-reduce of the adapter weight
+gradients (DistributedDataParallel in the reference, scripts/train_contrast.py:611-614).  Both run here as plain
+kernels that store into / load from the peers' buffers over NVLink, with arrival flags and epochs in device memory:
+no NCCL call sits on the data path, nothing touches the host, and the whole sharded step is capturable in one CUDA
+graph (`graph.GraphedContrastiveStep(..., exchange=...)`).  `torch.distributed` is used once, at construction, to
+pass the 64-byte IPC handles around.
+
+    gather = PeerAllGather(rows=B, cols=2 * H, dtype=torch.float32)          # once
+    gather.push(t_local)                                                      # every step: returns immediately
+    ... plan / pack kernels of the protein side overlap the transfer ...
+    t_global = gather.arrive()                                                # (W*B, 2H), rank-major
+
+    reducer = PeerGradAllReduce([p for p in adapter.parameters() if p.requires_grad])
+    reducer.reduce_([p.grad for p in ...])                                    # grads := mean over ranks, in place
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+_PUSH, _ARRIVE = 1, 2
+_READY, _REDUCE, _WAIT = 1, 2, 4
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _rank_world(group) -> tuple:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+class PeerBuffer:
+    """One zero-initialised device buffer per rank, mapped into every rank of `group` (same node).
+
+    `ptrs[r]` is this process's address of rank r's buffer; `table` is the same as a ctypes array for the C ABI.
+    """
+
+    def __init__(self, nbytes: int, group=None, _virtual: Optional[tuple] = None, _local: bool = False):
+        if not torch.cuda.is_available():
+            raise _lib.P2TError("PeerBuffer needs a CUDA device: this package has no CPU path")
+        self.nbytes = int(nbytes)
+        self.group = group
+        self._own = None
+        self._opened: List[int] = []
+        if _virtual is not None:  # several ranks simulated in one process (tests): buffers handed in by the factory
+            self.rank, self.world, self.ptrs = _virtual
+            self._finish()
+            return
+        self.rank, self.world = (0, 1) if _local else _rank_world(group)
+        torch.cuda.current_device()  # make sure the primary context exists before the runtime call below
+        torch.zeros(1, device="cuda")
+        own = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        _lib.call("p2t_peer_alloc", self.nbytes, C.byref(own), handle)
+        self._own = own.value
+        self.ptrs = [None] * self.world
+        self.ptrs[self.rank] = self._own
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, handle.raw, group=group)
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    continue
+                p = C.c_void_p()
+                _lib.call("p2t_peer_open", bytes(h), C.byref(p))
+                self.ptrs[r] = p.value
+                self._opened.append(p.value)
+            dist.barrier(group=group)
+        self._finish()
+
+    def _finish(self):
+        self.table = (C.c_void_p * self.world)(*self.ptrs)
+        self.base = self.ptrs[self.rank]
+
+    @classmethod
+    def virtual(cls, nbytes: int, world: int) -> List["PeerBuffer"]:
+        """`world` buffers in THIS process, one PeerBuffer view per simulated rank (single-GPU tests of the
+        exchange kernels: the launches of all simulated ranks are issued phase by phase on one stream)."""
+        owners = [cls(nbytes, _local=True) for _ in range(world)]
+        ptrs = [o.base for o in owners]
+        views = [cls(nbytes, _virtual=(r, world, list(ptrs))) for r in range(world)]
+        for v in views:
+            v._keepalive = owners
+        return views
+
+    def status(self) -> int:
+        """0, or 1 + the rank this rank timed out waiting for (synchronises the device)."""
+        s = C.c_uint(0)
+        _lib.call("p2t_peer_status", self.base, C.byref(s))
+        return int(s.value)
+
+    def check(self) -> None:
+        s = self.status()
+        if s:
+            raise _lib.P2TError(f"rank {self.rank}: timed out waiting for the peer-memory flag of rank {s - 1}")
+
+    def close(self) -> None:
+        for p in self._opened:
+            _lib.call("p2t_peer_close", p)
+        self._opened = []
+        if self.world > 1 and self._own is not None and dist.is_initialized():
+            dist.barrier(group=self.group)
+        if self._own is not None:
+            _lib.call("p2t_peer_free", self._own)
+            self._own = None
+
+
+class PeerAllGather:
+    """(rows, cols) per rank -> (world*rows, cols), rank-major, pushed over NVLink (SURVEY.md §8e exchange step)."""
+
+    def __init__(self, rows: int, cols: int, dtype=torch.float32, group=None, _buffer: Optional[PeerBuffer] = None):
+        self.rows, self.cols, self.dtype = int(rows), int(cols), dtype
+        self.bytes_per_rank = self.rows * self.cols * torch.empty((), dtype=dtype).element_size()
+        if self.bytes_per_rank % 16:
+            raise ValueError("rows * cols * element size must be a multiple of 16 bytes")
+        ctrl = int(_lib.load().p2t_peer_ctrl_bytes())
+        rank, world = (_buffer.rank, _buffer.world) if _buffer is not None else _rank_world(group)
+        self.buffer = _buffer if _buffer is not None else PeerBuffer(ctrl + 2 * world * self.bytes_per_rank, group)
+        self.rank, self.world = rank, world
+
+    @staticmethod
+    def buffer_bytes(rows: int, cols: int, dtype, world: int) -> int:
+        return int(_lib.load().p2t_peer_ctrl_bytes()) + 2 * world * rows * cols * torch.empty((), dtype=dtype).element_size()
+
+    def push(self, src: torch.Tensor) -> None:
+        if src.shape != (self.rows, self.cols) or src.dtype != self.dtype or not src.is_cuda:
+            raise ValueError(f"expected a CUDA {self.dtype} tensor of shape {(self.rows, self.cols)}, got {tuple(src.shape)} {src.dtype}")
+        src = src.contiguous()
+        _lib.call("p2t_peer_allgather", self.buffer.table, self.world, self.rank, src.data_ptr(), self.bytes_per_rank,
+                  None, _PUSH, _stream())
+        self._src_keepalive = src
+
+    def arrive(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if out is None:
+            out = torch.empty(self.world * self.rows, self.cols, dtype=self.dtype, device="cuda")
+        _lib.call("p2t_peer_allgather", self.buffer.table, self.world, self.rank, None, self.bytes_per_rank,
+                  out.data_ptr(), _ARRIVE, _stream())
+        return out
+
+    def __call__(self, src: torch.Tensor) -> torch.Tensor:
+        self.push(src)
+        return self.arrive()
+
+    def close(self) -> None:
+        self.buffer.close()
+
+
+class PeerGradAllReduce:
+    """grads := mean over ranks, for a fixed list of bf16 tensors (the adapter's fc1/fc2 weights and biases).
+
+    Two-shot over peer memory: rank k reduces slice k of the flattened gradients out of every peer's buffer in fp32,
+    in rank order, and stores the bf16 mean into every peer's result area — all ranks end with identical bits."""
+
+    def __init__(self, like: Sequence[torch.Tensor], group=None, _buffer: Optional[PeerBuffer] = None):
+        self.shapes = [tuple(t.shape) for t in like]
+        self.offsets = []
+        off = 0
+        for t in like:
+            if t.dtype != torch.bfloat16:
+                raise _lib.P2TError("PeerGradAllReduce reduces bfloat16 gradients")
+            self.offsets.append(off)
+            off += (t.numel() * 2 + 15) // 16 * 16
+        self.n_bytes = off
+        self.ctrl = int(_lib.load().p2t_peer_ctrl_bytes())
+        rank, world = (_buffer.rank, _buffer.world) if _buffer is not None else _rank_world(group)
+        self.buffer = _buffer if _buffer is not None else PeerBuffer(self.ctrl + 2 * self.n_bytes, group)
+        self.rank, self.world = rank, world
+
+    @staticmethod
+    def buffer_bytes(like: Sequence[torch.Tensor]) -> int:
+        n = sum((t.numel() * 2 + 15) // 16 * 16 for t in like)
+        return int(_lib.load().p2t_peer_ctrl_bytes()) + 2 * n
+
+    def _check(self, grads):
+        if len(grads) != len(self.shapes):
+            raise ValueError("gradient list does not match the tensors this reducer was built for")
+        for g, s in zip(grads, self.shapes):
+            if tuple(g.shape) != s or g.dtype != torch.bfloat16 or not g.is_cuda or not g.is_contiguous():
+                raise ValueError("gradients must be contiguous CUDA bfloat16 tensors of the registered shapes")
+
+    def stage(self, grads: Sequence[torch.Tensor]) -> None:
+        """Copy this rank's gradients into its channel buffer and announce them (phase 0)."""
+        self._check(grads)
+        st = _stream()
+        for g, off in zip(grads, self.offsets):
+            _lib.call("p2t_copy_d2d", self.buffer.base + self.ctrl + off, g.data_ptr(), g.numel() * 2, st)
+        _lib.call("p2t_peer_allreduce_mean_bf16", self.buffer.table, self.world, self.rank, self.n_bytes, None, _READY, st)
+
+    def reduce(self) -> None:
+        _lib.call("p2t_peer_allreduce_mean_bf16", self.buffer.table, self.world, self.rank, self.n_bytes, None, _REDUCE, _stream())
+
+    def finish(self, grads: Sequence[torch.Tensor]) -> None:
+        """Wait for every slice of the mean and copy it over `grads` (phase 2)."""
+        st = _stream()
+        _lib.call("p2t_peer_allreduce_mean_bf16", self.buffer.table, self.world, self.rank, self.n_bytes, None, _WAIT, st)
+        for g, off in zip(grads, self.offsets):
+            _lib.call("p2t_copy_d2d", g.data_ptr(), self.buffer.base + self.ctrl + self.n_bytes + off, g.numel() * 2, st)
+
+    def reduce_(self, grads: Sequence[torch.Tensor]) -> Sequence[torch.Tensor]:
+        self.stage(grads)
+        self.reduce()
+        self.finish(grads)
+        return grads
+
+    def close(self) -> None:
+        self.buffer.close()

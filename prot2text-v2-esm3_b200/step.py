@@ -158,6 +158,15 @@ def _default_labels(n: int, device) -> torch.Tensor:
     return t
 
 
+def _rank_labels(rank: int, n: int, device) -> torch.Tensor:
+    """arange(rank*n, (rank+1)*n) int32: rank `rank`'s rows of the global pairing (sharded step)."""
+    key = (rank, n, str(device))
+    t = _LABELS.get(key)
+    if t is None:
+        t = _LABELS[key] = torch.arange(rank * n, (rank + 1) * n, device=device, dtype=torch.int32)
+    return t
+
+
 def contrastive_step(residue_states: torch.Tensor, protein_mask: Optional[torch.Tensor], adapter: ModalityAdapter,
                      text_hidden: Optional[torch.Tensor] = None, text_mask: Optional[torch.Tensor] = None, *,
                      residue_lengths: Optional[torch.Tensor] = None, text_lengths: Optional[torch.Tensor] = None,

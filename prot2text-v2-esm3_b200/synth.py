@@ -35,10 +35,19 @@ class SynthBatch:
 
 
 def make_batch(d_in, d_mid, d_out, batch, lmin, lmax, tmin, tmax, seed: int = 1234, rank: int = 0,
-               weight_gain: float = 1.0, left_pad: bool = False, plant: float = 0.0) -> SynthBatch:
+               weight_gain: float = 1.0, left_pad: bool = False, plant: float = 0.0,
+               same_lengths_as_rank0: bool = False) -> SynthBatch:
+    """`same_lengths_as_rank0`: every rank gets rank 0's multiset of sequence lengths (in a rank-specific order) with
+    its own random data — per-GPU work is then exactly fixed as ranks are added (weak-scaling benchmark)."""
     g = torch.Generator().manual_seed(seed + rank)
     lens = torch.randint(lmin, lmax + 1, (batch,), generator=g)
     tlens = torch.randint(tmin, tmax + 1, (batch,), generator=g)
+    if same_lengths_as_rank0 and rank != 0:
+        g0 = torch.Generator().manual_seed(seed)
+        lens0 = torch.randint(lmin, lmax + 1, (batch,), generator=g0)
+        tlens0 = torch.randint(tmin, tmax + 1, (batch,), generator=g0)
+        perm = torch.randperm(batch, generator=torch.Generator().manual_seed(seed + 7919 * rank))
+        lens, tlens = lens0[perm], tlens0[perm]
     L, T = int(lens.max()), int(tlens.max())
     x = torch.randn(batch, L, d_in, generator=g).to(torch.bfloat16)
     text = torch.randn(batch, T, d_out, generator=g).to(torch.bfloat16)

@@ -1,0 +1,300 @@
+"""GPU parity tests of the SURVEY.md §8 "next" rows and of the peer-memory exchange (run on the B200 box:
+`pytest -m gpu`).  Everything under test goes through the C-ABI CUDA library; the checkers are
+
+  * tests/golden/next_scatter.npz — the reference's own prepare_decoder_inputs fed by its ModalityAdapter,
+  * tests/golden/next_adamw.npz   — torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW, the calls of
+                                    scripts/train_contrast.py:455-465,
+  * oracle/restatement.py         — CPU restatements (mean all-reduce, AdamW at adapter size, scatter).
+
+The exchange kernels are exercised on ONE device with several simulated ranks (`PeerBuffer.virtual`): every rank's
+launch of a phase is issued before any rank's launch of the next phase, which is the order the flag protocol needs on a
+single stream; tools/dist_check.py runs the same kernels across real processes over NVLink (tests/test_gpu_dist.py).
+Bar: bit-exact for the exchange (byte moves, fixed-order fp32 sums), reference tolerances for floating point."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restatement as R
+
+pytestmark = pytest.mark.gpu
+PARAMS = ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device: the product path has no CPU fallback")
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def mods(p2t):
+    p2t._lib.load()
+    return {n: importlib.import_module("p2t_b200." + n) for n in ("peer", "optim", "handoff", "dist", "synth", "graph")}
+
+
+def _load(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name))
+    return {k: torch.from_numpy(np.asarray(z[k])) for k in z.files}
+
+
+def bf(t):
+    return t.to(torch.bfloat16)
+
+
+def maxrel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-300)).item()
+
+
+def cosine(a, b):
+    a, b = a.detach().double().cpu().flatten(), b.detach().double().cpu().flatten()
+    return torch.nn.functional.cosine_similarity(a, b, dim=0).item()
+
+
+def make_adapter(p2t, dev, w1, b1, w2, b2, train=False, p=0.3):
+    cfg = p2t.ModalityAdapterConfig(input_dim=w1.shape[1], intermediate_dim=w1.shape[0], output_dim=w2.shape[0], dropout_rate=p)
+    ad = p2t.ModalityAdapter(cfg).to(dev).to(torch.bfloat16)
+    with torch.no_grad():
+        ad.fc1.weight.copy_(w1); ad.fc1.bias.copy_(b1); ad.fc2.weight.copy_(w2); ad.fc2.bias.copy_(b2)
+    return ad.train() if train else ad.eval()
+
+
+# --------------------------------------------------------------------------------------------------
+# exchange over peer memory
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world,rows,cols,dtype", [(1, 32, 8192, torch.float32), (2, 32, 8192, torch.float32),
+                                                   (3, 5, 24, torch.float32), (8, 16, 4096, torch.bfloat16),
+                                                   (16, 2, 64, torch.float32)])
+def test_peer_allgather_moves_every_block_bit_exactly(mods, dev, world, rows, cols, dtype):
+    peer = mods["peer"]
+    bufs = peer.PeerBuffer.virtual(peer.PeerAllGather.buffer_bytes(rows, cols, dtype, world), world)
+    chans = [peer.PeerAllGather(rows, cols, dtype, _buffer=b) for b in bufs]
+    g = torch.Generator().manual_seed(world * 1000 + rows)
+    for rnd in range(5):  # odd and even epochs: both halves of the double buffer, and the flag comparison across rounds
+        blocks = [torch.randn(rows, cols, generator=g).to(dtype).to(dev) for _ in range(world)]
+        for c, blk in zip(chans, blocks):
+            c.push(blk)
+        outs = [c.arrive() for c in chans]
+        want = torch.cat(blocks)
+        for r, o in enumerate(outs):
+            assert torch.equal(o, want), (rnd, r)
+    for b in bufs:
+        b.check()
+
+
+def test_peer_allgather_rejects_wrong_blocks(p2t, mods, dev):
+    peer = mods["peer"]
+    ch = peer.PeerAllGather(4, 8, torch.float32)
+    with pytest.raises(ValueError):
+        ch.push(torch.zeros(4, 9, device=dev))
+    with pytest.raises(ValueError):
+        ch.push(torch.zeros(4, 8, device=dev, dtype=torch.bfloat16))
+    with pytest.raises(ValueError):
+        peer.PeerAllGather(1, 3, torch.float32)  # 12 bytes: not a multiple of 16
+    with pytest.raises(p2t.P2TError, match="world"):
+        p2t._lib.call("p2t_peer_allgather", ch.buffer.table, 17, 0, None, 16, None, 1, None)
+    ch.close()
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_peer_allreduce_is_the_fixed_order_fp32_mean(mods, dev, world):
+    peer = mods["peer"]
+    shapes = [(64, 40), (64,), (24, 64), (20,)]  # (20,) = 40 bytes: padded to 48 inside the channel
+    like = [torch.empty(s, dtype=torch.bfloat16) for s in shapes]
+    bufs = peer.PeerBuffer.virtual(peer.PeerGradAllReduce.buffer_bytes(like), world)
+    reds = [peer.PeerGradAllReduce(like, _buffer=b) for b in bufs]
+    g = torch.Generator().manual_seed(7 + world)
+    for rnd in range(3):
+        per_rank = [[(torch.randn(s, generator=g) * (1 + r)).to(torch.bfloat16) for s in shapes] for r in range(world)]
+        on_dev = [[t.to(dev) for t in grads] for grads in per_rank]
+        for red, grads in zip(reds, on_dev):
+            red.stage(grads)
+        for red in reds:
+            red.reduce()
+        for red, grads in zip(reds, on_dev):
+            red.finish(grads)
+        for i in range(len(shapes)):
+            want = R.mean_allreduce_bf16([per_rank[r][i] for r in range(world)])
+            for r in range(world):
+                assert torch.equal(on_dev[r][i].cpu(), want), (rnd, r, i)
+    for b in bufs:
+        b.check()
+
+
+def test_peer_allreduce_adapter_sized(mods, dev):
+    """config 2's adapter: 13.6 M gradient elements, 4 simulated ranks — bit-exact against the CPU restatement."""
+    peer = mods["peer"]
+    shapes = [(2048, 2560), (2048,), (4096, 2048), (4096,)]
+    like = [torch.empty(s, dtype=torch.bfloat16) for s in shapes]
+    world = 4
+    bufs = peer.PeerBuffer.virtual(peer.PeerGradAllReduce.buffer_bytes(like), world)
+    reds = [peer.PeerGradAllReduce(like, _buffer=b) for b in bufs]
+    g = torch.Generator(device=dev).manual_seed(3)
+    on_dev = [[torch.randn(s, generator=g, device=dev).to(torch.bfloat16) for s in shapes] for _ in range(world)]
+    per_rank = [[t.cpu() for t in grads] for grads in on_dev]
+    for red, grads in zip(reds, on_dev):
+        red.stage(grads)
+    for red in reds:
+        red.reduce()
+    for red, grads in zip(reds, on_dev):
+        red.finish(grads)
+    for i in range(4):
+        want = R.mean_allreduce_bf16([per_rank[r][i] for r in range(world)])
+        for r in range(world):
+            assert torch.equal(on_dev[r][i].cpu(), want)
+
+
+def test_graphed_step_through_the_exchange_equals_the_plain_step(p2t, mods, dev):
+    """World of one: the sharded step's exchange (push, arrive, gradient mean) inside the captured graph must leave the
+    step's numbers untouched — the same kernels then run across ranks in tools/dist_check.py."""
+    synth, pdist, peer = mods["synth"], mods["dist"], mods["peer"]
+    sb = synth.make_config_batch("tiny", weight_gain=8.0)
+    ad = make_adapter(p2t, dev, sb.w1, sb.b1, sb.w2, sb.b2)
+    x, pm, th, tm = (t.to(dev) for t in (sb.x, sb.prot_mask, sb.text, sb.text_mask))
+    plain = p2t.GraphedContrastiveStep(ad, x, pm, th, tm)
+    l0 = plain.replay().clone()
+    g0 = [g.clone() for g in plain.grads]
+    ex = pdist.ShardedExchange(x.shape[0], 2 * sb.w2.shape[0], symmetric=True)
+    red = peer.PeerGradAllReduce([ad.fc1.weight, ad.fc1.bias, ad.fc2.weight, ad.fc2.bias])
+    for sym in (False, True):
+        ref = p2t.GraphedContrastiveStep(ad, x, pm, th, tm, symmetric=sym)
+        sharded = p2t.GraphedContrastiveStep(ad, x, pm, th, tm, symmetric=sym, exchange=ex, grad_reducer=red)
+        for _ in range(3):
+            la, lb = ref.replay(), sharded.replay()
+            assert torch.equal(la, lb)
+            for a, b in zip(ref.grads, sharded.grads):
+                assert torch.equal(a, b)
+        if not sym:
+            assert torch.equal(l0, la) and all(torch.equal(a, b) for a, b in zip(g0, ref.grads))
+    ex.check()
+    assert sharded.launches_per_replay > ref.launches_per_replay
+    ex.close(); red.close()
+
+
+# --------------------------------------------------------------------------------------------------
+# clip_grad_norm_ + AdamW
+# --------------------------------------------------------------------------------------------------
+def test_fused_adamw_matches_torch_golden(p2t, mods, dev, golden_dir):
+    g = _load(golden_dir, "next_adamw.npz")
+    n, lr, max_norm = int(g["n_steps"]), float(g["lr"]), float(g["max_norm"])
+    params = [torch.nn.Parameter(bf(g[f"p0.{i}"]).to(dev)) for i in range(4)]  # the fixture's p0 lies on the bf16 grid
+    opt = mods["optim"].FusedAdamW(params, lr=lr, eps=1e-6, betas=(0.9, 0.999), max_grad_norm=max_norm)
+    for step in range(n):
+        for i, p in enumerate(params):
+            p.grad = bf(g[f"g{step}.{i}"]).to(dev)
+            assert torch.equal(p.grad.float().cpu(), g[f"g{step}.{i}"])  # gradients on the bf16 grid too
+        opt.step()
+        torch.testing.assert_close(opt.grad_norm.cpu(), g[f"norm{step}"], rtol=1e-5, atol=0)
+        for i, p in enumerate(params):
+            master = opt.state[p]["master"]
+            torch.testing.assert_close(master.cpu(), g[f"p{step + 1}.{i}"], rtol=1e-5, atol=1e-7)
+            assert torch.equal(p.detach(), master.to(torch.bfloat16))  # the parameter is the rounding of its master
+            assert torch.equal(p.grad.float().cpu(), g[f"g{step}.{i}"])  # gradients are left as they were
+
+
+def test_fused_adamw_adapter_sized_against_the_oracle(p2t, mods, dev):
+    shapes = [(2048, 2560), (2048,), (4096, 2048), (4096,)]
+    gen = torch.Generator().manual_seed(5)
+    p0 = [bf(torch.randn(s, generator=gen) * 0.02) for s in shapes]
+    for master in (True, False):
+        params = [torch.nn.Parameter(p.clone().to(dev)) for p in p0]
+        opt = mods["optim"].FusedAdamW(params, lr=1e-3, eps=1e-6, weight_decay=0.01, max_grad_norm=1.0, master_weights=master,
+                                       zero_grad_in_step=True)
+        ref_p = [p.float() for p in p0]
+        m = [torch.zeros_like(p) for p in ref_p]
+        v = [torch.zeros_like(p) for p in ref_p]
+        for step in range(1, 4):
+            grads = [bf(torch.randn(s, generator=gen) * (0.01 if step != 2 else 1e-5)) for s in shapes]
+            for p, gr in zip(params, grads):
+                p.grad = gr.clone().to(dev)
+            opt.step()
+            norm, cg = R.clip_grad_norm([gr.float() for gr in grads], 1.0)
+            assert abs(opt.grad_norm.item() - norm.item()) <= 1e-5 * norm.item()
+            ref_p, m, v = R.adamw_step(ref_p, cg, m, v, step, 1e-3, weight_decay=0.01)
+            for p, rp in zip(params, ref_p):
+                if master:
+                    torch.testing.assert_close(opt.state[p]["master"].cpu(), rp, rtol=2e-5, atol=1e-8)
+                    assert torch.equal(p.detach().cpu(), rp.to(torch.bfloat16)) or maxrel(p, rp) <= 2 ** -8
+                else:  # bf16 parameter is the state: one rounding per step on top of the fp32 trajectory
+                    assert maxrel(p, rp) <= step * 2 ** -8
+                assert not p.grad.any()  # zero_grad_in_step
+            if not master:
+                ref_p = [p.detach().float().cpu() for p in params]  # follow the bf16 trajectory like the kernel does
+
+
+def test_fused_adamw_is_capturable_and_follows_the_scheduler(p2t, mods, dev):
+    w = torch.nn.Parameter(bf(torch.ones(64, 64)).to(dev))
+    w.grad = bf(torch.full((64, 64), 0.5)).to(dev)
+    opt = mods["optim"].FusedAdamW([w], lr=1e-2, weight_decay=0.0)
+    opt.step()  # eager: state allocated, lr written
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        opt.step()
+    before = opt.state[w]["master"].clone()
+    opt.set_lr(0.0)
+    graph.replay()
+    assert torch.equal(opt.state[w]["master"], before)  # lr is read from the device at replay time
+    opt.set_lr(1e-2)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert int(opt._dev[0]["step"].item()) == 3 and (opt.state[w]["master"] < before).all()  # 1 eager + 2 replays
+    with pytest.raises(p2t.P2TError, match="bfloat16"):
+        f = torch.nn.Parameter(torch.ones(8, 8, device=dev))
+        f.grad = torch.ones_like(f)
+        mods["optim"].FusedAdamW([f]).step()
+
+
+# --------------------------------------------------------------------------------------------------
+# Stage-2 hand-off: adapter rows straight into the placeholder slots
+# --------------------------------------------------------------------------------------------------
+def test_adapter_into_embeds_matches_reference_golden(p2t, mods, dev, golden_dir):
+    g = _load(golden_dir, "next_scatter.npz")
+    ad = make_adapter(p2t, dev, *(g["sd." + k] for k in PARAMS))
+    ids = g["input_ids"]
+    ph_mask = (ids == int(g["placeholder_id"])).to(dev)
+    base = bf(g["table"])[ids].to(dev)  # what llm.get_input_embeddings()(input_ids) returns (table on the bf16 grid)
+    embeds = base.clone().requires_grad_()
+    out = mods["handoff"].adapter_into_embeds(ad, bf(g["x"]).to(dev), g["enc_mask"].to(dev), embeds * 1, ph_mask, check=True)
+    assert out.dtype == torch.bfloat16 and out.shape == g["embeds"].shape
+    assert torch.equal(out[~ph_mask].cpu(), bf(g["embeds"])[~ph_mask.cpu()])  # token rows: byte moves
+    assert maxrel(out[ph_mask], g["embeds"][ph_mask.cpu()]) <= 6e-3  # adapter rows: bf16 output of the adapter
+    (out.float() * g["gy"].to(dev)).sum().backward()
+    grads = {"fc1.weight": ad.fc1.weight.grad, "fc1.bias": ad.fc1.bias.grad, "fc2.weight": ad.fc2.weight.grad,
+             "fc2.bias": ad.fc2.bias.grad}
+    for k in PARAMS:
+        c, m = cosine(grads[k], g["grad." + k]), maxrel(grads[k], g["grad." + k])
+        assert c >= 0.999 and m <= 1e-2, (k, c, m)
+    # gradient w.r.t. the token embeddings: upstream gradient outside the placeholders, zero inside
+    want = g["gy"].clone()
+    want[ph_mask.cpu()] = 0
+    assert torch.equal(embeds.grad.float().cpu(), bf(want).float())
+    with pytest.raises(ValueError, match="must match"):
+        bad = ph_mask.clone()
+        bad[0, 0] = ~bad[0, 0]
+        mods["handoff"].adapter_into_embeds(ad, bf(g["x"]).to(dev), g["enc_mask"].to(dev), base.clone(), bad, check=True)
+
+
+@pytest.mark.parametrize("left_pad", [False, True])
+def test_adapter_into_embeds_equals_adapter_then_scatter(p2t, mods, dev, left_pad):
+    """Against the composition the reference performs — adapter on the padded batch, then the masked assignment
+    (oracle: placeholder_scatter) — at a realistic width; the rows that move are bit-identical to the module's."""
+    synth = mods["synth"]
+    sb = synth.make_batch(320, 512, 264, 5, 3, 90, 2, 8, seed=9, weight_gain=6.0, left_pad=left_pad)
+    ad = make_adapter(p2t, dev, sb.w1, sb.b1, sb.w2, sb.b2)
+    B, L, _ = sb.x.shape
+    S = L + 7
+    gen = torch.Generator().manual_seed(2)
+    base = bf(torch.randn(B, S, 264, generator=gen))
+    ph = torch.zeros(B, S, dtype=torch.bool)
+    for b, n in enumerate(sb.prot_lens.tolist()):
+        ph[b, 2 + b:2 + b + n] = True
+    with torch.no_grad():
+        y = ad(sb.x.to(dev))
+        out = mods["handoff"].adapter_into_embeds(ad, sb.x.to(dev), sb.prot_mask.to(dev), base.clone().to(dev), ph.to(dev))
+    want = R.placeholder_scatter(base, ph, y.cpu(), sb.prot_mask)
+    assert torch.equal(out.cpu(), want)

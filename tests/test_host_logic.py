@@ -76,3 +76,19 @@ def test_bench_reference_arm_runs_on_cpu(monkeypatch, capsys):
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "pairs/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_balanced_shards_equalise_residue_rows(p2t):
+    import importlib
+    pdist = importlib.import_module("p2t_b200.dist")
+    g = torch.Generator().manual_seed(1234)
+    lengths = torch.randint(50, 1025, (256,), generator=g).tolist()
+    shards = pdist.balanced_shards(lengths, 8)
+    assert sorted(i for s in shards for i in s) == list(range(256)) and all(len(s) == 32 for s in shards)
+    totals = [sum(lengths[i] for i in s) for s in shards]
+    mean = sum(totals) / 8
+    assert max(totals) <= 1.01 * mean, totals
+    random_totals = [sum(lengths[r * 32:(r + 1) * 32]) for r in range(8)]
+    assert max(random_totals) > max(totals)
+    with pytest.raises(ValueError):
+        pdist.balanced_shards(lengths[:10], 4)

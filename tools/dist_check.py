@@ -3,8 +3,10 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
         tools/dist_check.py [workload] [weight_gain]
 
-Every rank runs `dist.distributed_contrastive_step` on its own shard (all-gathered text negatives over NCCL, with
-and without the symmetric column term); gradients are averaged across ranks the way DDP does.  Rank 0 rebuilds the
+Every rank runs `dist.distributed_contrastive_step` on its own shard, with and without the symmetric column term, in
+three forms: NCCL all-gather (eager), the peer-memory exchange (eager), and the peer-memory exchange captured in a
+CUDA graph together with the peer-memory mean all-reduce of the weight gradients.  Gradients of the first two are
+averaged across ranks with NCCL the way DDP does.  Rank 0 rebuilds the
 GLOBAL batch on the CPU and runs the oracle on it in one process: the mean of the local losses must
 equal the global-batch loss, the averaged gradients the global-batch gradients.  Exit code 0 = parity.
 """
@@ -39,19 +41,45 @@ def main():
     with torch.no_grad():
         ad.fc1.weight.copy_(sb.w1); ad.fc1.bias.copy_(sb.b1); ad.fc2.weight.copy_(sb.w2); ad.fc2.bias.copy_(sb.b2)
     ok = True
-    for sym in (False, True):
+    peer = importlib.import_module("p2t_b200.peer")
+    prms = (ad.fc1.weight, ad.fc1.bias, ad.fc2.weight, ad.fc2.bias)
+    exchange = pdist.ShardedExchange(sb.x.shape[0], 2 * sb.w2.shape[0], symmetric=True)
+    reducer = peer.PeerGradAllReduce(list(prms))
+    dx, dpm, dtx, dtm = sb.x.to(dev), sb.prot_mask.to(dev), sb.text.to(dev), sb.text_mask.to(dev)
+    for sym, form in ((False, "nccl"), (True, "nccl"), (False, "peer"), (True, "peer"), (False, "peer+graph"), (True, "peer+graph")):
         ad.zero_grad(set_to_none=True)
         aux = pkg.StepAux()
-        loss = pdist.distributed_contrastive_step(sb.x.to(dev), sb.prot_mask.to(dev), ad, sb.text.to(dev),
-                                                  sb.text_mask.to(dev), symmetric=sym, aux=aux)
-        loss.backward()
+        torch.cuda.synchronize()
+        dist.barrier()  # rank 0 has finished the CPU oracle of the previous form: peer-memory waits give up after 20 s
+        if form == "peer+graph":
+            gstep = pkg.GraphedContrastiveStep(ad, dx, dpm, dtx, dtm, symmetric=sym, exchange=exchange, grad_reducer=reducer)
+            for _ in range(3):
+                loss = gstep.replay()
+            aux = gstep.aux
+            reduced = [g.float().cpu() for g in gstep.grads]  # already the mean over ranks, identical bits everywhere
+            same = torch.tensor([1], device=dev)
+            for g in gstep.grads:
+                g0 = g.clone()
+                dist.broadcast(g0, 0)
+                same &= torch.equal(g0, g)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            ok &= bool(same.item())
+        else:
+            loss = pdist.distributed_contrastive_step(dx, dpm, ad, dtx, dtm, symmetric=sym, aux=aux,
+                                                      exchange=exchange if form == "peer" else None)
+            loss.backward()
         lt = loss.detach().clone()
         dist.all_reduce(lt)
         grads = {}
-        for k, prm in zip(PARAMS, (ad.fc1.weight, ad.fc1.bias, ad.fc2.weight, ad.fc2.bias)):
-            g = prm.grad.float().clone()
-            dist.all_reduce(g)
-            grads[k] = (g / world).cpu()
+        for i, (k, prm) in enumerate(zip(PARAMS, prms)):
+            if form == "peer+graph":
+                grads[k] = reduced[i]
+            else:
+                g = prm.grad.float().clone()
+                dist.all_reduce(g)
+                grads[k] = (g / world).cpu()
+        exchange.check()
+        reducer.buffer.check()
         am_row = [torch.empty_like(aux.argmax_row) for _ in range(world)]
         dist.all_gather(am_row, aux.argmax_row)
         if rank == 0:
@@ -71,7 +99,7 @@ def main():
             st = R.step_forward(X, PM, sb.w1.to(f), sb.b1.to(f), sb.w2.to(f), sb.b2.to(f), TX, TM, 0.05, 1, sym)
             ref = R.step_backward(st, X, PM, sb.w1.to(f), sb.w2.to(f), 0.05, 1, sym)
             lrel = abs(lt.item() / world - st.loss.item()) / abs(st.loss.item())
-            line = f"world={world} {name} symmetric={sym}: loss {lt.item() / world:.6f} vs global oracle {st.loss.item():.6f} rel={lrel:.2e}"
+            line = f"world={world} {name} symmetric={sym} exchange={form}: loss {lt.item() / world:.6f} vs global oracle {st.loss.item():.6f} rel={lrel:.2e}"
             ok &= lrel <= 1e-3
             for k in PARAMS:
                 a, b = grads[k].double().flatten(), ref[k].double().flatten()
@@ -87,7 +115,10 @@ def main():
             line += f" | argmax_row exact={torch.equal(am, am_ref)}"
             print(line, flush=True)
     flag = torch.tensor([1 if ok else 0], device=dev)
-    dist.broadcast(flag, 0)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    torch.cuda.synchronize()
+    exchange.close()
+    reducer.close()
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)
 
