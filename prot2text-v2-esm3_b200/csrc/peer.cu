@@ -143,26 +143,43 @@ peer_allreduce_reduce_kernel(PeerTable peers, int world, int rank, long long n_v
   const long long per = (n_vec + world - 1) / world;
   const long long lo = per * rank, hi = min(n_vec, lo + per);
   const size_t in_off = kCtrlBytes, out_off = kCtrlBytes + (size_t)n_vec * sizeof(uint4);
-  for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x) {
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += 2 * stride) {
+    // two vectors per trip, every peer's load of both in flight together (NVLink round trip ~2 us)
+    const long long idx[2] = {i, i + stride};
+    float acc[2][8];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[u][k] = 0.f;
     for (int r0 = 0; r0 < world; r0 += 8) {  // fixed rank order: every rank computes bit-identical sums
-      uint4 u[8];
+      uint4 v[2][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)  // all loads of a batch are in flight together (NVLink latency ~2 us)
-        if (r0 + j < world) u[j] = ld_sys_v4(reinterpret_cast<const uint4*>(static_cast<char*>(peers.base[r0 + j]) + in_off) + i);
+      for (int u = 0; u < 2; ++u)
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (r0 + j < world) {
-          const float2 a = unpack_bf16x2(u[j].x), b = unpack_bf16x2(u[j].y), c = unpack_bf16x2(u[j].z), d = unpack_bf16x2(u[j].w);
-          acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
-          acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
-        }
+        for (int j = 0; j < 8; ++j)
+          if (r0 + j < world && idx[u] < hi)
+            v[u][j] = ld_sys_v4(reinterpret_cast<const uint4*>(static_cast<char*>(peers.base[r0 + j]) + in_off) + idx[u]);
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (r0 + j < world && idx[u] < hi) {
+            const float2 a = unpack_bf16x2(v[u][j].x), b = unpack_bf16x2(v[u][j].y), c = unpack_bf16x2(v[u][j].z),
+                         d = unpack_bf16x2(v[u][j].w);
+            acc[u][0] += a.x; acc[u][1] += a.y; acc[u][2] += b.x; acc[u][3] += b.y;
+            acc[u][4] += c.x; acc[u][5] += c.y; acc[u][6] += d.x; acc[u][7] += d.y;
+          }
     }
-    const uint4 o = make_uint4(pack_bf16x2(acc[0] * scale, acc[1] * scale), pack_bf16x2(acc[2] * scale, acc[3] * scale),
-                               pack_bf16x2(acc[4] * scale, acc[5] * scale), pack_bf16x2(acc[6] * scale, acc[7] * scale));
-    for (int r = 0; r < world; ++r) {
-      const int dst = (rank + r) % world;
-      reinterpret_cast<uint4*>(static_cast<char*>(peers.base[dst]) + out_off)[i] = o;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (idx[u] >= hi) continue;
+      const uint4 o = make_uint4(pack_bf16x2(acc[u][0] * scale, acc[u][1] * scale), pack_bf16x2(acc[u][2] * scale, acc[u][3] * scale),
+                                 pack_bf16x2(acc[u][4] * scale, acc[u][5] * scale), pack_bf16x2(acc[u][6] * scale, acc[u][7] * scale));
+      for (int r = 0; r < world; ++r) {
+        const int dst = (rank + r) % world;
+        reinterpret_cast<uint4*>(static_cast<char*>(peers.base[dst]) + out_off)[idx[u]] = o;
+      }
     }
   }
   publish_when_grid_done(peers, world, rank, flag_row_off(1), epoch, ctrl + 2, nullptr);
@@ -193,9 +210,11 @@ int fill_table(PeerTable& t, void* const* peers, int world, int rank, const char
   return 0;
 }
 
-int grid_for(long long vecs) {
+// Waiting CTAs depend only on flags raised by kernels that precede this one in some rank's stream, never on each other,
+// so the grid need not be co-resident; `per_sm` bounds how much of the GPU a channel kernel may take.
+int grid_for(long long vecs, int per_sm_x2 = 1) {
   const long long want = (vecs + 255) / 256;
-  const long long cap = sm_count() / 2 > 0 ? sm_count() / 2 : 1;  // all CTAs of a waiting kernel must be co-resident
+  const long long cap = sm_count() * per_sm_x2 / 2 > 0 ? sm_count() * per_sm_x2 / 2 : 1;
   return (int)(want < 1 ? 1 : (want > cap ? cap : want));
 }
 
@@ -274,11 +293,11 @@ int peer_allreduce_mean(void* const* peers, int world, int rank, long long n_byt
     if (int r = check_launch("peer_allreduce_ready_kernel")) return r;
   }
   if (phases & 2) {
-    peer_allreduce_reduce_kernel<<<grid_for((n_vec + world - 1) / world), 256, 0, st>>>(t, world, rank, n_vec, 1.f / (float)world);
+    peer_allreduce_reduce_kernel<<<grid_for((n_vec + world - 1) / world / 2, 4), 256, 0, st>>>(t, world, rank, n_vec, 1.f / (float)world);
     if (int r = check_launch("peer_allreduce_reduce_kernel")) return r;
   }
   if (phases & 4) {
-    peer_allreduce_wait_kernel<<<grid_for(n_vec), 256, 0, st>>>(t, world, rank, n_vec, static_cast<uint4*>(dst));
+    peer_allreduce_wait_kernel<<<grid_for(n_vec, 4), 256, 0, st>>>(t, world, rank, n_vec, static_cast<uint4*>(dst));
     if (int r = check_launch("peer_allreduce_wait_kernel")) return r;
   }
   return 0;

@@ -157,24 +157,36 @@ __device__ __forceinline__ int find_segment(const int* __restrict__ off, int n, 
 }
 
 // inverse L2 norm of each adapter output row from the fc2 epilogue's partial sums of squares
-// rowsq is [nblk][cap] (partial index major): consecutive threads read consecutive rows
-__global__ void row_inv_norm_kernel(const float* __restrict__ rowsq, int nblk, const int* __restrict__ n_rows, int cap,
-                                    float* __restrict__ inv_norm) {
+// rowsq is [nblk][cap] (partial index major).  Block = 32 rows (lanes) x 8 groups (warps): group g sums partials
+// g, g+8, ... of its row with all loads in flight, the 8 group sums meet in shared memory in a fixed order — two
+// dependent memory trips per row instead of nblk/4.
+__global__ void __launch_bounds__(256)
+row_inv_norm_kernel(const float* __restrict__ rowsq, int nblk, const int* __restrict__ n_rows, int cap,
+                    float* __restrict__ inv_norm) {
+  __shared__ float part[8][33];
   const int n = min(*n_rows, cap);
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
-    // fixed summation order (four interleaved partial sums), all loads of a trip in flight together
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int j = 0;
-#pragma unroll 4
-    for (; j + 4 <= nblk; j += 4) {
-      s0 += rowsq[(long long)j * cap + r];
-      s1 += rowsq[(long long)(j + 1) * cap + r];
-      s2 += rowsq[(long long)(j + 2) * cap + r];
-      s3 += rowsq[(long long)(j + 3) * cap + r];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  for (int r0 = blockIdx.x * 32; r0 < n; r0 += gridDim.x * 32) {
+    const int r = r0 + lane;
+    float s = 0.f;
+    if (r < n) {
+      float v[8];
+      for (int j0 = g; j0 < nblk; j0 += 64) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (j0 + 8 * u < nblk) ? rowsq[(long long)(j0 + 8 * u) * cap + r] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
+      }
     }
-    for (; j < nblk; ++j) s0 += rowsq[(long long)j * cap + r];
-    const float s = (s0 + s1) + (s2 + s3);
-    inv_norm[r] = 1.f / fmaxf(sqrtf(s), kEpsNorm);
+    part[g][lane] = s;
+    __syncthreads();
+    if (g == 0 && r < n) {
+      float tot = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tot += part[k][lane];
+      inv_norm[r] = 1.f / fmaxf(sqrtf(tot), kEpsNorm);
+    }
+    __syncthreads();
   }
 }
 
@@ -519,11 +531,16 @@ __global__ void pool_bwd_coef_kernel(const float* __restrict__ de, long long ld_
 // Rows i >= R were dropped by the segment split: dp = 0.  dS fp32 [R][C] already carries the 1/R of the mean.
 // ------------------------------------------------------------------------------------------------
 constexpr int LBW_SLICE = 64;
+constexpr int LBW_JC = 64;  // columns of dS (= rows of t) staged per trip
 __global__ void __launch_bounds__(256)
 loss_bwd_dp_kernel(const float* __restrict__ dS, const float* __restrict__ t, const float* __restrict__ p,
                    const float* __restrict__ dloss, int R, int B, int C, int E, float inv_tau, float* __restrict__ dp,
                    float* __restrict__ dotp) {
-  // thread = (row group rg of 8 -> rows rg, rg+8, ...; column quad cq -> 4 columns), 16 column quads x 16 row groups
+  // thread = (row group rg of 16 -> rows rg, rg+16, ...; column quad cq -> 4 columns), 16 column quads x 16 row groups.
+  // t's 64-column slab and the matching block of dS are staged in shared memory 64 logit-columns at a time by all
+  // 256 threads (every load of a trip in flight together): the cost per CTA is C/64 trips, not C dependent loads.
+  __shared__ __align__(16) float ts[LBW_JC][LBW_SLICE];
+  __shared__ float ws[64][LBW_JC + 1];
   const int e0 = blockIdx.x * LBW_SLICE;
   const int cq = threadIdx.x & 15, rg = threadIdx.x >> 4;
   const int col = e0 + cq * 4;
@@ -533,14 +550,30 @@ loss_bwd_dp_kernel(const float* __restrict__ dS, const float* __restrict__ t, co
     float4 acc[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (col < E) {
+    for (int j0 = 0; j0 < C; j0 += LBW_JC) {
+      __syncthreads();
+#pragma unroll
+      for (int m = 0; m < (LBW_JC * LBW_SLICE / 4) / 256; ++m) {
+        const int idx = threadIdx.x + 256 * m;
+        const int jr = idx >> 4, ev = (idx & 15) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j0 + jr < C && e0 + ev < E) v = __ldg(reinterpret_cast<const float4*>(t + (long long)(j0 + jr) * E + e0 + ev));
+        *reinterpret_cast<float4*>(&ts[jr][ev]) = v;
+      }
+#pragma unroll
+      for (int m = 0; m < (64 * LBW_JC) / 256; ++m) {
+        const int idx = threadIdx.x + 256 * m;
+        const int r = idx >> 6, c = idx & 63;
+        const int i = i0 + r, j = j0 + c;
+        ws[r][c] = (i < R && j < C) ? __ldg(dS + (long long)i * C + j) : 0.f;
+      }
+      __syncthreads();
 #pragma unroll 8
-      for (int j = 0; j < C; ++j) {
-        const float4 tv = __ldg(reinterpret_cast<const float4*>(t + (long long)j * E + col));
+      for (int jj = 0; jj < LBW_JC; ++jj) {
+        const float4 tv = *reinterpret_cast<const float4*>(&ts[jj][cq * 4]);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int i = i0 + rg + 16 * q;
-          const float w = (i < R) ? __ldg(dS + (long long)i * C + j) : 0.f;
+          const float w = ws[rg + 16 * q][jj];
           acc[q].x = fmaf(w, tv.x, acc[q].x); acc[q].y = fmaf(w, tv.y, acc[q].y);
           acc[q].z = fmaf(w, tv.z, acc[q].z); acc[q].w = fmaf(w, tv.w, acc[q].w);
         }
@@ -964,7 +997,7 @@ int gather_rows(const void* src, long long ld_src, const int* row_src, const int
 }
 
 int row_inv_norm(const float* rowsq, int nblk, const int* n_rows, int cap, float* inv_norm, cudaStream_t st) {
-  const int blocks = std::min((cap + 255) / 256, sm_count() * 8);
+  const int blocks = std::min((cap + 31) / 32, sm_count() * 8);
   row_inv_norm_kernel<<<blocks, 256, 0, st>>>(rowsq, nblk, n_rows, cap, inv_norm);
   return check_launch("row_inv_norm_kernel");
 }

@@ -298,3 +298,46 @@ def test_adapter_into_embeds_equals_adapter_then_scatter(p2t, mods, dev, left_pa
         out = mods["handoff"].adapter_into_embeds(ad, sb.x.to(dev), sb.prot_mask.to(dev), base.clone().to(dev), ph.to(dev))
     want = R.placeholder_scatter(base, ph, y.cpu(), sb.prot_mask)
     assert torch.equal(out.cpu(), want)
+
+
+# --------------------------------------------------------------------------------------------------
+# medium similarity blocks (the sharded step's B x B_global block with fp32 embeddings)
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("R_,B_,C_,D_", [(32, 32, 256, 4096), (30, 32, 200, 96), (70, 70, 130, 64), (16, 16, 32, 2048)])
+def test_fp32_similarity_and_loss_backward_head_at_sharded_sizes(p2t, dev, R_, B_, C_, D_):
+    """p2t_similarity (fp32 operands: register-tiled kernel from 512 logits up) and p2t_loss_bwd_coef (t slab staged in
+    shared memory) against fp64: S = p t^T / tau; dp = dS t / tau; F.normalize backward; 'mix' coefficients."""
+    core = sys.modules["p2t_b200._core"]
+    E, tau = 2 * D_, 0.05
+    g = torch.Generator().manual_seed(R_ * 7 + C_)
+    t = torch.nn.functional.normalize(torch.randn(C_, E, generator=g), dim=-1)
+    e = torch.randn(B_, E, generator=g) + 3.0  # un-normalised pooled embeddings (mean | std), std part positive
+    e[:, D_:] = e[:, D_:].abs() + 0.5
+    pnorm = e.norm(dim=-1)
+    p = e / pnorm[:, None]
+    S = torch.empty(R_, C_, dtype=torch.float32, device=dev)
+    p2t._lib.call("p2t_similarity", None, None, p[:R_].contiguous().to(dev).data_ptr(), t.to(dev).data_ptr(), R_, C_, E,
+                  tau, S.data_ptr(), 2, None)
+    want = p[:R_].double() @ t.double().T / tau
+    assert maxrel(S, want) <= 2e-6
+    # backward head
+    dS = (torch.randn(R_, C_, generator=g) / R_).float()
+    lens = torch.randint(3, 40, (B_,), generator=g)
+    seq_off = torch.cat([torch.zeros(1, dtype=torch.long), lens.cumsum(0)]).to(torch.int32)
+    ws = torch.empty(B_, E + (E + 63) // 64, dtype=torch.float32, device=dev)
+    c1 = torch.empty(B_, D_, dtype=torch.float32, device=dev)
+    c2 = torch.empty(B_, D_, dtype=torch.float32, device=dev)
+    dl = torch.tensor([0.7], dtype=torch.float32, device=dev)
+    td, pd, nd, ed, so, dSd = (x.to(dev).contiguous() for x in (t, p, pnorm, e, seq_off, dS))
+    p2t._lib.call("p2t_loss_bwd_coef", dSd.data_ptr(), td.data_ptr(), pd.data_ptr(), nd.data_ptr(), ed.data_ptr(),
+                  so.data_ptr(), dl.data_ptr(), R_, B_, C_, D_, tau, ws.data_ptr(), c1.data_ptr(), c2.data_ptr(), None)
+    dp = torch.zeros(B_, E, dtype=torch.float64)
+    dp[:R_] = 0.7 * (dS.double() @ t.double()) / tau
+    got_dp = ws.flatten()[:B_ * E].view(B_, E)
+    assert maxrel(got_dp, dp) <= 2e-6
+    pdd = p.double()
+    de = (dp - pdd * (pdd * dp).sum(-1, keepdim=True)) / pnorm.double()[:, None]
+    n = lens.double()[:, None]
+    k2 = de[:, D_:] / (n * e[:, D_:].double())
+    k1 = de[:, :D_] / n - k2 * e[:, :D_].double()
+    assert maxrel(c2, k2) <= 1e-4 and maxrel(c1, k1) <= 1e-4  # (dp - p (p.dp)) cancels ~2 digits in fp32
