@@ -316,8 +316,8 @@ def test_fp32_similarity_and_loss_backward_head_at_sharded_sizes(p2t, dev, R_, B
     pnorm = e.norm(dim=-1)
     p = e / pnorm[:, None]
     S = torch.empty(R_, C_, dtype=torch.float32, device=dev)
-    p2t._lib.call("p2t_similarity", None, None, p[:R_].contiguous().to(dev).data_ptr(), t.to(dev).data_ptr(), R_, C_, E,
-                  tau, S.data_ptr(), 2, None)
+    p_dev, t_dev = p[:R_].contiguous().to(dev), t.to(dev)  # keep both alive: the call only sees raw pointers
+    p2t._lib.call("p2t_similarity", None, None, p_dev.data_ptr(), t_dev.data_ptr(), R_, C_, E, tau, S.data_ptr(), 2, None)
     want = p[:R_].double() @ t.double().T / tau
     assert maxrel(S, want) <= 2e-6
     # backward head
