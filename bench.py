@@ -380,8 +380,23 @@ def main():
         e1.record()
         barrier()
         e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))
+        # what bounds it: the step's inputs cross PCIe once (packed valid rows); compare with one large pinned copy
+        probe_h = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+        probe_d = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        probe_d.copy_(probe_h, non_blocking=True)
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(4):
+            probe_d.copy_(probe_h, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        pcie_peak = 4 * (256 << 20) / 1e9 / (c0.elapsed_time(c1) / 1e3)
+        del probe_h, probe_d
         e2e = {"value": world * B * args.steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps,
                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
+               "bound": "pcie", "h2d_gb_per_s": (h2d / args.steps) / 1e9 / (e2e_ms / args.steps / 1e3),
+               "h2d_peak_gb_per_s": pcie_peak, "h2d_peak_how": "4 x 256 MiB pinned cudaMemcpyAsync on this box, rank 0's link",
                "how": "pinned host batch -> HostStager (valid rows only, copy stream, next step's copy overlaps this "
                       "step's kernels) -> contrastive_step(packed rows + lengths) -> backward -> loss.item()"}
 
