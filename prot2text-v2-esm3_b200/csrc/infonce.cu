@@ -91,55 +91,58 @@ sim_small_kernel(const void* __restrict__ pv, const void* __restrict__ tv, int R
 // one CTA per 4 rows x 8 columns, its 256 threads split E (each thread: 12 independent 16-byte loads per trip feed
 // 128 FMAs), so p and t are streamed from L2 (R/4)(C/8) x 12 row-lengths in total instead of R (C/4) x 5.
 // Reduction in a fixed order (xor-shuffle tree, then warps 0..7): deterministic.
-constexpr int SIM_RT = 4, SIM_CT = 8;
-__global__ void __launch_bounds__(256)
+// Two shapes: 4 x 8 tiles with 256 threads from 4096 logits up; 2 x 4 tiles with 1024 threads below (4x the CTAs and
+// a quarter of the dependent trips over E when there are too few tiles to fill the SMs).
+template <int RT, int CT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 sim_tile_f32_kernel(const float* __restrict__ p, const float* __restrict__ t, int R, int C, int E, float alpha,
                     float* __restrict__ S) {
+  constexpr int NW = THREADS / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int i0 = blockIdx.x * SIM_RT, j0 = blockIdx.y * SIM_CT;
-  const float4* pr[SIM_RT];
-  const float4* tr[SIM_CT];
+  const int i0 = blockIdx.x * RT, j0 = blockIdx.y * CT;
+  const float4* pr[RT];
+  const float4* tr[CT];
 #pragma unroll
-  for (int a = 0; a < SIM_RT; ++a) pr[a] = reinterpret_cast<const float4*>(p + (long long)min(i0 + a, R - 1) * E);
+  for (int a = 0; a < RT; ++a) pr[a] = reinterpret_cast<const float4*>(p + (long long)min(i0 + a, R - 1) * E);
 #pragma unroll
-  for (int b = 0; b < SIM_CT; ++b) tr[b] = reinterpret_cast<const float4*>(t + (long long)min(j0 + b, C - 1) * E);
-  float acc[SIM_RT][SIM_CT];
+  for (int b = 0; b < CT; ++b) tr[b] = reinterpret_cast<const float4*>(t + (long long)min(j0 + b, C - 1) * E);
+  float acc[RT][CT];
 #pragma unroll
-  for (int a = 0; a < SIM_RT; ++a)
+  for (int a = 0; a < RT; ++a)
 #pragma unroll
-    for (int b = 0; b < SIM_CT; ++b) acc[a][b] = 0.f;
+    for (int b = 0; b < CT; ++b) acc[a][b] = 0.f;
   const int nvec = E >> 2;
-  for (int v = threadIdx.x; v < nvec; v += 256) {
-    float4 pv[SIM_RT], tv[SIM_CT];
+  for (int v = threadIdx.x; v < nvec; v += THREADS) {
+    float4 pv[RT], tv[CT];
 #pragma unroll
-    for (int a = 0; a < SIM_RT; ++a) pv[a] = __ldg(pr[a] + v);
+    for (int a = 0; a < RT; ++a) pv[a] = __ldg(pr[a] + v);
 #pragma unroll
-    for (int b = 0; b < SIM_CT; ++b) tv[b] = __ldg(tr[b] + v);
+    for (int b = 0; b < CT; ++b) tv[b] = __ldg(tr[b] + v);
 #pragma unroll
-    for (int a = 0; a < SIM_RT; ++a)
+    for (int a = 0; a < RT; ++a)
 #pragma unroll
-      for (int b = 0; b < SIM_CT; ++b) {
+      for (int b = 0; b < CT; ++b) {
         acc[a][b] = fmaf(pv[a].x, tv[b].x, acc[a][b]);
         acc[a][b] = fmaf(pv[a].y, tv[b].y, acc[a][b]);
         acc[a][b] = fmaf(pv[a].z, tv[b].z, acc[a][b]);
         acc[a][b] = fmaf(pv[a].w, tv[b].w, acc[a][b]);
       }
   }
-  __shared__ float red[8][SIM_RT * SIM_CT];
+  __shared__ float red[NW][RT * CT];
 #pragma unroll
-  for (int a = 0; a < SIM_RT; ++a)
+  for (int a = 0; a < RT; ++a)
 #pragma unroll
-    for (int b = 0; b < SIM_CT; ++b) {
+    for (int b = 0; b < CT; ++b) {
       const float s = warp_sum(acc[a][b]);
-      if (lane == 0) red[warp][a * SIM_CT + b] = s;
+      if (lane == 0) red[warp][a * CT + b] = s;
     }
   __syncthreads();
-  if (threadIdx.x < SIM_RT * SIM_CT) {
-    const int i = i0 + threadIdx.x / SIM_CT, j = j0 + threadIdx.x % SIM_CT;
+  if (threadIdx.x < RT * CT) {
+    const int i = i0 + threadIdx.x / CT, j = j0 + threadIdx.x % CT;
     if (i < R && j < C) {
       float s = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+      for (int w = 0; w < NW; ++w) s += red[w][threadIdx.x];
       S[(long long)i * C + j] = s * alpha;
     }
   }
@@ -319,9 +322,14 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, long lo
 // ================================================================================================
 int sim_small(const void* p, const void* t, bool in_f32, int R, int C, int E, float alpha, float* S, cudaStream_t st) {
   if (E % 8) return set_error(-1, "similarity: E must be a multiple of 8");
+  if (in_f32 && (long long)R * C >= 4096) {
+    const dim3 tiles((R + 3) / 4, (C + 7) / 8);
+    sim_tile_f32_kernel<4, 8, 256><<<tiles, 256, 0, st>>>(static_cast<const float*>(p), static_cast<const float*>(t), R, C, E, alpha, S);
+    return check_launch("sim_tile_f32_kernel");
+  }
   if (in_f32 && (long long)R * C >= 512) {
-    const dim3 tiles((R + SIM_RT - 1) / SIM_RT, (C + SIM_CT - 1) / SIM_CT);
-    sim_tile_f32_kernel<<<tiles, 256, 0, st>>>(static_cast<const float*>(p), static_cast<const float*>(t), R, C, E, alpha, S);
+    const dim3 tiles((R + 1) / 2, (C + 3) / 4);
+    sim_tile_f32_kernel<2, 4, 1024><<<tiles, 1024, 0, st>>>(static_cast<const float*>(p), static_cast<const float*>(t), R, C, E, alpha, S);
     return check_launch("sim_tile_f32_kernel");
   }
   const dim3 grid(R, (C + 3) / 4);

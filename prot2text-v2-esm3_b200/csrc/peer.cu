@@ -10,8 +10,9 @@
 // with cudaIpcOpenMemHandle; the handles travel through torch.distributed on the host side (peer.py).
 //
 // Flag protocol.  A channel owns, in its peer buffer, `world` arrival words per phase; a writer publishes with
-// data stores -> __threadfence_system() -> (last CTA) st.release.sys flag := epoch; a reader spins with
-// ld.acquire.sys until flag - epoch >= 0 and then reads the data with L1-bypassing loads.  The epoch lives in device
+// data stores -> CTA barrier -> thread 0: __threadfence_system(), count the CTA in -> (last CTA) fence, flag := epoch;
+// a reader polls the flag with relaxed system-scope loads until flag - epoch >= 0, fences, and then reads the data
+// with L1-bypassing loads.  The epoch lives in device
 // memory and is advanced by the channel's last kernel of a round, so graph replays need no host-side argument.
 // A reader that waits longer than `timeout_ns` gives up, records it in `status` and lets the stream drain (the host
 // raises on the next status check) instead of hanging the GPU.
@@ -29,14 +30,6 @@ struct PeerTable {
   void* base[kPeerMaxWorld];  // base[r] = this process's mapping of rank r's peer buffer (base[rank] = own)
 };
 
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ uint4 ld_sys_v4(const uint4* p) {  // relaxed system-scope load: never served from a stale L1 line
   uint4 v;
   asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
@@ -48,35 +41,49 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
-// Threads [0, world) of the CTA wait for flags[t] to reach `epoch`; returns after a CTA-wide barrier.
+__device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned* p, unsigned v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Threads [0, world) of the CTA wait for flags[t] to reach `epoch` (relaxed polls, then one system fence = acquire);
+// the CTA barrier that follows extends the ordering to every thread of the CTA.  System-scope fences cost a few
+// microseconds each (they wait for the thread's outstanding NVLink traffic), so they are issued by the polling /
+// publishing threads only, never by all threads.
 __device__ __forceinline__ void wait_flags(const unsigned* flags, int world, unsigned epoch, unsigned* status) {
   if ((int)threadIdx.x < world) {
     const unsigned long long t0 = global_ns();
-    while ((int)(ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) {
+    while ((int)(ld_relaxed_sys(flags + threadIdx.x) - epoch) < 0) {
       if (global_ns() - t0 > kTimeoutNs) {
         atomicExch(status, 1u + threadIdx.x);
         break;
       }
-      __nanosleep(64);
+      __nanosleep(32);
     }
+    __threadfence_system();
   }
   __syncthreads();
-  __threadfence_system();
 }
 
-// Every thread has fenced its stores; the last CTA of the grid to get here publishes `epoch` in slot `rank` of the
-// flag row at byte offset `flag_off` of every peer buffer (and, optionally, advances the local epoch word).
+// The CTA's stores are done (barrier), thread 0 fences them at system scope (cumulative over the barrier, the pattern
+// of a cooperative grid sync) and counts the CTA in; the last CTA of the grid to get here fences once more (acquire
+// of the other CTAs' counts + release of everything) and publishes `epoch` in slot `rank` of the flag row at byte
+// offset `flag_off` of every peer buffer with plain system-scope stores (and, optionally, advances the local epoch).
 __device__ __forceinline__ void publish_when_grid_done(const PeerTable& peers, int world, int rank, size_t flag_off,
                                                        unsigned epoch, unsigned* grid_counter, unsigned* epoch_word) {
-  __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();
     const unsigned done = atomicAdd(grid_counter, 1u);
     if (done == gridDim.x - 1) {
       __threadfence_system();
       if (flag_off != (size_t)-1)
         for (int r = 0; r < world; ++r)
-          st_release_sys(reinterpret_cast<unsigned*>(static_cast<char*>(peers.base[r]) + flag_off) + rank, epoch);
+          st_relaxed_sys(reinterpret_cast<unsigned*>(static_cast<char*>(peers.base[(rank + r) % world]) + flag_off) + rank, epoch);
       *grid_counter = 0;
       if (epoch_word) *epoch_word = epoch;
     }
@@ -134,7 +141,10 @@ __global__ void peer_allreduce_ready_kernel(PeerTable peers, int world, int rank
   publish_when_grid_done(peers, world, rank, flag_row_off(0), epoch, ctrl + 1, nullptr);
 }
 
-// phase 1: reduce my slice out of every peer's `in`, store the mean into every peer's `out`
+// phase 1: reduce my slice out of every peer's `in`, store the mean into every peer's `out`.
+// RB ranks x U vectors = 16 independent 16-byte loads in flight per thread whatever the world size (an NVLink round
+// trip is ~2 us); ranks are always added in rank order, so every rank computes bit-identical sums.
+template <int RB, int U>
 __global__ void __launch_bounds__(256)
 peer_allreduce_reduce_kernel(PeerTable peers, int world, int rank, long long n_vec, float scale) {
   unsigned* ctrl = static_cast<unsigned*>(peers.base[rank]);
@@ -144,27 +154,25 @@ peer_allreduce_reduce_kernel(PeerTable peers, int world, int rank, long long n_v
   const long long lo = per * rank, hi = min(n_vec, lo + per);
   const size_t in_off = kCtrlBytes, out_off = kCtrlBytes + (size_t)n_vec * sizeof(uint4);
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += 2 * stride) {
-    // two vectors per trip, every peer's load of both in flight together (NVLink round trip ~2 us)
-    const long long idx[2] = {i, i + stride};
-    float acc[2][8];
+  for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += U * stride) {
+    float acc[U][8];
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < U; ++u)
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[u][k] = 0.f;
-    for (int r0 = 0; r0 < world; r0 += 8) {  // fixed rank order: every rank computes bit-identical sums
-      uint4 v[2][8];
+    for (int r0 = 0; r0 < world; r0 += RB) {
+      uint4 v[U][RB];
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
+      for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (r0 + j < world && idx[u] < hi)
-            v[u][j] = ld_sys_v4(reinterpret_cast<const uint4*>(static_cast<char*>(peers.base[r0 + j]) + in_off) + idx[u]);
+        for (int j = 0; j < RB; ++j)
+          if (r0 + j < world && i + u * stride < hi)
+            v[u][j] = ld_sys_v4(reinterpret_cast<const uint4*>(static_cast<char*>(peers.base[r0 + j]) + in_off) + i + u * stride);
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
+      for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (r0 + j < world && idx[u] < hi) {
+        for (int j = 0; j < RB; ++j)
+          if (r0 + j < world && i + u * stride < hi) {
             const float2 a = unpack_bf16x2(v[u][j].x), b = unpack_bf16x2(v[u][j].y), c = unpack_bf16x2(v[u][j].z),
                          d = unpack_bf16x2(v[u][j].w);
             acc[u][0] += a.x; acc[u][1] += a.y; acc[u][2] += b.x; acc[u][3] += b.y;
@@ -172,13 +180,13 @@ peer_allreduce_reduce_kernel(PeerTable peers, int world, int rank, long long n_v
           }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (idx[u] >= hi) continue;
+    for (int u = 0; u < U; ++u) {
+      if (i + u * stride >= hi) continue;
       const uint4 o = make_uint4(pack_bf16x2(acc[u][0] * scale, acc[u][1] * scale), pack_bf16x2(acc[u][2] * scale, acc[u][3] * scale),
                                  pack_bf16x2(acc[u][4] * scale, acc[u][5] * scale), pack_bf16x2(acc[u][6] * scale, acc[u][7] * scale));
       for (int r = 0; r < world; ++r) {
         const int dst = (rank + r) % world;
-        reinterpret_cast<uint4*>(static_cast<char*>(peers.base[dst]) + out_off)[idx[u]] = o;
+        reinterpret_cast<uint4*>(static_cast<char*>(peers.base[dst]) + out_off)[i + u * stride] = o;
       }
     }
   }
@@ -293,7 +301,15 @@ int peer_allreduce_mean(void* const* peers, int world, int rank, long long n_byt
     if (int r = check_launch("peer_allreduce_ready_kernel")) return r;
   }
   if (phases & 2) {
-    peer_allreduce_reduce_kernel<<<grid_for((n_vec + world - 1) / world / 2, 4), 256, 0, st>>>(t, world, rank, n_vec, 1.f / (float)world);
+    const float scale = 1.f / (float)world;
+    const long long slice = (n_vec + world - 1) / world;
+    if (world <= 2) {
+      peer_allreduce_reduce_kernel<2, 8><<<grid_for(slice / 8, 4), 256, 0, st>>>(t, world, rank, n_vec, scale);
+    } else if (world <= 4) {
+      peer_allreduce_reduce_kernel<4, 4><<<grid_for(slice / 4, 4), 256, 0, st>>>(t, world, rank, n_vec, scale);
+    } else {
+      peer_allreduce_reduce_kernel<8, 2><<<grid_for(slice / 2, 4), 256, 0, st>>>(t, world, rank, n_vec, scale);
+    }
     if (int r = check_launch("peer_allreduce_reduce_kernel")) return r;
   }
   if (phases & 4) {

@@ -568,8 +568,9 @@ loss_bwd_dp_kernel(const float* __restrict__ dS, const float* __restrict__ t, co
         ws[r][c] = (i < R && j < C) ? __ldg(dS + (long long)i * C + j) : 0.f;
       }
       __syncthreads();
+      const int jn = min(LBW_JC, C - j0);
 #pragma unroll 8
-      for (int jj = 0; jj < LBW_JC; ++jj) {
+      for (int jj = 0; jj < jn; ++jj) {
         const float4 tv = *reinterpret_cast<const float4*>(&ts[jj][cq * 4]);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
