@@ -131,8 +131,8 @@ def distributed_contrastive_step(residue_states, protein_mask, adapter, text_hid
     else:
         rank, world = dist.get_rank(group), dist.get_world_size(group)
     t_local = _step.text_embeddings(text_hidden, text_mask, dtype=torch.float32, text_lengths=text_lengths)
-    # the gather travels behind the plan/pack kernels of the protein side and is waited for right before the
-    # (persistent, one-CTA-per-SM) adapter GEMMs
+    # the gather travels behind the protein side's kernels; the NCCL form is waited for right before the (persistent,
+    # one-CTA-per-SM) adapter GEMMs, the in-stream peer-memory arrive right before the similarity
     if exchange is not None:
         exchange.text.push(t_local)
         t_global = exchange.text.arrive
@@ -148,4 +148,5 @@ def distributed_contrastive_step(residue_states, protein_mask, adapter, text_hid
     return _step.contrastive_step(residue_states, protein_mask, adapter, text_embeds=t_global,
                                   residue_lengths=residue_lengths,
                                   temperature=temperature, symmetric=symmetric, labels=labels, aux=aux,
-                                  col_stats_hook=hook, all_cols_labelled=symmetric and world > 1, **step_kw)
+                                  col_stats_hook=hook, all_cols_labelled=symmetric and world > 1,
+                                  late_text=exchange is not None, **step_kw)

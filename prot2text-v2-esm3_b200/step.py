@@ -74,15 +74,21 @@ def step_forward(x, prot_mask, w1, b1, w2, b2, t_in, labels, cfg: dict, aux: Ste
         plan = _core.plan_rows(prot_mask)
         xp = _core.gather_rows(x.contiguous().view(B * L, d_in), plan)
         x_rows = plan.rows_cap
-    if callable(t_in):
-        # deferred text embeddings (the all-gather of the sharded step): the collective has been running behind the
-        # plan/pack kernels above; it must be OVER before the persistent GEMMs start — they assume one CTA per SM, and
-        # a communication kernel still holding SMs delays a whole tile share (measured: fc1 163 -> 250 us)
+    if callable(t_in) and not cfg.get("late_text", False):
+        # deferred text embeddings (the NCCL all-gather of the sharded step): the collective has been running on its
+        # own stream behind the plan/pack kernels above; it must be OVER before the persistent GEMMs start — they
+        # assume one CTA per SM, and a communication kernel still holding SMs delays a whole tile share (measured:
+        # fc1 163 -> 250 us)
         t_in = t_in()
     acts = _core.adapter_forward(xp, x_rows, plan.rows_cap, plan.n_rows, w1c, b1c, w2c, b2c,
                                  cfg["dropout_p"], cfg["seed"], need_grad, seed_dev=cfg.get("seed_dev"))
     inv_norm = _core.row_inv_norm(acts)
     stats, p_bf, p_f32, pnorm = _core.pool_forward(acts.a, plan, d_out, row_src=None, inv_norm=inv_norm, normalize=True)
+    if callable(t_in):
+        # peer-memory exchange: its arrive kernel runs IN this stream (it never overlaps the GEMMs), so it is placed
+        # where the gathered rows are first needed.  The peers' pushes were issued at the start of their steps: every
+        # rank may lag the fastest one by the whole adapter forward (~0.45 ms at config 2) before anybody waits.
+        t_in = t_in()
     if t_in.dtype == torch.float32:
         t_f32 = t_in.contiguous()
         # the bf16 copy is an operand of the tensor-core loss path only (large similarity blocks)
@@ -175,7 +181,7 @@ def contrastive_step(residue_states: torch.Tensor, protein_mask: Optional[torch.
                      labels: Optional[torch.Tensor] = None, aux: Optional[StepAux] = None,
                      col_stats_hook=None, loss_scale: Optional[float] = None,
                      all_cols_labelled: bool = False, seed_dev: Optional[torch.Tensor] = None,
-                     _raw: bool = False) -> torch.Tensor:
+                     late_text: bool = False, _raw: bool = False) -> torch.Tensor:
     """One Stage-1 step from trunk outputs to the (differentiable) fp32 loss.
 
     residue_states (B, L, D_in) bf16 and protein_mask (B, L) come from the frozen protein encoder
@@ -183,8 +189,8 @@ def contrastive_step(residue_states: torch.Tensor, protein_mask: Optional[torch.
     LLM with its attention mask (scripts/train_contrast.py:304), or pass already normalised
     `text_embeds` (B_t, 2H), float32 (preferred) or bfloat16 — e.g. the all-gathered global negatives — or a
     zero-argument callable returning them, which is invoked after the residue rows have been packed and before
-    the adapter GEMMs (so a collective overlaps the plan/pack kernels but never shares SMs with the persistent
-    GEMMs).  `labels[i]` is the text row
+    the adapter GEMMs (so a collective on another stream overlaps the plan/pack kernels but never shares SMs with
+    the persistent GEMMs) or, with `late_text`, right before the similarity (in-stream peer-memory arrive).  `labels[i]` is the text row
     paired with protein i (default: i).  Ragged hand-over: with `residue_lengths` (B,),
     `residue_states` is the PACKED (sum L_b, D_in) row buffer and `protein_mask` is ignored; likewise
     `text_lengths` with packed `text_hidden` (see host_io.HostStager).  `contrastive_num_segments` reproduces the reference's
@@ -211,7 +217,8 @@ def contrastive_step(residue_states: torch.Tensor, protein_mask: Optional[torch.
     cfg = dict(tau=float(temperature), w_row=0.5 if symmetric else 1.0, w_col=0.5 if symmetric else 0.0,
                dropout_p=p, seed=_draw_seed() if (p > 0 and seed_dev is None) else 0, seed_dev=seed_dev,
                rows_used=seg * contrastive_num_segments, packed=packed,
-               col_stats_hook=col_stats_hook, loss_scale=loss_scale, all_cols_labelled=all_cols_labelled)
+               col_stats_hook=col_stats_hook, loss_scale=loss_scale, all_cols_labelled=all_cols_labelled,
+               late_text=late_text)
     aux = aux if aux is not None else StepAux()
     if _raw:  # graph capture: no autograd, the caller runs step_backward itself
         return step_forward(residue_states, residue_lengths if packed else protein_mask, adapter.fc1.weight.detach(),
