@@ -46,32 +46,64 @@ class FusedAdamW(torch.optim.Optimizer):
 
     # ------------------------------------------------------------------------------------------
     def _group_state(self, gi: int, tensors):
-        st = self._dev.get(gi)
-        key = tuple(t.data_ptr() for t in tensors)
-        if st is not None and st["key"] == key:
-            return st
+        """Device-side scalars and workspace of a parameter group, plus this call's pointer tables.  Per-parameter
+        state (`exp_avg`, `exp_avg_sq`, `master`: fp32; `step`: int64, one shared counter per group, kept in the
+        first parameter's state so that it travels with state_dict) is created on first use and re-read on every
+        call, so a `load_state_dict` in between is picked up."""
         dev = tensors[0].device
+        st = self._dev.get(gi)
+        if st is None:
+            st = self._dev[gi] = dict(lr=torch.zeros(1, dtype=torch.float32, device=dev), lr_host=None,
+                                      scal=torch.zeros(4, dtype=torch.float32, device=dev), nws=-1, partial=None)
         numel = (C.c_longlong * len(tensors))(*[t.numel() for t in tensors])
         nws = int(_lib.load().p2t_adamw_workspace_floats(len(tensors), numel))
-        if st is None:
-            st = dict(step=torch.zeros(1, dtype=torch.int64, device=dev),
-                      lr=torch.zeros(1, dtype=torch.float32, device=dev), lr_host=None,
-                      scal=torch.zeros(4, dtype=torch.float32, device=dev))
-        st.update(key=key, numel=numel, partial=torch.empty(max(nws, 1), dtype=torch.float32, device=dev))
+        if nws != st["nws"]:
+            st["partial"], st["nws"] = torch.empty(max(nws, 1), dtype=torch.float32, device=dev), nws
         for t in tensors:
             s = self.state[t]
             if "exp_avg" not in s:
                 s["exp_avg"] = torch.zeros(t.shape, dtype=torch.float32, device=dev)
                 s["exp_avg_sq"] = torch.zeros(t.shape, dtype=torch.float32, device=dev)
-                if self.master_weights:
-                    s["master"] = t.detach().to(torch.float32).clone()
+            if self.master_weights and "master" not in s:
+                s["master"] = t.detach().to(torch.float32).clone()
+            for k in ("exp_avg", "exp_avg_sq", "master"):
+                if k in s and (s[k].dtype != torch.float32 or s[k].device != dev or not s[k].is_contiguous()):
+                    s[k] = s[k].to(device=dev, dtype=torch.float32).contiguous()
+        s0 = self.state[tensors[0]]
+        step = s0.get("step")
+        if step is None:
+            s0["step"] = torch.zeros(1, dtype=torch.int64, device=dev)
+        elif step.dtype != torch.int64 or step.device != dev or step.numel() != 1:
+            s0["step"] = step.to(device=dev, dtype=torch.int64).reshape(1).clone()
         vp = C.c_void_p * len(tensors)
+        st["numel"] = numel
+        st["step"] = s0["step"]
         st["params"] = vp(*[t.data_ptr() for t in tensors])
         st["m"] = vp(*[self.state[t]["exp_avg"].data_ptr() for t in tensors])
         st["v"] = vp(*[self.state[t]["exp_avg_sq"].data_ptr() for t in tensors])
         st["w"] = vp(*[self.state[t]["master"].data_ptr() if self.master_weights else None for t in tensors])
-        self._dev[gi] = st
         return st
+
+    def load_state_dict(self, state_dict) -> None:
+        """torch casts floating-point optimizer state to the parameter's dtype on load (bf16 here); the moments and
+        master weights of this optimizer are fp32 whatever the parameter is, so they are restored from the incoming
+        dict afterwards, uncast."""
+        super().load_state_dict(state_dict)
+        by_id = {}
+        for saved, group in zip(state_dict["param_groups"], self.param_groups):
+            for pid, p in zip(saved["params"], group["params"]):
+                by_id[pid] = p
+        for pid, saved in state_dict["state"].items():
+            p = by_id.get(pid)
+            if p is None:
+                continue
+            for k in ("exp_avg", "exp_avg_sq", "master"):
+                if k in saved:
+                    self.state[p][k] = saved[k].detach().to(device=p.device, dtype=torch.float32).clone()
+            if "step" in saved:
+                self.state[p]["step"] = torch.as_tensor(saved["step"]).detach().to(device=p.device, dtype=torch.int64).reshape(1).clone()
+        for st in self._dev.values():
+            st["lr_host"] = None  # re-send the (possibly restored) learning rate
 
     def set_lr(self, lr: float, group: int = 0) -> None:
         """Write the learning rate of a group to the device (use this between CUDA-graph replays)."""
@@ -80,6 +112,11 @@ class FusedAdamW(torch.optim.Optimizer):
         if st is not None:
             st["lr"].fill_(float(lr))
             st["lr_host"] = float(lr)
+
+    def step_count(self, group: int = 0) -> int:
+        """Optimizer steps taken by a group so far (reads the device counter: synchronises)."""
+        st = self._dev.get(group)
+        return 0 if st is None or "step" not in st else int(st["step"].item())
 
     @torch.no_grad()
     def step(self, closure=None):

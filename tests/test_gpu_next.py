@@ -242,7 +242,16 @@ def test_fused_adamw_is_capturable_and_follows_the_scheduler(p2t, mods, dev):
     opt.set_lr(1e-2)
     graph.replay()
     torch.cuda.synchronize()
-    assert int(opt._dev[0]["step"].item()) == 3 and (opt.state[w]["master"] < before).all()  # 1 eager + 2 replays
+    assert opt.step_count() == 3 and (opt.state[w]["master"] < before).all()  # 1 eager + 2 replays
+    # checkpoint round trip: fp32 moments / master weights and the step counter survive (torch would cast them to bf16)
+    sd = opt.state_dict()
+    w2 = torch.nn.Parameter(w.detach().clone())
+    w2.grad = w.grad.clone()
+    opt2 = mods["optim"].FusedAdamW([w2], lr=1e-2, weight_decay=0.0)
+    opt2.load_state_dict(sd)
+    assert opt2.state[w2]["master"].dtype == torch.float32 and torch.equal(opt2.state[w2]["master"], opt.state[w]["master"])
+    opt.step(); opt2.step()
+    assert opt2.step_count() == 4 and torch.equal(w2, w) and torch.equal(opt2.state[w2]["exp_avg_sq"], opt.state[w]["exp_avg_sq"])
     with pytest.raises(p2t.P2TError, match="bfloat16"):
         f = torch.nn.Parameter(torch.ones(8, 8, device=dev))
         f.grad = torch.ones_like(f)

@@ -127,3 +127,23 @@ def test_next_row_entries_have_no_cpu_path(p2t):
     with pytest.raises(p2t.P2TError, match="CUDA"):
         handoff.adapter_into_embeds(ad, torch.zeros(1, 2, 16, dtype=torch.bfloat16), None,
                                     torch.zeros(1, 4, 24, dtype=torch.bfloat16), torch.zeros(1, 4, dtype=torch.bool))
+
+
+def test_fused_adamw_state_dict_keeps_fp32_state(p2t):
+    """torch's Optimizer.load_state_dict casts floating state to the parameter dtype (bf16); FusedAdamW restores its fp32
+    moments / master weights and the int64 step counter from the incoming dict (host logic, no kernel involved)."""
+    optim = importlib.import_module("p2t_b200.optim")
+    w = torch.nn.Parameter(torch.zeros(4, 8, dtype=torch.bfloat16))
+    opt = optim.FusedAdamW([w], lr=1e-3)
+    fine = torch.full((4, 8), 1.0 + 2.0 ** -12)  # not representable in bf16
+    opt.state[w] = {"exp_avg": fine.clone(), "exp_avg_sq": fine.clone() * 2, "master": fine.clone() * 3,
+                    "step": torch.tensor([7], dtype=torch.int64)}
+    sd = opt.state_dict()
+    w2 = torch.nn.Parameter(torch.zeros(4, 8, dtype=torch.bfloat16))
+    opt2 = optim.FusedAdamW([w2], lr=5e-4)
+    opt2.load_state_dict(sd)
+    st = opt2.state[w2]
+    assert st["exp_avg"].dtype == torch.float32 and torch.equal(st["exp_avg"], fine)
+    assert torch.equal(st["exp_avg_sq"], fine * 2) and torch.equal(st["master"], fine * 3)
+    assert st["step"].dtype == torch.int64 and int(st["step"]) == 7
+    assert opt2.param_groups[0]["lr"] == 1e-3  # hyper-parameters come from the checkpoint, as in torch
