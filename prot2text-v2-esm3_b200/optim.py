@@ -52,6 +52,11 @@ class FusedAdamW(torch.optim.Optimizer):
         call, so a `load_state_dict` in between is picked up."""
         dev = tensors[0].device
         st = self._dev.get(gi)
+        # fast path: same parameter storage and same state tensor objects as last call -> the tables are still valid
+        key = tuple((t.data_ptr(), id(s.get("exp_avg")), id(s.get("exp_avg_sq")), id(s.get("master")))
+                    for t, s in ((t, self.state[t]) for t in tensors)) + (id(self.state[tensors[0]].get("step")),)
+        if st is not None and st.get("key") == key:
+            return st
         if st is None:
             st = self._dev[gi] = dict(lr=torch.zeros(1, dtype=torch.float32, device=dev), lr_host=None,
                                       scal=torch.zeros(4, dtype=torch.float32, device=dev), nws=-1, partial=None)
@@ -82,6 +87,8 @@ class FusedAdamW(torch.optim.Optimizer):
         st["m"] = vp(*[self.state[t]["exp_avg"].data_ptr() for t in tensors])
         st["v"] = vp(*[self.state[t]["exp_avg_sq"].data_ptr() for t in tensors])
         st["w"] = vp(*[self.state[t]["master"].data_ptr() if self.master_weights else None for t in tensors])
+        st["key"] = tuple((t.data_ptr(), id(s.get("exp_avg")), id(s.get("exp_avg_sq")), id(s.get("master")))
+                          for t, s in ((t, self.state[t]) for t in tensors)) + (id(s0["step"]),)
         return st
 
     def load_state_dict(self, state_dict) -> None:

@@ -147,3 +147,24 @@ def test_fused_adamw_state_dict_keeps_fp32_state(p2t):
     assert torch.equal(st["exp_avg_sq"], fine * 2) and torch.equal(st["master"], fine * 3)
     assert st["step"].dtype == torch.int64 and int(st["step"]) == 7
     assert opt2.param_groups[0]["lr"] == 1e-3  # hyper-parameters come from the checkpoint, as in torch
+
+
+def test_fused_adamw_pointer_tables_follow_the_state(p2t):
+    """The per-call pointer tables are cached while parameters and state tensors stay the same objects and rebuilt when
+    a load_state_dict (or anything else) swaps them — exercised on CPU tensors, no kernel involved."""
+    optim = importlib.import_module("p2t_b200.optim")
+    w = torch.nn.Parameter(torch.zeros(4, 8, dtype=torch.bfloat16))
+    b = torch.nn.Parameter(torch.zeros(8, dtype=torch.bfloat16))
+    opt = optim.FusedAdamW([w, b], lr=1e-3)
+    st = opt._group_state(0, [w, b])
+    assert st["m"][0] == opt.state[w]["exp_avg"].data_ptr() and st["w"][1] == opt.state[b]["master"].data_ptr()
+    assert opt.state[w]["step"].dtype == torch.int64 and "step" not in opt.state[b]
+    tables = (st["m"], st["step"])
+    assert opt._group_state(0, [w, b])["m"] is tables[0]          # cached
+    sd = opt.state_dict()
+    opt.load_state_dict(sd)                                        # new state tensor objects
+    st2 = opt._group_state(0, [w, b])
+    assert st2["m"] is not tables[0] and st2["m"][0] == opt.state[w]["exp_avg"].data_ptr()
+    assert st2["step"] is opt.state[w]["step"]
+    nomaster = optim.FusedAdamW([w], master_weights=False)
+    assert nomaster._group_state(0, [w])["w"][0] is None and "master" not in nomaster.state[w]
