@@ -1,5 +1,5 @@
 // Element math shared by all kernels: exact-erf GELU and its derivative, bf16 helpers, vector row
-// load/store, and the counter-based (Philox4x32-10) dropout mask that every kernel can regenerate
+// load/store, and the counter-based (Philox4x32-7) dropout mask that every kernel can regenerate
 // from (seed, layer, row, column) so no mask is ever stored.
 #pragma once
 #include <cuda_runtime.h>

@@ -1,7 +1,7 @@
 """Multi-GPU parity check of the sharded contrastive step (run under torchrun, one rank per GPU).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
-        tools/dist_check.py [workload] [weight_gain]
+        tests/dist_check.py [workload] [weight_gain]
 
 Every rank runs `dist.distributed_contrastive_step` on its own shard, with and without the symmetric column term, in
 three forms: NCCL all-gather (eager), the peer-memory exchange (eager), and the peer-memory exchange captured in a

@@ -1,6 +1,6 @@
 """Stage-by-stage parity report of the CUDA path against the oracle (prints, never asserts).
 
-    python tools/stage_probe.py [config-name] [weight_gain]
+    python tests/stage_probe.py [config-name] [weight_gain]
 
 Used during bring-up on the GPU box; the assertions proper live in tests/ (-m gpu).
 """

@@ -82,3 +82,18 @@ def test_product_package_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "oracle." not in text and "oracle/" not in text, f
+
+
+def test_oracle_is_only_reached_from_the_checker_sites():
+    """Outside tests/, the oracle may be imported by bench.py's CPU-baseline function and by smoke() only."""
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith((".py", ".sh")):
+            assert "oracle" not in open(os.path.join(ROOT, "tools", f)).read(), f
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    sites = [m.start() for m in re.finditer(r"^\s*from oracle\b|^\s*import oracle\b", bench, flags=re.M)]
+    assert len(sites) == 1
+    fn_start = bench.rfind("\ndef ", 0, sites[0])
+    assert bench[fn_start:].lstrip().startswith("def cpu_oracle_step_time")
+    entry = open(os.path.join(ROOT, "__graft_entry__.py")).read()
+    sites = [m.start() for m in re.finditer(r"^\s*from oracle\b|^\s*import oracle\b", entry, flags=re.M)]
+    assert len(sites) == 1 and entry[entry.rfind("\ndef ", 0, sites[0]):].lstrip().startswith("def smoke")

@@ -8,7 +8,7 @@
 
 The exchange kernels are exercised on ONE device with several simulated ranks (`PeerBuffer.virtual`): every rank's
 launch of a phase is issued before any rank's launch of the next phase, which is the order the flag protocol needs on a
-single stream; tools/dist_check.py runs the same kernels across real processes over NVLink (tests/test_gpu_dist.py).
+single stream; tests/dist_check.py runs the same kernels across real processes over NVLink (tests/test_gpu_dist.py).
 Bar: bit-exact for the exchange (byte moves, fixed-order fp32 sums), reference tolerances for floating point."""
 import importlib
 import os
@@ -151,7 +151,7 @@ def test_peer_allreduce_adapter_sized(mods, dev):
 
 def test_graphed_step_through_the_exchange_equals_the_plain_step(p2t, mods, dev):
     """World of one: the sharded step's exchange (push, arrive, gradient mean) inside the captured graph must leave the
-    step's numbers untouched — the same kernels then run across ranks in tools/dist_check.py."""
+    step's numbers untouched — the same kernels then run across ranks in tests/dist_check.py."""
     synth, pdist, peer = mods["synth"], mods["dist"], mods["peer"]
     sb = synth.make_config_batch("tiny", weight_gain=8.0)
     ad = make_adapter(p2t, dev, sb.w1, sb.b1, sb.w2, sb.b2)
