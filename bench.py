@@ -47,6 +47,9 @@ def parse_args():
     ap.add_argument("--no-optimizer", action="store_true", help="skip the (separately reported) optimizer leg")
     ap.add_argument("--eval-mode", action="store_true", help="dropout off (parity runs); default is training mode")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--device-synth", action="store_true",
+                    help="draw the synthetic residue/text states on the GPU (big sweep configs: no multi-GB host "
+                         "buffers); implies --no-e2e and --no-cpu-baseline, which need host copies")
     return ap.parse_args()
 
 
@@ -235,7 +238,10 @@ def main():
 
     cfg = synth.CONFIGS[args.workload]
     nbatches = 2
-    batches = [synth.make_config_batch(args.workload, seed=1234 + 17 * i, rank=rank, same_lengths_as_rank0=True)
+    if args.device_synth:
+        args.no_e2e = args.no_cpu_baseline = True
+    batches = [synth.make_config_batch(args.workload, seed=1234 + 17 * i, rank=rank, same_lengths_as_rank0=True,
+                                       device=dev if args.device_synth else None)
                for i in range(nbatches)]
     B = cfg["batch"]
     acfg = pkg.ModalityAdapterConfig(input_dim=cfg["d_in"], intermediate_dim=cfg["d_mid"], output_dim=cfg["d_out"], dropout_rate=0.3)
@@ -247,9 +253,13 @@ def main():
     adapter.eval() if args.eval_mode else adapter.train()
     params = [adapter.fc1.weight, adapter.fc1.bias, adapter.fc2.weight, adapter.fc2.bias]
 
-    host = [dict(x=b.x.pin_memory(), pm=b.prot_mask.pin_memory(), text=b.text.pin_memory(), tm=b.text_mask.pin_memory())
-            for b in batches]
-    resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
+    if args.device_synth:
+        host = None
+        resident = [dict(x=b.x, pm=b.prot_mask.to(dev), text=b.text, tm=b.text_mask.to(dev)) for b in batches]
+    else:
+        host = [dict(x=b.x.pin_memory(), pm=b.prot_mask.pin_memory(), text=b.text.pin_memory(), tm=b.text_mask.pin_memory())
+                for b in batches]
+        resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
     valid_rows = [int(b.prot_lens.sum()) for b in batches]
 
     # N > 1: the exchange step of the sharded batch runs as peer-memory kernels (no NCCL on the data path)
@@ -477,7 +487,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
+            "dtype": "bf16", "data": "synthetic (drawn on the device)" if args.device_synth else "synthetic",
             "config": {"workload": args.workload, "d_in": d_in, "d_mid": d_mid, "d_out": d_out, "pairs_per_gpu": B,
                        "global_pairs": world * B, "residue_len": [cfg["lmin"], cfg["lmax"]],
                        "valid_rows_per_step": valid_rows[0], "dropout_p": 0.0 if args.eval_mode else 0.3,

@@ -36,9 +36,12 @@ class SynthBatch:
 
 def make_batch(d_in, d_mid, d_out, batch, lmin, lmax, tmin, tmax, seed: int = 1234, rank: int = 0,
                weight_gain: float = 1.0, left_pad: bool = False, plant: float = 0.0,
-               same_lengths_as_rank0: bool = False) -> SynthBatch:
+               same_lengths_as_rank0: bool = False, device=None) -> SynthBatch:
     """`same_lengths_as_rank0`: every rank gets rank 0's multiset of sequence lengths (in a rank-specific order) with
-    its own random data — per-GPU work is then exactly fixed as ranks are added (weak-scaling benchmark)."""
+    its own random data — per-GPU work is then exactly fixed as ranks are added (weak-scaling benchmark).
+    `device`: draw the residue / text states there with a device generator (same lengths and masks as the host
+    path, different values) — the big sweep configurations are 5 GB of residue states per rank, which is minutes of
+    single-threaded host randn under torchrun; everything else stays on the host."""
     g = torch.Generator().manual_seed(seed + rank)
     lens = torch.randint(lmin, lmax + 1, (batch,), generator=g)
     tlens = torch.randint(tmin, tmax + 1, (batch,), generator=g)
@@ -49,16 +52,25 @@ def make_batch(d_in, d_mid, d_out, batch, lmin, lmax, tmin, tmax, seed: int = 12
         perm = torch.randperm(batch, generator=torch.Generator().manual_seed(seed + 7919 * rank))
         lens, tlens = lens0[perm], tlens0[perm]
     L, T = int(lens.max()), int(tlens.max())
-    x = torch.randn(batch, L, d_in, generator=g).to(torch.bfloat16)
-    text = torch.randn(batch, T, d_out, generator=g).to(torch.bfloat16)
     ar_l, ar_t = torch.arange(L)[None, :], torch.arange(T)[None, :]
     pm = (ar_l >= (L - lens)[:, None]) if left_pad else (ar_l < lens[:, None])
     tm = ar_t < tlens[:, None]
-    x = x * pm[..., None].to(torch.bfloat16)
-    if plant > 0.0:
-        # plant a per-pair signature so that retrieval has a margin (bit-exact argmax tests)
-        sig = torch.randn(batch, 1, d_out, generator=g).to(torch.bfloat16)
-        text = (text + plant * sig).to(torch.bfloat16)
+    if device is None:
+        x = torch.randn(batch, L, d_in, generator=g).to(torch.bfloat16)
+        text = torch.randn(batch, T, d_out, generator=g).to(torch.bfloat16)
+        x = x * pm[..., None].to(torch.bfloat16)
+        if plant > 0.0:
+            # plant a per-pair signature so that retrieval has a margin (bit-exact argmax tests)
+            sig = torch.randn(batch, 1, d_out, generator=g).to(torch.bfloat16)
+            text = (text + plant * sig).to(torch.bfloat16)
+    else:
+        dg = torch.Generator(device=device).manual_seed(seed + rank)
+        x = torch.randn(batch, L, d_in, generator=dg, device=device, dtype=torch.bfloat16)
+        text = torch.randn(batch, T, d_out, generator=dg, device=device, dtype=torch.bfloat16)
+        x.mul_(pm.to(device=device, dtype=torch.bfloat16)[..., None])
+        if plant > 0.0:
+            sig = torch.randn(batch, 1, d_out, generator=dg, device=device, dtype=torch.bfloat16)
+            text = (text + plant * sig).to(torch.bfloat16)
     wg = torch.Generator().manual_seed(0)  # weights are the same on every rank
     w1 = (torch.randn(d_mid, d_in, generator=wg) * 0.02 * weight_gain).to(torch.bfloat16)
     w2 = (torch.randn(d_out, d_mid, generator=wg) * 0.02 * weight_gain).to(torch.bfloat16)

@@ -92,3 +92,15 @@ def test_balanced_shards_equalise_residue_rows(p2t):
     assert max(random_totals) > max(totals)
     with pytest.raises(ValueError):
         pdist.balanced_shards(lengths[:10], 4)
+
+
+def test_device_side_synthetic_batch_has_the_same_ragged_structure(p2t):
+    import importlib
+    synth = importlib.import_module("p2t_b200.synth")
+    a = synth.make_config_batch("tiny", rank=3, same_lengths_as_rank0=True)
+    b = synth.make_config_batch("tiny", rank=3, same_lengths_as_rank0=True, device=torch.device("cpu"))
+    assert torch.equal(a.prot_lens, b.prot_lens) and torch.equal(a.prot_mask, b.prot_mask) and torch.equal(a.text_mask, b.text_mask)
+    assert b.x.dtype == torch.bfloat16 and b.x.shape == a.x.shape and b.text.shape == a.text.shape
+    assert not b.x[b.prot_mask == 0].any() and torch.equal(a.w1, b.w1)
+    r0 = synth.make_config_batch("tiny", rank=0)
+    assert sorted(a.prot_lens.tolist()) == sorted(r0.prot_lens.tolist())  # rank 0's multiset, permuted
