@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-optimizer", action="store_true", help="skip the (separately reported) optimizer leg")
+    ap.add_argument("--no-exchange-probe", action="store_true", help="skip timing the exchange kernels alone (N > 1)")
     ap.add_argument("--eval-mode", action="store_true", help="dropout off (parity runs); default is training mode")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     ap.add_argument("--device-synth", action="store_true",
@@ -448,6 +449,33 @@ def main():
         if reducer is not None:
             reducer.buffer.check()
 
+    # ------------------------------ the exchange step alone (N > 1): NVLink roofline ------------------------------
+    exchange_leg = None
+    if exchange is not None and not args.no_exchange_probe:
+        try:
+            E = 2 * cfg["d_out"]
+            t_probe = torch.randn(B, E, device=dev, dtype=torch.float32)
+            for _ in range(3):
+                exchange.text(t_probe)
+            barrier()
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_x = 20
+            x0.record()
+            for _ in range(n_x):
+                exchange.text(t_probe)  # push kernel + arrive kernel, the pair the step launches
+            x1.record()
+            barrier()
+            us = max_over_ranks(x0.elapsed_time(x1)) / n_x * 1e3
+            sent = (world - 1) * B * E * 4
+            exchange_leg = {"us_per_exchange": us, "bytes_sent_per_rank": sent,
+                            "gb_per_s_sent_per_rank": sent / 1e9 / (us / 1e6), "peak_gb_per_s": 900.0,
+                            "peak_source": "nominal NVLink 5 per direction per GPU (not measured by the driver)",
+                            "note": "push + arrive kernels back to back, eager launches, both launch latencies included; "
+                                    "at B*E*4 bytes per peer the pair is latency-bound, not link-bound"}
+            exchange.check()
+        except Exception as exc:  # noqa: BLE001 - a probe must never cost the benchmark its line
+            exchange_leg = {"error": f"{type(exc).__name__}: {exc}"}
+
     # ------------------------------ roofline of the dominant kernel ------------------------------
     d_in, d_mid, d_out = cfg["d_in"], cfg["d_mid"], cfg["d_out"]
     flops_per_row = 2.0 * d_in * d_mid + 2.0 * d_mid * d_out + 2.0 * d_in * d_mid + 4.0 * d_mid * d_out
@@ -499,7 +527,7 @@ def main():
                        "cta_group": int(os.environ.get("P2T_CTA_GROUP", "2"))},
             "loss": last_loss, "gpu_launches": int(launches), "cuda_graph": bool(use_graph),
             "eager_ms_per_step": eager_ms_total / args.steps, "host_issue_ms_per_step_eager": host_issue_ms, "clocks": clocks, "e2e": e2e, "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "optimizer": optim_leg,
+            "cpu_baseline": cpu_baseline, "optimizer": optim_leg, "exchange": exchange_leg,
         }
         print(json.dumps(line), flush=True)
     if exchange is not None:
