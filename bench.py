@@ -47,6 +47,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-optimizer", action="store_true", help="skip the (separately reported) optimizer leg")
     ap.add_argument("--no-exchange-probe", action="store_true", help="skip timing the exchange kernels alone (N > 1)")
+    ap.add_argument("--stages", action="store_true",
+                    help="extra eager pass with a CUDA event after EVERY library launch: per-kernel share of the step and "
+                         "achieved fraction of the HBM / tensor roofline (adds a `stages` list to the JSON line)")
     ap.add_argument("--eval-mode", action="store_true", help="dropout off (parity runs); default is training mode")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     ap.add_argument("--device-synth", action="store_true",
@@ -349,6 +352,61 @@ def main():
     ms_per_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total / 1e3)
 
+    # ------------------------------ per-kernel breakdown (optional) ------------------------------
+    stages = None
+    if args.stages:
+        lib.launch_timing_enable(True)
+        cur = torch.cuda.current_stream().cuda_stream
+        for i in range(args.steps):
+            lib.launch_timing_mark(cur)
+            step(resident[i % nbatches])
+        barrier()
+        stamps = lib.launch_timing_collect()
+        lib.launch_timing_enable(False)
+        per, order, seen = {}, [], {}
+        for name, ms in stamps:
+            if name == "mark":
+                seen = {}
+                continue
+            k = seen[name] = seen.get(name, 0) + 1
+            key = f"{name}#{k}"
+            if key not in per:
+                per[key] = 0.0
+                order.append(key)
+            per[key] += ms
+        rows = sum(valid_rows[i % nbatches] for i in range(args.steps)) / args.steps
+        trows = sum(int(batches[i % nbatches].text_mask.sum()) for i in range(args.steps)) / args.steps
+        di, dm, do = cfg["d_in"], cfg["d_mid"], cfg["d_out"]
+        hbm_peak = 6545.0
+        ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(ppath):
+            hbm_peak = float(json.load(open(ppath)).get("hbm_gbs", hbm_peak))
+        tf_peak = 1412.7
+        if os.path.exists(ppath):
+            pk = json.load(open(ppath))
+            tf_peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", tf_peak)))
+        algo = {  # algorithmic bytes (HBM kernels) or flops (GEMMs) per step, SURVEY.md §8d
+            "pool_partial_kernel#1": ("hbm", 2.0 * trows * do), "pool_partial_kernel#2": ("hbm", 2.0 * rows * do),
+            "gather_rows_kernel#1": ("hbm", 4.0 * rows * di), "adapter_tail_bwd_kernel#1": ("hbm", 6.0 * rows * do),
+            "colsum_partial_kernel#1": ("hbm", 2.0 * rows * dm),
+            "gemm_fc1#1": ("tensor", 2.0 * rows * di * dm), "gemm_fc2#1": ("tensor", 2.0 * rows * dm * do),
+            "gemm_dgrad#1": ("tensor", 2.0 * rows * dm * do), "gemm_wgrad#1": ("tensor", 2.0 * rows * dm * do),
+            "gemm_wgrad#2": ("tensor", 2.0 * rows * di * dm)}
+        total_ms = sum(per.values())
+        stages = []
+        for key in order:
+            us = per[key] / args.steps * 1e3
+            ent = {"kernel": key, "us": round(us, 2), "share": round(per[key] / total_ms, 4)}
+            if key in algo and us > 0:
+                bound, work = algo[key]
+                if bound == "hbm":
+                    ent.update(bound="hbm", achieved=round(work / 1e9 / (us / 1e6), 1), unit="GB/s",
+                               frac=round(work / 1e9 / (us / 1e6) / hbm_peak, 3))
+                else:
+                    ent.update(bound="tensor", achieved=round(work / 1e12 / (us / 1e6), 1), unit="TFLOP/s",
+                               frac=round(work / 1e12 / (us / 1e6) / tf_peak, 3))
+            stages.append(ent)
+
     # ------------------------------ end to end (host buffers) ------------------------------
     # Inputs start in pinned HOST memory.  The public HostStager copies only the valid rows of the step's residue
     # states and text hidden states to the device (packed) on a copy stream; the copy of step i+1 is issued before
@@ -532,7 +590,7 @@ def main():
                        "cta_group": int(os.environ.get("P2T_CTA_GROUP", "2"))},
             "loss": last_loss, "gpu_launches": int(launches), "cuda_graph": bool(use_graph),
             "eager_ms_per_step": eager_ms_total / args.steps, "host_issue_ms_per_step_eager": host_issue_ms, "clocks": clocks, "e2e": e2e, "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "optimizer": optim_leg, "exchange": exchange_leg,
+            "cpu_baseline": cpu_baseline, "optimizer": optim_leg, "exchange": exchange_leg, "stages": stages,
         }
         print(json.dumps(line), flush=True)
     if exchange is not None:

@@ -47,6 +47,15 @@ void p2t_reset_launch_count(void);
 void p2t_gemm_timing_enable(int on);
 int p2t_gemm_timing_collect(double* total_ms, int* launches, double* each_ms, int each_cap);
 
+/* per-launch timing of EVERY kernel of the library (bench.py --stages): when enabled, an event is recorded on the
+ * launching stream after each launch; p2t_launch_timing_mark records a "mark" that opens a step.  After synchronising,
+ * collect returns, in launch order, the kernel names (newline separated, truncated to names_cap) and the time from the
+ * previous stamp to each stamp in ms (0 for marks): on an in-order stream that is the kernel's duration plus its
+ * launch gap.  HOST pointers.  Not for use under stream capture. */
+void p2t_launch_timing_enable(int on);
+int p2t_launch_timing_mark(void* stream);
+int p2t_launch_timing_collect(double* ms, int cap, int* n, char* names, int names_cap);
+
 /* ---------------------------------------------------------------------------------------------
  * tcgen05 GEMM  D[m][n] = alpha * sum_k A[m][k] * B[n][k]      (bf16 in, fp32 accumulate in TMEM)
  * Replaces: torch.mm / nn.Linear / their autograd GEMMs (cuBLAS in the reference):

@@ -53,11 +53,13 @@ SIGNATURES = {
     "p2t_peer_status": [_vp, C.POINTER(C.c_uint)],
     "p2t_adamw_step": [_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
                        C.POINTER(_ll), _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _i, _vp],
+    "p2t_launch_timing_mark": [_vp],
+    "p2t_launch_timing_collect": [C.POINTER(C.c_double), _i, C.POINTER(C.c_int), C.c_char_p, _i],
     "p2t_gemm_timing_collect": [C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_double), _i],
 }
 NON_STATUS = {"p2t_abi_version": (_i, []), "p2t_last_error": (C.c_char_p, []),
               "p2t_launch_count": (_ull, []), "p2t_reset_launch_count": (None, []),
-              "p2t_gemm_timing_enable": (None, [_i]), "p2t_gemm_workspace_bytes": (_ull, []),
+              "p2t_gemm_timing_enable": (None, [_i]), "p2t_launch_timing_enable": (None, [_i]), "p2t_gemm_workspace_bytes": (_ull, []),
               "p2t_peer_ctrl_bytes": (_ull, []), "p2t_adamw_workspace_floats": (_i, [_i, C.POINTER(_ll)])}
 
 _lib = None
@@ -116,3 +118,22 @@ def gemm_timing_collect(cap: int = 4096):
     each = (C.c_double * cap)()
     call("p2t_gemm_timing_collect", C.byref(ms), C.byref(n), each, cap)
     return ms.value, n.value, list(each[:min(n.value, cap)])
+
+
+def launch_timing_enable(on: bool) -> None:
+    load().p2t_launch_timing_enable(int(on))
+
+
+def launch_timing_mark(stream: int) -> None:
+    call("p2t_launch_timing_mark", stream)
+
+
+def launch_timing_collect(cap: int = 1 << 16):
+    """[(kernel name, ms since the previous stamp)] in launch order since enable; "mark" entries open a step.
+    Synchronise first."""
+    n = C.c_int(0)
+    ms = (C.c_double * cap)()
+    names = C.create_string_buffer(cap * 40)
+    call("p2t_launch_timing_collect", ms, cap, C.byref(n), names, len(names))
+    labels = names.value.decode().split("\n")[:n.value]
+    return list(zip(labels, list(ms[:len(labels)])))

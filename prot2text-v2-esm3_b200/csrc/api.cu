@@ -64,6 +64,16 @@ int p2t_gemm_timing_collect(double* total_ms, int* launches, double* each_ms, in
   return gemm_timing_collect(total_ms, launches, each_ms, each_cap);
 }
 
+void p2t_launch_timing_enable(int on) { launch_timing_enable(on != 0); }
+int p2t_launch_timing_mark(void* stream) {
+  stamp_launch("mark", S(stream));
+  return 0;
+}
+int p2t_launch_timing_collect(double* ms, int cap, int* n, char* names, int names_cap) {
+  if (!n) return set_error(-1, "p2t_launch_timing_collect: null pointer");
+  return launch_timing_collect(ms, cap, n, names, names_cap);
+}
+
 unsigned long long p2t_gemm_workspace_bytes(void) { return (unsigned long long)gemm_streamk_workspace_bytes(); }
 
 int p2t_gemm_bf16(const void* a, long long lda, int a_mn_major, const void* b, long long ldb, int b_mn_major,
@@ -350,7 +360,7 @@ int p2t_dropout_mask(int rows, int cols, float dropout_p, unsigned long long see
   if (!out) return set_error(-1, "p2t_dropout_mask: null pointer");
   DropoutParams d = make_dropout(dropout_p, seed, layer);
   dropout_mask_kernel<<<256, 256, 0, S(stream)>>>(rows, cols, d, out);
-  return check_launch("dropout_mask_kernel");
+  return check_launch("dropout_mask_kernel", S(stream));
 }
 
 /* ---- Stage-2 hand-off: adapter rows straight into the LLM's inputs_embeds slots ---- */

@@ -11,8 +11,13 @@ namespace p2t {
 int set_error(int code, const char* fmt, ...);
 // Every kernel launch made by the library bumps this counter (bench.py reports it as gpu_launches).
 void count_launch();
-// cudaGetLastError() after a <<<>>> launch -> 0 or a recorded error
-int check_launch(const char* what);
+// cudaGetLastError() after a <<<>>> launch on `st` -> 0 or a recorded error; counts the launch and, when launch
+// timing is on, stamps it (see stamp_launch)
+int check_launch(const char* what, cudaStream_t st);
+// Per-launch timing of EVERY kernel of the library (bench.py --stages): an event is recorded on the launching stream
+// after each launch; consecutive stamps on an in-order stream bracket one kernel (plus its launch gap), and a
+// "mark" stamp (p2t_launch_timing_mark) opens each step.  Off by default; not for use under stream capture.
+void stamp_launch(const char* name, cudaStream_t st);
 
 int sm_count();
 

@@ -140,6 +140,8 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   if (timed) gemm_timing_record(stream, false);
   if (e != cudaSuccess) return set_error((int)e, "GEMM launch failed: %s", cudaGetErrorString(e));
   count_launch();
+  stamp_launch(EPI == EPI_FC1 ? "gemm_fc1" : EPI == EPI_FC2 ? "gemm_fc2" : EPI == EPI_MUL_AUX ? "gemm_dgrad"
+               : (A_MN && B_MN) ? "gemm_wgrad" : "gemm_plain", stream);
   return 0;
 }
 

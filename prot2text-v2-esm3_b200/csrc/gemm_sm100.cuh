@@ -221,6 +221,7 @@ struct EpiArgs {
   long long ldd0, ldd1, ldaux;
   const __half* aux;
   float alpha, scale;
+  float gscale;  // dropout multiplier folded into the GELU pair (1 when dropout is off)
   uint32_t threshold, layer;
   uint2 key;
   int nostore;
@@ -293,15 +294,14 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ep
       float bias[8], der[8];
       load_bias8(e.bias, col + 8 * j, e.n, bias);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) gelu_erf_both_fast(val[i] + bias[i], val[i], der[i]);
-      if (e.threshold != 0) {
+      for (int i = 0; i < 8; ++i) gelu_erf_both_scaled(val[i] + bias[i], e.gscale, val[i], der[i]);
+      if (e.threshold != 0) {  // the multiplier 1/(1-p) is already inside val/der: dropped elements are zeroed
         const uint32_t w[4] = {rnd[j].x, rnd[j].y, rnd[j].z, rnd[j].w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float k0 = ((w[i] & 0xFFFFu) >= e.threshold) ? e.scale : 0.f;
-          const float k1 = ((w[i] >> 16) >= e.threshold) ? e.scale : 0.f;
-          val[2 * i] *= k0; der[2 * i] *= k0;
-          val[2 * i + 1] *= k1; der[2 * i + 1] *= k1;
+          const bool k0 = (w[i] & 0xFFFFu) >= e.threshold, k1 = (w[i] >> 16) >= e.threshold;
+          val[2 * i] = k0 ? val[2 * i] : 0.f; der[2 * i] = k0 ? der[2 * i] : 0.f;
+          val[2 * i + 1] = k1 ? val[2 * i + 1] : 0.f; der[2 * i + 1] = k1 ? der[2 * i + 1] : 0.f;
         }
       }
       if constexpr (EPI == EPI_FC2) {
@@ -332,15 +332,14 @@ __device__ __forceinline__ void epilogue_chunk_staged(const uint32_t (&v)[32], c
       float bias[8];
       load_bias8(e.bias, col + 8 * j, e.n, bias);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) gelu_erf_both_fast(__uint_as_float(v[8 * j + i]) + bias[i], val[i], der[i]);
-      if (e.threshold != 0) {
+      for (int i = 0; i < 8; ++i) gelu_erf_both_scaled(__uint_as_float(v[8 * j + i]) + bias[i], e.gscale, val[i], der[i]);
+      if (e.threshold != 0) {  // the multiplier 1/(1-p) is already inside val/der: dropped elements are zeroed
         const uint32_t w[4] = {rnd[j].x, rnd[j].y, rnd[j].z, rnd[j].w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float k0 = ((w[i] & 0xFFFFu) >= e.threshold) ? e.scale : 0.f;
-          const float k1 = ((w[i] >> 16) >= e.threshold) ? e.scale : 0.f;
-          val[2 * i] *= k0; der[2 * i] *= k0;
-          val[2 * i + 1] *= k1; der[2 * i + 1] *= k1;
+          const bool k0 = (w[i] & 0xFFFFu) >= e.threshold, k1 = (w[i] >> 16) >= e.threshold;
+          val[2 * i] = k0 ? val[2 * i] : 0.f; der[2 * i] = k0 ? der[2 * i] : 0.f;
+          val[2 * i + 1] = k1 ? val[2 * i + 1] : 0.f; der[2 * i + 1] = k1 ? der[2 * i + 1] : 0.f;
         }
       }
       if constexpr (EPI == EPI_FC2) {
@@ -546,6 +545,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     e.d0 = reinterpret_cast<char*>(p.d0); e.d1 = reinterpret_cast<char*>(p.d1);
     e.ldd0 = p.ldd0; e.ldd1 = p.ldd1; e.ldaux = p.ldaux; e.aux = p.aux;
     e.alpha = p.alpha; e.scale = p.drop.scale; e.threshold = p.drop.threshold; e.layer = p.drop.layer;
+    e.gscale = p.drop.threshold != 0 ? p.drop.scale : 1.f;
     const unsigned long long seed = p.drop.seed + (p.drop.seed_dev ? *p.drop.seed_dev : 0ull);
     e.key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
     e.nostore = p.debug_nostore;

@@ -325,30 +325,30 @@ int sim_small(const void* p, const void* t, bool in_f32, int R, int C, int E, fl
   if (in_f32 && (long long)R * C >= 4096) {
     const dim3 tiles((R + 3) / 4, (C + 7) / 8);
     sim_tile_f32_kernel<4, 8, 256><<<tiles, 256, 0, st>>>(static_cast<const float*>(p), static_cast<const float*>(t), R, C, E, alpha, S);
-    return check_launch("sim_tile_f32_kernel");
+    return check_launch("sim_tile_f32_kernel", st);
   }
   if (in_f32 && (long long)R * C >= 512) {
     const dim3 tiles((R + 1) / 2, (C + 3) / 4);
     sim_tile_f32_kernel<2, 4, 1024><<<tiles, 1024, 0, st>>>(static_cast<const float*>(p), static_cast<const float*>(t), R, C, E, alpha, S);
-    return check_launch("sim_tile_f32_kernel");
+    return check_launch("sim_tile_f32_kernel", st);
   }
   const dim3 grid(R, (C + 3) / 4);
   if (in_f32) sim_small_kernel<true><<<grid, 256, 0, st>>>(p, t, R, C, E, alpha, S);
   else sim_small_kernel<false><<<grid, 256, 0, st>>>(p, t, R, C, E, alpha, S);
-  return check_launch("sim_small_kernel");
+  return check_launch("sim_small_kernel", st);
 }
 
 int col_stats(const float* S, int R, int C, float* col_max, float* col_sum, int* col_argmax, int row_index_base,
               cudaStream_t st) {
   col_stats_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(S, R, C, col_max, col_sum, col_argmax, row_index_base);
-  return check_launch("col_stats_kernel");
+  return check_launch("col_stats_kernel", st);
 }
 
 int mark_labelled(const int* labels, int R, int C, unsigned char* marks, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(marks, 0, C, st);
   if (e != cudaSuccess) return set_error((int)e, "memset: %s", cudaGetErrorString(e));
   mark_labelled_kernel<<<(R + 255) / 256, 256, 0, st>>>(labels, R, C, marks);
-  return check_launch("mark_labelled_kernel");
+  return check_launch("mark_labelled_kernel", st);
 }
 
 int ce_rows(float* S, const int* labels, int R, int C, float w_row, float w_col, float inv_rn, const float* col_max,
@@ -357,12 +357,12 @@ int ce_rows(float* S, const int* labels, int R, int C, float w_row, float w_col,
   ce_rows_kernel<<<(R + 7) / 8, 256, 0, st>>>(S, labels, R, C, w_row, w_col, inv_rn, col_max, col_sum, col_labelled,
                                               row_loss, row_lse, argmax_row, reinterpret_cast<__nv_bfloat16*>(dS_bf16),
                                               write_ds);
-  return check_launch("ce_rows_kernel");
+  return check_launch("ce_rows_kernel", st);
 }
 
 int loss_mean(const float* row_loss, int R, float scale, float* loss, int accumulate, cudaStream_t st) {
   loss_mean_kernel<<<1, 256, 0, st>>>(row_loss, R, scale, loss, accumulate);
-  return check_launch("loss_mean_kernel");
+  return check_launch("loss_mean_kernel", st);
 }
 
 int contract_small(const float* W, int ldw, bool transpose_w, const void* X, bool x_f32, int n_out, int n_red, int E,
@@ -376,18 +376,18 @@ int contract_small(const float* W, int ldw, bool transpose_w, const void* X, boo
     if (x_f32) contract_small_kernel<false, true><<<g, 256, 0, st>>>(W, ldw, X, n_out, n_red, E, alpha, out);
     else contract_small_kernel<false, false><<<g, 256, 0, st>>>(W, ldw, X, n_out, n_red, E, alpha, out);
   }
-  return check_launch("contract_small_kernel");
+  return check_launch("contract_small_kernel", st);
 }
 
 int convert_f32_to_bf16(const float* in, long long n, void* out, cudaStream_t st) {
   const int blocks = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 8);
   f32_to_bf16_kernel<<<blocks, 256, 0, st>>>(in, n, reinterpret_cast<__nv_bfloat16*>(out));
-  return check_launch("f32_to_bf16_kernel");
+  return check_launch("f32_to_bf16_kernel", st);
 }
 int convert_bf16_to_f32(const void* in, long long n, float* out, cudaStream_t st) {
   const int blocks = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 8);
   bf16_to_f32_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in), n, out);
-  return check_launch("bf16_to_f32_kernel");
+  return check_launch("bf16_to_f32_kernel", st);
 }
 
 }  // namespace p2t

@@ -52,6 +52,22 @@ __device__ __forceinline__ void gelu_erf_both_fast(float z, float& val, float& d
   val = z * cdf;
   der = fmaf(z * 0.39894228040143268f, e, cdf);
 }
+// The same pair already multiplied by the dropout multiplier s = 1/(1-p): val = s z Phi(z), der = s (Phi(z) + z phi(z)).
+// s rides on the shared exponential (one FMUL) and on the "1 -" of the cdf; the 0.5 of erfc and the 1/sqrt2 of its
+// argument are folded into immediates.  Two instructions fewer per element than gelu_erf_both_fast followed by two
+// scalings, and no constant beyond s lives in a register.
+__device__ __forceinline__ void gelu_erf_both_scaled(float z, float s, float& val, float& der) {
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752f, fabsf(z), 1.0f));
+  const float es = ex2_approx((z * -0.72134752044448170f) * z) * s;  // s exp(-z^2/2)
+  float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  const float h = poly * t * es;                 // s/2 erfc(|z|/sqrt2)
+  const float cdf = (z >= 0.f) ? s - h : h;      // s Phi(z)
+  val = z * cdf;
+  der = fmaf(z * 0.39894228040143268f, es, cdf);
+}
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 // ------------------------------------------------------------------------------------------------

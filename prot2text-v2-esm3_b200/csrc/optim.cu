@@ -191,11 +191,11 @@ int adamw_step(AdamTable t, float* partial_ws, float* scal, const float* lr_dev,
     blocks += adamw_blocks(t.numel[i]);
   }
   grad_sqnorm_partial_kernel<<<blocks, kOptThreads, 0, st>>>(t, partial_ws);
-  if (int r = check_launch("grad_sqnorm_partial_kernel")) return r;
+  if (int r = check_launch("grad_sqnorm_partial_kernel", st)) return r;
   adamw_prepare_kernel<<<1, kOptThreads, 0, st>>>(partial_ws, blocks, max_norm, beta1, beta2, lr_dev, step_dev, scal);
-  if (int r = check_launch("adamw_prepare_kernel")) return r;
+  if (int r = check_launch("adamw_prepare_kernel", st)) return r;
   adamw_update_kernel<<<blocks, kOptThreads, 0, st>>>(t, scal, lr_dev, beta1, beta2, eps, weight_decay, zero_grad);
-  return check_launch("adamw_update_kernel");
+  return check_launch("adamw_update_kernel", st);
 }
 
 }  // namespace p2t

@@ -281,12 +281,12 @@ int peer_allgather(void* const* peers, int world, int rank, const void* src, lon
   if (phases & 1) {
     if (!src) return set_error(-1, "p2t_peer_allgather: null src");
     peer_allgather_push_kernel<<<grid_for(vecs), 256, 0, st>>>(t, world, rank, static_cast<const uint4*>(src), vecs);
-    if (int r = check_launch("peer_allgather_push_kernel")) return r;
+    if (int r = check_launch("peer_allgather_push_kernel", st)) return r;
   }
   if (phases & 2) {
     if (!dst) return set_error(-1, "p2t_peer_allgather: null dst");
     peer_allgather_wait_kernel<<<grid_for(vecs * world), 256, 0, st>>>(t, world, rank, static_cast<uint4*>(dst), vecs);
-    if (int r = check_launch("peer_allgather_wait_kernel")) return r;
+    if (int r = check_launch("peer_allgather_wait_kernel", st)) return r;
   }
   return 0;
 }
@@ -298,7 +298,7 @@ int peer_allreduce_mean(void* const* peers, int world, int rank, long long n_byt
   const long long n_vec = n_bytes / 16;
   if (phases & 1) {
     peer_allreduce_ready_kernel<<<1, 32, 0, st>>>(t, world, rank);
-    if (int r = check_launch("peer_allreduce_ready_kernel")) return r;
+    if (int r = check_launch("peer_allreduce_ready_kernel", st)) return r;
   }
   if (phases & 2) {
     const float scale = 1.f / (float)world;
@@ -310,11 +310,11 @@ int peer_allreduce_mean(void* const* peers, int world, int rank, long long n_byt
     } else {
       peer_allreduce_reduce_kernel<8, 2><<<grid_for(slice / 2, 4), 256, 0, st>>>(t, world, rank, n_vec, scale);
     }
-    if (int r = check_launch("peer_allreduce_reduce_kernel")) return r;
+    if (int r = check_launch("peer_allreduce_reduce_kernel", st)) return r;
   }
   if (phases & 4) {
     peer_allreduce_wait_kernel<<<grid_for(n_vec, 4), 256, 0, st>>>(t, world, rank, n_vec, static_cast<uint4*>(dst));
-    if (int r = check_launch("peer_allreduce_wait_kernel")) return r;
+    if (int r = check_launch("peer_allreduce_wait_kernel", st)) return r;
   }
   return 0;
 }

@@ -974,9 +974,9 @@ int rows_plan(const void* mask, int mask_bytes, int B, int L, int rc, int* count
               int* n_rows, int* row_src, int* chunk_seq, cudaStream_t st) {
   if (B <= 0 || L <= 0) return set_error(-1, "rows_plan: empty batch");
   plan_count_kernel<<<B, 256, 0, st>>>(mask, mask_bytes, B, L, counts);
-  if (int rc_ = check_launch("plan_count_kernel")) return rc_;
+  if (int rc_ = check_launch("plan_count_kernel", st)) return rc_;
   plan_fill_kernel<<<B, 256, 0, st>>>(mask, mask_bytes, B, L, counts, rc, seq_off, chunk_off, n_rows, row_src, chunk_seq);
-  return check_launch("plan_fill_kernel");
+  return check_launch("plan_fill_kernel", st);
 }
 
 // plan for rows that are ALREADY packed: only the per-sequence counts are given
@@ -984,7 +984,7 @@ int rows_plan_counts(const int* counts, int B, int rc, int* seq_off, int* chunk_
                      cudaStream_t st) {
   if (B <= 0) return set_error(-1, "rows_plan_counts: empty batch");
   plan_fill_kernel<<<B, 256, 0, st>>>(nullptr, 0, B, 0, counts, rc, seq_off, chunk_off, n_rows, nullptr, chunk_seq);
-  return check_launch("plan_fill_kernel");
+  return check_launch("plan_fill_kernel", st);
 }
 
 int gather_rows(const void* src, long long ld_src, const int* row_src, const int* n_rows, int cap, int D, void* out,
@@ -994,13 +994,13 @@ int gather_rows(const void* src, long long ld_src, const int* row_src, const int
   const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
   gather_rows_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), ld_src, row_src, n_rows, cap, D,
                                              reinterpret_cast<__nv_bfloat16*>(out));
-  return check_launch("gather_rows_kernel");
+  return check_launch("gather_rows_kernel", st);
 }
 
 int row_inv_norm(const float* rowsq, int nblk, const int* n_rows, int cap, float* inv_norm, cudaStream_t st) {
   const int blocks = std::min((cap + 31) / 32, sm_count() * 8);
   row_inv_norm_kernel<<<blocks, 256, 0, st>>>(rowsq, nblk, n_rows, cap, inv_norm);
-  return check_launch("row_inv_norm_kernel");
+  return check_launch("row_inv_norm_kernel", st);
 }
 
 int pool_forward(const void* src, bool src_is_f16, long long ld_src, int src_rows, const int* row_src, const float* inv_norm,
@@ -1029,7 +1029,7 @@ int pool_forward(const void* src, bool src_is_f16, long long ld_src, int src_row
     pool_partial_kernel<true><<<grid, POOL_THREADS, smem, st>>>(tmap, sp, ld_src, row_src, inv_norm, chunk_off, desc, B, D, partial);
   else
     pool_partial_kernel<false><<<grid, POOL_THREADS, smem, st>>>(tmap, sp, ld_src, row_src, inv_norm, chunk_off, desc, B, D, partial);
-  if (int r = check_launch("pool_partial_kernel")) return r;
+  if (int r = check_launch("pool_partial_kernel", st)) return r;
   if (norm_p_bf16 != nullptr || norm_p_f32 != nullptr) {
     if (mode != 3 || ld_out != 2LL * D) return set_error(-1, "pool_forward: fused normalise needs the dense 'mix' layout");
     cudaLaunchConfig_t cfg{};
@@ -1047,26 +1047,27 @@ int pool_forward(const void* src, bool src_is_f16, long long ld_src, int src_row
                                         out, reinterpret_cast<__nv_bfloat16*>(norm_p_bf16), norm_p_f32, norm_out);
     if (le != cudaSuccess) return set_error((int)le, "pool_finalize_normalize_kernel: %s", cudaGetErrorString(le));
     count_launch();
+    stamp_launch("pool_finalize_normalize_kernel", st);
     return 0;
   }
   dim3 g2(B, (D + 255) / 256);
   pool_finalize_kernel<<<g2, 256, 0, st>>>(partial, seq_off, chunk_off, B, D, rc, mode, out, ld_out);
-  return check_launch("pool_finalize_kernel");
+  return check_launch("pool_finalize_kernel", st);
 }
 
 int l2norm_forward(const float* e, int B, int E, void* p_bf16, float* p_f32, float* norm, cudaStream_t st) {
   l2norm_fwd_kernel<<<B, 256, 0, st>>>(e, E, reinterpret_cast<__nv_bfloat16*>(p_bf16), p_f32, norm);
-  return check_launch("l2norm_fwd_kernel");
+  return check_launch("l2norm_fwd_kernel", st);
 }
 int l2norm_backward(const float* dp, const float* p, const float* norm, int B, int E, float* de, cudaStream_t st) {
   l2norm_bwd_kernel<<<B, 256, 0, st>>>(dp, p, norm, E, de);
-  return check_launch("l2norm_bwd_kernel");
+  return check_launch("l2norm_bwd_kernel", st);
 }
 int pool_bwd_coef(const float* de, long long ld_de, const float* stats, long long ld_stats, const int* seq_off, int B,
                   int D, int mode, float* c1, float* c2, cudaStream_t st) {
   dim3 g(B, (D + 255) / 256);
   pool_bwd_coef_kernel<<<g, 256, 0, st>>>(de, ld_de, stats, ld_stats, seq_off, D, mode, c1, c2);
-  return check_launch("pool_bwd_coef_kernel");
+  return check_launch("pool_bwd_coef_kernel", st);
 }
 
 int loss_bwd_coef(const float* dS, const float* t, const float* p, const float* pnorm, const float* stats,
@@ -1078,9 +1079,9 @@ int loss_bwd_coef(const float* dS, const float* t, const float* p, const float* 
   float* dp = dp_ws;                         // [B][E]
   float* dotp = dp_ws + (size_t)B * E;       // [B][nslice]
   loss_bwd_dp_kernel<<<nslice, 256, 0, st>>>(dS, t, p, dloss, R, B, C, E, 1.f / tau, dp, dotp);
-  if (int r = check_launch("loss_bwd_dp_kernel")) return r;
+  if (int r = check_launch("loss_bwd_dp_kernel", st)) return r;
   loss_bwd_coef_kernel<<<B, 1024, 0, st>>>(dp, dotp, nslice, p, pnorm, stats, seq_off, D, c1, c2);
-  return check_launch("loss_bwd_coef_kernel");
+  return check_launch("loss_bwd_coef_kernel", st);
 }
 
 int adapter_tail_backward(const void* a, const void* g, const float* inv_norm, const int* seq_off, const int* chunk_off,
@@ -1097,12 +1098,12 @@ int adapter_tail_backward(const void* a, const void* g, const float* inv_norm, c
     adapter_tail_bwd_kernel<512><<<grid, 512, 0, st>>>(ap, gp, inv_norm, seq_off, chunk_off, chunk_seq, B, c1, c2, n_rows, cap, D, rc, op, colsum_partial);
   else
     adapter_tail_bwd_kernel<1024><<<grid, 1024, 0, st>>>(ap, gp, inv_norm, seq_off, chunk_off, chunk_seq, B, c1, c2, n_rows, cap, D, rc, op, colsum_partial);
-  if (int r = check_launch("adapter_tail_bwd_kernel")) return r;
+  if (int r = check_launch("adapter_tail_bwd_kernel", st)) return r;
   if (db2 != nullptr) {
     if (!colsum_partial) return set_error(-1, "adapter_tail_backward: db2 needs the partial workspace");
     parts_colsum_final_kernel<<<(D + 31) / 32, dim3(32, PARTS_Y), 0, st>>>(colsum_partial, chunk_off, B, nullptr, 0, D,
                                                                      reinterpret_cast<__nv_bfloat16*>(db2), nullptr);
-    return check_launch("parts_colsum_final_kernel");
+    return check_launch("parts_colsum_final_kernel", st);
   }
   return 0;
 }
@@ -1114,7 +1115,7 @@ static int tail_bwd_dy_launch(const void* a, const void* g, const float* inv_nor
   adapter_tail_bwd_dy_kernel<NV><<<blocks, 256, 0, st>>>(
       reinterpret_cast<const __half*>(a), reinterpret_cast<const __half*>(g), inv_norm,
       reinterpret_cast<const __nv_bfloat16*>(dy), n, n_dev, cap, D, reinterpret_cast<__nv_bfloat16*>(dz2));
-  return check_launch("adapter_tail_bwd_dy_kernel");
+  return check_launch("adapter_tail_bwd_dy_kernel", st);
 }
 int adapter_tail_backward_dy(const void* a, const void* g, const float* inv_norm, const void* dy, int n,
                              const int* n_dev, int cap, int D, void* dz2, cudaStream_t st) {
@@ -1135,7 +1136,7 @@ int scatter_scaled_rows(const void* a, const float* rowsq, int nblk, int cap, in
   const int blocks = min((n + 7) / 8, sm_count() * 8);
   scale_rows_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __half*>(a), rowsq, nblk, cap, n, D,
                                             reinterpret_cast<__nv_bfloat16*>(y), ld_y, row_dst, n_dev, n_dst_dev, inv_norm_out);
-  return check_launch("scale_rows_kernel");
+  return check_launch("scale_rows_kernel", st);
 }
 
 int readout_backward(const void* x, const void* mask, int mask_bytes, int B, int S, int D, const float* c1,
@@ -1144,7 +1145,7 @@ int readout_backward(const void* x, const void* mask, int mask_bytes, int B, int
   const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
   readout_bwd_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), mask, mask_bytes, B, S, D, c1, c2,
                                              reinterpret_cast<__nv_bfloat16*>(dx));
-  return check_launch("readout_bwd_kernel");
+  return check_launch("readout_bwd_kernel", st);
 }
 
 int colsum(const void* x, const int* n_rows, int n_static, int D, float* partial, void* out_bf16, float* out_f32,
@@ -1153,15 +1154,15 @@ int colsum(const void* x, const int* n_rows, int n_static, int D, float* partial
   if (n_static <= 0) return set_error(-1, "colsum: empty matrix");
   dim3 g((n_static + 63) / 64, (D / 8 + 63) / 64);
   colsum_partial_kernel<<<g, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), n_rows, n_static, D, partial);
-  if (int r = check_launch("colsum_partial_kernel")) return r;
+  if (int r = check_launch("colsum_partial_kernel", st)) return r;
   parts_colsum_final_kernel<<<(D + 31) / 32, dim3(32, PARTS_Y), 0, st>>>(partial, nullptr, 0, n_rows, n_static, D,
                                                                    reinterpret_cast<__nv_bfloat16*>(out_bf16), out_f32);
-  return check_launch("parts_colsum_final_kernel");
+  return check_launch("parts_colsum_final_kernel", st);
 }
 
 int readout_last(const void* x, const int* counts, int B, int S, int D, float* out, cudaStream_t st) {
   readout_last_kernel<<<B, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), counts, S, D, out);
-  return check_launch("readout_last_kernel");
+  return check_launch("readout_last_kernel", st);
 }
 
 }  // namespace p2t

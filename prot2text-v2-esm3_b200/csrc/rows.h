@@ -86,6 +86,8 @@ size_t gemm_streamk_workspace_bytes();
 const char* last_error();
 unsigned long long launches();
 void reset_launches();
+void launch_timing_enable(bool on);
+int launch_timing_collect(double* ms, int cap, int* n_out, char* names, int names_cap);
 void gemm_timing_enable(bool on);
 int gemm_timing_collect(double* total_ms, int* pairs, double* each_ms, int each_cap);
 

@@ -28,7 +28,7 @@ class GraphedContrastiveStep:
     def __init__(self, adapter: ModalityAdapter, residue_states: torch.Tensor, protein_mask: torch.Tensor,
                  text_hidden: torch.Tensor, text_mask: torch.Tensor, *, temperature: float = 0.05,
                  contrastive_num_segments: int = 1, symmetric: bool = False, seed: int = 0, warmup: int = 2,
-                 exchange=None, grad_reducer=None):
+                 exchange=None, grad_reducer=None, optimizer=None):
         if not residue_states.is_cuda:
             raise _lib.P2TError("GraphedContrastiveStep needs CUDA tensors: this package has no CPU path")
         self.adapter = adapter
@@ -37,7 +37,12 @@ class GraphedContrastiveStep:
         # exchange is captured with everything else.  (Capturing the NCCL all-gather instead hung on this stack —
         # torch 2.11, NCCL 2.28.9, async_op + wait inside capture.)  `grad_reducer` (peer.PeerGradAllReduce) appends
         # the mean all-reduce of the four weight gradients, DDP's job in the reference (scripts/train_contrast.py:611-614).
-        self.exchange, self.grad_reducer = exchange, grad_reducer
+        # `optimizer` (optim.FusedAdamW over the adapter's four tensors) appends clip + AdamW: one replay is then a whole
+        # training step — forward, backward, gradient mean over ranks, parameter update.  The warm-up passes below run
+        # without it (they must not move the weights); its state is created by one dry step at learning rate 0 whose
+        # moments and step count are zeroed again before the capture.
+        self.exchange, self.grad_reducer, self.optimizer = exchange, grad_reducer, optimizer
+        self._with_optimizer = False
         if exchange is not None and contrastive_num_segments != 1:
             raise ValueError("the sharded step averages over the whole local batch: contrastive_num_segments must be 1")
         self.kw = dict(temperature=temperature, contrastive_num_segments=contrastive_num_segments, symmetric=symmetric)
@@ -56,7 +61,10 @@ class GraphedContrastiveStep:
                 self._eager_step()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        if optimizer is not None:
+            self._prime_optimizer(dev)
         before = _lib.launch_count()
+        self._with_optimizer = optimizer is not None
         with torch.cuda.graph(self.graph):
             self.loss, self.grads = self._eager_step()  # static tensors owned by the graph's memory pool
         self.launches_per_replay = _lib.launch_count() - before
@@ -77,7 +85,32 @@ class GraphedContrastiveStep:
         grads = list(step_backward(state, None))
         if self.grad_reducer is not None:
             self.grad_reducer.reduce_(grads)
+        if self._with_optimizer:
+            for p, g in zip(self.params, grads):
+                p.grad = g
+            self.optimizer.step()
         return loss, grads
+
+    def _prime_optimizer(self, dev) -> None:
+        """Allocate the optimizer's state outside the capture without moving weights, moments or the step count."""
+        opt = self.optimizer
+        if opt._dev and all("exp_avg" in opt.state[p] for p in self.params):
+            return  # already stepped before: nothing would be allocated inside the capture
+        lrs = [g["lr"] for g in opt.param_groups]
+        for p in self.params:
+            p.grad = torch.zeros_like(p)
+        for g in opt.param_groups:
+            g["lr"] = 0.0
+        opt.step()  # fresh state, lr 0, zero gradients: parameters and (zero) moments keep their values; only the counter moves
+        for p in self.params:
+            st = opt.state[p]
+            if "step" in st:
+                st["step"].zero_()
+        for g, lr in zip(opt.param_groups, lrs):
+            g["lr"] = lr
+        for gi, lr in enumerate(lrs):
+            opt.set_lr(lr, gi)
+        torch.cuda.synchronize(dev)
 
     def replay(self) -> torch.Tensor:
         """Run the captured step on the current contents of the input tensors; returns the (static) loss tensor."""

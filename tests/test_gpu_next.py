@@ -350,3 +350,27 @@ def test_fp32_similarity_and_loss_backward_head_at_sharded_sizes(p2t, dev, R_, B
     k2 = de[:, D_:] / (n * e[:, D_:].double())
     k1 = de[:, :D_] / n - k2 * e[:, :D_].double()
     assert maxrel(c2, k2) <= 1e-4 and maxrel(c1, k1) <= 1e-4  # (dp - p (p.dp)) cancels ~2 digits in fp32
+
+
+def test_graphed_training_step_with_optimizer_equals_eager_step_then_optimizer(p2t, mods, dev):
+    """(r2-prep, not yet run on a GPU) one replay = forward + backward + clip + AdamW."""
+    synth = mods["synth"]
+    sb = synth.make_config_batch("tiny", weight_gain=8.0)
+    x, pm, th, tm = (t.to(dev) for t in (sb.x, sb.prot_mask, sb.text, sb.text_mask))
+    a1 = make_adapter(p2t, dev, sb.w1, sb.b1, sb.w2, sb.b2)
+    a2 = make_adapter(p2t, dev, sb.w1, sb.b1, sb.w2, sb.b2)
+    prm = lambda a: [a.fc1.weight, a.fc1.bias, a.fc2.weight, a.fc2.bias]
+    o1 = mods["optim"].FusedAdamW(prm(a1), lr=1e-2, eps=1e-6, max_grad_norm=1.0)
+    o2 = mods["optim"].FusedAdamW(prm(a2), lr=1e-2, eps=1e-6, max_grad_norm=1.0)
+    fused = p2t.GraphedContrastiveStep(a1, x, pm, th, tm, optimizer=o1)
+    for w_a, w_b in zip(prm(a1), (sb.w1, sb.b1, sb.w2, sb.b2)):
+        assert torch.equal(w_a.detach().cpu(), w_b)  # building the graph moved nothing
+    plain = p2t.GraphedContrastiveStep(a2, x, pm, th, tm)
+    for _ in range(3):
+        l1 = fused.replay()
+        l2 = plain.replay()
+        o2.step()
+        assert torch.equal(l1, l2)
+        for w_a, w_b in zip(prm(a1), prm(a2)):
+            assert torch.equal(w_a, w_b)
+    assert o1.step_count() == 3 == o2.step_count()
