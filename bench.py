@@ -479,7 +479,7 @@ def main():
         if exchange is not None:
             exchange.check()
         opt = pkg.FusedAdamW(params, lr=1e-4, eps=1e-6, betas=(0.9, 0.999), max_grad_norm=1.0)
-        reducer = peer.PeerGradAllReduce(params) if world > 1 else None
+        reducer = peer.PeerGradAllReduce(params) if world > 1 else None  # eager form: stage, reduce, copy back
         step(resident[0])
         grads = [p.grad for p in params]
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define P2T_ABI_VERSION 1
+#define P2T_ABI_VERSION 2
 
 /* readout modes — scripts/train_contrast.py:198-248 readout_fn */
 #define P2T_READOUT_MEAN 1
@@ -171,12 +171,13 @@ int p2t_readout_bwd(const void* x, const void* mask, int mask_bytes, int B, int 
 
 /* backward through normalise -> GELU(fc2) on packed rows (autograd of :65-67):
  *   dz2 = ((dy - y (y.dy)) / |a|) * g2,  dy = c1[b] + c2[b]*y   (pooled)   or given per row (_dy)
- * The pooled form runs one CTA per pooling chunk and also emits db2 = colsum(dz2) (colsum_ws: fp32
- * [max_chunks][d_out]; db2 bf16 [d_out], may be NULL). */
-int p2t_adapter_tail_bwd(const void* a, const void* g2, const float* inv_norm, const int* seq_off, const int* chunk_off,
-                         const int* chunk_seq, int B, const float* c1, const float* c2, const int* n_rows_dev,
-                         int rows_cap, int d_out, int chunk_rows, int max_chunks, void* dz2, float* colsum_ws, void* db2,
-                         void* stream);
+ * The pooled form is persistent (every CTA streams an equal share of the valid rows, crossing sequence boundaries) and
+ * also emits the column sums of dz2 (fc2.bias gradient) as ONE partial row per CTA: colsum_ws fp32 [ws_rows][d_out]
+ * (ws_rows bounds the grid; 2 * #SM is always enough), *nparts_dev = rows written.  db2 (bf16 [d_out]) != NULL
+ * finishes the sum here; the fused step passes NULL and finishes both biases with p2t_bias_grads. */
+int p2t_adapter_tail_bwd(const void* a, const void* g2, const float* inv_norm, const int* seq_off, int B, const float* c1,
+                         const float* c2, const int* n_rows_dev, int rows_cap, int d_out, void* dz2, float* colsum_ws,
+                         int ws_rows, int* nparts_dev, void* db2, void* stream);
 /* (_dy form: rows < min(n, *n_rows_dev) are computed — n_rows_dev may be NULL —, rows up to the next multiple of 256
  * are zeroed) */
 int p2t_adapter_tail_bwd_dy(const void* a, const void* g2, const float* inv_norm, const void* dy, int n,
@@ -186,14 +187,25 @@ int p2t_adapter_tail_bwd_dy(const void* a, const void* g2, const float* inv_norm
  * backward GEMMs of the adapter (autograd of :62-65; scripts/train_contrast.py:448):
  *   dz1 = (dz2 W2) * g1;  dW2 = dz2^T h1;  db2 = colsum dz2;  dW1 = dz1^T x;  db1 = colsum dz1
  *   dx  = dz1 W1 (only when dx != NULL; the encoder is frozen in Stage 1, :186)
- * Gradients are written (not accumulated) in bf16, nn.Linear layout.  db1/db2/dx may be NULL (db2
- * is normally produced by p2t_adapter_tail_bwd).  colsum_ws: fp32 [ceil(rows_cap/64)][max(d_mid, d_out)].
+ * Gradients are in bf16, nn.Linear layout; written, or — accumulate != 0 — added to what dw1/dw2 hold (the reference
+ * accumulates .grad over gradient_accumulation_steps micro-batches, scripts/train_contrast.py:448-465).
+ * db1/db2/dx may be NULL (db2 is normally produced by p2t_adapter_tail_bwd).
+ * colsum_ws: fp32 [ceil(rows_cap/32)][d_mid] — the dgrad GEMM's epilogue leaves the column sums of dz1 over every
+ * 32-row block there (db1 = their sum: db1 != NULL finishes it here, else p2t_bias_grads does) — followed, only when
+ * db2 != NULL, by [ceil(rows_cap/64)][d_out].
  * gemm_ws: optional split-K scratch for the two weight-gradient GEMMs (see p2t_gemm_bf16).
  * ------------------------------------------------------------------------------------------- */
 int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, const void* h1, const void* g1, const void* dz2,
                     int d_in, int d_mid, int d_out, int rows_cap, const int* n_rows_dev, void* dz1, void* dw1,
-                    void* db1, void* dw2, void* db2, void* dx, float* colsum_ws, void* gemm_ws, int cta_group,
-                    void* stream);
+                    void* db1, void* dw2, void* db2, void* dx, float* colsum_ws, void* gemm_ws, int accumulate,
+                    int cta_group, void* stream);
+/* Both bias gradients of the fused step in one launch, summed in a fixed order from the partial rows left by
+ * p2t_adapter_bwd (db1_partial = its colsum_ws) and p2t_adapter_tail_bwd (db2_partial = its colsum_ws, nparts2_dev,
+ * ws_rows2).  Outputs in fp32 (what the gradient all-reduce carries: ONE rounding to bf16, after the mean over ranks)
+ * and/or bf16 (the parameter's .grad).  accumulate != 0 adds to the fp32 outputs.  Either job may be NULL. */
+int p2t_bias_grads(const float* db1_partial, int rows_cap, const int* n_rows_dev, int d_mid, void* db1_bf16, float* db1_f32,
+                   const float* db2_partial, const int* nparts2_dev, int ws_rows2, int d_out, void* db2_bf16,
+                   float* db2_f32, int accumulate, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * InfoNCE — scripts/train_contrast.py:86-91 (BatchInfoNCELoss), :100-114 (Segmented...).
@@ -218,6 +230,27 @@ int p2t_infonce_grad(const float* dS, const void* dS_bf16, const void* p, const 
                      const float* t_f32, int R, int C, int E, float tau, float* dp, float* dt, int cta_group,
                      void* stream);
 int p2t_loss_mean(const float* row_loss, int R, float scale, float* loss, int accumulate, void* stream);
+
+/* The loss block of the fused step for small similarity blocks in ONE cooperative kernel (north_star (3): similarity,
+ * row- and column-wise online-softmax cross-entropy, loss and dLogits in one pass, logits and probabilities never in
+ * HBM as an autograd graph would keep them) — scripts/train_contrast.py:100-114, :354/:365, :237-248 and their
+ * autograd down to the pooling coefficients c1, c2 (dy_r = c1[b] + c2[b] y_r).
+ *   p_f32 [B][E] (rows < R enter the loss), t_f32 [C][E]; or t_f32 == NULL and (gather_peers, world, rank,
+ *   gather_bytes_per_rank) name a p2t_peer_allgather channel whose push half has been issued: the kernel waits for
+ *   the round itself, reads the gathered rows in place and closes the round (no arrive kernel, no copy).
+ *   labels int32 [R]; loss = loss_scale * sum_i [w_row (lse_j S_ij - S_i,lab) + w_col (lse_col[lab] - S_i,lab)].
+ *   need_grad != 0: dp = dloss/tau dLogits t, F.normalize backward (pnorm [B]), 'mix' coefficients (stats [B][E],
+ *   seq_off [B+1]) -> c1, c2 fp32 [B][E/2]; rows >= R get zero gradient.  dloss: device scalar or NULL (= 1).
+ *   Workspaces: S_ws fp32 [R][C]; dp_ws fp32 [B][E + ceil(E/64)]; barrier_ws 16 bytes, zero before the FIRST use
+ *   (the kernel re-arms it).  Outputs other than loss may be NULL.  A label outside [0, C), a timed-out exchange
+ *   round or a stuck grid barrier yields a NaN loss.  Eligible when R*C <= 16384 (p2t_loss_fused_eligible). */
+int p2t_loss_fused(const float* p_f32, const float* t_f32, void* const* gather_peers, int world, int rank,
+                   long long gather_bytes_per_rank, const int* labels, int R, int B, int C, int E, float tau, float w_row,
+                   float w_col, float loss_scale, int all_cols_labelled, int want_col_stats, int need_grad,
+                   const float* dloss, const float* pnorm, const float* stats, const int* seq_off, float* S_ws,
+                   float* dp_ws, void* barrier_ws, float* loss, float* row_lse, int* argmax_row, int* argmax_col,
+                   float* col_max, float* col_sum, float* c1, float* c2, void* stream);
+int p2t_loss_fused_eligible(int R, int B, int C, int E);
 
 /* dtype helpers used by the host layer around the fp32 <-> bf16 boundaries */
 int p2t_f32_to_bf16(const float* in, long long n, void* out, void* stream);
@@ -258,12 +291,17 @@ int p2t_adapter_scatter_rows(const void* a, const float* rowsq, int nblk, int ro
  * for all ranks' blocks of this round and copy the world * bytes_per_rank gathered bytes, rank-major, to `dst`.
  * Kernels between the two halves overlap the transfer.  Rounds are double-buffered: a rank may run one round ahead.
  *
- * p2t_peer_allreduce_mean_bf16: buffer size ctrl + 2 * n_bytes; the caller has written its contribution
- * (bf16, n_bytes multiple of 16) at offset ctrl.  phases bit 0: announce; bit 1: sum slice `rank` over all peers in
- * rank order in fp32, store mean (bf16) to every peer at offset ctrl + n_bytes; bit 2: wait for all slices and copy
- * the result to `dst` (may be NULL: read it in place).  Every rank obtains bit-identical results.
+ * p2t_peer_allreduce_mean: buffer size ctrl + 2 * n_bytes; the caller has written its contribution (n_bytes multiple
+ * of 16: bf16 values in [0, f32_from_byte), fp32 values from f32_from_byte on — the bias gradients travel in fp32 and
+ * are rounded once, after the mean; f32_from_byte < 0 or == n_bytes: all bf16) at offset ctrl.  phases bit 0: announce;
+ * bit 1: sum slice `rank` over all peers in rank order in fp32, store the mean (same format) to every peer at offset
+ * ctrl + n_bytes; bit 2: wait for all slices and copy the result to `dst` (may be NULL: read it in place).  Every rank
+ * obtains bit-identical results.
  *
- * A rank that waits more than 20 s for a peer stores 1 + that peer's rank in control word 4 and carries on.
+ * A rank that waits more than 20 s for a peer stores 1 + that peer's rank in control word 4 (sticky) and POISONS what
+ * the round produces: the gathered rows / the reduced gradients become NaN, so the step's loss (or the next
+ * optimizer step's gradient norm) is NaN instead of silently stale.  p2t_peer_reset (collective: every rank, between
+ * two host-side barriers, with no round in flight) re-initialises the control block.
  * ------------------------------------------------------------------------------------------- */
 unsigned long long p2t_peer_ctrl_bytes(void);
 int p2t_peer_alloc(unsigned long long bytes, void** dptr, unsigned char* handle64);
@@ -272,8 +310,9 @@ int p2t_peer_close(void* dptr);
 int p2t_peer_free(void* dptr);
 int p2t_peer_allgather(void* const* peers, int world, int rank, const void* src, long long bytes_per_rank, void* dst,
                        int phases, void* stream);
-int p2t_peer_allreduce_mean_bf16(void* const* peers, int world, int rank, long long n_bytes, void* dst, int phases,
-                                 void* stream);
+int p2t_peer_allreduce_mean(void* const* peers, int world, int rank, long long n_bytes, long long f32_from_byte, void* dst,
+                            int phases, void* stream);
+int p2t_peer_reset(void* channel_base, void* stream);
 /* cudaMemcpyAsync device -> device on `stream` (moving contributions into / results out of a channel buffer, which
  * torch cannot address as a tensor) */
 int p2t_copy_d2d(void* dst, const void* src, unsigned long long bytes, void* stream);

@@ -16,14 +16,14 @@ from .losses import BatchInfoNCELoss, SegmentedBatchInfoNCELoss, SymmetricInfoNC
 from .readout import readout_embeddings
 from .graph import GraphedContrastiveStep
 from .host_io import HostStager, StagedBatch
-from .step import StepAux, contrastive_step, text_embeddings
+from .step import StepAux, contrastive_step, segment_pooling_mask, text_embeddings
 from .optim import FusedAdamW
 from .peer import PeerAllGather, PeerBuffer, PeerGradAllReduce
 from .handoff import adapter_into_embeds, llm_hidden_states_at
 
 __all__ = [
     "ModalityAdapter", "ModalityAdapterConfig", "readout_embeddings", "BatchInfoNCELoss",
-    "SegmentedBatchInfoNCELoss", "SymmetricInfoNCELoss", "contrastive_step", "text_embeddings", "StepAux",
+    "SegmentedBatchInfoNCELoss", "SymmetricInfoNCELoss", "contrastive_step", "text_embeddings", "segment_pooling_mask", "StepAux",
     "HostStager", "StagedBatch", "GraphedContrastiveStep",
     "FusedAdamW", "PeerAllGather", "PeerBuffer", "PeerGradAllReduce", "adapter_into_embeds", "llm_hidden_states_at",
     "P2TError",

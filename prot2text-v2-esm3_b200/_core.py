@@ -181,24 +181,48 @@ def adapter_forward(x: torch.Tensor, x_rows: int, rows_cap: int, n_rows: torch.T
 
 
 def adapter_backward(acts: AdapterActs, dz2: torch.Tensor, w1, w2, need_dx: bool = False, need_db2: bool = True,
-                     cta_group: Optional[int] = None):
-    """Returns (dw1, db1, dw2, db2_or_None, dx_or_None) in bf16, nn.Linear layout."""
+                     cta_group: Optional[int] = None, need_db1: bool = True, accumulate: bool = False,
+                     dw1_out: Optional[torch.Tensor] = None, dw2_out: Optional[torch.Tensor] = None):
+    """Returns (dw1, db1, dw2, db2_or_None, dx_or_None) in bf16, nn.Linear layout.
+
+    `need_db1=False`: db1 is returned as the fp32 partial column sums [ceil(rows_cap/32)][d_mid] the dgrad GEMM's
+    epilogue left behind (finish them with `bias_grads`).  `dw1_out`/`dw2_out`: write (or, with `accumulate`, add)
+    the weight gradients into the caller's tensors instead of fresh ones."""
     d_mid, d_in = w1.shape
     d_out = w2.shape[0]
     dev = dz2.device
     bf = torch.bfloat16
     dz1 = torch.empty(acts.rows_cap, d_mid, dtype=bf, device=dev)
-    dw1 = torch.empty(d_mid, d_in, dtype=bf, device=dev)
-    db1 = torch.empty(d_mid, dtype=bf, device=dev)
-    dw2 = torch.empty(d_out, d_mid, dtype=bf, device=dev)
+    if accumulate and (dw1_out is None or dw2_out is None):
+        raise _lib.P2TError("accumulate needs dw1_out and dw2_out")
+    dw1 = dw1_out if dw1_out is not None else torch.empty(d_mid, d_in, dtype=bf, device=dev)
+    dw2 = dw2_out if dw2_out is not None else torch.empty(d_out, d_mid, dtype=bf, device=dev)
+    db1 = torch.empty(d_mid, dtype=bf, device=dev) if need_db1 else None
     db2 = torch.empty(d_out, dtype=bf, device=dev) if need_db2 else None
     dx = torch.empty(acts.rows_cap, d_in, dtype=bf, device=dev) if need_dx else None
-    ws = torch.empty((acts.rows_cap + 63) // 64, max(d_mid, d_out) if need_db2 else d_mid, dtype=torch.float32, device=dev)
+    n32, n64 = (acts.rows_cap + 31) // 32, (acts.rows_cap + 63) // 64
+    ws = torch.empty(n32 * d_mid + (n64 * d_out if need_db2 else 0), dtype=torch.float32, device=dev)
     _lib.call("p2t_adapter_bwd", _ptr(acts.x), acts.x_rows, _ptr(w1), _ptr(w2), _ptr(acts.h1), _ptr(acts.g1),
               _ptr(dz2), d_in, d_mid, d_out, acts.rows_cap, _ptr(acts.n_rows), _ptr(dz1), _ptr(dw1), _ptr(db1),
-              _ptr(dw2), _ptr(db2), _ptr(dx), _ptr(ws), _ptr(gemm_workspace(dev)), cta_group or default_cta_group(),
-              _stream())
-    return dw1, db1, dw2, db2, dx
+              _ptr(dw2), _ptr(db2), _ptr(dx), _ptr(ws), _ptr(gemm_workspace(dev)), int(accumulate),
+              cta_group or default_cta_group(), _stream())
+    return dw1, (db1 if need_db1 else ws), dw2, db2, dx
+
+
+def bias_grads(db1_partial: torch.Tensor, rows_cap: int, n_rows: torch.Tensor, d_mid: int, db2_partial: torch.Tensor,
+               nparts2: torch.Tensor, d_out: int, *, accumulate: bool = False,
+               out_f32: Optional[tuple] = None, out_bf16: Optional[tuple] = None):
+    """(db1_bf16, db2_bf16, db1_f32, db2_f32) from the partial column sums of the dgrad GEMM's epilogue and of the
+    tail backward, one launch.  `out_f32` / `out_bf16`: (db1, db2) tensors to write into (fp32 is added to when
+    `accumulate`)."""
+    dev = db1_partial.device
+    f1, f2 = out_f32 if out_f32 is not None else (torch.empty(d_mid, dtype=torch.float32, device=dev),
+                                                  torch.empty(d_out, dtype=torch.float32, device=dev))
+    b1, b2 = out_bf16 if out_bf16 is not None else (torch.empty(d_mid, dtype=torch.bfloat16, device=dev),
+                                                    torch.empty(d_out, dtype=torch.bfloat16, device=dev))
+    _lib.call("p2t_bias_grads", _ptr(db1_partial), rows_cap, _ptr(n_rows), d_mid, _ptr(b1), _ptr(f1), _ptr(db2_partial),
+              _ptr(nparts2), db2_partial.shape[0], d_out, _ptr(b2), _ptr(f2), int(accumulate), _stream())
+    return b1, b2, f1, f2
 
 
 # --------------------------------------------------------------------------------------------------
@@ -274,17 +298,31 @@ def pool_backward_coef(de: torch.Tensor, stats: torch.Tensor, plan: RowPlan, D: 
     return c1, c2
 
 
-def adapter_tail_backward(acts: AdapterActs, inv_norm: torch.Tensor, plan: RowPlan, c1, c2):
-    """dz2 (bf16 [rows_cap, d_out]) and db2 = colsum(dz2) (bf16 [d_out])."""
+_SM_COUNT = {}
+
+
+def sm_count(device) -> int:
+    idx = torch.device(device).index
+    idx = torch.cuda.current_device() if idx is None else idx
+    if idx not in _SM_COUNT:
+        _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _SM_COUNT[idx]
+
+
+def adapter_tail_backward(acts: AdapterActs, inv_norm: torch.Tensor, plan: RowPlan, c1, c2, finish_db2: bool = True):
+    """dz2 (bf16 [rows_cap, d_out]) and db2 = colsum(dz2): as bf16 [d_out] (`finish_db2`), or as the tuple
+    (partial fp32 [ws_rows, d_out], nparts int32 [1]) for `bias_grads`."""
     d_out = acts.a.shape[1]
     dev = acts.a.device
     dz2 = torch.empty(acts.rows_cap, d_out, dtype=torch.bfloat16, device=dev)
-    ws = torch.empty(plan.max_chunks + 8, d_out, dtype=torch.float32, device=dev)
-    db2 = torch.empty(d_out, dtype=torch.bfloat16, device=dev)
-    _lib.call("p2t_adapter_tail_bwd", _ptr(acts.a), _ptr(acts.g2), _ptr(inv_norm), _ptr(plan.seq_off),
-              _ptr(plan.chunk_off), _ptr(plan.chunk_seq), plan.B, _ptr(c1), _ptr(c2), _ptr(acts.n_rows), acts.rows_cap,
-              d_out, CHUNK_ROWS, plan.max_chunks, _ptr(dz2), _ptr(ws), _ptr(db2), _stream())
-    return dz2, db2
+    ws_rows = 2 * sm_count(dev)
+    ws = torch.empty(ws_rows, d_out, dtype=torch.float32, device=dev)
+    nparts = torch.empty(1, dtype=torch.int32, device=dev)
+    db2 = torch.empty(d_out, dtype=torch.bfloat16, device=dev) if finish_db2 else None
+    _lib.call("p2t_adapter_tail_bwd", _ptr(acts.a), _ptr(acts.g2), _ptr(inv_norm), _ptr(plan.seq_off), plan.B,
+              _ptr(c1), _ptr(c2), _ptr(acts.n_rows), acts.rows_cap, d_out, _ptr(dz2), _ptr(ws), ws_rows, _ptr(nparts),
+              _ptr(db2), _stream())
+    return dz2, (db2 if finish_db2 else (ws, nparts))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -367,6 +405,77 @@ def infonce_backward(res: InfoNCEResult, p_bf, t_bf, tau: float, need_dp: bool =
     _lib.call("p2t_infonce_grad", _ptr(res.dS), _ptr(res.dS_bf16), _ptr(p_bf), _ptr(t_bf), _ptr(p_f32), _ptr(t_f32),
               R, C, E, float(tau), _ptr(dp), _ptr(dt), cta_group or default_cta_group(), _stream())
     return dp, dt
+
+
+_BARRIER_WS = {}
+
+
+def _barrier_ws(device) -> torch.Tensor:
+    """16 zero bytes per device for the fused loss kernel's grid barrier (the kernel re-arms them itself)."""
+    key = str(device)
+    t = _BARRIER_WS.get(key)
+    if t is None:
+        t = _BARRIER_WS[key] = torch.zeros(4, dtype=torch.int32, device=device)
+    return t
+
+
+def loss_fused_eligible(R: int, B: int, C: int, E: int) -> bool:
+    return bool(_lib.load().p2t_loss_fused_eligible(R, B, C, E))
+
+
+@dataclass
+class FusedLossResult:
+    loss: torch.Tensor
+    row_lse: torch.Tensor
+    argmax_row: torch.Tensor
+    argmax_col: torch.Tensor
+    col_max: torch.Tensor
+    col_sum: torch.Tensor
+    c1: Optional[torch.Tensor]
+    c2: Optional[torch.Tensor]
+
+
+def loss_fused(p_f32: torch.Tensor, t_f32: Optional[torch.Tensor], labels: torch.Tensor, R: int, tau: float, *,
+               w_row: float = 1.0, w_col: float = 0.0, loss_scale: Optional[float] = None,
+               all_cols_labelled: bool = False, need_grad: bool = True, dloss: Optional[torch.Tensor] = None,
+               pnorm: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
+               seq_off: Optional[torch.Tensor] = None, gather=None) -> FusedLossResult:
+    """Similarity -> InfoNCE (-> pooling coefficients of the backward pass) in one cooperative kernel
+    (csrc/loss_fused.cu).  `gather`: a peer.PeerAllGather whose push has been issued — the kernel waits for the round
+    and reads the gathered text embeddings in place (then `t_f32` is None)."""
+    B, E = p_f32.shape
+    dev = p_f32.device
+    if gather is not None:
+        C = gather.world * gather.rows
+        peers, world, rank, bpr = gather.buffer.table, gather.world, gather.rank, gather.bytes_per_rank
+        if gather.cols != E or gather.dtype != torch.float32:
+            raise _lib.P2TError("the gather channel must carry fp32 rows of the embedding width")
+    else:
+        C = t_f32.shape[0]
+        peers, world, rank, bpr = None, 0, 0, 0
+    labels32 = labels.to(device=dev, dtype=torch.int32).contiguous()
+    D = E // 2
+    f32 = torch.float32
+    S_ws = torch.empty(R, C, dtype=f32, device=dev)
+    nslice = (E + 63) // 64
+    dp_ws = torch.empty(B, E + nslice, dtype=f32, device=dev) if need_grad else None
+    loss = torch.empty((), dtype=f32, device=dev)
+    row_lse = torch.empty(R, dtype=f32, device=dev)
+    argmax_row = torch.empty(R, dtype=torch.int32, device=dev)
+    argmax_col = torch.empty(C, dtype=torch.int32, device=dev)
+    col_max = torch.empty(C, dtype=f32, device=dev)
+    col_sum = torch.empty(C, dtype=f32, device=dev)
+    c1 = torch.empty(B, D, dtype=f32, device=dev) if need_grad else None
+    c2 = torch.empty(B, D, dtype=f32, device=dev) if need_grad else None
+    scale = (1.0 / R) if loss_scale is None else float(loss_scale)
+    _lib.call("p2t_loss_fused", _ptr(p_f32), _ptr(t_f32), peers, world, rank, bpr, _ptr(labels32), R, B, C, E,
+              float(tau), float(w_row), float(w_col), scale, int(all_cols_labelled), 1, int(need_grad), _ptr(dloss),
+              _ptr(pnorm), _ptr(stats), _ptr(seq_off), _ptr(S_ws), _ptr(dp_ws), _ptr(_barrier_ws(dev)), _ptr(loss),
+              _ptr(row_lse), _ptr(argmax_row), _ptr(argmax_col), _ptr(col_max), _ptr(col_sum), _ptr(c1), _ptr(c2),
+              _stream())
+    if gather is not None:
+        gather.note_arrived()
+    return FusedLossResult(loss, row_lse, argmax_row, argmax_col, col_max, col_sum, c1, c2)
 
 
 def dropout_mask(rows: int, cols: int, p: float, seed: int, layer: int, device) -> torch.Tensor:

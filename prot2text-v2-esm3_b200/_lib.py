@@ -30,9 +30,12 @@ SIGNATURES = {
     "p2t_l2norm_bwd": [_vp, _vp, _vp, _i, _i, _vp, _vp],
     "p2t_pool_bwd_coef": [_vp, _ll, _vp, _ll, _vp, _i, _i, _i, _vp, _vp, _vp],
     "p2t_readout_bwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
-    "p2t_adapter_tail_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "p2t_adapter_tail_bwd": [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp],
     "p2t_adapter_tail_bwd_dy": [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp],
-    "p2t_adapter_bwd": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+    "p2t_adapter_bwd": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "p2t_bias_grads": [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp],
+    "p2t_loss_fused": [_vp, _vp, C.POINTER(_vp), _i, _i, _ll, _vp, _i, _i, _i, _i, _f, _f, _f, _f, _i, _i, _i,
+                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "p2t_similarity": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i, _vp],
     "p2t_infonce_col_stats": [_vp, _i, _i, _vp, _vp, _vp, _i, _vp],
     "p2t_infonce_ce": [_vp, _vp, _i, _i, _f, _f, _f, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp],
@@ -48,7 +51,8 @@ SIGNATURES = {
     "p2t_peer_close": [_vp],
     "p2t_peer_free": [_vp],
     "p2t_peer_allgather": [C.POINTER(_vp), _i, _i, _vp, _ll, _vp, _i, _vp],
-    "p2t_peer_allreduce_mean_bf16": [C.POINTER(_vp), _i, _i, _ll, _vp, _i, _vp],
+    "p2t_peer_allreduce_mean": [C.POINTER(_vp), _i, _i, _ll, _ll, _vp, _i, _vp],
+    "p2t_peer_reset": [_vp, _vp],
     "p2t_copy_d2d": [_vp, _vp, _ull, _vp],
     "p2t_peer_status": [_vp, C.POINTER(C.c_uint)],
     "p2t_adamw_step": [_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
@@ -60,7 +64,7 @@ SIGNATURES = {
 NON_STATUS = {"p2t_abi_version": (_i, []), "p2t_last_error": (C.c_char_p, []),
               "p2t_launch_count": (_ull, []), "p2t_reset_launch_count": (None, []),
               "p2t_gemm_timing_enable": (None, [_i]), "p2t_launch_timing_enable": (None, [_i]), "p2t_gemm_workspace_bytes": (_ull, []),
-              "p2t_peer_ctrl_bytes": (_ull, []), "p2t_adamw_workspace_floats": (_i, [_i, C.POINTER(_ll)])}
+              "p2t_peer_ctrl_bytes": (_ull, []), "p2t_loss_fused_eligible": (_i, [_i, _i, _i, _i]), "p2t_adamw_workspace_floats": (_i, [_i, C.POINTER(_ll)])}
 
 _lib = None
 

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libp2t_b200.so")
 STAMP = os.path.join(HERE, "build", "stamp.txt")
-SOURCES = ["common.cu", "gemm_host.cu", "rows.cu", "infonce.cu", "peer.cu", "optim.cu", "api.cu"]
+SOURCES = ["common.cu", "gemm_host.cu", "rows.cu", "infonce.cu", "loss_fused.cu", "peer.cu", "optim.cu", "api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

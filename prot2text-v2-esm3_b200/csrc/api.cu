@@ -209,14 +209,14 @@ int p2t_readout_bwd(const void* x, const void* mask, int mask_bytes, int B, int 
   return readout_backward(x, mask, mask_bytes, B, S_, D, c1, c2, dx, S(stream));
 }
 
-int p2t_adapter_tail_bwd(const void* a, const void* g2, const float* inv_norm, const int* seq_off, const int* chunk_off,
-                         const int* chunk_seq, int B, const float* c1, const float* c2, const int* n_rows_dev,
-                         int rows_cap, int d_out, int chunk_rows, int max_chunks, void* dz2, float* colsum_ws, void* db2,
-                         void* stream) {
-  if (!a || !g2 || !inv_norm || !seq_off || !chunk_off || !chunk_seq || !c1 || !c2 || !n_rows_dev || !dz2)
+int p2t_adapter_tail_bwd(const void* a, const void* g2, const float* inv_norm, const int* seq_off, int B, const float* c1,
+                         const float* c2, const int* n_rows_dev, int rows_cap, int d_out, void* dz2, float* colsum_ws,
+                         int ws_rows, int* nparts_dev, void* db2, void* stream) {
+  if (!a || !g2 || !inv_norm || !seq_off || !c1 || !c2 || !n_rows_dev || !dz2)
     return set_error(-1, "p2t_adapter_tail_bwd: null pointer");
-  return adapter_tail_backward(a, g2, inv_norm, seq_off, chunk_off, chunk_seq, B, c1, c2, n_rows_dev, rows_cap, d_out,
-                               chunk_rows, max_chunks, dz2, colsum_ws, db2, S(stream));
+  if (B < 1) return set_error(-1, "p2t_adapter_tail_bwd: empty batch");
+  return adapter_tail_backward(a, g2, inv_norm, seq_off, B, c1, c2, n_rows_dev, rows_cap, d_out, dz2, colsum_ws, ws_rows,
+                               nparts_dev, db2, S(stream));
 }
 int p2t_adapter_tail_bwd_dy(const void* a, const void* g2, const float* inv_norm, const void* dy, int n,
                             const int* n_rows_dev, int rows_cap, int d_out, void* dz2, void* stream) {
@@ -226,17 +226,21 @@ int p2t_adapter_tail_bwd_dy(const void* a, const void* g2, const float* inv_norm
 
 int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, const void* h1, const void* g1, const void* dz2,
                     int d_in, int d_mid, int d_out, int rows_cap, const int* n_rows_dev, void* dz1, void* dw1,
-                    void* db1, void* dw2, void* db2, void* dx, float* colsum_ws, void* gemm_ws, int cta_group,
-                    void* stream) {
+                    void* db1, void* dw2, void* db2, void* dx, float* colsum_ws, void* gemm_ws, int accumulate,
+                    int cta_group, void* stream) {
   if (!x || !w2 || !h1 || !g1 || !dz2 || !dz1 || !dw1 || !dw2 || !colsum_ws)
     return set_error(-1, "p2t_adapter_bwd: null pointer");
   cudaStream_t st = S(stream);
+  float* db1_partial = colsum_ws;                                               // [ceil(rows_cap/32)][d_mid]
+  float* db2_ws = colsum_ws + (size_t)((rows_cap + 31) / 32) * (size_t)d_mid;   // [ceil(rows_cap/64)][d_out], only with db2
   // dz1 = (dz2 W2) * g1      A = dz2 [rows][d_out] (K-major), B[n][k] = W2[k][n] (MN-major, ld d_mid)
+  // + per-32-row column sums of dz1 from the epilogue (db1 without a second pass over dz1)
   {
     GemmParams p = base_params(rows_cap, d_mid, d_out);
     p.dyn_m = n_rows_dev;
     p.d0 = dz1; p.ldd0 = d_mid;
     p.aux = reinterpret_cast<const __half*>(g1); p.ldaux = d_mid;
+    p.colsum = db1_partial;
     if (int rc = launch_gemm(dz2, d_out, false, w2, d_mid, true, EPI_MUL_AUX, p, cta_group, st)) return rc;
   }
   // dW2 = dz2^T h1           both operands MN-major, K = residue rows
@@ -245,6 +249,7 @@ int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, c
     p.dyn_k = n_rows_dev;
     p.sk_ws = gemm_ws;
     p.d0 = dw2; p.ldd0 = d_mid;
+    p.accumulate = accumulate;
     if (int rc = launch_gemm(dz2, d_out, true, h1, d_mid, true, EPI_STORE_BF16, p, cta_group, st)) return rc;
   }
   // dW1 = dz1^T x
@@ -254,10 +259,16 @@ int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, c
     p.sk_ws = gemm_ws;
     p.d0 = dw1; p.ldd0 = d_in;
     p.b_extent = x_rows;
+    p.accumulate = accumulate;
     if (int rc = launch_gemm(dz1, d_mid, true, x, d_in, true, EPI_STORE_BF16, p, cta_group, st)) return rc;
   }
-  if (db2) if (int rc = colsum(dz2, n_rows_dev, rows_cap, d_out, colsum_ws, db2, nullptr, st)) return rc;
-  if (db1) if (int rc = colsum(dz1, n_rows_dev, rows_cap, d_mid, colsum_ws, db1, nullptr, st)) return rc;
+  if (db2) if (int rc = colsum(dz2, n_rows_dev, rows_cap, d_out, db2_ws, db2, nullptr, st)) return rc;
+  if (db1) {
+    BiasJob j{}, none{};
+    j.partial = db1_partial; j.D = d_mid; j.nparts_max = (rows_cap + 31) / 32; j.n_rows = n_rows_dev; j.n_static = rows_cap;
+    j.block_rows = 32; j.out_bf16 = db1;
+    if (int rc = bias_grads_final(j, none, st)) return rc;
+  }
   if (dx) {
     if (!w1) return set_error(-1, "p2t_adapter_bwd: w1 required for dx");
     GemmParams p = base_params(rows_cap, d_in, d_mid);
@@ -267,6 +278,42 @@ int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, c
   }
   return 0;
 }
+
+int p2t_bias_grads(const float* db1_partial, int rows_cap, const int* n_rows_dev, int d_mid, void* db1_bf16, float* db1_f32,
+                   const float* db2_partial, const int* nparts2_dev, int ws_rows2, int d_out, void* db2_bf16,
+                   float* db2_f32, int accumulate, void* stream) {
+  if (!db1_partial && !db2_partial) return set_error(-1, "p2t_bias_grads: null pointer");
+  if (accumulate && ((db1_partial && !db1_f32) || (db2_partial && !db2_f32)))
+    return set_error(-1, "p2t_bias_grads: accumulation runs in the fp32 outputs");
+  BiasJob j0{}, j1{};
+  if (db1_partial) {
+    if (!n_rows_dev) return set_error(-1, "p2t_bias_grads: n_rows_dev required");
+    j0.partial = db1_partial; j0.D = d_mid; j0.nparts_max = (rows_cap + 31) / 32; j0.n_rows = n_rows_dev; j0.n_static = rows_cap;
+    j0.block_rows = 32; j0.out_bf16 = db1_bf16; j0.out_f32 = db1_f32; j0.accumulate = accumulate;
+  }
+  if (db2_partial) {
+    if (!nparts2_dev) return set_error(-1, "p2t_bias_grads: nparts2_dev required");
+    j1.partial = db2_partial; j1.D = d_out; j1.nparts_dev = nparts2_dev; j1.nparts_max = ws_rows2;
+    j1.out_bf16 = db2_bf16; j1.out_f32 = db2_f32; j1.accumulate = accumulate;
+  }
+  return bias_grads_final(j0, j1, S(stream));
+}
+
+int p2t_loss_fused(const float* p_f32, const float* t_f32, void* const* gather_peers, int world, int rank,
+                   long long gather_bytes_per_rank, const int* labels, int R, int B, int C, int E, float tau, float w_row,
+                   float w_col, float loss_scale, int all_cols_labelled, int want_col_stats, int need_grad,
+                   const float* dloss, const float* pnorm, const float* stats, const int* seq_off, float* S_ws,
+                   float* dp_ws, void* barrier_ws, float* loss, float* row_lse, int* argmax_row, int* argmax_col,
+                   float* col_max, float* col_sum, float* c1, float* c2, void* stream) {
+  if (!p_f32 || !labels || !S_ws || !barrier_ws || !loss) return set_error(-1, "p2t_loss_fused: null pointer");
+  if (need_grad && (!pnorm || !stats || !seq_off || !dp_ws || !c1 || !c2))
+    return set_error(-1, "p2t_loss_fused: the backward half needs pnorm, stats, seq_off, dp_ws, c1 and c2");
+  return loss_fused(p_f32, t_f32, gather_peers, world, rank, gather_bytes_per_rank, labels, R, B, C, E, tau, w_row, w_col,
+                    loss_scale, all_cols_labelled, want_col_stats, need_grad, dloss, pnorm, stats, seq_off, S_ws, dp_ws,
+                    static_cast<unsigned*>(barrier_ws), loss, row_lse, argmax_row, argmax_col, col_max, col_sum, c1, c2,
+                    S(stream));
+}
+int p2t_loss_fused_eligible(int R, int B, int C, int E) { return loss_fused_eligible(R, B, C, E) ? 1 : 0; }
 
 static bool small_problem(int R, int C, int E) { return (long long)R * C * E <= (1LL << 26); }
 
@@ -382,10 +429,11 @@ int p2t_peer_allgather(void* const* peers, int world, int rank, const void* src,
                        int phases, void* stream) {
   return peer_allgather(peers, world, rank, src, bytes_per_rank, dst, phases, S(stream));
 }
-int p2t_peer_allreduce_mean_bf16(void* const* peers, int world, int rank, long long n_bytes, void* dst, int phases,
-                                 void* stream) {
-  return peer_allreduce_mean(peers, world, rank, n_bytes, dst, phases, S(stream));
+int p2t_peer_allreduce_mean(void* const* peers, int world, int rank, long long n_bytes, long long f32_from_byte, void* dst,
+                            int phases, void* stream) {
+  return peer_allreduce_mean(peers, world, rank, n_bytes, f32_from_byte, dst, phases, S(stream));
 }
+int p2t_peer_reset(void* channel_base, void* stream) { return peer_reset(channel_base, S(stream)); }
 
 int p2t_copy_d2d(void* dst, const void* src, unsigned long long bytes, void* stream) {
   if (!dst || !src) return set_error(-1, "p2t_copy_d2d: null pointer");

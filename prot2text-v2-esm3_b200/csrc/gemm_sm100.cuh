@@ -31,7 +31,8 @@
 //                rowsq[4*n_blk + part][row] = sum over 64 columns of a^2                         (:65-67)
 //   (fp16 for tensors only our own streaming kernels read: bf16's 8-bit mantissa adds rounding noise
 //    of 2^-9*|a| to every residue, which inflates the pooled std and its 1/std backward)
-//   EPI_MUL_AUX: D0 = alpha * acc * aux   (fc2 dgrad chained into GELU'(z1): aux = g1)
+//   EPI_MUL_AUX: D0 = alpha * acc * aux   (fc2 dgrad chained into GELU'(z1): aux = g1); optionally the column sums of
+//                D0 over each 32-row block (db1 = sum over rows of dz1, finished by bias_grads_final_kernel)
 // Storing (value, derivative) pairs instead of the pre-activation keeps every later HBM-bound pass
 // free of erf/exp and of Philox re-generation: the dropout multiplier is folded into both.
 #pragma once
@@ -72,6 +73,10 @@ struct GemmParams {
   long long ldaux;
   float* rowsq;               // EPI_FC2: [4 * n_blocks][ld_rowsq = rows_cap] partial sums of squares (four per 256-column N block)
   int ld_rowsq;
+  float* colsum;              // EPI_MUL_AUX (optional): [ceil(rows_cap / 32)][n] column sums of D0 over each 32-row block
+                              // (fixed-order shuffle tree; the bias gradient db1 without a second pass over dz1)
+  int accumulate;             // EPI_STORE_BF16: D0 += alpha * acc (bf16 read-modify-write: gradient accumulation over
+                              // micro-batches, scripts/train_contrast.py:448 without optimizer.zero_grad in between)
   float alpha;
   DropoutParams drop;         // p == 0 -> disabled
   // split-K tail (see header comment); sk_ws == nullptr -> whole tiles only
@@ -195,6 +200,40 @@ __device__ __forceinline__ void load8(const T* src, float (&f)[8], int n_ok) {
   }
 }
 
+// bf16 read-modify-write partner of store8 (accumulating epilogue): ordinary loads, never the read-only path
+__device__ __forceinline__ void load8_plain(const __nv_bfloat16* src, float (&f)[8], int n_ok, bool vec_ok) {
+  if (n_ok == 8 && vec_ok) {
+    const uint4 u = *reinterpret_cast<const uint4*>(src);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 x = unpack_bf16x2(w[i]);
+      f[2 * i] = x.x;
+      f[2 * i + 1] = x.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = (i < n_ok) ? __bfloat162float(src[i]) : 0.f;
+  }
+}
+
+// Column sums of a 32 x 32 block held one row per lane (v[c] = element (lane, c)): a butterfly that halves the
+// number of live columns per step (16 + 8 + 4 + 2 + 1 shuffles).  Returns, in lane l, the sum of column l over the
+// 32 lanes; the pairing is fixed, so the result is deterministic.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = upper ? v[i] : v[i + half];
+      const float keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return v[0];
+}
+
 // bias[col .. col+8) as fp32: one 16-byte load when the eight bf16 values are in range and aligned (every lane of
 // the warp reads the same address: a broadcast served by L1), element-wise at the ragged end of N
 __device__ __forceinline__ void load_bias8(const __nv_bfloat16* __restrict__ bias, int col, int n, float (&b)[8]) {
@@ -225,6 +264,7 @@ struct EpiArgs {
   uint32_t threshold, layer;
   uint2 key;
   int nostore;
+  int accumulate;
 };
 
 // One 32-column chunk of one accumulator row.  `ncols` < 32 only in the last chunk of a ragged N; columns
@@ -233,12 +273,16 @@ struct EpiArgs {
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const EpiArgs& e, const uint4 (&rnd)[4],
                                                int row, int col, int ncols, bool row_valid,
-                                               bool row_in_buf, bool vec_ok, float& sumsq) {
+                                               bool row_in_buf, bool vec_ok, float& sumsq, float (&res)[32]) {
   using T0 = typename std::conditional<EPI == EPI_STORE_F32, float,
              typename std::conditional<EPI == EPI_FC2, __half, __nv_bfloat16>::type>::type;
   T0* dst0 = reinterpret_cast<T0*>(e.d0) + (long long)row * e.ldd0 + col;
   __half* dst1 = reinterpret_cast<__half*>(e.d1) + (long long)row * e.ldd1 + col;
   const bool want_der = (EPI == EPI_FC1 || EPI == EPI_FC2) && e.d1 != nullptr;
+  if constexpr (EPI == EPI_MUL_AUX) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) res[i] = 0.f;
+  }
   if (!row_valid) {
     if constexpr (EPI == EPI_FC1 || EPI == EPI_FC2 || EPI == EPI_MUL_AUX) {
       if (row_in_buf) {
@@ -280,6 +324,14 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ep
     if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_STORE_F32) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) val[i] *= e.alpha;
+      if constexpr (EPI == EPI_STORE_BF16) {
+        if (e.accumulate) {  // plain loads: this kernel writes the same addresses
+          float old[8];
+          load8_plain(dst0 + 8 * j, old, n_ok, vec_ok);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) val[i] += old[i];
+        }
+      }
       store8(dst0 + 8 * j, val, n_ok, vec_ok);
     } else if constexpr (EPI == EPI_MUL_AUX) {
       const uint32_t w[4] = {g4[j].x, g4[j].y, g4[j].z, g4[j].w};
@@ -289,6 +341,8 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ep
         val[2 * i] *= e.alpha * g.x;
         val[2 * i + 1] *= e.alpha * g.y;
       }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) res[8 * j + i] = (i < n_ok) ? val[i] : 0.f;
       store8(dst0 + 8 * j, val, n_ok, vec_ok);
     } else {
       float bias[8], der[8];
@@ -549,6 +603,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const unsigned long long seed = p.drop.seed + (p.drop.seed_dev ? *p.drop.seed_dev : 0ull);
     e.key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
     e.nostore = p.debug_nostore;
+    e.accumulate = p.accumulate;
     const int rows_cap = p.rows_cap;
     // the interior path moves 16-byte vectors: every row of every output/aux tensor must start 16-byte aligned
     auto rows_aligned = [](const void* ptr, long long ld, int elem_bytes) {
@@ -638,7 +693,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               continue;
             }
           }
-          epilogue_chunk<EPI>(v, e, rnd, row, col, min(32, N - col), row_valid, row_in_buf, vec_ok, sumsq);
+          float res[32];
+          epilogue_chunk<EPI>(v, e, rnd, row, col, min(32, N - col), row_valid, row_in_buf, vec_ok, sumsq, res);
+          if constexpr (EPI == EPI_MUL_AUX) {
+            if (p.colsum != nullptr) {  // warp-uniform: every lane takes part in the shuffles, invalid rows hold zeros
+              const float cs = warp_colsum32(res, lane);
+              const int row0 = row - lane;
+              if (row0 < rows_cap && col + lane < N) p.colsum[(long long)(row0 >> 5) * N + col + lane] = cs;
+            }
+          }
         }
       }
       if constexpr (EPI == EPI_FC2) {

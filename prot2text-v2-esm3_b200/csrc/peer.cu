@@ -19,55 +19,10 @@
 #include "common.h"
 #include "mathfn.cuh"
 #include "rows.h"
+#include "peer_dev.cuh"
 
 namespace p2t {
 namespace {
-
-constexpr int kPeerMaxWorld = 16;
-constexpr unsigned long long kTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;  // 20 s
-
-struct PeerTable {
-  void* base[kPeerMaxWorld];  // base[r] = this process's mapping of rank r's peer buffer (base[rank] = own)
-};
-
-__device__ __forceinline__ uint4 ld_sys_v4(const uint4* p) {  // relaxed system-scope load: never served from a stale L1 line
-  uint4 v;
-  asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-
-__device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed_sys(unsigned* p, unsigned v) {
-  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// Threads [0, world) of the CTA wait for flags[t] to reach `epoch` (relaxed polls, then one system fence = acquire);
-// the CTA barrier that follows extends the ordering to every thread of the CTA.  System-scope fences cost a few
-// microseconds each (they wait for the thread's outstanding NVLink traffic), so they are issued by the polling /
-// publishing threads only, never by all threads.
-__device__ __forceinline__ void wait_flags(const unsigned* flags, int world, unsigned epoch, unsigned* status) {
-  if ((int)threadIdx.x < world) {
-    const unsigned long long t0 = global_ns();
-    while ((int)(ld_relaxed_sys(flags + threadIdx.x) - epoch) < 0) {
-      if (global_ns() - t0 > kTimeoutNs) {
-        atomicExch(status, 1u + threadIdx.x);
-        break;
-      }
-      __nanosleep(32);
-    }
-    __threadfence_system();
-  }
-  __syncthreads();
-}
 
 // The CTA's stores are done (barrier), thread 0 fences them at system scope (cumulative over the barrier, the pattern
 // of a cooperative grid sync) and counts the CTA in; the last CTA of the grid to get here fences once more (acquire
@@ -90,13 +45,9 @@ __device__ __forceinline__ void publish_when_grid_done(const PeerTable& peers, i
   }
 }
 
-// ---- control block at the start of every channel buffer ----
-//   u32 [0]            epoch of the last completed round
-//   u32 [1], [2], [3]  grid counters of the channel's kernels
-//   u32 [4]            status (0 = ok, 1 + r = timed out waiting for rank r)
-//   u32 [64 + ph*16 + r]  arrival flag of phase ph (0, 1) from rank r
-constexpr size_t kCtrlBytes = 1024;
-__host__ __device__ constexpr size_t flag_row_off(int phase) { return (64 + phase * 16) * sizeof(unsigned); }
+constexpr size_t kCtrlBytes = kPeerCtrlBytes;
+__host__ __device__ constexpr size_t flag_row_off(int phase) { return peer_flag_row_off(phase); }
+constexpr unsigned kPoison = 0x7fffffffu;  // NaN as fp32 and as a pair of bf16
 
 // ------------------------------------------------------------------------------------------------
 // all-gather, push half: slot (epoch parity, rank) of every peer's buffer := src
@@ -116,17 +67,19 @@ peer_allgather_push_kernel(PeerTable peers, int world, int rank, const uint4* __
   publish_when_grid_done(peers, world, rank, flag_row_off(0), epoch, ctrl + 1, nullptr);
 }
 
-// all-gather, arrival half: wait for every rank's block of this epoch, copy the gathered rows out, close the round
+// all-gather, arrival half: wait for every rank's block of this epoch, copy the gathered rows out, close the round.
+// A wait that gave up (or a channel whose status word is already set) writes NaN instead of the rows: the loss of
+// the step becomes NaN, which no caller can miss, instead of a silently stale set of negatives.
 __global__ void __launch_bounds__(256)
 peer_allgather_wait_kernel(PeerTable peers, int world, int rank, uint4* __restrict__ dst, long long vecs_per_rank) {
   unsigned* ctrl = static_cast<unsigned*>(peers.base[rank]);
   const unsigned epoch = ctrl[0] + 1;
-  wait_flags(reinterpret_cast<const unsigned*>(static_cast<char*>(peers.base[rank]) + flag_row_off(0)), world, epoch, ctrl + 4);
+  const bool ok = wait_flags(reinterpret_cast<const unsigned*>(static_cast<char*>(peers.base[rank]) + flag_row_off(0)), world, epoch, ctrl + 4);
   const uint4* slots = reinterpret_cast<const uint4*>(static_cast<char*>(peers.base[rank]) + kCtrlBytes +
                                                       (size_t)(epoch & 1) * world * (size_t)vecs_per_rank * sizeof(uint4));
   const long long total = vecs_per_rank * world;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
-    dst[i] = ld_sys_v4(slots + i);
+    dst[i] = ok ? ld_sys_v4(slots + i) : make_uint4(kPoison, kPoison, kPoison, kPoison);
   publish_when_grid_done(peers, world, rank, (size_t)-1, epoch, ctrl + 2, ctrl);
 }
 
@@ -144,12 +97,23 @@ __global__ void peer_allreduce_ready_kernel(PeerTable peers, int world, int rank
 // phase 1: reduce my slice out of every peer's `in`, store the mean into every peer's `out`.
 // RB ranks x U vectors = 16 independent 16-byte loads in flight per thread whatever the world size (an NVLink round
 // trip is ~2 us); ranks are always added in rank order, so every rank computes bit-identical sums.
+// Vectors below `f32_begin` hold 8 bf16 values (mean stored as bf16), vectors from `f32_begin` on hold 4 fp32 values
+// (mean stored as fp32: the bias gradients travel unrounded and are rounded to bf16 once, after the mean).
+__device__ __forceinline__ void acc_vec(float (&acc)[8], const uint4& v, bool f32) {
+  if (f32) {
+    acc[0] += __uint_as_float(v.x); acc[1] += __uint_as_float(v.y); acc[2] += __uint_as_float(v.z); acc[3] += __uint_as_float(v.w);
+  } else {
+    const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+    acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+    acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+  }
+}
 template <int RB, int U>
 __global__ void __launch_bounds__(256)
-peer_allreduce_reduce_kernel(PeerTable peers, int world, int rank, long long n_vec, float scale) {
+peer_allreduce_reduce_kernel(PeerTable peers, int world, int rank, long long n_vec, long long f32_begin, float scale) {
   unsigned* ctrl = static_cast<unsigned*>(peers.base[rank]);
   const unsigned epoch = ctrl[0] + 1;
-  wait_flags(reinterpret_cast<const unsigned*>(static_cast<char*>(peers.base[rank]) + flag_row_off(0)), world, epoch, ctrl + 4);
+  const bool ok = wait_flags(reinterpret_cast<const unsigned*>(static_cast<char*>(peers.base[rank]) + flag_row_off(0)), world, epoch, ctrl + 4);
   const long long per = (n_vec + world - 1) / world;
   const long long lo = per * rank, hi = min(n_vec, lo + per);
   const size_t in_off = kCtrlBytes, out_off = kCtrlBytes + (size_t)n_vec * sizeof(uint4);
@@ -172,18 +136,20 @@ peer_allreduce_reduce_kernel(PeerTable peers, int world, int rank, long long n_v
       for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int j = 0; j < RB; ++j)
-          if (r0 + j < world && i + u * stride < hi) {
-            const float2 a = unpack_bf16x2(v[u][j].x), b = unpack_bf16x2(v[u][j].y), c = unpack_bf16x2(v[u][j].z),
-                         d = unpack_bf16x2(v[u][j].w);
-            acc[u][0] += a.x; acc[u][1] += a.y; acc[u][2] += b.x; acc[u][3] += b.y;
-            acc[u][4] += c.x; acc[u][5] += c.y; acc[u][6] += d.x; acc[u][7] += d.y;
-          }
+          if (r0 + j < world && i + u * stride < hi) acc_vec(acc[u], v[u][j], i + u * stride >= f32_begin);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (i + u * stride >= hi) continue;
-      const uint4 o = make_uint4(pack_bf16x2(acc[u][0] * scale, acc[u][1] * scale), pack_bf16x2(acc[u][2] * scale, acc[u][3] * scale),
-                                 pack_bf16x2(acc[u][4] * scale, acc[u][5] * scale), pack_bf16x2(acc[u][6] * scale, acc[u][7] * scale));
+      uint4 o;
+      if (!ok)
+        o = make_uint4(kPoison, kPoison, kPoison, kPoison);  // a contribution never arrived: NaN, not a partial mean
+      else if (i + u * stride >= f32_begin)
+        o = make_uint4(__float_as_uint(acc[u][0] * scale), __float_as_uint(acc[u][1] * scale), __float_as_uint(acc[u][2] * scale),
+                       __float_as_uint(acc[u][3] * scale));
+      else
+        o = make_uint4(pack_bf16x2(acc[u][0] * scale, acc[u][1] * scale), pack_bf16x2(acc[u][2] * scale, acc[u][3] * scale),
+                       pack_bf16x2(acc[u][4] * scale, acc[u][5] * scale), pack_bf16x2(acc[u][6] * scale, acc[u][7] * scale));
       for (int r = 0; r < world; ++r) {
         const int dst = (rank + r) % world;
         reinterpret_cast<uint4*>(static_cast<char*>(peers.base[dst]) + out_off)[i + u * stride] = o;
@@ -193,16 +159,20 @@ peer_allreduce_reduce_kernel(PeerTable peers, int world, int rank, long long n_v
   publish_when_grid_done(peers, world, rank, flag_row_off(1), epoch, ctrl + 2, nullptr);
 }
 
-// phase 2: every slice of `out` has arrived -> (optionally) copy it to the caller's flat buffer, close the round
+// phase 2: every slice of `out` has arrived -> (optionally) copy it to the caller's flat buffer, close the round.
+// After a timed-out wait the result area is overwritten with NaN (see peer_allgather_wait_kernel).
 __global__ void __launch_bounds__(256)
 peer_allreduce_wait_kernel(PeerTable peers, int world, int rank, long long n_vec, uint4* __restrict__ dst) {
   unsigned* ctrl = static_cast<unsigned*>(peers.base[rank]);
   const unsigned epoch = ctrl[0] + 1;
-  wait_flags(reinterpret_cast<const unsigned*>(static_cast<char*>(peers.base[rank]) + flag_row_off(1)), world, epoch, ctrl + 4);
-  if (dst != nullptr) {
-    const uint4* out = reinterpret_cast<const uint4*>(static_cast<char*>(peers.base[rank]) + kCtrlBytes) + n_vec;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x)
-      dst[i] = ld_sys_v4(out + i);
+  const bool ok = wait_flags(reinterpret_cast<const unsigned*>(static_cast<char*>(peers.base[rank]) + flag_row_off(1)), world, epoch, ctrl + 4);
+  uint4* out = reinterpret_cast<uint4*>(static_cast<char*>(peers.base[rank]) + kCtrlBytes) + n_vec;
+  if (dst != nullptr || !ok) {
+    const uint4 poison = make_uint4(kPoison, kPoison, kPoison, kPoison);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
+      if (!ok) out[i] = poison;
+      if (dst != nullptr) dst[i] = ok ? ld_sys_v4(out + i) : poison;
+    }
   }
   publish_when_grid_done(peers, world, rank, (size_t)-1, epoch, ctrl + 3, ctrl);
 }
@@ -272,6 +242,15 @@ int peer_free(void* dptr) {
   return 0;
 }
 
+// Collective re-initialisation of a channel after a timed-out round (every rank, between two host-side barriers):
+// epochs, grid counters, status word and arrival flags go back to zero.
+int peer_reset(void* base, cudaStream_t st) {
+  if (!base) return set_error(-1, "p2t_peer_reset: null pointer");
+  cudaError_t e = cudaMemsetAsync(base, 0, kCtrlBytes, st);
+  if (e != cudaSuccess) return set_error((int)e, "p2t_peer_reset: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 int peer_allgather(void* const* peers, int world, int rank, const void* src, long long bytes_per_rank, void* dst,
                    int phases, cudaStream_t st) {
   PeerTable t{};
@@ -291,11 +270,15 @@ int peer_allgather(void* const* peers, int world, int rank, const void* src, lon
   return 0;
 }
 
-int peer_allreduce_mean(void* const* peers, int world, int rank, long long n_bytes, void* dst, int phases, cudaStream_t st) {
+int peer_allreduce_mean(void* const* peers, int world, int rank, long long n_bytes, long long f32_from_byte, void* dst, int phases,
+                        cudaStream_t st) {
   PeerTable t{};
   if (int r = fill_table(t, peers, world, rank, "p2t_peer_allreduce_mean_bf16")) return r;
   if (n_bytes <= 0 || n_bytes % 16) return set_error(-1, "p2t_peer_allreduce_mean_bf16: n_bytes must be a positive multiple of 16");
   const long long n_vec = n_bytes / 16;
+  if (f32_from_byte < 0 || f32_from_byte > n_bytes) f32_from_byte = n_bytes;
+  if (f32_from_byte % 16) return set_error(-1, "p2t_peer_allreduce_mean: the fp32 part must start on a 16-byte boundary");
+  const long long f32_begin = f32_from_byte / 16;
   if (phases & 1) {
     peer_allreduce_ready_kernel<<<1, 32, 0, st>>>(t, world, rank);
     if (int r = check_launch("peer_allreduce_ready_kernel", st)) return r;
@@ -304,11 +287,11 @@ int peer_allreduce_mean(void* const* peers, int world, int rank, long long n_byt
     const float scale = 1.f / (float)world;
     const long long slice = (n_vec + world - 1) / world;
     if (world <= 2) {
-      peer_allreduce_reduce_kernel<2, 8><<<grid_for(slice / 8, 4), 256, 0, st>>>(t, world, rank, n_vec, scale);
+      peer_allreduce_reduce_kernel<2, 8><<<grid_for(slice / 8, 4), 256, 0, st>>>(t, world, rank, n_vec, f32_begin, scale);
     } else if (world <= 4) {
-      peer_allreduce_reduce_kernel<4, 4><<<grid_for(slice / 4, 4), 256, 0, st>>>(t, world, rank, n_vec, scale);
+      peer_allreduce_reduce_kernel<4, 4><<<grid_for(slice / 4, 4), 256, 0, st>>>(t, world, rank, n_vec, f32_begin, scale);
     } else {
-      peer_allreduce_reduce_kernel<8, 2><<<grid_for(slice / 2, 4), 256, 0, st>>>(t, world, rank, n_vec, scale);
+      peer_allreduce_reduce_kernel<8, 2><<<grid_for(slice / 2, 4), 256, 0, st>>>(t, world, rank, n_vec, f32_begin, scale);
     }
     if (int r = check_launch("peer_allreduce_reduce_kernel", st)) return r;
   }

@@ -626,122 +626,129 @@ loss_bwd_coef_kernel(const float* __restrict__ dp, const float* __restrict__ dot
 }
 
 // ------------------------------------------------------------------------------------------------
-// adapter tail backward over packed rows, one CTA per pooling chunk (<= rc rows of ONE sequence):
+// adapter tail backward over packed rows, persistent: CTA k owns the contiguous row range [k*per, (k+1)*per) of the
+// n valid rows (per = ceil(n / grid) rounded to the batch size), so every SM streams the same number of rows whatever
+// the sequence lengths are (one CTA per 64-row pooling chunk left 541 CTAs for 148 SMs at config 2: 3.65 waves).
 //   y = a * inv;  dy = c1[b] + c2[b] * y;  da = (dy - y (y.dy)) * inv;  dz2 = da * g
-// thread = 8 columns (c1/c2 of the sequence live in registers), 2 rows per batch, double-buffered so that 8
-// independent 16-byte loads are in flight per thread; the per-row dot product y.dy is a block reduction.
-// The column sums of dz2 (the fc2 bias gradient) accumulate in registers and leave as one partial
-// row per chunk.  a, g fp16 [rows][D]; dz2 bf16.  CTAs beyond the last chunk zero the rows in
-// [n, roundup(n,256)) so the weight-gradient GEMMs can run their K loop over whole 64-row blocks.
+// thread = 8 columns; inside one sequence the coefficient vectors c1[b], c2[b] live in registers and rows go through
+// in batches of 2, double-buffered so that 8 independent 16-byte loads are in flight per thread; the per-row dot
+// product y.dy is a block reduction (one barrier per batch).  A range that crosses a sequence boundary restarts the
+// pipeline there with the next sequence's coefficients.
+// The column sums of dz2 (the fc2 bias gradient) accumulate in registers over the CTA's whole range and leave as ONE
+// partial row per CTA (fixed row -> CTA assignment: deterministic).  a, g fp16 [rows][D]; dz2 bf16.  Rows in
+// [n, roundup(n,256)) are zeroed so the weight-gradient GEMMs can run their K loop over whole 64-row blocks.
 // ------------------------------------------------------------------------------------------------
 constexpr int TAIL_R = 2;
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 adapter_tail_bwd_kernel(const __half* __restrict__ a, const __half* __restrict__ g, const float* __restrict__ inv_norm,
-                        const int* __restrict__ seq_off, const int* __restrict__ chunk_off,
-                        const int* __restrict__ chunk_seq, int B, const float* __restrict__ c1,
-                        const float* __restrict__ c2, const int* __restrict__ n_rows, int cap, int D, int rc,
-                        __nv_bfloat16* __restrict__ dz2, float* __restrict__ colsum_partial) {
-  const int chunk = blockIdx.x;
-  const int total_chunks = chunk_off[B];
+                        const int* __restrict__ seq_off, int B, const float* __restrict__ c1,
+                        const float* __restrict__ c2, const int* __restrict__ n_rows, int cap, int D,
+                        __nv_bfloat16* __restrict__ dz2, float* __restrict__ colsum_partial, int* __restrict__ nparts_out) {
+  const int n = min(*n_rows, cap);
+  const int n_pad = min(cap, (n + 255) & ~255);
   const int nvec = D >> 3;
   const int tid = threadIdx.x;
-  if (chunk >= total_chunks) {
-    const int n = min(*n_rows, cap);
-    const int n_pad = min(cap, (n + 255) & ~255);
-    const int extra = gridDim.x - total_chunks;
-    for (int row = n + (chunk - total_chunks); row < n_pad; row += extra)
-      if (tid < nvec) reinterpret_cast<uint4*>(dz2 + (long long)row * D)[tid] = make_uint4(0, 0, 0, 0);
-    return;
-  }
-  const int4 desc = __ldg(reinterpret_cast<const int4*>(chunk_seq) + chunk);
-  const int b = desc.z, r0 = desc.x, r1 = desc.y;
+  const int G = gridDim.x;
   const bool active = tid < nvec;
   const int warp = tid >> 5, lane = tid & 31;
   constexpr int NWARPS = THREADS / 32;
   __shared__ float red[2][NWARPS][TAIL_R];
+  if (blockIdx.x == 0 && tid == 0 && nparts_out != nullptr) nparts_out[0] = G;
+  // pad rows
+  for (int row = n + blockIdx.x; row < n_pad; row += G)
+    if (active) reinterpret_cast<uint4*>(dz2 + (long long)row * D)[tid] = make_uint4(0, 0, 0, 0);
+  const int per = (((n + G - 1) / G) + 2 * TAIL_R - 1) / (2 * TAIL_R) * (2 * TAIL_R);
+  const int lo = (int)min((long long)n, (long long)blockIdx.x * per), hi = min(n, lo + per);
   float k1[8], k2[8], csum[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { k1[i] = 0.f; k2[i] = 0.f; csum[i] = 0.f; }
-  if (active) {
-    const float4* p1 = reinterpret_cast<const float4*>(c1 + (long long)b * D) + 2 * tid;
-    const float4* p2 = reinterpret_cast<const float4*>(c2 + (long long)b * D) + 2 * tid;
-    const float4 x0 = __ldg(p1), x1 = __ldg(p1 + 1), y0 = __ldg(p2), y1 = __ldg(p2 + 1);
-    k1[0] = x0.x; k1[1] = x0.y; k1[2] = x0.z; k1[3] = x0.w; k1[4] = x1.x; k1[5] = x1.y; k1[6] = x1.z; k1[7] = x1.w;
-    k2[0] = y0.x; k2[1] = y0.y; k2[2] = y0.z; k2[3] = y0.w; k2[4] = y1.x; k2[5] = y1.y; k2[6] = y1.z; k2[7] = y1.w;
-  }
   struct Batch {
     uint4 av[TAIL_R], gv[TAIL_R];
     float inv[TAIL_R];
   };
-  auto load = [&](Batch& bt, int rb) {
-#pragma unroll
-    for (int q = 0; q < TAIL_R; ++q) {
-      const int r = min(rb + q, r1 - 1);
-      bt.av[q] = active ? __ldg(reinterpret_cast<const uint4*>(a + (long long)r * D) + tid) : make_uint4(0, 0, 0, 0);
-      bt.gv[q] = active ? __ldg(reinterpret_cast<const uint4*>(g + (long long)r * D) + tid) : make_uint4(0, 0, 0, 0);
-      bt.inv[q] = inv_norm[r];
+  int b = (lo < hi) ? find_segment(seq_off, B, lo) : 0;
+  for (int r0 = lo; r0 < hi;) {
+    while (b + 1 < B && r0 >= __ldg(seq_off + b + 1)) ++b;  // (sequences without rows are stepped over)
+    const int r1 = min(hi, __ldg(seq_off + b + 1));
+    if (active) {
+      const float4* p1 = reinterpret_cast<const float4*>(c1 + (long long)b * D) + 2 * tid;
+      const float4* p2 = reinterpret_cast<const float4*>(c2 + (long long)b * D) + 2 * tid;
+      const float4 x0 = __ldg(p1), x1 = __ldg(p1 + 1), y0 = __ldg(p2), y1 = __ldg(p2 + 1);
+      k1[0] = x0.x; k1[1] = x0.y; k1[2] = x0.z; k1[3] = x0.w; k1[4] = x1.x; k1[5] = x1.y; k1[6] = x1.z; k1[7] = x1.w;
+      k2[0] = y0.x; k2[1] = y0.y; k2[2] = y0.z; k2[3] = y0.w; k2[4] = y1.x; k2[5] = y1.y; k2[6] = y1.z; k2[7] = y1.w;
     }
-  };
-  auto process = [&](const Batch& bt, int rb, int buf) {
-    float dot[TAIL_R];
+    auto load = [&](Batch& bt, int rb) {
 #pragma unroll
-    for (int q = 0; q < TAIL_R; ++q) {
-      float f[8];
-      unpack8<true>(bt.av[q], f);
-      float d = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float y = f[i] * bt.inv[q];
-        d = fmaf(y, fmaf(k2[i], y, k1[i]), d);
+      for (int q = 0; q < TAIL_R; ++q) {
+        const int r = min(rb + q, r1 - 1);
+        bt.av[q] = active ? __ldg(reinterpret_cast<const uint4*>(a + (long long)r * D) + tid) : make_uint4(0, 0, 0, 0);
+        bt.gv[q] = active ? __ldg(reinterpret_cast<const uint4*>(g + (long long)r * D) + tid) : make_uint4(0, 0, 0, 0);
+        bt.inv[q] = inv_norm[r];
       }
-      dot[q] = warp_sum(d);
-    }
-    if (lane == 0) {
+    };
+    auto process = [&](const Batch& bt, int rb, int buf) {
+      float dot[TAIL_R];
 #pragma unroll
-      for (int q = 0; q < TAIL_R; ++q) red[buf][warp][q] = dot[q];
-    }
-    __syncthreads();  // the only barrier per batch: every thread then adds the NWARPS partials itself (smem broadcasts)
-    float totq[TAIL_R];
-#pragma unroll
-    for (int q = 0; q < TAIL_R; ++q) totq[q] = 0.f;
-#pragma unroll
-    for (int w = 0; w < NWARPS; ++w) {
-#pragma unroll
-      for (int q = 0; q < TAIL_R; ++q) totq[q] += red[buf][w][q];
-    }
-#pragma unroll
-    for (int q = 0; q < TAIL_R; ++q) {
-      if (active && rb + q < r1) {
-        const float dt = totq[q];
-        float f[8], gg[8], o[8];
+      for (int q = 0; q < TAIL_R; ++q) {
+        float f[8];
         unpack8<true>(bt.av[q], f);
-        unpack8<true>(bt.gv[q], gg);
+        float d = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float y = f[i] * bt.inv[q];
-          const float dy = fmaf(k2[i], y, k1[i]);
-          o[i] = (dy - y * dt) * bt.inv[q] * gg[i];
-          csum[i] += o[i];
+          d = fmaf(y, fmaf(k2[i], y, k1[i]), d);
         }
-        reinterpret_cast<uint4*>(dz2 + (long long)(rb + q) * D)[tid] =
-            make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+        dot[q] = warp_sum(d);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < TAIL_R; ++q) red[buf][warp][q] = dot[q];
+      }
+      __syncthreads();  // the only barrier per batch: every thread then adds the NWARPS partials itself (smem broadcasts)
+      float totq[TAIL_R];
+#pragma unroll
+      for (int q = 0; q < TAIL_R; ++q) totq[q] = 0.f;
+#pragma unroll
+      for (int w = 0; w < NWARPS; ++w) {
+#pragma unroll
+        for (int q = 0; q < TAIL_R; ++q) totq[q] += red[buf][w][q];
+      }
+#pragma unroll
+      for (int q = 0; q < TAIL_R; ++q) {
+        if (active && rb + q < r1) {
+          const float dt = totq[q];
+          float f[8], gg[8], o[8];
+          unpack8<true>(bt.av[q], f);
+          unpack8<true>(bt.gv[q], gg);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float y = f[i] * bt.inv[q];
+            const float dy = fmaf(k2[i], y, k1[i]);
+            o[i] = (dy - y * dt) * bt.inv[q] * gg[i];
+            csum[i] += o[i];
+          }
+          reinterpret_cast<uint4*>(dz2 + (long long)(rb + q) * D)[tid] =
+              make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+        }
+      }
+    };
+    // double-buffered: the loads of batch i+1 are in flight while batch i is reduced and written
+    __syncthreads();  // the previous sequence's last batch may still be reading red[0]
+    Batch b0, b1;
+    load(b0, r0);
+    for (int rb = r0; rb < r1; rb += 2 * TAIL_R) {
+      if (rb + TAIL_R < r1) load(b1, rb + TAIL_R);
+      process(b0, rb, 0);
+      if (rb + TAIL_R < r1) {
+        if (rb + 2 * TAIL_R < r1) load(b0, rb + 2 * TAIL_R);
+        process(b1, rb + TAIL_R, 1);
       }
     }
-  };
-  // double-buffered: the loads of batch i+1 are in flight while batch i is reduced and written
-  Batch b0, b1;
-  load(b0, r0);
-  for (int rb = r0; rb < r1; rb += 2 * TAIL_R) {
-    if (rb + TAIL_R < r1) load(b1, rb + TAIL_R);
-    process(b0, rb, 0);
-    if (rb + TAIL_R < r1) {
-      if (rb + 2 * TAIL_R < r1) load(b0, rb + 2 * TAIL_R);
-      process(b1, rb + TAIL_R, 1);
-    }
+    r0 = r1;
   }
   if (active && colsum_partial != nullptr) {
-    float4* o = reinterpret_cast<float4*>(colsum_partial + (long long)chunk * D) + 2 * tid;
+    float4* o = reinterpret_cast<float4*>(colsum_partial + (long long)blockIdx.x * D) + 2 * tid;
     o[0] = make_float4(csum[0], csum[1], csum[2], csum[3]);
     o[1] = make_float4(csum[4], csum[5], csum[6], csum[7]);
   }
@@ -778,6 +785,33 @@ parts_colsum_final_kernel(const float* __restrict__ partial, const int* __restri
     for (int y = 0; y < PARTS_Y; ++y) s += sm[y][threadIdx.x];
     if (out_bf16) out_bf16[col] = __float2bfloat16_rn(s);
     if (out_f32) out_f32[col] = s;
+  }
+}
+
+// Both bias gradients of the step in one launch: db = sum of the partial rows of a job, in a fixed order.
+//   job 0 (fc1.bias): partials written by the dgrad GEMM's epilogue, one row per 32 residue rows
+//   job 1 (fc2.bias): partials written by adapter_tail_bwd_kernel, one row per CTA
+// Outputs: fp32 (what the gradient all-reduce carries: a single rounding to bf16 AFTER the mean over ranks) and/or
+// bf16 (what the parameter's .grad holds).  `accumulate`: add to the fp32 output first (micro-batch accumulation).
+__global__ void __launch_bounds__(32 * PARTS_Y)
+bias_grads_final_kernel(BiasJob j0, BiasJob j1, int blocks0) {
+  const bool first = (int)blockIdx.x < blocks0;
+  const BiasJob& j = first ? j0 : j1;
+  const int blk = first ? blockIdx.x : blockIdx.x - blocks0;
+  int nparts;
+  if (j.nparts_dev != nullptr) nparts = min(*j.nparts_dev, j.nparts_max);
+  else nparts = min(((j.n_rows ? min(*j.n_rows, j.n_static) : j.n_static) + j.block_rows - 1) / j.block_rows, j.nparts_max);
+  const int col = blk * 32 + threadIdx.x;
+  __shared__ float sm[PARTS_Y][33];
+  sm[threadIdx.y][threadIdx.x] = (col < j.D) ? sum_parts(j.partial, nparts, j.D, col) : 0.f;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < j.D) {
+    float s = 0.f;
+#pragma unroll
+    for (int y = 0; y < PARTS_Y; ++y) s += sm[y][threadIdx.x];
+    if (j.accumulate && j.out_f32) s += j.out_f32[col];
+    if (j.out_f32) j.out_f32[col] = s;
+    if (j.out_bf16) reinterpret_cast<__nv_bfloat16*>(j.out_bf16)[col] = __float2bfloat16_rn(s);
   }
 }
 
@@ -1084,28 +1118,42 @@ int loss_bwd_coef(const float* dS, const float* t, const float* p, const float* 
   return check_launch("loss_bwd_coef_kernel", st);
 }
 
-int adapter_tail_backward(const void* a, const void* g, const float* inv_norm, const int* seq_off, const int* chunk_off,
-                          const int* chunk_seq, int B, const float* c1, const float* c2, const int* n_rows, int cap, int D,
-                          int rc, int max_chunks, void* dz2, float* colsum_partial, void* db2, cudaStream_t st) {
+int adapter_tail_backward(const void* a, const void* g, const float* inv_norm, const int* seq_off, int B, const float* c1,
+                          const float* c2, const int* n_rows, int cap, int D, void* dz2, float* colsum_partial, int ws_rows,
+                          int* nparts_dev, void* db2, cudaStream_t st) {
   if (D % 8 || D > 8192) return set_error(-1, "adapter_tail_backward: D must be a multiple of 8 and <= 8192");
   const __half* ap = reinterpret_cast<const __half*>(a);
   const __half* gp = reinterpret_cast<const __half*>(g);
   __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(dz2);
-  const int grid = max_chunks + 8;
-  if (D <= 2048)
-    adapter_tail_bwd_kernel<256><<<grid, 256, 0, st>>>(ap, gp, inv_norm, seq_off, chunk_off, chunk_seq, B, c1, c2, n_rows, cap, D, rc, op, colsum_partial);
-  else if (D <= 4096)
-    adapter_tail_bwd_kernel<512><<<grid, 512, 0, st>>>(ap, gp, inv_norm, seq_off, chunk_off, chunk_seq, B, c1, c2, n_rows, cap, D, rc, op, colsum_partial);
+  const int threads = D <= 2048 ? 256 : (D <= 4096 ? 512 : 1024);
+  int grid = sm_count() * std::max(1, 512 / threads);
+  if (colsum_partial != nullptr) {
+    if (ws_rows < 1 || nparts_dev == nullptr) return set_error(-1, "adapter_tail_backward: the column-sum workspace needs rows and a count word");
+    grid = std::min(grid, ws_rows);
+  }
+  grid = std::max(1, std::min(grid, (cap + 2 * TAIL_R - 1) / (2 * TAIL_R)));
+  if (threads == 256)
+    adapter_tail_bwd_kernel<256><<<grid, 256, 0, st>>>(ap, gp, inv_norm, seq_off, B, c1, c2, n_rows, cap, D, op, colsum_partial, nparts_dev);
+  else if (threads == 512)
+    adapter_tail_bwd_kernel<512><<<grid, 512, 0, st>>>(ap, gp, inv_norm, seq_off, B, c1, c2, n_rows, cap, D, op, colsum_partial, nparts_dev);
   else
-    adapter_tail_bwd_kernel<1024><<<grid, 1024, 0, st>>>(ap, gp, inv_norm, seq_off, chunk_off, chunk_seq, B, c1, c2, n_rows, cap, D, rc, op, colsum_partial);
+    adapter_tail_bwd_kernel<1024><<<grid, 1024, 0, st>>>(ap, gp, inv_norm, seq_off, B, c1, c2, n_rows, cap, D, op, colsum_partial, nparts_dev);
   if (int r = check_launch("adapter_tail_bwd_kernel", st)) return r;
   if (db2 != nullptr) {
     if (!colsum_partial) return set_error(-1, "adapter_tail_backward: db2 needs the partial workspace");
-    parts_colsum_final_kernel<<<(D + 31) / 32, dim3(32, PARTS_Y), 0, st>>>(colsum_partial, chunk_off, B, nullptr, 0, D,
-                                                                     reinterpret_cast<__nv_bfloat16*>(db2), nullptr);
-    return check_launch("parts_colsum_final_kernel", st);
+    BiasJob none{};
+    BiasJob j{};
+    j.partial = colsum_partial; j.D = D; j.nparts_dev = nparts_dev; j.nparts_max = ws_rows; j.out_bf16 = db2;
+    return bias_grads_final(none, j, st);
   }
   return 0;
+}
+
+int bias_grads_final(const BiasJob& j0, const BiasJob& j1, cudaStream_t st) {
+  const int blocks0 = j0.partial ? (j0.D + 31) / 32 : 0, blocks1 = j1.partial ? (j1.D + 31) / 32 : 0;
+  if (blocks0 + blocks1 == 0) return 0;
+  bias_grads_final_kernel<<<blocks0 + blocks1, dim3(32, PARTS_Y), 0, st>>>(j0, j1, blocks0);
+  return check_launch("bias_grads_final_kernel", st);
 }
 
 template <int NV>

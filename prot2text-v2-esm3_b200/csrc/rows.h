@@ -25,9 +25,23 @@ int l2norm_forward(const float* e, int B, int E, void* p_bf16, float* p_f32, flo
 int l2norm_backward(const float* dp, const float* p, const float* norm, int B, int E, float* de, cudaStream_t st);
 int pool_bwd_coef(const float* de, long long ld_de, const float* stats, long long ld_stats, const int* seq_off, int B,
                   int D, int mode, float* c1, float* c2, cudaStream_t st);
-int adapter_tail_backward(const void* a, const void* g, const float* inv_norm, const int* seq_off, const int* chunk_off,
-                          const int* chunk_seq, int B, const float* c1, const float* c2, const int* n_rows, int cap, int D,
-                          int rc, int max_chunks, void* dz2, float* colsum_partial, void* db2, cudaStream_t st);
+// one column-sum job of bias_grads_final (rows.cu)
+struct BiasJob {
+  const float* partial;   // [nparts][D] partial rows (nullptr: no job)
+  int D;
+  const int* nparts_dev;  // device count of partial rows, or nullptr: ceil(min(*n_rows, n_static) / block_rows)
+  int nparts_max;         // rows physically present in `partial`
+  const int* n_rows;
+  int n_static;
+  int block_rows;
+  void* out_bf16;         // optional
+  float* out_f32;         // optional
+  int accumulate;         // add to out_f32 before storing
+};
+int bias_grads_final(const BiasJob& j0, const BiasJob& j1, cudaStream_t st);
+int adapter_tail_backward(const void* a, const void* g, const float* inv_norm, const int* seq_off, int B, const float* c1,
+                          const float* c2, const int* n_rows, int cap, int D, void* dz2, float* colsum_partial, int ws_rows,
+                          int* nparts_dev, void* db2, cudaStream_t st);
 int adapter_tail_backward_dy(const void* a, const void* g, const float* inv_norm, const void* dy, int n,
                              const int* n_dev, int cap, int D, void* dz2, cudaStream_t st);
 int scale_rows(const void* a, const float* rowsq, int nblk, int cap, int n, int D, void* y, float* inv_norm_out,
@@ -64,7 +78,18 @@ int peer_close(void* dptr);
 int peer_free(void* dptr);
 int peer_allgather(void* const* peers, int world, int rank, const void* src, long long bytes_per_rank, void* dst,
                    int phases, cudaStream_t st);
-int peer_allreduce_mean(void* const* peers, int world, int rank, long long n_bytes, void* dst, int phases, cudaStream_t st);
+int peer_allreduce_mean(void* const* peers, int world, int rank, long long n_bytes, long long f32_from_byte, void* dst, int phases,
+                        cudaStream_t st);
+int peer_reset(void* base, cudaStream_t st);
+
+// loss_fused.cu: similarity -> InfoNCE -> pooling coefficients of the backward pass in one cooperative kernel
+bool loss_fused_eligible(int R, int B, int C, int E);
+int loss_fused(const float* p, const float* t, void* const* peers, int world, int rank, long long bytes_per_rank,
+               const int* labels, int R, int B, int C, int E, float tau, float w_row, float w_col, float scale,
+               int all_cols_labelled, int want_col, int need_grad, const float* dloss, const float* pnorm,
+               const float* stats, const int* seq_off, float* S_ws, float* dp_ws, unsigned* bar_ws, float* loss,
+               float* row_lse, int* argmax_row, int* argmax_col, float* col_max, float* col_sum, float* c1, float* c2,
+               cudaStream_t st);
 
 // optim.cu: clip_grad_norm_ + AdamW over a table of tensors
 constexpr int kAdamMaxTensors = 8;

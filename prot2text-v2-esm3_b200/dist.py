@@ -15,6 +15,7 @@ gradient of the global-batch mean loss.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -130,13 +131,19 @@ def distributed_contrastive_step(residue_states, protein_mask, adapter, text_hid
         rank, world = exchange.rank, exchange.world
     else:
         rank, world = dist.get_rank(group), dist.get_world_size(group)
-    t_local = _step.text_embeddings(text_hidden, text_mask, dtype=torch.float32, text_lengths=text_lengths)
-    # the gather travels behind the protein side's kernels; the NCCL form is waited for right before the (persistent,
-    # one-CTA-per-SM) adapter GEMMs, the in-stream peer-memory arrive right before the similarity
+    # the gather travels behind the protein side's kernels.  Peer-memory form: text branch and push run on the side
+    # stream, which joins in front of the (persistent, one-CTA-per-SM) adapter GEMMs; the loss kernel waits for the
+    # gathered rows itself and reads them in place (or, symmetric form, an arrive kernel right before the similarity).
+    # NCCL form: the collective is waited for right before the adapter GEMMs.
+    text_join = None
     if exchange is not None:
-        exchange.text.push(t_local)
-        t_global = exchange.text.arrive
+        if os.environ.get("P2T_TEXT_STREAM", "1") != "0":
+            _, text_join = _step._text_branch(text_hidden, text_mask, text_lengths, after=exchange.text.push)
+        else:
+            exchange.text.push(_step.text_embeddings(text_hidden, text_mask, dtype=torch.float32, text_lengths=text_lengths))
+        t_global = exchange.text
     else:
+        t_local = _step.text_embeddings(text_hidden, text_mask, dtype=torch.float32, text_lengths=text_lengths)
         t_global = all_gather_embeddings(t_local, group, async_op=True) if world > 1 else t_local
     B = residue_lengths.shape[0] if residue_lengths is not None else residue_states.shape[0]
     labels = _step._rank_labels(rank, B, residue_states.device)
@@ -149,4 +156,4 @@ def distributed_contrastive_step(residue_states, protein_mask, adapter, text_hid
                                   residue_lengths=residue_lengths,
                                   temperature=temperature, symmetric=symmetric, labels=labels, aux=aux,
                                   col_stats_hook=hook, all_cols_labelled=symmetric and world > 1,
-                                  late_text=exchange is not None, **step_kw)
+                                  late_text=exchange is not None, _text_join=text_join, **step_kw)

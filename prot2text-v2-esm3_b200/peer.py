@@ -19,6 +19,7 @@ pass the 64-byte IPC handles around.
 from __future__ import annotations
 
 import ctypes as C
+import math
 from typing import List, Optional, Sequence
 
 import torch
@@ -38,6 +39,23 @@ def _rank_world(group) -> tuple:
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(group), dist.get_world_size(group)
     return 0, 1
+
+
+class _RawCuda:
+    """Minimal __cuda_array_interface__ carrier: lets torch alias device memory it did not allocate."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2,
+                                         "strides": None}
+
+
+def raw_view(ptr: int, nbytes: int, dtype, shape, owner) -> torch.Tensor:
+    """A torch tensor aliasing `nbytes` of device memory at `ptr` (a region of a peer buffer, which is cudaMalloc'ed by
+    the library because it must be exportable over CUDA IPC); `owner` is kept alive by the tensor."""
+    t = torch.as_tensor(_RawCuda(ptr, nbytes), device=torch.device("cuda", torch.cuda.current_device()))
+    t = t.view(dtype).view(shape)
+    t._p2t_owner = owner
+    return t
 
 
 class PeerBuffer:
@@ -103,7 +121,19 @@ class PeerBuffer:
     def check(self) -> None:
         s = self.status()
         if s:
-            raise _lib.P2TError(f"rank {self.rank}: timed out waiting for the peer-memory flag of rank {s - 1}")
+            raise _lib.P2TError(f"rank {self.rank}: timed out waiting for the peer-memory flag of rank {s - 1}; the "
+                                "round's results were poisoned with NaN.  Call reset() on every rank to resynchronise")
+
+    def reset(self) -> None:
+        """Collective: bring the channel's control block (epochs, counters, status, flags) back to zero on every rank
+        after a timed-out round, so that pushes and arrivals pair up again."""
+        torch.cuda.synchronize()
+        if self.world > 1 and dist.is_initialized() and not hasattr(self, "_keepalive"):
+            dist.barrier(group=self.group)
+        _lib.call("p2t_peer_reset", self.base, _stream())
+        torch.cuda.synchronize()
+        if self.world > 1 and dist.is_initialized() and not hasattr(self, "_keepalive"):
+            dist.barrier(group=self.group)
 
     def close(self) -> None:
         for p in self._opened:
@@ -128,6 +158,7 @@ class PeerAllGather:
         rank, world = (_buffer.rank, _buffer.world) if _buffer is not None else _rank_world(group)
         self.buffer = _buffer if _buffer is not None else PeerBuffer(ctrl + 2 * world * self.bytes_per_rank, group)
         self.rank, self.world = rank, world
+        self._pushed = False  # host-side pairing guard: every push is followed by exactly one arrival
 
     @staticmethod
     def buffer_bytes(rows: int, cols: int, dtype, world: int) -> int:
@@ -136,17 +167,34 @@ class PeerAllGather:
     def push(self, src: torch.Tensor) -> None:
         if src.shape != (self.rows, self.cols) or src.dtype != self.dtype or not src.is_cuda:
             raise ValueError(f"expected a CUDA {self.dtype} tensor of shape {(self.rows, self.cols)}, got {tuple(src.shape)} {src.dtype}")
+        if self._pushed:
+            raise _lib.P2TError("PeerAllGather.push: the previous round was never closed by arrive() — an exception "
+                                "between push and arrive leaves the ranks out of step; call buffer.reset() on every rank")
         src = src.contiguous()
         _lib.call("p2t_peer_allgather", self.buffer.table, self.world, self.rank, src.data_ptr(), self.bytes_per_rank,
                   None, _PUSH, _stream())
         self._src_keepalive = src
+        self._pushed = True
 
     def arrive(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if not self._pushed:
+            raise _lib.P2TError("PeerAllGather.arrive without a push in this round")
         if out is None:
             out = torch.empty(self.world * self.rows, self.cols, dtype=self.dtype, device="cuda")
         _lib.call("p2t_peer_allgather", self.buffer.table, self.world, self.rank, None, self.bytes_per_rank,
                   out.data_ptr(), _ARRIVE, _stream())
+        self._pushed = False
         return out
+
+    def note_arrived(self) -> None:
+        """The round was closed by a kernel that waited for the flags itself (the fused loss kernel)."""
+        if not self._pushed:
+            raise _lib.P2TError("PeerAllGather: arrival without a push in this round")
+        self._pushed = False
+
+    def reset(self) -> None:
+        self._pushed = False
+        self.buffer.reset()
 
     def __call__(self, src: torch.Tensor) -> torch.Tensor:
         self.push(src)
@@ -157,55 +205,104 @@ class PeerAllGather:
 
 
 class PeerGradAllReduce:
-    """grads := mean over ranks, for a fixed list of bf16 tensors (the adapter's fc1/fc2 weights and biases).
+    """grads := mean over ranks, for a fixed list of tensors (the adapter's fc1/fc2 weights and biases).
 
     Two-shot over peer memory: rank k reduces slice k of the flattened gradients out of every peer's buffer in fp32,
-    in rank order, and stores the bf16 mean into every peer's result area — all ranks end with identical bits."""
+    in rank order, and stores the mean into every peer's result area — all ranks end with identical bits.
+    bfloat16 tensors travel and return as bf16; float32 tensors (the bias gradients of the fused step) travel and
+    return in fp32, so they are rounded to bf16 once, after the mean.
+
+    Zero-copy form: `views_in()` are tensors aliasing this rank's contribution area — let the backward kernels write
+    the gradients there — then `exchange()` runs the three phases and `views_out()` alias the reduced result."""
 
     def __init__(self, like: Sequence[torch.Tensor], group=None, _buffer: Optional[PeerBuffer] = None):
         self.shapes = [tuple(t.shape) for t in like]
-        self.offsets = []
-        off = 0
+        self.dtypes = [t.dtype for t in like]
         for t in like:
-            if t.dtype != torch.bfloat16:
-                raise _lib.P2TError("PeerGradAllReduce reduces bfloat16 gradients")
-            self.offsets.append(off)
-            off += (t.numel() * 2 + 15) // 16 * 16
+            if t.dtype not in (torch.bfloat16, torch.float32):
+                raise _lib.P2TError("PeerGradAllReduce reduces bfloat16 or float32 gradients")
+        self.offsets = [0] * len(like)
+        off = 0
+        for want in (torch.bfloat16, torch.float32):  # all bf16 tensors first, then the fp32 ones
+            if want == torch.float32:
+                self.f32_from = off
+            for i, t in enumerate(like):
+                if t.dtype == want:
+                    self.offsets[i] = off
+                    off += (t.numel() * t.element_size() + 15) // 16 * 16
         self.n_bytes = off
         self.ctrl = int(_lib.load().p2t_peer_ctrl_bytes())
         rank, world = (_buffer.rank, _buffer.world) if _buffer is not None else _rank_world(group)
         self.buffer = _buffer if _buffer is not None else PeerBuffer(self.ctrl + 2 * self.n_bytes, group)
         self.rank, self.world = rank, world
+        self._in = self._out = None
+
+    @staticmethod
+    def adapter_like(adapter) -> List[torch.Tensor]:
+        """[dW1 bf16, db1 fp32, dW2 bf16, db2 fp32] (meta tensors): what the fused step's backward produces."""
+        w1, w2 = adapter.fc1.weight, adapter.fc2.weight
+        bf, f32 = torch.bfloat16, torch.float32
+        return [torch.empty(tuple(w1.shape), dtype=bf, device="meta"), torch.empty(w1.shape[0], dtype=f32, device="meta"),
+                torch.empty(tuple(w2.shape), dtype=bf, device="meta"), torch.empty(w2.shape[0], dtype=f32, device="meta")]
+
+    @classmethod
+    def for_adapter(cls, adapter, group=None, _buffer: Optional[PeerBuffer] = None) -> "PeerGradAllReduce":
+        """The reducer `graph.GraphedContrastiveStep(grad_reducer=...)` expects: weights in bf16, biases in fp32."""
+        return cls(cls.adapter_like(adapter), group, _buffer)
 
     @staticmethod
     def buffer_bytes(like: Sequence[torch.Tensor]) -> int:
-        n = sum((t.numel() * 2 + 15) // 16 * 16 for t in like)
+        n = sum((t.numel() * t.element_size() + 15) // 16 * 16 for t in like)
         return int(_lib.load().p2t_peer_ctrl_bytes()) + 2 * n
+
+    def _views(self, base_off: int):
+        return [raw_view(self.buffer.base + base_off + off, math.prod(shape) * torch.empty((), dtype=dt).element_size(),
+                         dt, shape, self.buffer)
+                for shape, dt, off in zip(self.shapes, self.dtypes, self.offsets)]
+
+    def views_in(self):
+        if self._in is None:
+            self._in = self._views(self.ctrl)
+        return self._in
+
+    def views_out(self):
+        if self._out is None:
+            self._out = self._views(self.ctrl + self.n_bytes)
+        return self._out
 
     def _check(self, grads):
         if len(grads) != len(self.shapes):
             raise ValueError("gradient list does not match the tensors this reducer was built for")
-        for g, s in zip(grads, self.shapes):
-            if tuple(g.shape) != s or g.dtype != torch.bfloat16 or not g.is_cuda or not g.is_contiguous():
-                raise ValueError("gradients must be contiguous CUDA bfloat16 tensors of the registered shapes")
+        for g, s, dt in zip(grads, self.shapes, self.dtypes):
+            if tuple(g.shape) != s or g.dtype != dt or not g.is_cuda or not g.is_contiguous():
+                raise ValueError("gradients must be contiguous CUDA tensors of the registered shapes and dtypes")
+
+    def _phase(self, bits: int) -> None:
+        _lib.call("p2t_peer_allreduce_mean", self.buffer.table, self.world, self.rank, self.n_bytes, self.f32_from,
+                  None, bits, _stream())
 
     def stage(self, grads: Sequence[torch.Tensor]) -> None:
         """Copy this rank's gradients into its channel buffer and announce them (phase 0)."""
         self._check(grads)
         st = _stream()
         for g, off in zip(grads, self.offsets):
-            _lib.call("p2t_copy_d2d", self.buffer.base + self.ctrl + off, g.data_ptr(), g.numel() * 2, st)
-        _lib.call("p2t_peer_allreduce_mean_bf16", self.buffer.table, self.world, self.rank, self.n_bytes, None, _READY, st)
+            _lib.call("p2t_copy_d2d", self.buffer.base + self.ctrl + off, g.data_ptr(), g.numel() * g.element_size(), st)
+        self._phase(_READY)
 
     def reduce(self) -> None:
-        _lib.call("p2t_peer_allreduce_mean_bf16", self.buffer.table, self.world, self.rank, self.n_bytes, None, _REDUCE, _stream())
+        self._phase(_REDUCE)
 
     def finish(self, grads: Sequence[torch.Tensor]) -> None:
         """Wait for every slice of the mean and copy it over `grads` (phase 2)."""
         st = _stream()
-        _lib.call("p2t_peer_allreduce_mean_bf16", self.buffer.table, self.world, self.rank, self.n_bytes, None, _WAIT, st)
+        self._phase(_WAIT)
         for g, off in zip(grads, self.offsets):
-            _lib.call("p2t_copy_d2d", g.data_ptr(), self.buffer.base + self.ctrl + self.n_bytes + off, g.numel() * 2, st)
+            _lib.call("p2t_copy_d2d", g.data_ptr(), self.buffer.base + self.ctrl + self.n_bytes + off,
+                      g.numel() * g.element_size(), st)
+
+    def exchange(self) -> None:
+        """Zero-copy form: the contribution is already in `views_in()`; after this call `views_out()` hold the mean."""
+        self._phase(_READY | _REDUCE | _WAIT)
 
     def reduce_(self, grads: Sequence[torch.Tensor]) -> Sequence[torch.Tensor]:
         self.stage(grads)
@@ -214,4 +311,5 @@ class PeerGradAllReduce:
         return grads
 
     def close(self) -> None:
+        self._in = self._out = None
         self.buffer.close()

@@ -9,14 +9,20 @@ the point where the two frozen trunks have produced their outputs:
     loss          : SegmentedBatchInfoNCELoss per segment, averaged (:356-379)
 
 Differences in HOW (not what): the padded (B, L, D_in) batch is packed to its valid rows on the
-device (no host sync), both adapter GEMMs run once over all rows (the segment loop only bounded
-memory in the reference; with equal segments the average of segment means IS the batch mean), and
-the handoffs between stages stay in fp32.
+device (no host sync), both adapter GEMMs run once over all rows, and the handoffs between stages
+stay in fp32.  With equal segments the average of the segment means IS the batch mean, so the
+segment loop itself costs nothing to drop.  What the loop DOES change in this fork is the pooling
+mask: `get_sequence_embeddings` (:251-281) encodes every segment on its own, padded
+to the segment's longest sequence, and pools with an all-ones mask over that length — pad rows
+included.  The mask is an input of this module; `segment_pooling_mask` builds the fork's mask from
+the sequence lengths, `protein_mask` = the true attention mask pools valid residues only.
 """
 from __future__ import annotations
 
 from dataclasses import dataclass
 from typing import Optional
+
+import os
 
 import torch
 
@@ -59,8 +65,29 @@ def text_embeddings(text_hidden: torch.Tensor, text_mask: Optional[torch.Tensor]
     return t_f32 if want_f32 else t_bf
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    """One extra stream per device for the text branch of the step (it does not depend on the protein side until the
+    similarity, so its launch-latency-bound kernels run beside the residue-row packing instead of in front of it)."""
+    key = str(device)
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return st
+
+
+def _is_gather(t_in) -> bool:
+    return hasattr(t_in, "note_arrived") and hasattr(t_in, "buffer")
+
+
 def step_forward(x, prot_mask, w1, b1, w2, b2, t_in, labels, cfg: dict, aux: StepAux, need_grad: bool):
-    """Forward of the fused step on raw tensors (no autograd): returns (loss, state for step_backward or None)."""
+    """Forward of the fused step on raw tensors (no autograd): returns (loss, state for step_backward or None).
+
+    `t_in`: the unit-norm text embeddings (fp32 or bf16 tensor), a zero-argument callable returning them, or a
+    `peer.PeerAllGather` whose push half has been issued (sharded step): the loss kernel then waits for the gathered
+    rows itself and reads them in place."""
     for t, name in ((x, "residue states"), (w1, "fc1.weight"), (b1, "fc1.bias"), (w2, "fc2.weight"), (b2, "fc2.bias")):
         _core.require_cuda_bf16(t, name)
     d_out = w2.shape[0]
@@ -74,31 +101,52 @@ def step_forward(x, prot_mask, w1, b1, w2, b2, t_in, labels, cfg: dict, aux: Ste
         plan = _core.plan_rows(prot_mask)
         xp = _core.gather_rows(x.contiguous().view(B * L, d_in), plan)
         x_rows = plan.rows_cap
-    if callable(t_in) and not cfg.get("late_text", False):
-        # deferred text embeddings (the NCCL all-gather of the sharded step): the collective has been running on its
-        # own stream behind the plan/pack kernels above; it must be OVER before the persistent GEMMs start — they
-        # assume one CTA per SM, and a communication kernel still holding SMs delays a whole tile share (measured:
-        # fc1 163 -> 250 us)
-        t_in = t_in()
+    join = cfg.get("text_join")
+    if join is not None:
+        # the text branch ran on the side stream beside the plan / pack kernels above; it must be OVER before the
+        # persistent GEMMs start — they assume one CTA per SM, and another kernel still holding SMs delays a whole
+        # tile share (measured with an NCCL kernel: fc1 163 -> 250 us)
+        join()
+    if callable(t_in) and not _is_gather(t_in) and not cfg.get("late_text", False):
+        t_in = t_in()  # deferred text embeddings (NCCL all-gather of the sharded step), same reason
     acts = _core.adapter_forward(xp, x_rows, plan.rows_cap, plan.n_rows, w1c, b1c, w2c, b2c,
                                  cfg["dropout_p"], cfg["seed"], need_grad, seed_dev=cfg.get("seed_dev"))
     inv_norm = _core.row_inv_norm(acts)
     stats, p_bf, p_f32, pnorm = _core.pool_forward(acts.a, plan, d_out, row_src=None, inv_norm=inv_norm, normalize=True)
-    if callable(t_in):
+    used = cfg["rows_used"]
+    hook = cfg.get("col_stats_hook")
+    E = 2 * d_out
+    fused = None
+    if hook is None and os.environ.get("P2T_FUSED_LOSS", "1") != "0":
+        if _is_gather(t_in):
+            if _core.loss_fused_eligible(used, plan.B, t_in.world * t_in.rows, E):
+                fused = dict(t_f32=None, gather=t_in)
+        elif torch.is_tensor(t_in) and t_in.dtype == torch.float32 and _core.loss_fused_eligible(used, plan.B, t_in.shape[0], E):
+            fused = dict(t_f32=t_in.contiguous(), gather=None)
+    if fused is not None:
+        # similarity -> online-softmax CE -> dLogits -> pooling coefficients: one cooperative kernel
+        res = _core.loss_fused(p_f32, fused["t_f32"], labels[:used], used, cfg["tau"], w_row=cfg["w_row"], w_col=cfg["w_col"],
+                               loss_scale=cfg.get("loss_scale"), all_cols_labelled=cfg.get("all_cols_labelled", False),
+                               need_grad=need_grad, dloss=cfg.get("dloss_dev"), pnorm=pnorm, stats=stats,
+                               seq_off=plan.seq_off, gather=fused["gather"])
+        aux.protein_embeddings, aux.text_embeddings = p_bf, fused["t_f32"]
+        aux.argmax_row, aux.argmax_col, aux.n_rows = res.argmax_row, res.argmax_col, plan.n_rows
+        state = (plan, acts, inv_norm, w1c, w2c, cfg, ("coef", res.c1, res.c2)) if need_grad else None
+        return res.loss, state
+    if _is_gather(t_in):
+        t_in = t_in.arrive()
+    elif callable(t_in):
         # peer-memory exchange: its arrive kernel runs IN this stream (it never overlaps the GEMMs), so it is placed
-        # where the gathered rows are first needed.  The peers' pushes were issued at the start of their steps: every
-        # rank may lag the fastest one by the whole adapter forward (~0.45 ms at config 2) before anybody waits.
+        # where the gathered rows are first needed.
         t_in = t_in()
     if t_in.dtype == torch.float32:
         t_f32 = t_in.contiguous()
         # the bf16 copy is an operand of the tensor-core loss path only (large similarity blocks)
-        big = cfg["rows_used"] * t_f32.shape[0] * t_f32.shape[1] > (1 << 26)
+        big = used * t_f32.shape[0] * t_f32.shape[1] > (1 << 26)
         t_bf = _core.to_bf16(t_f32) if big else None
     else:
         _core.require_cuda_bf16(t_in, "text_embeds")
         t_f32, t_bf = None, t_in.contiguous()
-    used = cfg["rows_used"]
-    hook = cfg.get("col_stats_hook")
     res = _core.infonce_forward(p_bf[:used], t_bf if t_bf is not None else t_f32, labels[:used], cfg["tau"],
                                 w_row=cfg["w_row"], w_col=cfg["w_col"],
                                 need_grad=need_grad, want_col_argmax=True, col_stats_hook=hook,
@@ -107,35 +155,52 @@ def step_forward(x, prot_mask, w1, b1, w2, b2, t_in, labels, cfg: dict, aux: Ste
                                 all_cols_labelled=cfg.get("all_cols_labelled", False))
     aux.protein_embeddings, aux.text_embeddings = p_bf, (t_bf if t_bf is not None else t_f32)
     aux.argmax_row, aux.argmax_col, aux.n_rows = res.argmax_row, res.argmax_col, plan.n_rows
-    state = (plan, acts, stats, inv_norm, p_bf, p_f32, pnorm, res, t_bf, t_f32, w1c, w2c, cfg) if need_grad else None
+    state = (plan, acts, inv_norm, w1c, w2c, cfg, ("logits", stats, p_bf, p_f32, pnorm, res, t_bf, t_f32)) if need_grad else None
     return res.loss, state
 
 
-def step_backward(state, dloss: Optional[torch.Tensor]):
-    """Backward of the fused step: (dW1, db1, dW2, db2) in bf16 for the upstream gradient `dloss` (device scalar;
-    None = 1)."""
-    plan, acts, stats, inv_norm, p_bf, p_f32, pnorm, res, t_bf, t_f32, w1c, w2c, cfg = state
+def step_backward(state, dloss: Optional[torch.Tensor], *, accumulate: bool = False, dw_out: Optional[tuple] = None,
+                  db_f32_out: Optional[tuple] = None, db_bf16_out: Optional[tuple] = None):
+    """Backward of the fused step: (dW1, db1, dW2, db2, db1_f32, db2_f32) — bf16 gradients in nn.Linear layout plus
+    the bias gradients in fp32 (what a gradient all-reduce should carry) — for the upstream gradient `dloss` (device
+    scalar; None = 1).  `dw_out` = (dW1, dW2) / `db_f32_out` / `db_bf16_out`: write into the caller's tensors;
+    `accumulate`: add to them (bf16 read-modify-write for the weights, fp32 for the biases) — the micro-batch
+    accumulation of scripts/train_contrast.py:448-465."""
+    plan, acts, inv_norm, w1c, w2c, cfg, head = state
     used = cfg["rows_used"]
     d_out = w2c.shape[0]
+    d_mid = w1c.shape[0]
     dl = None if dloss is None else dloss.to(torch.float32).contiguous()
-    if t_f32 is not None and res.dS_bf16 is None:
-        # small similarity block with fp32 embeddings: dLogits -> (c1, c2) in one kernel
-        c1, c2 = _core.loss_backward_coef(res, t_f32, p_f32, pnorm, stats, plan, d_out, cfg["tau"], dl)
+    if head[0] == "coef":
+        _, c1, c2 = head
+        if dl is not None:  # the coefficients were formed for an upstream gradient of 1 (or cfg['dloss_dev']): linear in it
+            c1, c2 = c1 * dl, c2 * dl
     else:
-        dp_used, _ = _core.infonce_backward(res, p_bf[:used], t_bf, cfg["tau"], need_dp=True, need_dt=False,
-                                            p_f32=p_f32[:used] if t_f32 is not None else None, t_f32=t_f32)
-        if used == p_bf.shape[0]:
-            dp = dp_used
-        else:  # rows dropped by the segment split get no gradient (reference :337, :357-359)
-            dp = torch.zeros_like(p_f32)
-            dp[:used] = dp_used
-        if dl is not None:
-            dp.mul_(dl)
-        de = _core.l2norm_backward(dp, p_f32, pnorm)
-        c1, c2 = _core.pool_backward_coef(de, stats, plan, d_out, "mix")
-    dz2, db2 = _core.adapter_tail_backward(acts, inv_norm, plan, c1, c2)
-    dw1, db1, dw2, _, _ = _core.adapter_backward(acts, dz2, w1c, w2c, need_db2=False)
-    return dw1, db1, dw2, db2
+        _, stats, p_bf, p_f32, pnorm, res, t_bf, t_f32 = head
+        if cfg.get("dloss_dev") is not None:
+            dl = cfg["dloss_dev"] if dl is None else dl * cfg["dloss_dev"]
+        if t_f32 is not None and res.dS_bf16 is None:
+            # small similarity block with fp32 embeddings: dLogits -> (c1, c2) in two kernels
+            c1, c2 = _core.loss_backward_coef(res, t_f32, p_f32, pnorm, stats, plan, d_out, cfg["tau"], dl)
+        else:
+            dp_used, _ = _core.infonce_backward(res, p_bf[:used], t_bf, cfg["tau"], need_dp=True, need_dt=False,
+                                                p_f32=p_f32[:used] if t_f32 is not None else None, t_f32=t_f32)
+            if used == p_bf.shape[0]:
+                dp = dp_used
+            else:  # rows dropped by the segment split get no gradient (reference :337, :357-359)
+                dp = torch.zeros_like(p_f32)
+                dp[:used] = dp_used
+            if dl is not None:
+                dp.mul_(dl)
+            de = _core.l2norm_backward(dp, p_f32, pnorm)
+            c1, c2 = _core.pool_backward_coef(de, stats, plan, d_out, "mix")
+    dz2, (ws2, nparts2) = _core.adapter_tail_backward(acts, inv_norm, plan, c1, c2, finish_db2=False)
+    dw1_out, dw2_out = dw_out if dw_out is not None else (None, None)
+    dw1, ws1, dw2, _, _ = _core.adapter_backward(acts, dz2, w1c, w2c, need_db2=False, need_db1=False,
+                                                 accumulate=accumulate, dw1_out=dw1_out, dw2_out=dw2_out)
+    db1, db2, db1_f32, db2_f32 = _core.bias_grads(ws1, acts.rows_cap, acts.n_rows, d_mid, ws2, nparts2, d_out,
+                                                  accumulate=accumulate, out_f32=db_f32_out, out_bf16=db_bf16_out)
+    return dw1, db1, dw2, db2, db1_f32, db2_f32
 
 
 class _ContrastiveStepFunction(torch.autograd.Function):
@@ -148,7 +213,7 @@ class _ContrastiveStepFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dloss):
         state, ctx.state = ctx.state, None
-        dw1, db1, dw2, db2 = step_backward(state, dloss)
+        dw1, db1, dw2, db2, _, _ = step_backward(state, dloss)
         return None, None, dw1, db1, dw2, db2, None, None, None, None
 
 
@@ -173,6 +238,45 @@ def _rank_labels(rank: int, n: int, device) -> torch.Tensor:
     return t
 
 
+def _text_branch(text_hidden, text_mask, text_lengths, after=None):
+    """Run `text_embeddings` (fp32) — and `after(t)` if given — on the device's side stream; returns (embeddings,
+    join) where join() makes the current stream wait for the branch."""
+    dev = text_hidden.device
+    side, cur = _side_stream(dev), torch.cuda.current_stream(dev)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        t = text_embeddings(text_hidden, text_mask, dtype=torch.float32, text_lengths=text_lengths)
+        if after is not None:
+            after(t)
+
+    def join():
+        now = torch.cuda.current_stream(dev)
+        now.wait_stream(side)
+        t.record_stream(now)  # allocated on the side stream, consumed on this one
+    return t, join
+
+
+def segment_pooling_mask(lengths, num_segments: int, total_len: Optional[int] = None, device=None) -> torch.Tensor:
+    """The protein pooling mask the fork's step EFFECTIVELY uses (scripts/train_contrast.py:251-281 with
+    :356-377): segment s = rows [s*seg, (s+1)*seg) is encoded on its own, zero-padded to ITS longest sequence, and
+    pooled with an all-ones mask over that length.  Row b of the result is therefore 1 on [0, max length of b's
+    segment) — pad rows of shorter sequences included.  Rows beyond the last whole segment (dropped by the loss,
+    :337) keep their own length.  `lengths`: (B,) ints; returns int64 (B, total_len or max(lengths))."""
+    lens = [int(v) for v in (lengths.tolist() if torch.is_tensor(lengths) else lengths)]
+    B = len(lens)
+    seg = B // num_segments
+    L = int(total_len) if total_len is not None else max(lens)
+    mask = torch.zeros(B, L, dtype=torch.long)
+    for b in range(B):
+        if seg > 0 and b < seg * num_segments:
+            s = b // seg
+            n = max(lens[s * seg:(s + 1) * seg])
+        else:
+            n = lens[b]
+        mask[b, :min(n, L)] = 1
+    return mask.to(device) if device is not None else mask
+
+
 def contrastive_step(residue_states: torch.Tensor, protein_mask: Optional[torch.Tensor], adapter: ModalityAdapter,
                      text_hidden: Optional[torch.Tensor] = None, text_mask: Optional[torch.Tensor] = None, *,
                      residue_lengths: Optional[torch.Tensor] = None, text_lengths: Optional[torch.Tensor] = None,
@@ -181,7 +285,8 @@ def contrastive_step(residue_states: torch.Tensor, protein_mask: Optional[torch.
                      labels: Optional[torch.Tensor] = None, aux: Optional[StepAux] = None,
                      col_stats_hook=None, loss_scale: Optional[float] = None,
                      all_cols_labelled: bool = False, seed_dev: Optional[torch.Tensor] = None,
-                     late_text: bool = False, _raw: bool = False) -> torch.Tensor:
+                     late_text: bool = False, dloss_dev: Optional[torch.Tensor] = None, _text_join=None,
+                     _raw: bool = False) -> torch.Tensor:
     """One Stage-1 step from trunk outputs to the (differentiable) fp32 loss.
 
     residue_states (B, L, D_in) bf16 and protein_mask (B, L) come from the frozen protein encoder
@@ -196,12 +301,20 @@ def contrastive_step(residue_states: torch.Tensor, protein_mask: Optional[torch.
     `text_lengths` with packed `text_hidden` (see host_io.HostStager).  `contrastive_num_segments` reproduces the reference's
     segment averaging including its dropping of the remainder rows; `symmetric` adds the
     text->protein term.  `seed_dev` (int64 device tensor, 1 element): dropout seed read on the device instead
-    of drawn from torch's CPU generator (CUDA-graph replays, see graph.GraphedContrastiveStep).
+    of drawn from torch's CPU generator (CUDA-graph replays, see graph.GraphedContrastiveStep).  `dloss_dev` (fp32
+    device scalar): constant factor on the gradient, e.g. 1 / gradient_accumulation_steps (the reference divides the
+    loss by it before backward, scripts/train_contrast.py:432); the returned loss is not scaled.
     """
+    text_join = _text_join
     if text_embeds is None:
         if text_hidden is None or (text_mask is None and text_lengths is None):
             raise ValueError("pass either text_hidden + text_mask (or text_lengths) or text_embeds")
-        text_embeds = text_embeddings(text_hidden, text_mask, dtype=torch.float32, text_lengths=text_lengths)
+        if os.environ.get("P2T_TEXT_STREAM", "1") != "0" and text_hidden.is_cuda:
+            # the text branch (plan, pool, normalise: no dependency on the protein side before the similarity) runs on
+            # a side stream beside the packing of the residue rows and joins in front of the adapter GEMMs
+            text_embeds, text_join = _text_branch(text_hidden, text_mask, text_lengths)
+        else:
+            text_embeds = text_embeddings(text_hidden, text_mask, dtype=torch.float32, text_lengths=text_lengths)
     packed = residue_lengths is not None
     if packed and residue_states.dim() != 2:
         raise ValueError("with residue_lengths, residue_states must be packed rows (sum L_b, D_in)")
@@ -218,7 +331,7 @@ def contrastive_step(residue_states: torch.Tensor, protein_mask: Optional[torch.
                dropout_p=p, seed=_draw_seed() if (p > 0 and seed_dev is None) else 0, seed_dev=seed_dev,
                rows_used=seg * contrastive_num_segments, packed=packed,
                col_stats_hook=col_stats_hook, loss_scale=loss_scale, all_cols_labelled=all_cols_labelled,
-               late_text=late_text)
+               late_text=late_text, text_join=text_join, dloss_dev=dloss_dev)
     aux = aux if aux is not None else StepAux()
     if _raw:  # graph capture: no autograd, the caller runs step_backward itself
         return step_forward(residue_states, residue_lengths if packed else protein_mask, adapter.fc1.weight.detach(),

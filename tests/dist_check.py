@@ -44,7 +44,7 @@ def main():
     peer = importlib.import_module("p2t_b200.peer")
     prms = (ad.fc1.weight, ad.fc1.bias, ad.fc2.weight, ad.fc2.bias)
     exchange = pdist.ShardedExchange(sb.x.shape[0], 2 * sb.w2.shape[0], symmetric=True)
-    reducer = peer.PeerGradAllReduce(list(prms))
+    reducer = peer.PeerGradAllReduce.for_adapter(ad)
     dx, dpm, dtx, dtm = sb.x.to(dev), sb.prot_mask.to(dev), sb.text.to(dev), sb.text_mask.to(dev)
     for sym, form in ((False, "nccl"), (True, "nccl"), (False, "peer"), (True, "peer"), (False, "peer+graph"), (True, "peer+graph")):
         ad.zero_grad(set_to_none=True)

@@ -44,7 +44,7 @@ def test_library_exports_every_declared_symbol(built):
 def test_ctypes_table_covers_the_header(built):
     bound = set(built._lib.SIGNATURES) | set(built._lib.NON_STATUS)
     assert bound == set(_header_functions())
-    assert built._lib.load().p2t_abi_version() == 1
+    assert built._lib.load().p2t_abi_version() == 2
 
 
 def test_argument_errors_are_reported_without_a_gpu(built):

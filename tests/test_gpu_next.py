@@ -11,6 +11,7 @@ launch of a phase is issued before any rank's launch of the next phase, which is
 single stream; tests/dist_check.py runs the same kernels across real processes over NVLink (tests/test_gpu_dist.py).
 Bar: bit-exact for the exchange (byte moves, fixed-order fp32 sums), reference tolerances for floating point."""
 import importlib
+import math
 import os
 import sys
 
@@ -160,7 +161,7 @@ def test_graphed_step_through_the_exchange_equals_the_plain_step(p2t, mods, dev)
     l0 = plain.replay().clone()
     g0 = [g.clone() for g in plain.grads]
     ex = pdist.ShardedExchange(x.shape[0], 2 * sb.w2.shape[0], symmetric=True)
-    red = peer.PeerGradAllReduce([ad.fc1.weight, ad.fc1.bias, ad.fc2.weight, ad.fc2.bias])
+    red = peer.PeerGradAllReduce.for_adapter(ad)
     for sym in (False, True):
         ref = p2t.GraphedContrastiveStep(ad, x, pm, th, tm, symmetric=sym)
         sharded = p2t.GraphedContrastiveStep(ad, x, pm, th, tm, symmetric=sym, exchange=ex, grad_reducer=red)
@@ -374,3 +375,151 @@ def test_graphed_training_step_with_optimizer_equals_eager_step_then_optimizer(p
         for w_a, w_b in zip(prm(a1), prm(a2)):
             assert torch.equal(w_a, w_b)
     assert o1.step_count() == 3 == o2.step_count()
+
+
+# --------------------------------------------------------------------------------------------------
+# round 2: the loss block as one cooperative kernel (csrc/loss_fused.cu)
+# --------------------------------------------------------------------------------------------------
+FUSED_CASES = [
+    # R, B, C, D, symmetric
+    (32, 32, 32, 4096, False), (32, 32, 256, 4096, False), (32, 32, 256, 4096, True), (30, 32, 200, 96, True),
+    (70, 70, 130, 64, True), (16, 16, 32, 2048, False), (6, 6, 6, 96, True), (3, 5, 7, 32, False), (64, 64, 256, 1792, False),
+]
+
+
+def _fused_inputs(R_, B_, C_, D_, seed):
+    E = 2 * D_
+    g = torch.Generator().manual_seed(seed)
+    t = torch.nn.functional.normalize(torch.randn(C_, E, generator=g), dim=-1)
+    labels = torch.randperm(C_, generator=g)[:R_]
+    e = torch.randn(B_, E, generator=g) + 3.0  # un-normalised pooled embeddings (mean | std), std part positive
+    e[:, D_:] = e[:, D_:].abs() + 0.5
+    e[:R_] = e[:R_] + 6.0 * t[labels] * e[:R_].norm(dim=-1, keepdim=True)  # planted positives: real retrieval margins
+    e[:, D_:] = e[:, D_:].abs() + 0.1
+    pnorm = e.norm(dim=-1)
+    p = e / pnorm[:, None]
+    lens = torch.randint(3, 40, (B_,), generator=g)
+    seq_off = torch.cat([torch.zeros(1, dtype=torch.long), lens.cumsum(0)]).to(torch.int32)
+    return t, labels, e, pnorm, p, lens, seq_off
+
+
+@pytest.mark.parametrize("R_,B_,C_,D_,sym", FUSED_CASES)
+def test_fused_loss_kernel_matches_fp64(p2t, dev, R_, B_, C_, D_, sym):
+    """similarity -> online-softmax CE (rows, and columns for the symmetric term) -> dLogits -> dp -> F.normalize
+    backward -> 'mix' coefficients in ONE cooperative kernel, against the fp64 restatement of
+    scripts/train_contrast.py:100-114 and its autograd.  Retrieval argmax bit-exact (planted positives)."""
+    core = sys.modules["p2t_b200._core"]
+    E, tau = 2 * D_, 0.05
+    t, labels, e, pnorm, p, lens, seq_off = _fused_inputs(R_, B_, C_, D_, R_ * 7 + C_ + D_)
+    wr, wc = (0.5, 0.5) if sym else (1.0, 0.0)
+    assert core.loss_fused_eligible(R_, B_, C_, E)
+    pd, td, nd, ed, so = (x.to(dev).contiguous() for x in (p.float(), t.float(), pnorm.float(), e.float(), seq_off))
+    dl = torch.tensor(0.7, dtype=torch.float32, device=dev)
+    res = core.loss_fused(pd, td, labels.to(dev), R_, tau, w_row=wr, w_col=wc, need_grad=True, dloss=dl, pnorm=nd,
+                          stats=ed, seq_off=so)
+    again = core.loss_fused(pd, td, labels.to(dev), R_, tau, w_row=wr, w_col=wc, need_grad=True, dloss=dl, pnorm=nd,
+                            stats=ed, seq_off=so)
+    pf, tf = p.float().double(), t.float().double()
+    ref = wr * R.infonce_rows(pf[:R_], tf, labels, tau) + (wc * R.infonce_cols(pf[:R_], tf, labels, tau) if wc else 0.0)
+    assert abs(res.loss.item() - float(ref)) <= 2e-5 * abs(float(ref)) + 1e-6
+    _, dpo, _ = R.infonce_backward(pf[:R_], tf, labels, tau, wr, wc)
+    dp = torch.zeros(B_, E, dtype=torch.float64)
+    dp[:R_] = 0.7 * dpo
+    de = (dp - pf * (pf * dp).sum(-1, keepdim=True)) / pnorm.double()[:, None]
+    n = lens.double()[:, None]
+    k2 = de[:, D_:] / (n * e[:, D_:].float().double())
+    k1 = de[:, :D_] / n - k2 * e[:, :D_].float().double()
+    assert maxrel(res.c2, k2) <= 5e-4 and maxrel(res.c1, k1) <= 5e-4  # (softmax - 1) and (dp - p (p.dp)) cancel digits in fp32
+    assert cosine(res.c1, k1) >= 0.99999 and cosine(res.c2, k2) >= 0.99999
+    am_r, am_c = R.retrieval_argmax(pf[:R_], tf)
+    assert torch.equal(res.argmax_row.cpu().long(), am_r)
+    assert torch.equal(res.argmax_col.cpu().long()[labels], am_c[labels])
+    lse = torch.logsumexp(pf[:R_] @ tf.T / tau, dim=1)
+    assert maxrel(res.row_lse, lse) <= 1e-5
+    # deterministic: fixed reduction orders everywhere
+    assert torch.equal(res.loss, again.loss) and torch.equal(res.c1, again.c1) and torch.equal(res.c2, again.c2)
+
+
+def test_fused_loss_kernel_forward_only_and_bad_labels(p2t, dev):
+    core = sys.modules["p2t_b200._core"]
+    t, labels, e, pnorm, p, lens, seq_off = _fused_inputs(8, 8, 24, 64, 5)
+    pd, td = p.float().to(dev), t.float().to(dev)
+    res = core.loss_fused(pd, td, labels.to(dev), 8, 0.05, need_grad=False)
+    ref = R.infonce_rows(p.float().double(), t.float().double(), labels, 0.05)
+    assert res.c1 is None and abs(res.loss.item() - float(ref)) <= 2e-5 * abs(float(ref))
+    bad = labels.clone()
+    bad[3] = 24  # outside [0, C): the loss is poisoned instead of reading out of bounds
+    assert math.isnan(core.loss_fused(pd, td, bad.to(dev), 8, 0.05, need_grad=False).loss.item())
+    assert not core.loss_fused_eligible(512, 512, 4096, 8192)  # large blocks run on the tensor cores
+    with pytest.raises(p2t.P2TError, match="not eligible"):
+        big_p = torch.zeros(512, 64, device=dev)
+        core.loss_fused(big_p, torch.zeros(4096, 64, device=dev), torch.zeros(512, dtype=torch.int32, device=dev), 512, 0.05,
+                        need_grad=False)
+    # the kernel re-armed its barrier words: another launch right after works
+    assert math.isfinite(core.loss_fused(pd, td, labels.to(dev), 8, 0.05, need_grad=False).loss.item())
+
+
+def test_step_bias_gradients_in_fp32_round_to_the_bf16_gradients(p2t, mods, dev):
+    """step_backward hands the bias gradients out twice: bf16 (param.grad) and fp32 (what the gradient mean over ranks
+    carries, so that the only rounding happens after the mean)."""
+    synth = mods["synth"]
+    step_mod = sys.modules["p2t_b200.step"]
+    sb = synth.make_config_batch("tiny", weight_gain=6.0)
+    ad = make_adapter(p2t, dev, sb.w1, sb.b1, sb.w2, sb.b2)
+    with torch.no_grad():
+        _, state = p2t.contrastive_step(sb.x.to(dev), sb.prot_mask.to(dev), ad, sb.text.to(dev), sb.text_mask.to(dev), _raw=True)
+        dw1, db1, dw2, db2, db1_f32, db2_f32 = step_mod.step_backward(state, None)
+    assert db1_f32.dtype == torch.float32 and torch.equal(db1, db1_f32.to(torch.bfloat16))
+    assert torch.equal(db2, db2_f32.to(torch.bfloat16))
+    f = torch.float32
+    st = R.step_forward(sb.x.to(f), sb.prot_mask, sb.w1.to(f), sb.b1.to(f), sb.w2.to(f), sb.b2.to(f), sb.text.to(f), sb.text_mask)
+    ref = R.step_backward(st, sb.x.to(f), sb.prot_mask, sb.w1.to(f), sb.w2.to(f))
+    assert maxrel(db1_f32, ref["fc1.bias"]) <= 1e-2 and maxrel(db2_f32, ref["fc2.bias"]) <= 1e-2
+    assert cosine(dw1, ref["fc1.weight"]) >= 0.999 and cosine(dw2, ref["fc2.weight"]) >= 0.999
+
+
+@pytest.mark.parametrize("k", [2, 3])
+def test_graphed_step_accumulates_micro_batches_like_the_reference(p2t, mods, dev, k):
+    """scripts/train_contrast.py:432,448-465: loss / k, backward on every micro-batch, optimizer.step() on the k-th.
+    The captured step adds into its static gradient buffers on the non-first micro-steps and binds param.grad on the
+    boundary step only; the result must equal eager autograd accumulation of the same micro-batches."""
+    synth = mods["synth"]
+    sbs = [synth.make_config_batch("tiny", weight_gain=6.0, seed=50 + i) for i in range(k)]
+    L = max(s.x.shape[1] for s in sbs)
+    T = max(s.text.shape[1] for s in sbs)
+    B, d_in, H = sbs[0].x.shape[0], sbs[0].x.shape[2], sbs[0].text.shape[2]
+    ad = make_adapter(p2t, dev, sbs[0].w1, sbs[0].b1, sbs[0].w2, sbs[0].b2)
+    x = torch.zeros(B, L, d_in, dtype=torch.bfloat16, device=dev)
+    pm = torch.zeros(B, L, dtype=torch.long, device=dev)
+    th = torch.zeros(B, T, H, dtype=torch.bfloat16, device=dev)
+    tm = torch.zeros(B, T, dtype=torch.long, device=dev)
+
+    def fill(s):
+        x.zero_(); pm.zero_(); th.zero_(); tm.zero_()
+        x[:, :s.x.shape[1]] = s.x.to(dev); pm[:, :s.x.shape[1]] = s.prot_mask.to(dev)
+        th[:, :s.text.shape[1]] = s.text.to(dev); tm[:, :s.text.shape[1]] = s.text_mask.to(dev)
+
+    fill(sbs[0])
+    step = p2t.GraphedContrastiveStep(ad, x, pm, th, tm, accumulation_steps=k)
+    for window in range(2):
+        ad.zero_grad(set_to_none=True)
+        losses = []
+        for i, s in enumerate(sbs):
+            fill(s)
+            assert step.is_boundary == (i == k - 1)
+            losses.append(step.replay().item())
+            if i < k - 1:
+                assert ad.fc1.weight.grad is None  # non-boundary micro-steps bind nothing (and reduce nothing)
+        got = {n: v.clone() for n, v in zip(("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"),
+                                            (ad.fc1.weight.grad, ad.fc1.bias.grad, ad.fc2.weight.grad, ad.fc2.bias.grad))}
+        ad.zero_grad(set_to_none=True)
+        want_losses = []
+        for s in sbs:
+            fill(s)
+            l = p2t.contrastive_step(x, pm, ad, th, tm)
+            want_losses.append(l.item())
+            (l / k).backward()
+        assert losses == want_losses
+        for n, prm in (("fc1.weight", ad.fc1.weight), ("fc1.bias", ad.fc1.bias), ("fc2.weight", ad.fc2.weight), ("fc2.bias", ad.fc2.bias)):
+            # same kernels, same micro-batches; the only difference is where the bf16 roundings of the running sum fall
+            assert cosine(got[n], prm.grad) >= 0.99999 and maxrel(got[n], prm.grad) <= 1.2e-2, n

@@ -94,7 +94,7 @@ def bf(t):
 # --------------------------------------------------------------------------------------------------
 def test_cuda_library_is_loaded_and_launches_kernels(p2t, core, dev):
     lib = p2t._lib
-    assert os.path.basename(lib.LIB_PATH) == "libp2t_b200.so" and lib.load().p2t_abi_version() == 1
+    assert os.path.basename(lib.LIB_PATH) == "libp2t_b200.so" and lib.load().p2t_abi_version() == 2
     lib.reset_launch_count()
     out = core.gemm(bf(torch.randn(128, 64, device=dev)), bf(torch.randn(256, 64, device=dev)), 128, 256, 64)
     torch.cuda.synchronize()
@@ -628,7 +628,7 @@ def test_graphed_step_replays_bit_identically_to_the_eager_step(p2t, synth, dev)
     l_ref = loss.detach().clone()
     ad.zero_grad(set_to_none=True)
     step = p2t.GraphedContrastiveStep(ad, x, pm, text, tm)
-    assert step.launches_per_replay >= 20
+    assert 8 <= step.launches_per_replay <= 20  # round 1: 25 launches; the loss block is one cooperative kernel now
     for _ in range(3):
         out = step.replay()
     assert torch.equal(out, l_ref) and all(torch.equal(g_ref[k], adapter_grads(ad)[k]) for k in PARAMS)

@@ -29,7 +29,7 @@ def main():
     params = [ad.fc1.weight, ad.fc1.bias, ad.fc2.weight, ad.fc2.bias]
     x, pm, th, tm = (t.to(dev) for t in (sb.x, sb.prot_mask, sb.text, sb.text_mask))
     ex = pdist.ShardedExchange(x.shape[0], 2 * sb.w2.shape[0])
-    red = pkg.PeerGradAllReduce(params)
+    red = pkg.PeerGradAllReduce(params)  # all-bf16 eager form
     opt = pkg.FusedAdamW(params, lr=1e-4, eps=1e-6, max_grad_norm=1.0)
     for _ in range(3):
         for p in params:
