@@ -1,9 +1,11 @@
 """TEST INFRASTRUCTURE ONLY — loads the *real* reference implementation for pinning the oracle.
 
 Only `tests/`, `oracle/make_golden.py` and nothing in the product package may import this.
-It works only where `/root/reference` is mounted (the authoring container); the GPU box has
-no such directory, so everything that must travel is dumped to `tests/golden/` by
-`oracle/make_golden.py`.
+It works where `/root/reference` is mounted (the authoring container) or where `oracle/build_ref.py`
+has staged the reference's own hot-path files as `oracle/_ref/ref_hotpath.tgz` (the GPU box, which
+has no /root/reference: the archive travels with the snapshot and is unpacked to a temporary
+directory).  The golden vectors that pin the oracle are dumped to `tests/golden/` by
+`oracle/make_golden.py` regardless.
 
 The reference cannot be imported plainly: `models/__init__.py` pulls torch_geometric and the
 EvolutionaryScale `esm` package, `scripts/train_contrast.py:37,44` pull `graphein` (through
@@ -27,10 +29,39 @@ from dataclasses import dataclass
 from typing import Any
 
 REFERENCE_ROOT = os.environ.get("P2T_REFERENCE_ROOT", "/root/reference")
+_ARCHIVE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "ref_hotpath.tgz")
+
+
+def _has_hot_path(root: str) -> bool:
+    return os.path.isfile(os.path.join(root, "scripts", "train_contrast.py"))
+
+
+def _staged_root() -> str | None:
+    """Where /root/reference is absent (the GPU box): unpack oracle/_ref/ref_hotpath.tgz (packed from the reference's
+    own files by oracle/build_ref.py, never committed) into a per-user temporary directory and use that as the root."""
+    if not os.path.isfile(_ARCHIVE):
+        return None
+    import hashlib
+    import tarfile
+    import tempfile
+    with open(_ARCHIVE, "rb") as fh:
+        tag = hashlib.sha256(fh.read()).hexdigest()[:16]
+    root = os.path.join(tempfile.gettempdir(), f"p2t_ref_{os.getuid()}_{tag}")
+    if not _has_hot_path(root):
+        os.makedirs(root, exist_ok=True)
+        with tarfile.open(_ARCHIVE, "r:gz") as tar:
+            tar.extractall(root, filter="data")
+    return root
+
+
+def reference_root() -> str | None:
+    if _has_hot_path(REFERENCE_ROOT):
+        return REFERENCE_ROOT
+    return _staged_root()
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "scripts", "train_contrast.py"))
+    return reference_root() is not None
 
 
 @dataclass
@@ -61,14 +92,15 @@ def load_reference() -> ReferenceApi:
     global _cached
     if _cached is not None:
         return _cached
-    if not reference_available():
-        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    root = reference_root()
+    if root is None:
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT} and no staged archive at {_ARCHIVE}")
+    if root not in sys.path:
+        sys.path.insert(0, root)
 
     # (1) a bare `models` package so models/__init__.py (torch_geometric, esm) never runs
     models_pkg = types.ModuleType("models")
-    models_pkg.__path__ = [os.path.join(REFERENCE_ROOT, "models")]
+    models_pkg.__path__ = [os.path.join(root, "models")]
     sys.modules["models"] = models_pkg
     modality_config = importlib.import_module("models.modality_config")
     modeling = importlib.import_module("models.modeling_esm2llama_instruct")
@@ -91,7 +123,7 @@ def load_reference() -> ReferenceApi:
 
     # (3) the script module itself (argparse object is built at import, nothing is parsed)
     scripts_pkg = types.ModuleType("scripts")
-    scripts_pkg.__path__ = [os.path.join(REFERENCE_ROOT, "scripts")]
+    scripts_pkg.__path__ = [os.path.join(root, "scripts")]
     sys.modules["scripts"] = scripts_pkg
     tc = importlib.import_module("scripts.train_contrast")
 

@@ -31,17 +31,36 @@ class ShardedExchange:
     (2, W*B) per-column (max, sum-exp) statistics of the symmetric loss.  With an exchange no NCCL call is on the data
     path and the sharded step is capturable in a CUDA graph (`graph.GraphedContrastiveStep(exchange=...)`)."""
 
-    def __init__(self, pairs_per_rank: int, embed_dim: int, group=None, symmetric: bool = False):
+    def __init__(self, pairs_per_rank: int, embed_dim: int, group=None, symmetric: bool = False, _buffers=None):
         self.group = group
-        self.text = PeerAllGather(pairs_per_rank, embed_dim, torch.float32, group)
+        tb, sb = _buffers if _buffers is not None else (None, None)
+        self.text = PeerAllGather(pairs_per_rank, embed_dim, torch.float32, group, _buffer=tb)
         self.rank, self.world = self.text.rank, self.text.world
-        self.stats = PeerAllGather(2, self.world * pairs_per_rank, torch.float32, group) if symmetric else None
+        self.stats = PeerAllGather(2, self.world * pairs_per_rank, torch.float32, group, _buffer=sb) if symmetric else None
 
-    def merge_column_stats(self, col_max: torch.Tensor, col_sum: torch.Tensor):
+    @classmethod
+    def virtual(cls, pairs_per_rank: int, embed_dim: int, world: int, symmetric: bool = False):
+        """`world` exchanges in THIS process, one per simulated rank, over peer buffers that all live on the current
+        device (single-GPU tests of the sharded step: the launches of all simulated ranks are issued phase by phase
+        on one stream — every rank's push before any rank's arrival)."""
+        from .peer import PeerBuffer
+        tb = PeerBuffer.virtual(PeerAllGather.buffer_bytes(pairs_per_rank, embed_dim, torch.float32, world), world)
+        sb = PeerBuffer.virtual(PeerAllGather.buffer_bytes(2, world * pairs_per_rank, torch.float32, world), world) \
+            if symmetric else [None] * world
+        return [cls(pairs_per_rank, embed_dim, symmetric=symmetric, _buffers=(tb[r], sb[r])) for r in range(world)]
+
+    def push_column_stats(self, col_max: torch.Tensor, col_sum: torch.Tensor) -> None:
         if self.stats is None:
             raise ValueError("build the exchange with symmetric=True to merge column statistics")
-        gathered = self.stats(torch.stack([col_max, col_sum])).view(self.world, 2, -1)
+        self.stats.push(torch.stack([col_max, col_sum]))
+
+    def arrive_column_stats(self):
+        gathered = self.stats.arrive().view(self.world, 2, -1)
         return _merge(gathered[:, 0], gathered[:, 1])
+
+    def merge_column_stats(self, col_max: torch.Tensor, col_sum: torch.Tensor):
+        self.push_column_stats(col_max, col_sum)
+        return self.arrive_column_stats()
 
     def check(self) -> None:
         """Raise if a peer-memory wait timed out since the last check (synchronises the device)."""

@@ -36,12 +36,14 @@ class SynthBatch:
 
 def make_batch(d_in, d_mid, d_out, batch, lmin, lmax, tmin, tmax, seed: int = 1234, rank: int = 0,
                weight_gain: float = 1.0, left_pad: bool = False, plant: float = 0.0,
-               same_lengths_as_rank0: bool = False, device=None) -> SynthBatch:
+               same_lengths_as_rank0: bool = False, device=None, lens=None, tlens=None) -> SynthBatch:
     """`same_lengths_as_rank0`: every rank gets rank 0's multiset of sequence lengths (in a rank-specific order) with
     its own random data — per-GPU work is then exactly fixed as ranks are added (weak-scaling benchmark).
     `device`: draw the residue / text states there with a device generator (same lengths and masks as the host
     path, different values) — the big sweep configurations are 5 GB of residue states per rank, which is minutes of
-    single-threaded host randn under torchrun; everything else stays on the host."""
+    single-threaded host randn under torchrun; everything else stays on the host.
+    `lens` / `tlens`: explicit protein / text lengths instead of drawing them."""
+    lens_override, tlens_override = lens, tlens
     g = torch.Generator().manual_seed(seed + rank)
     lens = torch.randint(lmin, lmax + 1, (batch,), generator=g)
     tlens = torch.randint(tmin, tmax + 1, (batch,), generator=g)
@@ -51,6 +53,10 @@ def make_batch(d_in, d_mid, d_out, batch, lmin, lmax, tmin, tmax, seed: int = 12
         tlens0 = torch.randint(tmin, tmax + 1, (batch,), generator=g0)
         perm = torch.randperm(batch, generator=torch.Generator().manual_seed(seed + 7919 * rank))
         lens, tlens = lens0[perm], tlens0[perm]
+    if lens_override is not None:  # explicit sequence lengths (e.g. a rank's share of a length-balanced global batch)
+        lens = torch.as_tensor(lens_override, dtype=torch.long)
+        tlens = torch.as_tensor(tlens_override, dtype=torch.long) if tlens_override is not None else tlens[:len(lens)]
+        batch = len(lens)
     L, T = int(lens.max()), int(tlens.max())
     ar_l, ar_t = torch.arange(L)[None, :], torch.arange(T)[None, :]
     pm = (ar_l >= (L - lens)[:, None]) if left_pad else (ar_l < lens[:, None])
@@ -77,6 +83,15 @@ def make_batch(d_in, d_mid, d_out, batch, lmin, lmax, tmin, tmax, seed: int = 12
     b1 = (torch.randn(d_mid, generator=wg) * 0.02).to(torch.bfloat16)
     b2 = (torch.randn(d_out, generator=wg) * 0.02).to(torch.bfloat16)
     return SynthBatch(x=x, prot_mask=pm.long(), prot_lens=lens, text=text, text_mask=tm.long(), w1=w1, b1=b1, w2=w2, b2=b2)
+
+
+def draw_lengths(name: str, seed: int = 1234, rank: int = 0):
+    """(protein lengths, text lengths) exactly as make_config_batch(name, seed=seed, rank=rank) draws them."""
+    cfg = CONFIGS[name]
+    g = torch.Generator().manual_seed(seed + rank)
+    lens = torch.randint(cfg["lmin"], cfg["lmax"] + 1, (cfg["batch"],), generator=g)
+    tlens = torch.randint(cfg["tmin"], cfg["tmax"] + 1, (cfg["batch"],), generator=g)
+    return lens, tlens
 
 
 def make_config_batch(name: str, **kw) -> SynthBatch:

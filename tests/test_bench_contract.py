@@ -27,7 +27,9 @@ def test_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["metric"] == "contrastive_step_pairs_per_sec" and d["unit"] == "pairs/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1 and d["vs_baseline"] is None
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "pairs" in cb["sample"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "pairs" in cb["sample"]
+    from oracle.reference_loader import reference_available
+    assert cb["kind"] == ("reference" if reference_available() else "port")
     assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"] == "cfg1_esm2_t6_llama1b" and "model" not in d["config"]
 

@@ -440,6 +440,7 @@ STEP_CASES = [
     ("tiny", 6.0, {}), ("tiny", 6.0, {"left_pad": True}), ("tiny", 6.0, {"symmetric": True}),
     ("tiny", 6.0, {"nseg": 3}), ("cfg1_esm2_t6_llama1b", 2.5, {}), ("cfg1_esm2_t6_llama1b", 2.5, {"symmetric": True}),
     ("cfg2_esm2_3b_llama8b", 1.0, {}), ("cfg4_esmc600m_qwen7b", 1.5, {"batch": 16}),
+    ("cfg4_esmc600m_qwen7b", 1.5, {}),  # BASELINE config 4 at its own per-rank size: 64 pairs
 ]
 
 
