@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-optimizer", action="store_true", help="skip the (separately reported) optimizer leg")
     ap.add_argument("--no-exchange-probe", action="store_true", help="skip timing the exchange kernels alone (N > 1)")
+    ap.add_argument("--pairs-per-gpu", type=int, default=0,
+                    help="override the workload's pairs per GPU (config 5: global batch 4096 -> 2048 / 1024 / 512 at 2 / 4 / 8 GPUs)")
     ap.add_argument("--no-stages", action="store_true", help="skip the per-kernel event-stamp pass")
     ap.add_argument("--no-imbalance-leg", action="store_true",
                     help="N > 1: skip the second weak-scaling leg with independent per-rank sequence lengths")
@@ -289,14 +291,26 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg = synth.CONFIGS[args.workload]
+    cfg = dict(synth.CONFIGS[args.workload])
+    if args.pairs_per_gpu > 0:
+        cfg["batch"] = args.pairs_per_gpu
     nbatches = 2
+    # saved activations of one step (packed rows x (x, h1, g1, a, g2, dz1, dz2) + padded inputs): above ~25 GB keep ONE
+    # resident batch (its inputs alone exceed the L2 a hundred times) and time eager launches — a captured graph would
+    # pin a second copy of every intermediate in its private pool, and at config 5 / 2 GPUs that no longer fits 180 GB
+    est_rows = cfg["batch"] * (cfg["lmin"] + cfg["lmax"]) / 2
+    est_bytes = est_rows * 2 * (2 * cfg["d_in"] + 3 * cfg["d_mid"] + 3 * cfg["d_out"]) + cfg["batch"] * cfg["lmax"] * cfg["d_in"] * 2
+    big_workload = est_bytes > 25e9
+    if big_workload:
+        nbatches = 1
+        args.no_graph = True
+        args.no_stages = True
     host_io = importlib.import_module("p2t_b200.host_io")
     numa_cpus = host_io.bind_host_thread_to_gpu(dev) if world > 1 else None  # before any pinned buffer exists
     if args.device_synth:
         args.no_e2e = args.no_cpu_baseline = True
     batches = [synth.make_config_batch(args.workload, seed=1234 + 17 * i, rank=rank, same_lengths_as_rank0=True,
-                                       device=dev if args.device_synth else None)
+                                       device=dev if args.device_synth else None, batch=cfg["batch"])
                for i in range(nbatches)]
     B = cfg["batch"]
     acfg = pkg.ModalityAdapterConfig(input_dim=cfg["d_in"], intermediate_dim=cfg["d_mid"], output_dim=cfg["d_out"], dropout_rate=0.3)
@@ -721,7 +735,8 @@ def main():
                        "exchange": None if world == 1 else "text embeddings all-gathered by peer-memory kernels over NVLink "
                                                            "(csrc/peer.cu), inside the step's CUDA graph; no NCCL on the data path",
                        "rank_lengths": "rank 0's multiset of sequence lengths on every rank, own data (fixed per-GPU work)",
-                       "l2": "inputs+activations per step exceed the 126 MB L2; 2 batches alternate",
+                       "l2": ("inputs+activations per step exceed the 126 MB L2; 2 batches alternate" if nbatches == 2 else
+                              "one resident batch whose inputs+activations exceed the 126 MB L2 a hundred times; eager launches"),
                        "cta_group": int(os.environ.get("P2T_CTA_GROUP", "2"))},
             "loss": last_loss, "gpu_launches": int(launches), "cuda_graph": bool(use_graph),
             "eager_ms_per_step": eager_ms_total / args.steps, "host_issue_ms_per_step_eager": host_issue_ms, "clocks": clocks, "e2e": e2e, "roofline": roofline,

@@ -115,12 +115,14 @@ int p2t_gather_rows(const void* src, long long ld_src, const int* row_src, const
  * x has x_rows rows allocated (TMA zero-fills beyond); outputs have rows_cap rows.
  * Weights in nn.Linear layout (out, in), bf16.  dropout_p = 0 is eval mode; otherwise a Philox
  * mask keyed by (seed, layer, row, column) with multiplier 1/(1-p) (nn.Dropout, :63,:66).
+ * gemm_ws (optional, p2t_gemm_workspace_bytes()): split-K scratch — the tiles of the incomplete last wave are cut into
+ * K ranges; the row count is ragged, so the kernel derives the cut from *n_rows_dev itself.
  * seed_dev (optional, device): its value is added to `seed` on the device — a CUDA-graph replay freezes
  * kernel arguments, so the replaying host bumps this word instead.
  * ------------------------------------------------------------------------------------------- */
 int p2t_adapter_fwd(const void* x, int x_rows, const void* w1, const void* b1, const void* w2, const void* b2, int d_in,
                     int d_mid, int d_out, int rows_cap, const int* n_rows_dev, void* h1, void* g1, void* a,
-                    void* g2, float* rowsq, float dropout_p, unsigned long long seed, const unsigned long long* seed_dev,
+                    void* g2, float* rowsq, float dropout_p, unsigned long long seed, const unsigned long long* seed_dev, void* gemm_ws,
                     int cta_group, void* stream);
 
 /* y[row] = a[row] / max(|a[row]|, 1e-12) for the first n rows: the (B, L, d_out) tensor that
@@ -138,7 +140,8 @@ int p2t_row_inv_norm(const float* rowsq, int nblk, const int* n_rows_dev, int ro
  * aligned rows (read by TMA);
  * row_src == NULL means rows are already packed.  With inv_norm != NULL every row is first scaled
  * by inv_norm[row] (adapter output: normalise fused into the pooling pass).
- * partial_ws: float2 [max_chunks][D]; out: fp32 [B][ld_out] (mean | std for mix).
+ * partial_ws: fp32 [max_chunks * (2 D + 1)] (float2 records [max_chunks][D], then one int32 row count per chunk);
+ * out: fp32 [B][ld_out] (mean | std for mix).
  * With p_bf16 and/or p_f32 given (mode MIX, ld_out == 2*D) the following F.normalize (:354/:365) is fused into
  * the final pass: p = out / max(|out|, 1e-12) [B][2*D], norm[B] = |out| (unclamped).
  * ------------------------------------------------------------------------------------------- */

@@ -126,6 +126,17 @@ def gemm_workspace(device) -> Optional[torch.Tensor]:
     return torch.empty(int(_lib.load().p2t_gemm_workspace_bytes()), dtype=torch.uint8, device=device)
 
 
+def _fwd_splitk_workspace(device) -> Optional[torch.Tensor]:
+    """Split-K tail for the GEMMs whose row count is ragged (fc1, fc2, fc2-dgrad): OFF unless P2T_SPLITK_DYN=1.
+    Measured at config 2 (560 / 1120 / 560 tiles on 74 CTA pairs: 5 % of the last wave idle): cutting the last
+    wave's tiles costs more than it saves there — the head pieces' heavy epilogues wait for the dumped partial
+    accumulators (13 % of the fc2 kernel's stall samples sat in that wait), fc1 132 -> 159 us, fc2 208 -> 252 us."""
+    import os
+    if os.environ.get("P2T_SPLITK_DYN", "0") != "1":
+        return None
+    return gemm_workspace(device)
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, m: int, n: int, k: int, *, a_mn: bool = False, b_mn: bool = False,
          out_dtype=torch.bfloat16, alpha: float = 1.0, cta_group: Optional[int] = None,
          dyn_m: Optional[torch.Tensor] = None, dyn_k: Optional[torch.Tensor] = None,
@@ -175,7 +186,8 @@ def adapter_forward(x: torch.Tensor, x_rows: int, rows_cap: int, n_rows: torch.T
     rowsq = torch.empty(nblk, rows_cap, dtype=torch.float32, device=dev)
     _lib.call("p2t_adapter_fwd", _ptr(x), x_rows, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), d_in, d_mid, d_out,
               rows_cap, _ptr(n_rows), _ptr(h1), _ptr(g1), _ptr(a), _ptr(g2), _ptr(rowsq), float(dropout_p),
-              int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(seed_dev), cta_group or default_cta_group(), _stream())
+              int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(seed_dev), _ptr(_fwd_splitk_workspace(dev)),
+              cta_group or default_cta_group(), _stream())
     return AdapterActs(x=x, x_rows=x_rows, h1=h1, g1=g1, a=a, g2=g2, rowsq=rowsq, nblk=nblk, rows_cap=rows_cap,
                        n_rows=n_rows)
 
@@ -241,7 +253,7 @@ def pool_forward(src: torch.Tensor, plan: RowPlan, D: int, *, row_src: Optional[
     each row optionally scaled by inv_norm[row] first.  With `normalize` the following F.normalize is fused in and
     (stats, p_bf16, p_f32 or None, norm) is returned."""
     dev = src.device
-    partial = torch.empty(plan.max_chunks, D, 2, dtype=torch.float32, device=dev)
+    partial = torch.empty(plan.max_chunks * (2 * D + 1), dtype=torch.float32, device=dev)  # records + per-chunk row counts
     stats = torch.empty(plan.B, 2 * D, dtype=torch.float32, device=dev)
     p_bf = p_f32 = norm = None
     if normalize:

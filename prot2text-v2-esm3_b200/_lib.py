@@ -21,7 +21,7 @@ SIGNATURES = {
     "p2t_stage_rows_h2d": [_vp, _ll, _ll, _vp, _vp, _i, _vp, _vp],
     "p2t_row_inv_norm": [_vp, _i, _vp, _i, _vp, _vp],
     "p2t_gather_rows": [_vp, _ll, _vp, _vp, _i, _i, _vp, _vp],
-    "p2t_adapter_fwd": [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _ull, _vp, _i, _vp],
+    "p2t_adapter_fwd": [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _ull, _vp, _vp, _i, _vp],
     "p2t_adapter_scale_rows": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "p2t_pool_fwd": [_vp, _i, _ll, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _ll, _vp, _vp, _vp, _vp],
     "p2t_loss_bwd_coef": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp],

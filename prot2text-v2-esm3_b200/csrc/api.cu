@@ -131,7 +131,7 @@ int p2t_gather_rows(const void* src, long long ld_src, const int* row_src, const
 int p2t_adapter_fwd(const void* x, int x_rows, const void* w1, const void* b1, const void* w2, const void* b2, int d_in,
                     int d_mid, int d_out, int rows_cap, const int* n_rows_dev, void* h1, void* g1, void* a,
                     void* g2, float* rowsq, float dropout_p, unsigned long long seed, const unsigned long long* seed_dev,
-                    int cta_group, void* stream) {
+                    void* gemm_ws, int cta_group, void* stream) {
   if (!x || !w1 || !w2 || !h1 || !a || !rowsq) return set_error(-1, "p2t_adapter_fwd: null pointer");
   if (d_in % 8 || d_mid % 8 || d_out % 8) return set_error(-1, "p2t_adapter_fwd: dims must be multiples of 8");
   if (dropout_p < 0.f || dropout_p >= 1.f) return set_error(-1, "p2t_adapter_fwd: dropout_p must be in [0, 1)");
@@ -141,6 +141,7 @@ int p2t_adapter_fwd(const void* x, int x_rows, const void* w1, const void* b1, c
   p.bias = reinterpret_cast<const __nv_bfloat16*>(b1);
   p.drop = make_dropout(dropout_p, seed, 1, seed_dev);
   p.a_extent = x_rows;
+  p.sk_ws = gemm_ws;  // split-K tail for the incomplete last wave of tiles (S chosen on the device: M is ragged)
   if (int rc = launch_gemm(x, d_in, false, w1, d_in, false, EPI_FC1, p, cta_group, S(stream))) return rc;
   GemmParams q = base_params(rows_cap, d_out, d_mid);
   q.dyn_m = n_rows_dev;
@@ -148,6 +149,7 @@ int p2t_adapter_fwd(const void* x, int x_rows, const void* w1, const void* b1, c
   q.bias = reinterpret_cast<const __nv_bfloat16*>(b2);
   q.rowsq = rowsq; q.ld_rowsq = rows_cap;
   q.drop = make_dropout(dropout_p, seed, 2, seed_dev);
+  q.sk_ws = gemm_ws;
   return launch_gemm(h1, d_mid, false, w2, d_mid, false, EPI_FC2, q, cta_group, S(stream));
 }
 

@@ -88,24 +88,26 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   static const int nostore = getenv("P2T_DEBUG_NOSTORE") ? atoi(getenv("P2T_DEBUG_NOSTORE")) : 0;
   q.debug_nostore = nostore;
   const int tail = (int)(tiles % all_workers);  // tiles of the incomplete last wave
-  if (p.sk_ws != nullptr && p.dyn_m == nullptr && tail != 0) {
-    // split-K tail (M is static here, so the tile count is known on the host): cut the last wave's tiles into S
-    // K ranges so that tail*S pieces fill the machine; cost model = rounds of pieces / S + a small per-dump charge
-    const int kb = (p.k + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
-    double best = 1.0;
-    int best_s = 1;
-    for (int sp = 2; sp <= GEMM_SK_MAX_SPLITS; ++sp) {
-      if ((long long)tail * sp > (long long)GEMM_SK_SLOTS_PER_SM * all_workers || kb / sp < 4) break;
-      const long long rounds = ((long long)tail * sp + all_workers - 1) / all_workers;
-      const double cost = (double)rounds / sp + 0.004 * (sp - 1);
-      if (cost < best - 1e-9) { best = cost; best_s = sp; }
-    }
-    if (best_s > 1 && best <= 0.92) {
+  const int kb = (p.k + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  bool reset_flags = false;
+  if (p.sk_ws != nullptr && p.dyn_m != nullptr && p.dyn_k == nullptr) {
+    // M is a device scalar (ragged row count): the kernel derives the tile count and picks S itself (same cost model)
+    q.sk_splits = -1;
+    workers = all_workers;
+    reset_flags = true;
+  } else if (p.sk_ws != nullptr && p.dyn_m == nullptr && tail != 0) {
+    // split-K tail with the tile count known on the host: cut the last wave's tiles into S K ranges so that tail*S
+    // pieces fill the machine; cost model = rounds of pieces / S + a small per-dump charge
+    const int best_s = choose_sk_splits((int)tiles, kb, all_workers);
+    if (best_s > 1) {
       q.sk_splits = best_s;
       workers = all_workers;
-      cudaError_t me = cudaMemsetAsync(p.sk_ws, 0, GEMM_SK_FLAG_BYTES, stream);
-      if (me != cudaSuccess) return set_error((int)me, "split-K flag reset failed: %s", cudaGetErrorString(me));
+      reset_flags = true;
     }
+  }
+  if (reset_flags) {
+    cudaError_t me = cudaMemsetAsync(p.sk_ws, 0, GEMM_SK_FLAG_BYTES, stream);
+    if (me != cudaSuccess) return set_error((int)me, "split-K flag reset failed: %s", cudaGetErrorString(me));
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(workers * CTA_GROUP);

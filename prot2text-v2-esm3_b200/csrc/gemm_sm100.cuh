@@ -81,7 +81,8 @@ struct GemmParams {
   DropoutParams drop;         // p == 0 -> disabled
   // split-K tail (see header comment); sk_ws == nullptr -> whole tiles only
   void* sk_ws;                // [GEMM_SK_FLAG_BYTES of int flags][GEMM_SK_SLOTS_PER_SM * #SM slots of 128x256 fp32]
-  int sk_splits;              // S, set by the launcher (1 = whole tiles only)
+  int sk_splits;              // S, set by the launcher (1 = whole tiles only; -1 = chosen on the device from the actual
+                              // tile count, for GEMMs whose M is a device scalar)
   int tma_store;              // FC epilogues: tmap_d0/tmap_d1 are valid, write outputs through shared memory + TMA
   int debug_nostore;          // bring-up aid (P2T_DEBUG_NOSTORE=1): run the epilogue math, skip its global stores
 };
@@ -143,6 +144,22 @@ struct PieceIter {
     return true;
   }
 };
+
+// The launcher's cost model for the split-K tail, evaluated on the device when M (hence the tile count) is only known
+// there: the tiles of the incomplete last wave are cut into the S that minimises rounds(S) / S + a per-dump charge.
+__host__ __device__ inline int choose_sk_splits(int tiles, int kb, int workers) {
+  const int tail = tiles % workers;
+  if (tail == 0) return 1;
+  float best = 1.f;
+  int best_s = 1;
+  for (int sp = 2; sp <= GEMM_SK_MAX_SPLITS; ++sp) {
+    if ((long long)tail * sp > (long long)GEMM_SK_SLOTS_PER_SM * workers || kb / sp < 4) break;
+    const int rounds = (tail * sp + workers - 1) / workers;
+    const float cost = (float)rounds / sp + 0.004f * (sp - 1);
+    if (cost < best - 1e-6f) { best = cost; best_s = sp; }
+  }
+  return (best_s > 1 && best <= 0.92f) ? best_s : 1;
+}
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   int v;
@@ -454,6 +471,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int num_tiles = num_m_blk * num_n_blk;
   const int worker = blockIdx.x / CTA_GROUP;
   const int num_workers = gridDim.x / CTA_GROUP;
+  const int sk_splits = (p.sk_splits < 0) ? choose_sk_splits(num_tiles, num_kb, num_workers) : p.sk_splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -486,7 +504,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
-      PieceIter pieces(num_tiles, num_kb, worker, num_workers, p.sk_splits);
+      PieceIter pieces(num_tiles, num_kb, worker, num_workers, sk_splits);
       int t, kb0, kb1, tail_r, split;
       while (pieces.next(t, kb0, kb1, tail_r, split)) {
         const int m_blk = t / num_n_blk, n_blk = t % num_n_blk;
@@ -549,7 +567,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      PieceIter pieces(num_tiles, num_kb, worker, num_workers, p.sk_splits);
+      PieceIter pieces(num_tiles, num_kb, worker, num_workers, sk_splits);
       int t, kb0, kb1, tail_r, split;
       while (pieces.next(t, kb0, kb1, tail_r, split)) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
@@ -614,7 +632,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     int* sk_flags = reinterpret_cast<int*>(p.sk_ws);
     float* sk_slots = reinterpret_cast<float*>(reinterpret_cast<char*>(p.sk_ws) + GEMM_SK_FLAG_BYTES);
     const int row_in_cta = quarter * 32 + lane;
-    const int S_ = p.sk_splits;
+    const int S_ = sk_splits;
     int acc = 0;
     uint32_t acc_phase = 0;
     PieceIter pieces(num_tiles, num_kb, worker, num_workers, S_);

@@ -197,8 +197,11 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 }
 
 // Persistent TMA-fed streaming kernel.  grid (ctas_per_slab, ceil(D/256)), at most one CTA per SM; block = 8 consumer
-// warps + 1 producer warp.  A CTA owns one 256-column slab and strides over the pooling chunks (<= 64 rows of ONE
-// sequence each, described by an int4 {first row, end row, sequence, 0}).  The rows of a chunk are contiguous in the
+// warps + 1 producer warp.  A CTA owns one 256-column slab and a CONTIGUOUS range of the pooling chunks (<= 64 rows of
+// ONE sequence each, described by an int4 {first row, end row, sequence, 0}); consecutive chunks of the same sequence
+// accumulate in registers and meet in shared memory only when the sequence changes, so a CTA merges its row subsets
+// and writes a partial record once per (CTA, sequence) segment (~5 times at config 2) instead of once per chunk (~33).
+// partial[c] = (mean, M2) and seg_rows[c] = row count of the segment that STARTS at chunk c (0 for the other chunks).  The rows of a chunk are contiguous in the
 // source (packed activations; padded tensors with contiguous masks), so the producer brings a chunk in with one 2D TMA
 // box (64 rows x 256 columns = 32 KB) into a 5-deep shared-memory ring, together with the rows' scale factors:
 // ~128 KB of loads stay in flight per SM independent of register pressure, which is what an HBM latency of ~2 us under
@@ -221,12 +224,13 @@ __global__ void __launch_bounds__(POOL_THREADS, 1)
 pool_partial_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16* __restrict__ src, long long ld_src,
                     const int* __restrict__ row_src, const float* __restrict__ inv_norm,
                     const int* __restrict__ chunk_off, const int4* __restrict__ chunk_desc, int B, int D,
-                    float2* __restrict__ partial) {
+                    float2* __restrict__ partial, int* __restrict__ seg_rows) {
   extern __shared__ uint8_t pool_smem_raw[];
   PoolSmem& sm = *reinterpret_cast<PoolSmem*>(pool_smem_raw + ((1024u - (smem_u32(pool_smem_raw) & 1023u)) & 1023u));
   const int total = chunk_off[B];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int stride = gridDim.x;
+  const int per = (total + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int c_lo = min(total, (int)blockIdx.x * per), c_hi = min(total, c_lo + per);
   const int col0 = blockIdx.y * POOL_BOX_COLS;
   if (tid == 0) {
     tma_prefetch_desc(&tmap);
@@ -239,34 +243,56 @@ pool_partial_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
   __syncthreads();
   if (warp == POOL_NSUB) {
     // ------------------------------- producer warp -------------------------------
+    // Software-pipelined: the chunk descriptor is loaded two iterations ahead, the chunk's per-row scale factors
+    // (and, for padded sources, its first source row) one iteration ahead, so that no iteration waits for a chain
+    // of dependent global loads before it can issue its TMA box.  (Round 2, first version: descriptor -> scale
+    // factors -> TMA issue cost ~1 us of exposed latency per 32 KB chunk, which capped a CTA at ~30 GB/s, the kernel
+    // at 0.67 of the HBM peak — ncu: the producer's STS of the scale factors held 70 % of its samples in long_scoreboard.)
     int stage = 0;
     uint32_t phase = 0;
-    for (int c = blockIdx.x; c < total; c += stride) {
-      mbar_wait(&sm.empty[stage], phase ^ 1);
-      const int4 d = __ldg(chunk_desc + c);
-      int first = d.x;
-      if (row_src != nullptr) {
+    auto load_desc = [&](int c) { return (c < c_hi) ? __ldg(chunk_desc + c) : make_int4(0, 0, -1, 0); };
+    auto load_aux = [&](const int4& d, float (&scv)[POOL_BOX_ROWS / 32], int& first) {
+      first = d.x;
+      if (row_src != nullptr && d.z >= 0) {
         first = __ldg(row_src + d.x);
         if (__ldg(row_src + d.y - 1) - first != d.y - 1 - d.x) first = -1;  // row_src is increasing: holes inside
       }
 #pragma unroll
       for (int h = 0; h < POOL_BOX_ROWS / 32; ++h) {
         const int r = d.x + lane + 32 * h;
-        sm.sc[stage][lane + 32 * h] = (r < d.y) ? (inv_norm ? __ldg(inv_norm + r) : 1.f) : 0.f;
+        scv[h] = (d.z >= 0 && r < d.y) ? (inv_norm ? __ldg(inv_norm + r) : 1.f) : 0.f;
       }
+    };
+    int4 d_cur = load_desc(c_lo), d_nxt = load_desc(c_lo + 1);
+    float sc_cur[POOL_BOX_ROWS / 32];
+    int first_cur;
+    load_aux(d_cur, sc_cur, first_cur);
+    for (int c = c_lo; c < c_hi; ++c) {
+      const int4 d_nn = load_desc(c + 2);
+      float sc_nxt[POOL_BOX_ROWS / 32];
+      int first_nxt;
+      load_aux(d_nxt, sc_nxt, first_nxt);  // in flight while this iteration waits for its ring slot
+      mbar_wait(&sm.empty[stage], phase ^ 1);
+#pragma unroll
+      for (int h = 0; h < POOL_BOX_ROWS / 32; ++h) sm.sc[stage][lane + 32 * h] = sc_cur[h];
       if (lane == 0) {
-        sm.desc[stage] = d;
-        sm.src_row[stage] = first;
+        sm.desc[stage] = d_cur;
+        sm.src_row[stage] = first_cur;
       }
       __syncwarp();
       if (lane == 0) {
-        if (first >= 0) {
+        if (first_cur >= 0) {
           mbar_arrive_expect_tx(&sm.full[stage], POOL_STAGE_BYTES);
-          tma_load_2d(sm.stage[stage], &tmap, &sm.full[stage], col0, first);
+          tma_load_2d(sm.stage[stage], &tmap, &sm.full[stage], col0, first_cur);
         } else {
           mbar_arrive(&sm.full[stage]);
         }
       }
+      d_cur = d_nxt;
+      d_nxt = d_nn;
+      first_cur = first_nxt;
+#pragma unroll
+      for (int h = 0; h < POOL_BOX_ROWS / 32; ++h) sc_cur[h] = sc_nxt[h];
       if (++stage == POOL_STAGES) { stage = 0; phase ^= 1; }
     }
     return;
@@ -277,16 +303,47 @@ pool_partial_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
   const bool active = colb < D;
   int stage = 0, buf = 0;
   uint32_t phase = 0;
-  for (int c = blockIdx.x; c < total; c += stride) {
+  int cur_seq = -1, seg_first = 0, seg_n = 0;
+  float s1[8], s2[8], K[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; K[i] = 0.f; }
+  // close the running segment: the 8 row subsets meet in shared memory (fixed order), thread (sub, grp) finishes
+  // column 8*grp + sub.  Called by all consumer threads together.
+  auto flush = [&]() {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sm.comb[buf][sub][grp][i] = s1[i]; sm.comb[buf][sub][grp][8 + i] = s2[i]; }
+    asm volatile("bar.sync 1, %0;" ::"n"(POOL_CONSUMERS) : "memory");  // consumers only; `buf` alternates
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < POOL_NSUB; ++k) {
+      t1 += sm.comb[buf][k][grp][sub];
+      t2 += sm.comb[buf][k][grp][8 + sub];
+    }
+    float kk = K[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) kk = (sub == i) ? K[i] : kk;
+    const float n = (float)seg_n;
+    if (colb + sub < D) partial[(long long)seg_first * D + colb + sub] = make_float2(kk + t1 / n, fmaxf(t2 - t1 * t1 / n, 0.f));
+    if (blockIdx.y == 0 && tid == 0) seg_rows[seg_first] = seg_n;
+    buf ^= 1;
+  };
+  for (int c = c_lo; c < c_hi; ++c) {
     mbar_wait(&sm.full[stage], phase);  // also orders the producer's desc / sc / src_row writes before these reads
     const int4 d = sm.desc[stage];
     const int first = sm.src_row[stage];
-    float s1[8], s2[8], K[8];
+    const bool new_seg = d.z != cur_seq;
+    if (new_seg) {
+      if (cur_seq >= 0) flush();
+      cur_seq = d.z; seg_first = c; seg_n = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+      for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+    } else if (blockIdx.y == 0 && tid == 0) {
+      seg_rows[c] = 0;  // this chunk continues a segment
+    }
+    seg_n += d.y - d.x;
     if (first >= 0) {
       const uint8_t* base = sm.stage[stage] + grp * 16;
-      {
+      if (new_seg) {  // shift of the segment: its first row
         float f[8];
         unpack8<F16>(*reinterpret_cast<const uint4*>(base), f);
         const float sc0 = sm.sc[stage][0];
@@ -321,10 +378,12 @@ pool_partial_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
       // rows scattered in the source: straight from global memory (rare; correctness path)
       if (active) {
         float f[8];
-        unpack8<F16>(__ldg(reinterpret_cast<const uint4*>(src + (long long)__ldg(row_src + d.x) * ld_src + colb)), f);
-        const float sc0 = sm.sc[stage][0];
+        if (new_seg) {
+          unpack8<F16>(__ldg(reinterpret_cast<const uint4*>(src + (long long)__ldg(row_src + d.x) * ld_src + colb)), f);
+          const float sc0 = sm.sc[stage][0];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) K[i] = f[i] * sc0;
+          for (int i = 0; i < 8; ++i) K[i] = f[i] * sc0;
+        }
         for (int r = d.x + sub; r < d.y; r += POOL_NSUB) {
           unpack8<F16>(__ldg(reinterpret_cast<const uint4*>(src + (long long)__ldg(row_src + r) * ld_src + colb)), f);
           const float scr = sm.sc[stage][r - d.x];
@@ -335,41 +394,21 @@ pool_partial_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
             s2[i] = fmaf(v, v, s2[i]);
           }
         }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) K[i] = 0.f;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.empty[stage]);
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { sm.comb[buf][sub][grp][i] = s1[i]; sm.comb[buf][sub][grp][8 + i] = s2[i]; }
-    asm volatile("bar.sync 1, %0;" ::"n"(POOL_CONSUMERS) : "memory");  // consumers only; `buf` alternates
-    {
-      // thread (sub, grp) finishes column 8*grp + sub: add the 8 row subsets in a fixed order
-      float t1 = 0.f, t2 = 0.f;
-#pragma unroll
-      for (int k = 0; k < POOL_NSUB; ++k) {
-        t1 += sm.comb[buf][k][grp][sub];
-        t2 += sm.comb[buf][k][grp][8 + sub];
-      }
-      float kk = K[0];
-#pragma unroll
-      for (int i = 1; i < 8; ++i) kk = (sub == i) ? K[i] : kk;
-      const float n = (float)(d.y - d.x);
-      if (colb + sub < D) partial[(long long)c * D + colb + sub] = make_float2(kk + t1 / n, fmaxf(t2 - t1 * t1 / n, 0.f));
-    }
-    buf ^= 1;
     if (++stage == POOL_STAGES) { stage = 0; phase ^= 1; }
   }
+  if (cur_seq >= 0) flush();
 }
 
 // phase 2: combine the chunks of each sequence in order (Chan), emit mean / std / mix.
 // grid (B, ceil(D/256)), block 256.  mode: 1 mean, 2 std, 3 mix.  out [B][ld_out] fp32.
 // stats[b] = (mean[D] | std[D]) is always written when `stats` != null (needed by backward).
-__global__ void pool_finalize_kernel(const float2* __restrict__ partial, const int* __restrict__ seq_off,
-                                     const int* __restrict__ chunk_off, int B, int D, int rc, int mode,
-                                     float* __restrict__ out, long long ld_out) {
+__global__ void pool_finalize_kernel(const float2* __restrict__ partial, const int* __restrict__ seg_rows,
+                                     const int* __restrict__ seq_off, const int* __restrict__ chunk_off, int B, int D,
+                                     int mode, float* __restrict__ out, long long ld_out) {
   const int b = blockIdx.x;
   const int col = blockIdx.y * blockDim.x + threadIdx.x;
   if (col >= D) return;
@@ -377,7 +416,9 @@ __global__ void pool_finalize_kernel(const float2* __restrict__ partial, const i
   const int n_total = seq_off[b + 1] - seq_off[b];
   float n = 0.f, mean = 0.f, m2 = 0.f;
   for (int c = c0; c < c1; ++c) {
-    const float nc = (float)min(rc, n_total - (c - c0) * rc);
+    const int rows_c = seg_rows[c];
+    if (rows_c == 0) continue;  // the chunk continues a segment: its rows are inside an earlier record
+    const float nc = (float)rows_c;
     const float2 pc = partial[(long long)c * D + col];
     const float tot = n + nc;
     const float delta = pc.x - mean;
@@ -402,8 +443,8 @@ __global__ void pool_finalize_kernel(const float2* __restrict__ partial, const i
 // than one CTA per sequence would give.
 constexpr int FIN_CLUSTER = 8, FIN_THREADS = 256;
 __global__ void __launch_bounds__(FIN_THREADS)
-pool_finalize_normalize_kernel(const float2* __restrict__ partial, const int* __restrict__ seq_off,
-                               const int* __restrict__ chunk_off, int D, int rc, float* __restrict__ stats,
+pool_finalize_normalize_kernel(const float2* __restrict__ partial, const int* __restrict__ seg_rows,
+                               const int* __restrict__ seq_off, const int* __restrict__ chunk_off, int D, float* __restrict__ stats,
                                __nv_bfloat16* __restrict__ p_bf16, float* __restrict__ p_f32, float* __restrict__ norm_out) {
   const int b = blockIdx.y;
   const uint32_t rank = cluster_ctarank();
@@ -415,9 +456,10 @@ pool_finalize_normalize_kernel(const float2* __restrict__ partial, const int* __
   float sq = 0.f;
   for (int col = rank * FIN_THREADS + threadIdx.x; col < D; col += FIN_CLUSTER * FIN_THREADS) {
     float n = 0.f, mean = 0.f, m2 = 0.f;
-#pragma unroll 4
     for (int c = c0; c < c1; ++c) {
-      const float nc = (float)min(rc, n_total - (c - c0) * rc);
+      const int rows_c = seg_rows[c];
+      if (rows_c == 0) continue;
+      const float nc = (float)rows_c;
       const float2 pc = partial[(long long)c * D + col];
       const float tot = n + nc;
       const float delta = pc.x - mean;
@@ -1059,10 +1101,11 @@ int pool_forward(const void* src, bool src_is_f16, long long ld_src, int src_row
     if (e1 != cudaSuccess || e2 != cudaSuccess) return set_error((int)(e1 != cudaSuccess ? e1 : e2), "pool_forward: cannot reserve %d bytes of shared memory", smem);
     configured = true;
   }
+  int* seg_rows = reinterpret_cast<int*>(partial + (size_t)max_chunks * D);  // behind the partial records
   if (src_is_f16)
-    pool_partial_kernel<true><<<grid, POOL_THREADS, smem, st>>>(tmap, sp, ld_src, row_src, inv_norm, chunk_off, desc, B, D, partial);
+    pool_partial_kernel<true><<<grid, POOL_THREADS, smem, st>>>(tmap, sp, ld_src, row_src, inv_norm, chunk_off, desc, B, D, partial, seg_rows);
   else
-    pool_partial_kernel<false><<<grid, POOL_THREADS, smem, st>>>(tmap, sp, ld_src, row_src, inv_norm, chunk_off, desc, B, D, partial);
+    pool_partial_kernel<false><<<grid, POOL_THREADS, smem, st>>>(tmap, sp, ld_src, row_src, inv_norm, chunk_off, desc, B, D, partial, seg_rows);
   if (int r = check_launch("pool_partial_kernel", st)) return r;
   if (norm_p_bf16 != nullptr || norm_p_f32 != nullptr) {
     if (mode != 3 || ld_out != 2LL * D) return set_error(-1, "pool_forward: fused normalise needs the dense 'mix' layout");
@@ -1077,15 +1120,15 @@ int pool_forward(const void* src, bool src_is_f16, long long ld_src, int src_row
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, pool_finalize_normalize_kernel, (const float2*)partial, seq_off, chunk_off, D, rc,
-                                        out, reinterpret_cast<__nv_bfloat16*>(norm_p_bf16), norm_p_f32, norm_out);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, pool_finalize_normalize_kernel, (const float2*)partial, (const int*)seg_rows, seq_off,
+                                        chunk_off, D, out, reinterpret_cast<__nv_bfloat16*>(norm_p_bf16), norm_p_f32, norm_out);
     if (le != cudaSuccess) return set_error((int)le, "pool_finalize_normalize_kernel: %s", cudaGetErrorString(le));
     count_launch();
     stamp_launch("pool_finalize_normalize_kernel", st);
     return 0;
   }
   dim3 g2(B, (D + 255) / 256);
-  pool_finalize_kernel<<<g2, 256, 0, st>>>(partial, seq_off, chunk_off, B, D, rc, mode, out, ld_out);
+  pool_finalize_kernel<<<g2, 256, 0, st>>>(partial, seg_rows, seq_off, chunk_off, B, D, mode, out, ld_out);
   return check_launch("pool_finalize_kernel", st);
 }
 

@@ -168,6 +168,27 @@ def test_gemm_split_k_tail_matches_fp64_matmul_and_is_deterministic(core, dev, c
     assert torch.equal(out, again)  # fixed summation order of the partial tiles
 
 
+@pytest.mark.parametrize("m_actual", [700, 2195, 4000])
+def test_gemm_split_k_tail_chosen_on_the_device_for_ragged_m(p2t, core, dev, m_actual):
+    """M read from device memory + split-K scratch: the kernel derives the tile count and the cut itself (same cost
+    model as the launcher) — opt-in for the ragged adapter GEMMs (P2T_SPLITK_DYN=1), exact and deterministic."""
+    m_cap, n, k = 4096, 512, 1024
+    g = torch.Generator().manual_seed(m_actual)
+    A = bf(torch.randn(m_cap, k, generator=g)).to(dev)
+    Bm = bf(torch.randn(n, k, generator=g)).to(dev)
+    dyn = torch.tensor([m_actual], dtype=torch.int32, device=dev)
+    outs = []
+    for _ in range(2):
+        out = torch.zeros(m_cap, n, dtype=torch.float32, device=dev)
+        ws = core.gemm_workspace(dev)
+        p2t._lib.call("p2t_gemm_bf16", A.data_ptr(), k, 0, Bm.data_ptr(), k, 0, out.data_ptr(), n, 1, m_cap, n, k, 1.0,
+                      dyn.data_ptr(), None, ws.data_ptr(), 2, None)
+        outs.append(out)
+    ref = A[:m_actual].double() @ Bm.double().t()
+    assert (outs[0][:m_actual].double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_gemm_device_side_extents(core, dev):
     """dyn_m / dyn_k are read from device memory: rows >= dyn_m are not written, the K loop stops at dyn_k."""
     m, n, k = 700, 256, 512
@@ -433,6 +454,36 @@ def test_step_matches_reference_teacher_forcing_forward_pass(p2t, dev, golden_di
     assert_grads(adapter_grads(ad), {k: g[f"seg{nseg}.grad.{k}"] for k in PARAMS}, f"golden step nseg={nseg}")
     if nseg == 1:
         assert maxrel(aux.protein_embeddings, g["p"]) <= 6e-3
+
+
+@pytest.mark.parametrize("nseg", [1, 2, 3, 4])
+def test_integration_recipe_reproduces_the_reference_step(p2t, dev, golden_dir, nseg):
+    """INTEGRATION.md §2 verbatim: the whole batch padded once to the batch's longest sequence, the pooling mask built
+    by `segment_pooling_mask(lengths, num_segments)` (NOT torch.ones_like: the fork pools each segment over the
+    segment's own padded length), against the outputs of the REAL teacher_forcing_forward_pass."""
+    g = _load(golden_dir, "grid_step.npz")
+    ad = make_adapter(p2t, dev, *(g["sd." + k] for k in PARAMS))
+    lens = [int(v) for v in g["lens"]]
+    B, L, d_in = len(lens), max(lens), g["x0"].shape[1]
+    residues = torch.zeros(B, L, d_in)
+    rmask = torch.zeros(B, L, dtype=torch.long)
+    for b, n in enumerate(lens):
+        residues[b, :n] = g[f"x{b}"]
+        rmask[b, :n] = 1
+    residues, rmask = bf(residues).to(dev), rmask.to(dev)
+    mask = p2t.segment_pooling_mask(rmask.sum(dim=1), nseg, rmask.shape[1], device=rmask.device)
+    assert torch.equal(mask.cpu(), _golden_step_inputs(g, nseg)[1])
+    loss = p2t.contrastive_step(residues, mask, ad, bf(g["text"]).to(dev), g["tmask"].to(dev),
+                                temperature=0.05, contrastive_num_segments=nseg)
+    loss.backward()
+    ref = g[f"seg{nseg}.loss"].item()
+    assert abs(loss.item() - ref) <= LOSS_RTOL * abs(ref)
+    assert_grads(adapter_grads(ad), {k: g[f"seg{nseg}.grad.{k}"] for k in PARAMS}, f"INTEGRATION recipe nseg={nseg}")
+    if nseg == 4:  # ... and the all-ones mask over the BATCH length is a different (wrong) computation
+        ad.zero_grad(set_to_none=True)
+        wrong = p2t.contrastive_step(residues, torch.ones_like(rmask), ad, bf(g["text"]).to(dev), g["tmask"].to(dev),
+                                     contrastive_num_segments=nseg)
+        assert abs(wrong.item() - ref) > LOSS_RTOL * abs(ref)
 
 
 STEP_CASES = [
