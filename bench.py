@@ -334,13 +334,17 @@ def main():
     # N > 1: the exchange step of the sharded batch runs as peer-memory kernels (no NCCL on the data path)
     exchange = pdist.ShardedExchange(B, 2 * cfg["d_out"]) if world > 1 else None
 
+    # the collater knows the sequence lengths: packed activations are sized for the valid rows, not for B * L_max
+    rows_bound = max(valid_rows) + 256
+
     def step(inp):
         for p in params:
             p.grad = None
         if world > 1:
-            loss = pdist.distributed_contrastive_step(inp["x"], inp["pm"], adapter, inp["text"], inp["tm"], exchange=exchange)
+            loss = pdist.distributed_contrastive_step(inp["x"], inp["pm"], adapter, inp["text"], inp["tm"], exchange=exchange,
+                                                      max_valid_rows=rows_bound)
         else:
-            loss = pkg.contrastive_step(inp["x"], inp["pm"], adapter, inp["text"], inp["tm"])
+            loss = pkg.contrastive_step(inp["x"], inp["pm"], adapter, inp["text"], inp["tm"], max_valid_rows=rows_bound)
         loss.backward()
         return loss
 
@@ -383,7 +387,7 @@ def main():
     sampler = ClockSampler(local_rank)
     if use_graph:
         graphs = [pkg.GraphedContrastiveStep(adapter, r["x"], r["pm"], r["text"], r["tm"], seed=1000 * (i + 1),
-                                             exchange=exchange)
+                                             exchange=exchange, max_valid_rows=rows_bound)
                   for i, r in enumerate(resident)]
         for i in range(args.warmup):
             graphs[i % nbatches].replay()

@@ -37,7 +37,8 @@ class GraphedContrastiveStep:
     def __init__(self, adapter: ModalityAdapter, residue_states: torch.Tensor, protein_mask: torch.Tensor,
                  text_hidden: torch.Tensor, text_mask: torch.Tensor, *, temperature: float = 0.05,
                  contrastive_num_segments: int = 1, symmetric: bool = False, seed: int = 0, warmup: int = 2,
-                 exchange=None, grad_reducer=None, optimizer=None, accumulation_steps: int = 1, check_every: int = 0):
+                 exchange=None, grad_reducer=None, optimizer=None, accumulation_steps: int = 1, check_every: int = 0,
+                 max_valid_rows: Optional[int] = None):
         if not residue_states.is_cuda:
             raise _lib.P2TError("GraphedContrastiveStep needs CUDA tensors: this package has no CPU path")
         self.adapter = adapter
@@ -54,7 +55,8 @@ class GraphedContrastiveStep:
             raise ValueError("the sharded step averages over the whole local batch: contrastive_num_segments must be 1")
         if accumulation_steps < 1:
             raise ValueError("accumulation_steps must be >= 1")
-        self.kw = dict(temperature=temperature, contrastive_num_segments=contrastive_num_segments, symmetric=symmetric)
+        self.kw = dict(temperature=temperature, contrastive_num_segments=contrastive_num_segments, symmetric=symmetric,
+                       max_valid_rows=max_valid_rows)
         self.params = [adapter.fc1.weight, adapter.fc1.bias, adapter.fc2.weight, adapter.fc2.bias]
         dev = residue_states.device
         self.device = dev
@@ -114,7 +116,8 @@ class GraphedContrastiveStep:
             from .dist import distributed_contrastive_step
             loss, state = distributed_contrastive_step(x, pm, self.adapter, th, tm, aux=aux, seed_dev=self.seed,
                                                        _raw=True, exchange=self.exchange, dloss_dev=self.dloss,
-                                                       temperature=self.kw["temperature"], symmetric=self.kw["symmetric"])
+                                                       temperature=self.kw["temperature"], symmetric=self.kw["symmetric"],
+                                                       max_valid_rows=self.kw["max_valid_rows"])
         # on a boundary step without a reducer the bf16 bias gradients land directly in what param.grad is bound to
         step_backward(state, None, accumulate=not first, dw_out=(self._dw1, self._dw2),
                       db_f32_out=(self._db1_f32, self._db2_f32), db_bf16_out=(self._db1, self._db2))

@@ -98,7 +98,7 @@ def step_forward(x, prot_mask, w1, b1, w2, b2, t_in, labels, cfg: dict, aux: Ste
         x_rows = xp.shape[0]
     else:
         B, L, d_in = x.shape
-        plan = _core.plan_rows(prot_mask)
+        plan = _core.plan_rows(prot_mask, max_valid_rows=cfg.get("max_valid_rows"))
         xp = _core.gather_rows(x.contiguous().view(B * L, d_in), plan)
         x_rows = plan.rows_cap
     join = cfg.get("text_join")
@@ -285,7 +285,8 @@ def contrastive_step(residue_states: torch.Tensor, protein_mask: Optional[torch.
                      labels: Optional[torch.Tensor] = None, aux: Optional[StepAux] = None,
                      col_stats_hook=None, loss_scale: Optional[float] = None,
                      all_cols_labelled: bool = False, seed_dev: Optional[torch.Tensor] = None,
-                     late_text: bool = False, dloss_dev: Optional[torch.Tensor] = None, _text_join=None,
+                     late_text: bool = False, dloss_dev: Optional[torch.Tensor] = None,
+                     max_valid_rows: Optional[int] = None, _text_join=None,
                      _raw: bool = False) -> torch.Tensor:
     """One Stage-1 step from trunk outputs to the (differentiable) fp32 loss.
 
@@ -304,6 +305,8 @@ def contrastive_step(residue_states: torch.Tensor, protein_mask: Optional[torch.
     of drawn from torch's CPU generator (CUDA-graph replays, see graph.GraphedContrastiveStep).  `dloss_dev` (fp32
     device scalar): constant factor on the gradient, e.g. 1 / gradient_accumulation_steps (the reference divides the
     loss by it before backward, scripts/train_contrast.py:432); the returned loss is not scaled.
+    `max_valid_rows`: host-side upper bound on sum(protein_mask) (the collater knows the sequence lengths): packed
+    activations are sized for it instead of for B*L.
     """
     text_join = _text_join
     if text_embeds is None:
@@ -331,7 +334,7 @@ def contrastive_step(residue_states: torch.Tensor, protein_mask: Optional[torch.
                dropout_p=p, seed=_draw_seed() if (p > 0 and seed_dev is None) else 0, seed_dev=seed_dev,
                rows_used=seg * contrastive_num_segments, packed=packed,
                col_stats_hook=col_stats_hook, loss_scale=loss_scale, all_cols_labelled=all_cols_labelled,
-               late_text=late_text, text_join=text_join, dloss_dev=dloss_dev)
+               late_text=late_text, text_join=text_join, dloss_dev=dloss_dev, max_valid_rows=max_valid_rows)
     aux = aux if aux is not None else StepAux()
     if _raw:  # graph capture: no autograd, the caller runs step_backward itself
         return step_forward(residue_states, residue_lengths if packed else protein_mask, adapter.fc1.weight.detach(),
