@@ -190,7 +190,9 @@ int p2t_adapter_tail_bwd_dy(const void* a, const void* g2, const float* inv_norm
  * backward GEMMs of the adapter (autograd of :62-65; scripts/train_contrast.py:448):
  *   dz1 = (dz2 W2) * g1;  dW2 = dz2^T h1;  db2 = colsum dz2;  dW1 = dz1^T x;  db1 = colsum dz1
  *   dx  = dz1 W1 (only when dx != NULL; the encoder is frozen in Stage 1, :186)
- * Gradients are in bf16, nn.Linear layout; written, or — accumulate != 0 — added to what dw1/dw2 hold (the reference
+ * Gradients are in nn.Linear layout, bf16 — or, dw_is_f32 != 0, dw1/dw2 in fp32 (the form a gradient mean over ranks
+ * should carry: a rank's gradient can be several times larger than the mean, so a bf16 rounding per rank costs several
+ * times 2^-9 of the mean) —; written, or — accumulate != 0 — added to what dw1/dw2 hold (the reference
  * accumulates .grad over gradient_accumulation_steps micro-batches, scripts/train_contrast.py:448-465).
  * db1/db2/dx may be NULL (db2 is normally produced by p2t_adapter_tail_bwd).
  * colsum_ws: fp32 [ceil(rows_cap/32)][d_mid] — the dgrad GEMM's epilogue leaves the column sums of dz1 over every
@@ -201,7 +203,7 @@ int p2t_adapter_tail_bwd_dy(const void* a, const void* g2, const float* inv_norm
 int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, const void* h1, const void* g1, const void* dz2,
                     int d_in, int d_mid, int d_out, int rows_cap, const int* n_rows_dev, void* dz1, void* dw1,
                     void* db1, void* dw2, void* db2, void* dx, float* colsum_ws, void* gemm_ws, int accumulate,
-                    int cta_group, void* stream);
+                    int dw_is_f32, int cta_group, void* stream);
 /* Both bias gradients of the fused step in one launch, summed in a fixed order from the partial rows left by
  * p2t_adapter_bwd (db1_partial = its colsum_ws) and p2t_adapter_tail_bwd (db2_partial = its colsum_ws, nparts2_dev,
  * ws_rows2).  Outputs in fp32 (what the gradient all-reduce carries: ONE rounding to bf16, after the mean over ranks)

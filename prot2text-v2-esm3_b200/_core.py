@@ -198,12 +198,14 @@ def adapter_forward(x: torch.Tensor, x_rows: int, rows_cap: int, n_rows: torch.T
 
 def adapter_backward(acts: AdapterActs, dz2: torch.Tensor, w1, w2, need_dx: bool = False, need_db2: bool = True,
                      cta_group: Optional[int] = None, need_db1: bool = True, accumulate: bool = False,
-                     dw1_out: Optional[torch.Tensor] = None, dw2_out: Optional[torch.Tensor] = None):
+                     dw1_out: Optional[torch.Tensor] = None, dw2_out: Optional[torch.Tensor] = None,
+                     dw_dtype=torch.bfloat16):
     """Returns (dw1, db1, dw2, db2_or_None, dx_or_None) in bf16, nn.Linear layout.
 
     `need_db1=False`: db1 is returned as the fp32 partial column sums [ceil(rows_cap/32)][d_mid] the dgrad GEMM's
     epilogue left behind (finish them with `bias_grads`).  `dw1_out`/`dw2_out`: write (or, with `accumulate`, add)
-    the weight gradients into the caller's tensors instead of fresh ones."""
+    the weight gradients into the caller's tensors instead of fresh ones.  `dw_dtype=torch.float32`: the weight
+    gradients leave the GEMMs unrounded (what a gradient mean over ranks should carry)."""
     d_mid, d_in = w1.shape
     d_out = w2.shape[0]
     dev = dz2.device
@@ -211,8 +213,10 @@ def adapter_backward(acts: AdapterActs, dz2: torch.Tensor, w1, w2, need_dx: bool
     dz1 = torch.empty(acts.rows_cap, d_mid, dtype=bf, device=dev)
     if accumulate and (dw1_out is None or dw2_out is None):
         raise _lib.P2TError("accumulate needs dw1_out and dw2_out")
-    dw1 = dw1_out if dw1_out is not None else torch.empty(d_mid, d_in, dtype=bf, device=dev)
-    dw2 = dw2_out if dw2_out is not None else torch.empty(d_out, d_mid, dtype=bf, device=dev)
+    dw1 = dw1_out if dw1_out is not None else torch.empty(d_mid, d_in, dtype=dw_dtype, device=dev)
+    dw2 = dw2_out if dw2_out is not None else torch.empty(d_out, d_mid, dtype=dw_dtype, device=dev)
+    if dw1.dtype != dw2.dtype or dw1.dtype not in (torch.bfloat16, torch.float32):
+        raise _lib.P2TError("weight-gradient outputs must both be bfloat16 or both float32")
     db1 = torch.empty(d_mid, dtype=bf, device=dev) if need_db1 else None
     db2 = torch.empty(d_out, dtype=bf, device=dev) if need_db2 else None
     dx = torch.empty(acts.rows_cap, d_in, dtype=bf, device=dev) if need_dx else None
@@ -221,7 +225,7 @@ def adapter_backward(acts: AdapterActs, dz2: torch.Tensor, w1, w2, need_dx: bool
     _lib.call("p2t_adapter_bwd", _ptr(acts.x), acts.x_rows, _ptr(w1), _ptr(w2), _ptr(acts.h1), _ptr(acts.g1),
               _ptr(dz2), d_in, d_mid, d_out, acts.rows_cap, _ptr(acts.n_rows), _ptr(dz1), _ptr(dw1), _ptr(db1),
               _ptr(dw2), _ptr(db2), _ptr(dx), _ptr(ws), _ptr(gemm_workspace(dev)), int(accumulate),
-              cta_group or default_cta_group(), _stream())
+              int(dw1.dtype == torch.float32), cta_group or default_cta_group(), _stream())
     return dw1, (db1 if need_db1 else ws), dw2, db2, dx
 
 

@@ -32,7 +32,7 @@ SIGNATURES = {
     "p2t_readout_bwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "p2t_adapter_tail_bwd": [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp],
     "p2t_adapter_tail_bwd_dy": [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp],
-    "p2t_adapter_bwd": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "p2t_adapter_bwd": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "p2t_bias_grads": [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp],
     "p2t_loss_fused": [_vp, _vp, C.POINTER(_vp), _i, _i, _ll, _vp, _i, _i, _i, _i, _f, _f, _f, _f, _i, _i, _i,
                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],

@@ -229,7 +229,7 @@ int p2t_adapter_tail_bwd_dy(const void* a, const void* g2, const float* inv_norm
 int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, const void* h1, const void* g1, const void* dz2,
                     int d_in, int d_mid, int d_out, int rows_cap, const int* n_rows_dev, void* dz1, void* dw1,
                     void* db1, void* dw2, void* db2, void* dx, float* colsum_ws, void* gemm_ws, int accumulate,
-                    int cta_group, void* stream) {
+                    int dw_is_f32, int cta_group, void* stream) {
   if (!x || !w2 || !h1 || !g1 || !dz2 || !dz1 || !dw1 || !dw2 || !colsum_ws)
     return set_error(-1, "p2t_adapter_bwd: null pointer");
   cudaStream_t st = S(stream);
@@ -252,7 +252,7 @@ int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, c
     p.sk_ws = gemm_ws;
     p.d0 = dw2; p.ldd0 = d_mid;
     p.accumulate = accumulate;
-    if (int rc = launch_gemm(dz2, d_out, true, h1, d_mid, true, EPI_STORE_BF16, p, cta_group, st)) return rc;
+    if (int rc = launch_gemm(dz2, d_out, true, h1, d_mid, true, dw_is_f32 ? EPI_STORE_F32 : EPI_STORE_BF16, p, cta_group, st)) return rc;
   }
   // dW1 = dz1^T x
   {
@@ -262,7 +262,7 @@ int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, c
     p.d0 = dw1; p.ldd0 = d_in;
     p.b_extent = x_rows;
     p.accumulate = accumulate;
-    if (int rc = launch_gemm(dz1, d_mid, true, x, d_in, true, EPI_STORE_BF16, p, cta_group, st)) return rc;
+    if (int rc = launch_gemm(dz1, d_mid, true, x, d_in, true, dw_is_f32 ? EPI_STORE_F32 : EPI_STORE_BF16, p, cta_group, st)) return rc;
   }
   if (db2) if (int rc = colsum(dz2, n_rows_dev, rows_cap, d_out, db2_ws, db2, nullptr, st)) return rc;
   if (db1) {

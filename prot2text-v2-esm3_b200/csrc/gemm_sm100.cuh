@@ -75,8 +75,8 @@ struct GemmParams {
   int ld_rowsq;
   float* colsum;              // EPI_MUL_AUX (optional): [ceil(rows_cap / 32)][n] column sums of D0 over each 32-row block
                               // (fixed-order shuffle tree; the bias gradient db1 without a second pass over dz1)
-  int accumulate;             // EPI_STORE_BF16: D0 += alpha * acc (bf16 read-modify-write: gradient accumulation over
-                              // micro-batches, scripts/train_contrast.py:448 without optimizer.zero_grad in between)
+  int accumulate;             // EPI_STORE_BF16 / EPI_STORE_F32: D0 += alpha * acc (read-modify-write: gradient accumulation
+                              // over micro-batches, scripts/train_contrast.py:448 without optimizer.zero_grad in between)
   float alpha;
   DropoutParams drop;         // p == 0 -> disabled
   // split-K tail (see header comment); sk_ws == nullptr -> whole tiles only
@@ -217,7 +217,16 @@ __device__ __forceinline__ void load8(const T* src, float (&f)[8], int n_ok) {
   }
 }
 
-// bf16 read-modify-write partner of store8 (accumulating epilogue): ordinary loads, never the read-only path
+// read-modify-write partner of store8 (accumulating epilogue): ordinary loads, never the read-only path
+__device__ __forceinline__ void load8_plain(const float* src, float (&f)[8], int n_ok, bool vec_ok) {
+  if (n_ok == 8 && vec_ok) {
+    const float4 a = reinterpret_cast<const float4*>(src)[0], b = reinterpret_cast<const float4*>(src)[1];
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = (i < n_ok) ? src[i] : 0.f;
+  }
+}
 __device__ __forceinline__ void load8_plain(const __nv_bfloat16* src, float (&f)[8], int n_ok, bool vec_ok) {
   if (n_ok == 8 && vec_ok) {
     const uint4 u = *reinterpret_cast<const uint4*>(src);
@@ -341,13 +350,11 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ep
     if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_STORE_F32) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) val[i] *= e.alpha;
-      if constexpr (EPI == EPI_STORE_BF16) {
-        if (e.accumulate) {  // plain loads: this kernel writes the same addresses
-          float old[8];
-          load8_plain(dst0 + 8 * j, old, n_ok, vec_ok);
+      if (e.accumulate) {  // plain loads: this kernel writes the same addresses
+        float old[8];
+        load8_plain(dst0 + 8 * j, old, n_ok, vec_ok);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) val[i] += old[i];
-        }
+        for (int i = 0; i < 8; ++i) val[i] += old[i];
       }
       store8(dst0 + 8 * j, val, n_ok, vec_ok);
     } else if constexpr (EPI == EPI_MUL_AUX) {

@@ -52,16 +52,27 @@ constexpr unsigned kPoison = 0x7fffffffu;  // NaN as fp32 and as a pair of bf16
 // ------------------------------------------------------------------------------------------------
 // all-gather, push half: slot (epoch parity, rank) of every peer's buffer := src
 // ------------------------------------------------------------------------------------------------
+// U independent 16-byte loads per thread and trip, each fanned out to every peer: (grid x 256 x U x 16) bytes per
+// destination are in flight against an NVLink round trip of ~2 us (one load per thread and 74 CTAs moved 67 MB at
+// 115 GB/s: latency-bound, not link-bound).
+template <int U>
 __global__ void __launch_bounds__(256)
 peer_allgather_push_kernel(PeerTable peers, int world, int rank, const uint4* __restrict__ src, long long vecs_per_rank) {
   unsigned* ctrl = static_cast<unsigned*>(peers.base[rank]);
   const unsigned epoch = ctrl[0] + 1;
   const size_t slot_off = kCtrlBytes + ((size_t)(epoch & 1) * world + rank) * (size_t)vecs_per_rank * sizeof(uint4);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < vecs_per_rank; i += (long long)gridDim.x * blockDim.x) {
-    const uint4 v = __ldg(src + i);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < vecs_per_rank; i += U * stride) {
+    uint4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (i + u * stride < vecs_per_rank) v[u] = __ldg(src + i + u * stride);
     for (int r = 0; r < world; ++r) {
       const int dst = (rank + r) % world;  // ranks start on different links
-      reinterpret_cast<uint4*>(static_cast<char*>(peers.base[dst]) + slot_off)[i] = v;
+      uint4* out = reinterpret_cast<uint4*>(static_cast<char*>(peers.base[dst]) + slot_off);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (i + u * stride < vecs_per_rank) out[i + u * stride] = v[u];
     }
   }
   publish_when_grid_done(peers, world, rank, flag_row_off(0), epoch, ctrl + 1, nullptr);
@@ -259,7 +270,10 @@ int peer_allgather(void* const* peers, int world, int rank, const void* src, lon
   const long long vecs = bytes_per_rank / 16;
   if (phases & 1) {
     if (!src) return set_error(-1, "p2t_peer_allgather: null src");
-    peer_allgather_push_kernel<<<grid_for(vecs), 256, 0, st>>>(t, world, rank, static_cast<const uint4*>(src), vecs);
+    if (vecs >= (1 << 18))  // >= 4 MB per rank: bandwidth matters, take every SM twice over
+      peer_allgather_push_kernel<4><<<grid_for(vecs / 4, 4), 256, 0, st>>>(t, world, rank, static_cast<const uint4*>(src), vecs);
+    else
+      peer_allgather_push_kernel<1><<<grid_for(vecs), 256, 0, st>>>(t, world, rank, static_cast<const uint4*>(src), vecs);
     if (int r = check_launch("peer_allgather_push_kernel", st)) return r;
   }
   if (phases & 2) {

@@ -18,9 +18,9 @@ read-modify-write in the weight-gradient GEMMs' epilogues, fp32 for the biases),
 binds `param.grad`.  That is DDP's `no_sync()` on the non-boundary micro-steps, which the reference lacks
 (SURVEY.md §8f-1).  Dropout (training mode) uses a device-side seed that every replay increments.
 
-With a `grad_reducer` (peer.PeerGradAllReduce built over [dW1 bf16, db1 fp32, dW2 bf16, db2 fp32]) the backward kernels
-write the gradients straight into the reducer's channel buffer and the reduced means are bound to `param.grad` in
-place: no staging copies.  The bias gradients cross the ranks in fp32 and are rounded to bf16 once, after the mean.
+With a `grad_reducer` (peer.PeerGradAllReduce.for_adapter: all four gradients in fp32) the backward kernels write
+the unrounded gradients straight into the reducer's channel buffer (no staging copies), the mean over ranks is formed
+in fp32 in rank order, and the only rounding is the final conversion to the bf16 tensors bound to `param.grad`.
 """
 from __future__ import annotations
 
@@ -75,13 +75,14 @@ class GraphedContrastiveStep:
         d_mid, d_in = adapter.fc1.weight.shape
         d_out = adapter.fc2.weight.shape[0]
         bf, f32 = torch.bfloat16, torch.float32
+        self._dw_f32 = grad_reducer is not None
         if grad_reducer is not None:
-            want = [((d_mid, d_in), bf), ((d_mid,), f32), ((d_out, d_mid), bf), ((d_out,), f32)]
+            want = [((d_mid, d_in), f32), ((d_mid,), f32), ((d_out, d_mid), f32), ((d_out,), f32)]
             if [(s, d) for s, d in zip(grad_reducer.shapes, grad_reducer.dtypes)] != want:
-                raise _lib.P2TError("grad_reducer must be built over [dW1 bf16, db1 fp32, dW2 bf16, db2 fp32] "
+                raise _lib.P2TError("grad_reducer must be built over the four fp32 gradients [dW1, db1, dW2, db2] "
                                     "(peer.PeerGradAllReduce.for_adapter)")
             self._dw1, self._db1_f32, self._dw2, self._db2_f32 = grad_reducer.views_in()
-            self._rw1, self._rb1_f32, self._rw2, self._rb2_f32 = grad_reducer.views_out()
+            self._reduced = grad_reducer.views_out()
         else:
             self._dw1 = torch.zeros(d_mid, d_in, dtype=bf, device=dev)
             self._dw2 = torch.zeros(d_out, d_mid, dtype=bf, device=dev)
@@ -91,7 +92,8 @@ class GraphedContrastiveStep:
         self._db1 = torch.zeros(d_mid, dtype=bf, device=dev)
         self._db2 = torch.zeros(d_out, dtype=bf, device=dev)
         if grad_reducer is not None:
-            self.grads = [self._rw1, self._db1, self._rw2, self._db2]
+            self.grads = [torch.zeros(d_mid, d_in, dtype=bf, device=dev), self._db1,
+                          torch.zeros(d_out, d_mid, dtype=bf, device=dev), self._db2]
         else:
             self.grads = [self._dw1, self._db1, self._dw2, self._db2]
         if optimizer is not None:
@@ -119,13 +121,13 @@ class GraphedContrastiveStep:
                                                        temperature=self.kw["temperature"], symmetric=self.kw["symmetric"],
                                                        max_valid_rows=self.kw["max_valid_rows"])
         # on a boundary step without a reducer the bf16 bias gradients land directly in what param.grad is bound to
-        step_backward(state, None, accumulate=not first, dw_out=(self._dw1, self._dw2),
+        step_backward(state, None, accumulate=not first, dw_out=(self._dw1, self._dw2), dw_f32=self._dw_f32,
                       db_f32_out=(self._db1_f32, self._db2_f32), db_bf16_out=(self._db1, self._db2))
         if last and with_tail:
             if self.grad_reducer is not None:
                 self.grad_reducer.exchange()
-                _lib.call("p2t_f32_to_bf16", self._rb1_f32.data_ptr(), self._rb1_f32.numel(), self._db1.data_ptr(), _core._stream())
-                _lib.call("p2t_f32_to_bf16", self._rb2_f32.data_ptr(), self._rb2_f32.numel(), self._db2.data_ptr(), _core._stream())
+                for mean_f32, grad_bf16 in zip(self._reduced, self.grads):  # the one rounding: mean (fp32) -> param.grad (bf16)
+                    _lib.call("p2t_f32_to_bf16", mean_f32.data_ptr(), mean_f32.numel(), grad_bf16.data_ptr(), _core._stream())
             if self.optimizer is not None:
                 for p, g in zip(self.params, self.grads):
                     p.grad = g

@@ -239,15 +239,18 @@ class PeerGradAllReduce:
 
     @staticmethod
     def adapter_like(adapter) -> List[torch.Tensor]:
-        """[dW1 bf16, db1 fp32, dW2 bf16, db2 fp32] (meta tensors): what the fused step's backward produces."""
+        """[dW1, db1, dW2, db2], all fp32 (meta tensors): the unrounded gradients of the fused step's backward."""
         w1, w2 = adapter.fc1.weight, adapter.fc2.weight
-        bf, f32 = torch.bfloat16, torch.float32
-        return [torch.empty(tuple(w1.shape), dtype=bf, device="meta"), torch.empty(w1.shape[0], dtype=f32, device="meta"),
-                torch.empty(tuple(w2.shape), dtype=bf, device="meta"), torch.empty(w2.shape[0], dtype=f32, device="meta")]
+        f32 = torch.float32
+        return [torch.empty(tuple(w1.shape), dtype=f32, device="meta"), torch.empty(w1.shape[0], dtype=f32, device="meta"),
+                torch.empty(tuple(w2.shape), dtype=f32, device="meta"), torch.empty(w2.shape[0], dtype=f32, device="meta")]
 
     @classmethod
     def for_adapter(cls, adapter, group=None, _buffer: Optional[PeerBuffer] = None) -> "PeerGradAllReduce":
-        """The reducer `graph.GraphedContrastiveStep(grad_reducer=...)` expects: weights in bf16, biases in fp32."""
+        """The reducer `graph.GraphedContrastiveStep(grad_reducer=...)` expects: all four gradients in fp32.  A rank's
+        gradient can be several times larger than the mean over ranks (different batches pull in different
+        directions), so rounding each rank's contribution to bf16 costs several times bf16's 2^-9 relative to the
+        mean; in fp32 the only rounding is the final one, to the bf16 of param.grad."""
         return cls(cls.adapter_like(adapter), group, _buffer)
 
     @staticmethod

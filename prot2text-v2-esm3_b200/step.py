@@ -38,6 +38,10 @@ class StepAux:
     argmax_row: Optional[torch.Tensor] = None           # int32 (B,)  protein -> text retrieval
     argmax_col: Optional[torch.Tensor] = None           # int32 (B_global,) text -> protein retrieval (local rows)
     n_rows: Optional[torch.Tensor] = None               # int32 (1,) valid residue rows
+    # filled by backward: the bias gradients in fp32, BEFORE their rounding to the bf16 of param.grad.  A gradient mean
+    # over ranks should carry these (peer.PeerGradAllReduce.for_adapter): per-rank gradients can be several times larger
+    # than their mean, so rounding each rank's value to bf16 first costs several times bf16's 2^-9 in the mean.
+    bias_grads_f32: Optional[tuple] = None
 
 
 @torch.no_grad()
@@ -160,10 +164,11 @@ def step_forward(x, prot_mask, w1, b1, w2, b2, t_in, labels, cfg: dict, aux: Ste
 
 
 def step_backward(state, dloss: Optional[torch.Tensor], *, accumulate: bool = False, dw_out: Optional[tuple] = None,
-                  db_f32_out: Optional[tuple] = None, db_bf16_out: Optional[tuple] = None):
+                  db_f32_out: Optional[tuple] = None, db_bf16_out: Optional[tuple] = None, dw_f32: bool = False):
     """Backward of the fused step: (dW1, db1, dW2, db2, db1_f32, db2_f32) — bf16 gradients in nn.Linear layout plus
     the bias gradients in fp32 (what a gradient all-reduce should carry) — for the upstream gradient `dloss` (device
-    scalar; None = 1).  `dw_out` = (dW1, dW2) / `db_f32_out` / `db_bf16_out`: write into the caller's tensors;
+    scalar; None = 1).  `dw_f32`: dW1/dW2 leave the GEMMs in fp32 instead (sharded training: the gradient mean over
+    ranks then rounds once, after the mean).  `dw_out` = (dW1, dW2) / `db_f32_out` / `db_bf16_out`: write into the caller's tensors;
     `accumulate`: add to them (bf16 read-modify-write for the weights, fp32 for the biases) — the micro-batch
     accumulation of scripts/train_contrast.py:448-465."""
     plan, acts, inv_norm, w1c, w2c, cfg, head = state
@@ -197,7 +202,8 @@ def step_backward(state, dloss: Optional[torch.Tensor], *, accumulate: bool = Fa
     dz2, (ws2, nparts2) = _core.adapter_tail_backward(acts, inv_norm, plan, c1, c2, finish_db2=False)
     dw1_out, dw2_out = dw_out if dw_out is not None else (None, None)
     dw1, ws1, dw2, _, _ = _core.adapter_backward(acts, dz2, w1c, w2c, need_db2=False, need_db1=False,
-                                                 accumulate=accumulate, dw1_out=dw1_out, dw2_out=dw2_out)
+                                                 accumulate=accumulate, dw1_out=dw1_out, dw2_out=dw2_out,
+                                                 dw_dtype=torch.float32 if dw_f32 else torch.bfloat16)
     db1, db2, db1_f32, db2_f32 = _core.bias_grads(ws1, acts.rows_cap, acts.n_rows, d_mid, ws2, nparts2, d_out,
                                                   accumulate=accumulate, out_f32=db_f32_out, out_bf16=db_bf16_out)
     return dw1, db1, dw2, db2, db1_f32, db2_f32
@@ -206,6 +212,7 @@ def step_backward(state, dloss: Optional[torch.Tensor], *, accumulate: bool = Fa
 class _ContrastiveStepFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, prot_mask, w1, b1, w2, b2, t_in, labels, cfg: dict, aux: StepAux):
+        ctx.aux = aux
         loss, ctx.state = step_forward(x, prot_mask, w1, b1, w2, b2, t_in, labels, cfg, aux,
                                        need_grad=any(ctx.needs_input_grad[2:6]))
         return loss
@@ -213,7 +220,8 @@ class _ContrastiveStepFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dloss):
         state, ctx.state = ctx.state, None
-        dw1, db1, dw2, db2, _, _ = step_backward(state, dloss)
+        dw1, db1, dw2, db2, db1_f32, db2_f32 = step_backward(state, dloss)
+        ctx.aux.bias_grads_f32 = (db1_f32, db2_f32)
         return None, None, dw1, db1, dw2, db2, None, None, None, None
 
 

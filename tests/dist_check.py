@@ -44,7 +44,9 @@ def main():
     peer = importlib.import_module("p2t_b200.peer")
     prms = (ad.fc1.weight, ad.fc1.bias, ad.fc2.weight, ad.fc2.bias)
     exchange = pdist.ShardedExchange(sb.x.shape[0], 2 * sb.w2.shape[0], symmetric=True)
-    reducer = peer.PeerGradAllReduce.for_adapter(ad)
+    reducer = peer.PeerGradAllReduce.for_adapter(ad)  # graph form: all four gradients cross the ranks in fp32
+    f32m = lambda n: torch.empty(n, dtype=torch.float32, device="meta")
+    reducer_mixed = peer.PeerGradAllReduce([prms[0], f32m(prms[1].numel()), prms[2], f32m(prms[3].numel())])  # eager form
     dx, dpm, dtx, dtm = sb.x.to(dev), sb.prot_mask.to(dev), sb.text.to(dev), sb.text_mask.to(dev)
     for sym, form in ((False, "nccl"), (True, "nccl"), (False, "peer"), (True, "peer"), (False, "peer+graph"), (True, "peer+graph")):
         ad.zero_grad(set_to_none=True)
@@ -71,15 +73,26 @@ def main():
         lt = loss.detach().clone()
         dist.all_reduce(lt)
         grads = {}
-        for i, (k, prm) in enumerate(zip(PARAMS, prms)):
-            if form == "peer+graph":
-                grads[k] = reduced[i]
-            else:
-                g = prm.grad.float().clone()
+        if form == "peer+graph":
+            grads = {k: reduced[i] for i, k in enumerate(PARAMS)}
+        elif form == "peer":
+            # eager form of the same gradient mean: the mixed bf16 / fp32 reducer over NVLink peer memory (stage, reduce,
+            # copy back).  The biases travel in fp32 (aux.bias_grads_f32) and are NOT rounded per rank first.
+            db1_f32, db2_f32 = aux.bias_grads_f32
+            mixed = [prms[0].grad.clone(), db1_f32.clone(), prms[2].grad.clone(), db2_f32.clone()]
+            reducer_mixed.reduce_(mixed)
+            grads = {k: g.float().cpu() for k, g in zip(PARAMS, mixed)}
+        else:
+            # what DDP does (scripts/train_contrast.py:611-614), with the biases taken in fp32 as above
+            db1_f32, db2_f32 = aux.bias_grads_f32
+            grads = {}
+            for k, g in zip(PARAMS, (prms[0].grad.float(), db1_f32, prms[2].grad.float(), db2_f32)):
+                g = g.clone()
                 dist.all_reduce(g)
                 grads[k] = (g / world).cpu()
         exchange.check()
         reducer.buffer.check()
+        reducer_mixed.buffer.check()
         am_row = [torch.empty_like(aux.argmax_row) for _ in range(world)]
         dist.all_gather(am_row, aux.argmax_row)
         if rank == 0:
@@ -141,6 +154,7 @@ def main():
     torch.cuda.synchronize()
     exchange.close()
     reducer.close()
+    reducer_mixed.close()
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)
 

@@ -585,7 +585,7 @@ def _virtual_sharded_step(p2t, mods, dev, shards, ad, sym):
             loss, state = p2t.contrastive_step(x, pm, ad, text_embeds=exs[r].text, symmetric=sym,
                                                labels=step_mod._rank_labels(r, B, dev), aux=aux, col_stats_hook=hook,
                                                all_cols_labelled=sym, late_text=True, _raw=True)
-            grads = step_mod.step_backward(state, None)
+            grads = step_mod.step_backward(state, None, dw_f32=True)  # unrounded: what the gradient reducer carries
         return loss, grads, aux
 
     outs = []
@@ -605,8 +605,9 @@ def _virtual_sharded_step(p2t, mods, dev, shards, ad, sym):
         ex.check()
     loss = sum(o[0].item() for o in outs) / W
     mean = lambda i: sum(o[1][i].float() for o in outs) / W
-    # weights: mean of the per-rank bf16 gradients; biases: mean of the fp32 gradients (what the gradient reducer carries)
-    grads = {"fc1.weight": mean(0), "fc1.bias": mean(4), "fc2.weight": mean(2), "fc2.bias": mean(5)}
+    # the mean over ranks of the fp32 gradients, as peer.PeerGradAllReduce.for_adapter forms it (one rounding, at the end)
+    grads = {"fc1.weight": mean(0).to(torch.bfloat16), "fc1.bias": mean(4).to(torch.bfloat16),
+             "fc2.weight": mean(2).to(torch.bfloat16), "fc2.bias": mean(5).to(torch.bfloat16)}
     am_row = torch.cat([o[2].argmax_row.cpu().long() for o in outs])
     return loss, grads, am_row
 
