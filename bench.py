@@ -663,6 +663,41 @@ def main():
         except Exception as exc:  # noqa: BLE001 - a probe must never cost the benchmark its line
             exchange_leg = {"error": f"{type(exc).__name__}: {exc}"}
 
+    # ------------------------------ one whole training step in one graph (outside the metric) ------------------------------
+    # forward + backward + gradient mean over ranks (fp32, zero-copy through the reducer's channel buffer) + clip +
+    # AdamW captured together: what the optimizer side costs ON TOP of `value`'s step when nothing is staged or relaunched
+    train_leg = None
+    if use_graph and not args.no_optimizer and not big_workload:
+        try:
+            peer = importlib.import_module("p2t_b200.peer")
+            opt2 = pkg.FusedAdamW(params, lr=1e-5, eps=1e-6, betas=(0.9, 0.999), max_grad_norm=1.0)
+            red2 = peer.PeerGradAllReduce.for_adapter(adapter) if world > 1 else None
+            r0 = resident[0]
+            full = pkg.GraphedContrastiveStep(adapter, r0["x"], r0["pm"], r0["text"], r0["tm"], seed=4242, exchange=exchange,
+                                              grad_reducer=red2, optimizer=opt2, max_valid_rows=rows_bound)
+            plain = graphs[0]
+            res_ms = {}
+            for name, g in (("step_only", plain), ("step_reduce_optimizer", full)):
+                for _ in range(3):
+                    g.replay()
+                barrier()
+                t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0e.record()
+                for _ in range(args.steps):
+                    g.replay()
+                t1e.record()
+                barrier()
+                res_ms[name] = max_over_ranks(t0e.elapsed_time(t1e)) / args.steps
+            train_leg = {"ms_per_step": res_ms["step_reduce_optimizer"], "step_only_ms": res_ms["step_only"],
+                         "optimizer_side_ms": res_ms["step_reduce_optimizer"] - res_ms["step_only"],
+                         "launches_per_replay": full.launches_per_replay,
+                         "includes": "fused step + " + ("fp32 gradient mean over ranks (peer memory, zero-copy) + " if world > 1 else "")
+                                     + "clip_grad_norm_ + AdamW, one CUDA graph per step (same batch replayed)"}
+            if red2 is not None:
+                red2.buffer.check()
+        except Exception as exc:  # noqa: BLE001 - an extra leg must never cost the benchmark its line
+            train_leg = {"error": f"{type(exc).__name__}: {exc}"}
+
     # ------------------------------ roofline of the dominant kernel ------------------------------
     d_in, d_mid, d_out = cfg["d_in"], cfg["d_mid"], cfg["d_out"]
     flops_per_row = 2.0 * d_in * d_mid + 2.0 * d_mid * d_out + 2.0 * d_in * d_mid + 4.0 * d_mid * d_out
@@ -744,7 +779,8 @@ def main():
                        "cta_group": int(os.environ.get("P2T_CTA_GROUP", "2"))},
             "loss": last_loss, "gpu_launches": int(launches), "cuda_graph": bool(use_graph),
             "eager_ms_per_step": eager_ms_total / args.steps, "host_issue_ms_per_step_eager": host_issue_ms, "clocks": clocks, "e2e": e2e, "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "optimizer": optim_leg, "exchange": exchange_leg, "imbalance": imbalance,
+            "cpu_baseline": cpu_baseline, "optimizer": optim_leg, "training_step": train_leg, "exchange": exchange_leg,
+            "imbalance": imbalance,
             "stages": stages,
         }
         print(json.dumps(line), flush=True)
