@@ -234,6 +234,23 @@ int p2t_infonce_ce(float* S, const int* labels, int R, int C, float w_row, float
 int p2t_infonce_grad(const float* dS, const void* dS_bf16, const void* p, const void* t, const float* p_f32,
                      const float* t_f32, int R, int C, int E, float tau, float* dp, float* dt, int cta_group,
                      void* stream);
+/* Large blocks (R*C*E > 2^26), logits never materialised (north_star (3)): p2t_infonce_stats runs the similarity as a
+ * tcgen05 GEMM whose epilogue reduces every 32 x 64 piece of a tile to online-softmax partials — per row (max, sum exp,
+ * argmax) and, when col_part_ws != NULL, per column over 32-row blocks (max, sum exp, arg-max row) — plus the label
+ * logit pos[i] = S[i][lab(i)], and merges the column partials into col_max / col_sum / col_argmax (the same
+ * quantities p2t_infonce_col_stats produces, so ranks can combine them).  p2t_infonce_finish merges the row partials
+ * (row_lse, argmax_row), forms row_loss as p2t_infonce_ce does, and — dS_bf16 != NULL — recomputes S tile by tile in a
+ * second GEMM whose epilogue writes dLogits = inv_rn (w_row (softmax_row - onehot) + w_col (softmax_col - onehot)) in
+ * bf16, the A operand of p2t_infonce_grad.  p, t: bf16 [R][E], [C][E].
+ * Workspaces: row_part_ws 16 B x 4 ceil(C/256) x R; col_part_ws 16 B x ceil(R/32) x C; col_labelled_ws C bytes;
+ * col_lse_ws C floats.  A label outside [0, C) yields a NaN row loss. */
+int p2t_infonce_stats(const void* p, const void* t, const int* labels, int R, int C, int E, float tau, void* row_part_ws,
+                      void* col_part_ws, float* pos, float* col_max, float* col_sum, int* col_argmax, int cta_group,
+                      void* stream);
+int p2t_infonce_finish(const void* p, const void* t, const int* labels, int R, int C, int E, float tau, float w_row,
+                       float w_col, float inv_rn, const void* row_part_ws, const float* pos, const float* col_max,
+                       const float* col_sum, int all_cols_labelled, unsigned char* col_labelled_ws, float* col_lse_ws,
+                       float* row_loss, float* row_lse, int* argmax_row, void* dS_bf16, int cta_group, void* stream);
 int p2t_loss_mean(const float* row_loss, int R, float scale, float* loss, int accumulate, void* stream);
 
 /* The loss block of the fused step for small similarity blocks in ONE cooperative kernel (north_star (3): similarity,

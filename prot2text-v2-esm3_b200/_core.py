@@ -387,6 +387,39 @@ def infonce_forward(p_bf: torch.Tensor, t_bf: torch.Tensor, labels: torch.Tensor
     dev = p_bf.device
     cg = cta_group or default_cta_group()
     labels32 = labels.to(device=dev, dtype=torch.int32).contiguous()
+    scale = (1.0 / R) if loss_scale is None else float(loss_scale)
+    big = (R * C * E > (1 << 26)) and C % 8 == 0
+    import os
+    if big and t_bf is not None and os.environ.get("P2T_FUSED_LARGE", "1") != "0":
+        # large block: similarity on the tensor cores with the online-softmax statistics reduced in the GEMM's epilogue,
+        # then (for the gradient) S recomputed tile by tile into bf16 dLogits — no R x C fp32 tensor is ever allocated
+        f32 = torch.float32
+        npart = 4 * ((C + 255) // 256)
+        want_cols = w_col != 0.0 or want_col_argmax
+        row_part = torch.empty(npart * R * 4, dtype=f32, device=dev)
+        col_part = torch.empty(((R + 31) // 32) * C * 4, dtype=f32, device=dev) if want_cols else None
+        pos = torch.empty(R, dtype=f32, device=dev)
+        col_max = torch.empty(C, dtype=f32, device=dev) if want_cols else None
+        col_sum = torch.empty(C, dtype=f32, device=dev) if want_cols else None
+        argmax_col = torch.empty(C, dtype=torch.int32, device=dev) if want_cols else None
+        _lib.call("p2t_infonce_stats", _ptr(p_bf), _ptr(t_bf), _ptr(labels32), R, C, E, float(tau), _ptr(row_part),
+                  _ptr(col_part), _ptr(pos), _ptr(col_max), _ptr(col_sum), _ptr(argmax_col), cg, _stream())
+        if col_stats_hook is not None and want_cols:
+            col_max, col_sum = col_stats_hook(col_max, col_sum)
+            col_max, col_sum = col_max.contiguous(), col_sum.contiguous()
+        row_loss = torch.empty(R, dtype=f32, device=dev)
+        row_lse = torch.empty(R, dtype=f32, device=dev)
+        argmax_row = torch.empty(R, dtype=torch.int32, device=dev)
+        marks = torch.empty(C, dtype=torch.uint8, device=dev) if w_col != 0.0 else None
+        col_lse = torch.empty(C, dtype=f32, device=dev) if w_col != 0.0 else None
+        dS_bf16 = torch.empty(R, C, dtype=torch.bfloat16, device=dev) if need_grad else None
+        _lib.call("p2t_infonce_finish", _ptr(p_bf), _ptr(t_bf), _ptr(labels32), R, C, E, float(tau), float(w_row), float(w_col),
+                  scale, _ptr(row_part), _ptr(pos), _ptr(col_max), _ptr(col_sum), int(all_cols_labelled), _ptr(marks),
+                  _ptr(col_lse), _ptr(row_loss), _ptr(row_lse), _ptr(argmax_row), _ptr(dS_bf16), cg, _stream())
+        loss = torch.empty((), dtype=f32, device=dev)
+        _lib.call("p2t_loss_mean", _ptr(row_loss), R, scale, _ptr(loss), 0, _stream())
+        return InfoNCEResult(loss=loss, dS=None, dS_bf16=dS_bf16, row_lse=row_lse, argmax_row=argmax_row,
+                             argmax_col=argmax_col, col_max=col_max, col_sum=col_sum)
     S = torch.empty(R, C, dtype=torch.float32, device=dev)
     _lib.call("p2t_similarity", _ptr(p_bf), _ptr(t_bf), _ptr(p_f32), _ptr(t_f32), R, C, E, float(tau), _ptr(S), cg,
               _stream())
@@ -402,9 +435,7 @@ def infonce_forward(p_bf: torch.Tensor, t_bf: torch.Tensor, labels: torch.Tensor
     row_loss = torch.empty(R, dtype=torch.float32, device=dev)
     row_lse = torch.empty(R, dtype=torch.float32, device=dev)
     argmax_row = torch.empty(R, dtype=torch.int32, device=dev)
-    big = (R * C * E > (1 << 26)) and C % 8 == 0
     dS_bf16 = torch.empty(R, C, dtype=torch.bfloat16, device=dev) if (need_grad and big) else None
-    scale = (1.0 / R) if loss_scale is None else float(loss_scale)
     _lib.call("p2t_infonce_ce", _ptr(S), _ptr(labels32), R, C, float(w_row), float(w_col), scale, _ptr(col_max),
               _ptr(col_sum), _ptr(marks), int(all_cols_labelled), _ptr(row_loss), _ptr(row_lse), _ptr(argmax_row), _ptr(dS_bf16),
               int(need_grad), _stream())

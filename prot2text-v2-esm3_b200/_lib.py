@@ -39,6 +39,8 @@ SIGNATURES = {
     "p2t_similarity": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i, _vp],
     "p2t_infonce_col_stats": [_vp, _i, _i, _vp, _vp, _vp, _i, _vp],
     "p2t_infonce_ce": [_vp, _vp, _i, _i, _f, _f, _f, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp],
+    "p2t_infonce_stats": [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+    "p2t_infonce_finish": [_vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "p2t_infonce_grad": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _i, _vp],
     "p2t_loss_mean": [_vp, _i, _f, _vp, _i, _vp],
     "p2t_f32_to_bf16": [_vp, _ll, _vp, _vp],

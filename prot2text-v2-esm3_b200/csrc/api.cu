@@ -356,13 +356,65 @@ int p2t_infonce_ce(float* Sm, const int* labels, int R, int C, float w_row, floa
                  argmax_row, dS_bf16, write_ds, S(stream));
 }
 
+int p2t_infonce_stats(const void* p, const void* t, const int* labels, int R, int C, int E, float tau, void* row_part_ws,
+                      void* col_part_ws, float* pos, float* col_max, float* col_sum, int* col_argmax, int cta_group,
+                      void* stream) {
+  if (!p || !t || !labels || !row_part_ws || !pos) return set_error(-1, "p2t_infonce_stats: null pointer");
+  if (tau <= 0.f) return set_error(-1, "p2t_infonce_stats: temperature must be positive");
+  if (col_part_ws && (!col_max || !col_sum)) return set_error(-1, "p2t_infonce_stats: column outputs required with the column workspace");
+  GemmParams q = base_params(R, C, E);
+  q.alpha = 1.f / tau;
+  q.sim_labels = labels;
+  q.sim_row_part = static_cast<float4*>(row_part_ws);
+  q.ld_rowsq = R;
+  q.sim_col_part = static_cast<float4*>(col_part_ws);
+  q.sim_pos = pos;
+  if (int rc = launch_gemm(p, E, false, t, E, false, EPI_SIM_STATS, q, cta_group, S(stream))) return rc;
+  if (col_part_ws)
+    return sim_cols_combine(static_cast<const float4*>(col_part_ws), (R + 31) / 32, C, col_max, col_sum, col_argmax, S(stream));
+  return 0;
+}
+
+int p2t_infonce_finish(const void* p, const void* t, const int* labels, int R, int C, int E, float tau, float w_row,
+                       float w_col, float inv_rn, const void* row_part_ws, const float* pos, const float* col_max,
+                       const float* col_sum, int all_cols_labelled, unsigned char* col_labelled_ws, float* col_lse_ws,
+                       float* row_loss, float* row_lse, int* argmax_row, void* dS_bf16, int cta_group, void* stream) {
+  if (!p || !t || !labels || !row_part_ws || !pos || !row_loss || !row_lse) return set_error(-1, "p2t_infonce_finish: null pointer");
+  if (w_col != 0.f && (!col_max || !col_sum || !col_labelled_ws || !col_lse_ws))
+    return set_error(-1, "p2t_infonce_finish: column statistics and workspaces required for the column term");
+  cudaStream_t st = S(stream);
+  const int npart = 4 * ((C + GEMM_BLOCK_N - 1) / GEMM_BLOCK_N);
+  if (int rc = sim_finish(static_cast<const float4*>(row_part_ws), npart, R, pos, labels, R, C, w_row, w_col, col_max, col_sum,
+                          w_col != 0.f ? col_lse_ws : nullptr, row_loss, row_lse, argmax_row, st)) return rc;
+  if (!dS_bf16) return 0;
+  if (C % 8) return set_error(-1, "p2t_infonce_finish: C must be a multiple of 8 for the bf16 dLogits");
+  if (w_col != 0.f) {
+    if (all_cols_labelled) {
+      cudaError_t e = cudaMemsetAsync(col_labelled_ws, 1, C, st);
+      if (e != cudaSuccess) return set_error((int)e, "memset: %s", cudaGetErrorString(e));
+    } else if (int rc = mark_labelled(labels, R, C, col_labelled_ws, st)) {
+      return rc;
+    }
+  }
+  GemmParams q = base_params(R, C, E);
+  q.alpha = 1.f / tau;
+  q.d0 = dS_bf16; q.ldd0 = C;
+  q.sim_labels = labels;
+  q.sim_row_lse = row_lse;
+  q.sim_col_lse = w_col != 0.f ? col_lse_ws : nullptr;
+  q.sim_col_marks = col_labelled_ws;
+  q.sim_wr = w_row * inv_rn; q.sim_wc = w_col * inv_rn;
+  return launch_gemm(p, E, false, t, E, false, EPI_SIM_DS, q, cta_group, st);
+}
+
 int p2t_infonce_grad(const float* dS, const void* dS_bf16, const void* p, const void* t, const float* p_f32,
                      const float* t_f32, int R, int C, int E, float tau, float* dp, float* dt, int cta_group,
                      void* stream) {
-  if (!dS) return set_error(-1, "p2t_infonce_grad: null pointer");
+  if (!dS && !dS_bf16) return set_error(-1, "p2t_infonce_grad: null pointer");
   cudaStream_t st = S(stream);
   const bool gemm_ok = !small_problem(R, C, E) && (C % 8 == 0) && dS_bf16 && (!dp || t) && (!dt || p);
   if (!gemm_ok) {
+    if (!dS) return set_error(-1, "p2t_infonce_grad: the CUDA-core path needs the fp32 dLogits");
     if (dp) {
       if (!t && !t_f32) return set_error(-1, "p2t_infonce_grad: t required for dp");
       if (int rc = contract_small(dS, C, false, t_f32 ? (const void*)t_f32 : t, t_f32 != nullptr, R, C, E, 1.f / tau, dp, st)) return rc;

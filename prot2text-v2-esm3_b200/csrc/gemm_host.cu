@@ -143,7 +143,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   if (timed) gemm_timing_record(stream, false);
   if (e != cudaSuccess) return set_error((int)e, "GEMM launch failed: %s", cudaGetErrorString(e));
   count_launch();
-  stamp_launch(EPI == EPI_FC1 ? "gemm_fc1" : EPI == EPI_FC2 ? "gemm_fc2" : EPI == EPI_MUL_AUX ? "gemm_dgrad"
+  stamp_launch(EPI == EPI_FC1 ? "gemm_fc1" : EPI == EPI_FC2 ? "gemm_fc2" : EPI == EPI_MUL_AUX ? "gemm_dgrad" : EPI == EPI_SIM_STATS ? "gemm_sim_stats" : EPI == EPI_SIM_DS ? "gemm_sim_dlogits"
                : (A_MN && B_MN) ? "gemm_wgrad" : "gemm_plain", stream);
   return 0;
 }
@@ -154,6 +154,10 @@ static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, con
     case EPI_STORE_BF16: return launch_inst<CTA_GROUP, A_MN, B_MN, EPI_STORE_BF16>(ta, tb, p, s);
     case EPI_STORE_F32: return launch_inst<CTA_GROUP, A_MN, B_MN, EPI_STORE_F32>(ta, tb, p, s);
     default: break;
+  }
+  if constexpr (!A_MN && !B_MN) {
+    if (epi == EPI_SIM_STATS) return launch_inst<CTA_GROUP, false, false, EPI_SIM_STATS>(ta, tb, p, s);
+    if (epi == EPI_SIM_DS) return launch_inst<CTA_GROUP, false, false, EPI_SIM_DS>(ta, tb, p, s);
   }
   if constexpr (!A_MN && !B_MN) {
     if (epi == EPI_FC1) return launch_inst<CTA_GROUP, false, false, EPI_FC1>(ta, tb, p, s);

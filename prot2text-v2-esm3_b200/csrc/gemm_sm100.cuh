@@ -33,6 +33,13 @@
 //    of 2^-9*|a| to every residue, which inflates the pooled std and its 1/std backward)
 //   EPI_MUL_AUX: D0 = alpha * acc * aux   (fc2 dgrad chained into GELU'(z1): aux = g1); optionally the column sums of
 //                D0 over each 32-row block (db1 = sum over rows of dz1, finished by bias_grads_final_kernel)
+//   EPI_SIM_STATS: S = alpha * acc (the temperature-scaled similarity, scripts/train_contrast.py:108) is NEVER stored:
+//                every warp reduces its 32 x 64 piece of the tile to per-row online-softmax partials (max, sum exp,
+//                argmax), per-column partials over its 32 rows (max, sum exp, arg-max row) and the label logit
+//                S[i][lab(i)] — the forward of the InfoNCE cross-entropy for blocks too large for one SM (:109-113)
+//   EPI_SIM_DS : S recomputed tile by tile (recomputation is not counted) and turned into dLogits
+//                = w_row (softmax_row - onehot) + w_col (softmax_col - onehot), written as the bf16 A operand of
+//                dp = dLogits t.  Probabilities and fp32 logits never exist in memory.
 // Storing (value, derivative) pairs instead of the pre-activation keeps every later HBM-bound pass
 // free of erf/exp and of Philox re-generation: the dropout multiplier is folded into both.
 #pragma once
@@ -43,7 +50,8 @@
 
 namespace p2t {
 
-enum GemmEpilogue : int { EPI_STORE_BF16 = 0, EPI_STORE_F32 = 1, EPI_FC1 = 2, EPI_FC2 = 3, EPI_MUL_AUX = 4 };
+enum GemmEpilogue : int { EPI_STORE_BF16 = 0, EPI_STORE_F32 = 1, EPI_FC1 = 2, EPI_FC2 = 3, EPI_MUL_AUX = 4,
+                          EPI_SIM_STATS = 5, EPI_SIM_DS = 6 };
 
 constexpr int GEMM_BLOCK_M = 128;  // rows per CTA
 constexpr int GEMM_BLOCK_N = 256;  // UMMA N
@@ -75,6 +83,15 @@ struct GemmParams {
   int ld_rowsq;
   float* colsum;              // EPI_MUL_AUX (optional): [ceil(rows_cap / 32)][n] column sums of D0 over each 32-row block
                               // (fixed-order shuffle tree; the bias gradient db1 without a second pass over dz1)
+  // EPI_SIM_STATS / EPI_SIM_DS (InfoNCE on large blocks; M = rows R, N = columns C)
+  const int* sim_labels;      // [M] column of each row's positive
+  float4* sim_row_part;       // STATS out: [4 * n_blocks][ld_rowsq] (max, sum exp, argmax as int bits, -)
+  float4* sim_col_part;       // STATS out: [ceil(M / 32)][n] (max, sum exp, arg-max row as int bits, -), or nullptr
+  float* sim_pos;             // STATS out: [M] S[i][lab(i)]
+  const float* sim_row_lse;   // DS in: [M]
+  const float* sim_col_lse;   // DS in: [n] (column term) or nullptr
+  const unsigned char* sim_col_marks;  // DS in: [n] 1 = the column's positive is among the rows of the (global) batch
+  float sim_wr, sim_wc;       // DS: w_row * scale, w_col * scale
   int accumulate;             // EPI_STORE_BF16 / EPI_STORE_F32: D0 += alpha * acc (read-modify-write: gradient accumulation
                               // over micro-batches, scripts/train_contrast.py:448 without optimizer.zero_grad in between)
   float alpha;
@@ -260,6 +277,35 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
+// same butterfly for the column maxima (returns, in lane l, max over the 32 lanes of column l) ...
+__device__ __forceinline__ float warp_colmax32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = upper ? v[i] : v[i + half];
+      const float keep = upper ? v[i + half] : v[i];
+      v[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, half));
+    }
+  }
+  return v[0];
+}
+// ... and for the column minima of integers (lowest row index among the rows that attain the column maximum)
+__device__ __forceinline__ int warp_colmin32(int (&v)[32], int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const int send = upper ? v[i] : v[i + half];
+      const int keep = upper ? v[i + half] : v[i];
+      v[i] = min(keep, __shfl_xor_sync(0xffffffffu, send, half));
+    }
+  }
+  return v[0];
+}
+
 // bias[col .. col+8) as fp32: one 16-byte load when the eight bf16 values are in range and aligned (every lane of
 // the warp reads the same address: a broadcast served by L1), element-wise at the ragged end of N
 __device__ __forceinline__ void load_bias8(const __nv_bfloat16* __restrict__ bias, int col, int n, float (&b)[8]) {
@@ -357,6 +403,8 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ep
         for (int i = 0; i < 8; ++i) val[i] += old[i];
       }
       store8(dst0 + 8 * j, val, n_ok, vec_ok);
+    } else if constexpr (EPI == EPI_SIM_DS) {
+      // (handled by epilogue_sim_ds: this generic body is never instantiated for it)
     } else if constexpr (EPI == EPI_MUL_AUX) {
       const uint32_t w[4] = {g4[j].x, g4[j].y, g4[j].z, g4[j].w};
 #pragma unroll
@@ -663,6 +711,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const bool row_valid = row < M;
       const bool row_in_buf = row < rows_cap;
       float sumsq = 0.f;
+      // EPI_SIM_*: this row's label and running online-softmax state over the warp's 64 columns of the tile
+      int sim_lab = -1;
+      float sim_m = -INFINITY, sim_s = 0.f, sim_lse = 0.f;
+      int sim_a = 0x7fffffff;
+      if constexpr (EPI == EPI_SIM_STATS || EPI == EPI_SIM_DS) {
+        if (row_valid) {
+          sim_lab = __ldg(p.sim_labels + row);
+          if constexpr (EPI == EPI_SIM_DS) sim_lse = __ldg(p.sim_row_lse + row);
+        }
+      }
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c) {
         uint32_t v[32];
@@ -700,6 +758,81 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __ldcg(slot + (size_t)i * GEMM_BLOCK_M));
           }
         }
+        if constexpr (EPI == EPI_SIM_STATS) {
+          if (col < N) {  // warp-uniform
+            // logits of this thread's row; -inf outside the block so that they drop out of every max / sum
+            float sv[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              sv[i] = (row_valid && col + i < N) ? __uint_as_float(v[i]) * e.alpha : -INFINITY;
+            // row side: online (max, sum exp, first arg-max) over the chunk
+            float cm = -INFINITY;
+            int ca = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (sv[i] > cm) { cm = sv[i]; ca = i; }
+            if (cm > -INFINITY) {
+              const float nm = fmaxf(sim_m, cm);
+              float add = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) add += __expf(sv[i] - nm);
+              sim_s = sim_s * __expf(sim_m - nm) + add;
+              if (cm > sim_m) sim_a = col + ca;  // strictly greater: ties keep the lower column
+              sim_m = nm;
+            }
+            if (sim_lab >= col && sim_lab < col + 32) {
+              float pos = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) pos = (sim_lab - col == i) ? sv[i] : pos;
+              p.sim_pos[row] = pos;
+            }
+            // column side over the warp's 32 rows: max -> exp against it -> sum; arg-max = lowest row attaining the max
+            if (p.sim_col_part != nullptr) {
+              float tmpf[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) tmpf[i] = sv[i];
+              const float cmax_l = warp_colmax32(tmpf, lane);  // lane l: column col + l
+              int cand[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float cs = __shfl_sync(0xffffffffu, cmax_l, i);
+                tmpf[i] = (sv[i] > -INFINITY) ? __expf(sv[i] - cs) : 0.f;
+                cand[i] = (sv[i] > -INFINITY && sv[i] == cs) ? row : 0x7fffffff;
+              }
+              const float csum_l = warp_colsum32(tmpf, lane);
+              const int carg_l = warp_colmin32(cand, lane);
+              const int row0 = row - lane;
+              if (col + lane < N && row0 < M)
+                p.sim_col_part[(long long)(row0 >> 5) * N + col + lane] = make_float4(cmax_l, csum_l, __int_as_float(carg_l), 0.f);
+            }
+          }
+          continue;
+        }
+        if constexpr (EPI == EPI_SIM_DS) {
+          if (col < N && row_valid) {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.d0) + (long long)row * e.ldd0 + col;
+            const int ncols = min(32, N - col);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int n_ok = min(8, ncols - 8 * j);
+              if (n_ok <= 0) break;
+              float d[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int cc = col + 8 * j + i;
+                const float sl = __uint_as_float(v[8 * j + i]) * e.alpha;
+                float g = p.sim_wr * __expf(sl - sim_lse);
+                if (p.sim_col_lse != nullptr && cc < N) {
+                  if (__ldg(p.sim_col_marks + cc)) g += p.sim_wc * __expf(sl - __ldg(p.sim_col_lse + cc));
+                }
+                if (cc == sim_lab) g -= (p.sim_wr + p.sim_wc);
+                d[i] = g;
+              }
+              store8(dst + 8 * j, d, n_ok, vec_ok);
+            }
+          }
+          continue;
+        }
         if (col < N) {
           if constexpr (S::TMA_STORE) {
             if (p.tma_store) {
@@ -731,6 +864,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
       if constexpr (EPI == EPI_FC2) {
         if (row_in_buf && is_head) p.rowsq[(long long)(n_blk * (GEMM_EPI_WARPS / 4) + part) * p.ld_rowsq + row] = sumsq;
+      }
+      if constexpr (EPI == EPI_SIM_STATS) {
+        if (row_valid && is_head)
+          p.sim_row_part[(long long)(n_blk * (GEMM_EPI_WARPS / 4) + part) * p.ld_rowsq + row] =
+              make_float4(sim_m, sim_s, __int_as_float(sim_a), 0.f);
       }
       tcgen05_fence_before();
       if (!is_head) __threadfence();  // the dumped piece must be visible before the flag

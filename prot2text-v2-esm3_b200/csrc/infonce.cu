@@ -319,6 +319,64 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, long lo
     out[i] = __bfloat162float(in[i]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Large blocks: the similarity GEMM's EPI_SIM_STATS epilogue (gemm_sm100.cuh) leaves per-tile partials instead of
+// logits; these two kernels merge them in a fixed order.
+//   columns: col_part [nrb][C] (max, sum exp, arg-max row) over 32-row blocks -> col_max, col_sum, argmax_col
+//   rows   : row_part [npart][ld] (max, sum exp, arg-max column) over 64-column pieces -> row_lse, argmax_row,
+//            row_loss = w_row (lse - S_i,lab) + w_col (lse_col[lab] - S_i,lab); the same launch writes
+//            col_lse[j] = col_max[j] + log col_sum[j] for the dLogits pass
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sim_cols_combine_kernel(const float4* __restrict__ col_part, int nrb, int C, float* __restrict__ col_max,
+                        float* __restrict__ col_sum, int* __restrict__ col_argmax) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= C) return;
+  float M = -INFINITY, S = 0.f;
+  int A = -1;
+  for (int rb = 0; rb < nrb; ++rb) {
+    const float4 q = col_part[(long long)rb * C + j];
+    const float m2 = q.x, s2 = q.y;
+    if (!(m2 > -INFINITY)) continue;
+    if (m2 > M) { S = S * __expf(M - m2) + s2; M = m2; A = __float_as_int(q.z); }  // ties keep the lower row block
+    else S += s2 * __expf(m2 - M);
+  }
+  col_max[j] = M;
+  col_sum[j] = S;
+  if (col_argmax) col_argmax[j] = A;
+}
+
+__global__ void __launch_bounds__(256)
+sim_finish_kernel(const float4* __restrict__ row_part, int npart, int ld, const float* __restrict__ pos,
+                  const int* __restrict__ labels, int R, int C, float w_row, float w_col,
+                  const float* __restrict__ col_max, const float* __restrict__ col_sum, float* __restrict__ col_lse,
+                  float* __restrict__ row_loss, float* __restrict__ row_lse, int* __restrict__ argmax_row) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C && col_lse != nullptr && col_max != nullptr) col_lse[i] = col_max[i] + __logf(col_sum[i]);
+  if (i >= R) return;
+  float M = -INFINITY, S = 0.f;
+  int A = 0x7fffffff;
+  for (int k = 0; k < npart; ++k) {
+    const float4 q = row_part[(long long)k * ld + i];
+    const float m2 = q.x, s2 = q.y;
+    if (!(m2 > -INFINITY)) continue;
+    if (m2 > M) { S = S * __expf(M - m2) + s2; M = m2; A = __float_as_int(q.z); }  // ties keep the lower column
+    else S += s2 * __expf(m2 - M);
+  }
+  const float lse = M + __logf(S);
+  const int lab = labels[i];
+  const bool lab_ok = lab >= 0 && lab < C;
+  float loss = __int_as_float(0x7fc00000);  // a label outside the block poisons the loss
+  if (lab_ok) {
+    const float ps = pos[i];
+    loss = w_row * (lse - ps);
+    if (w_col != 0.f) loss += w_col * (col_max[lab] + __logf(col_sum[lab]) - ps);
+  }
+  row_loss[i] = loss;
+  if (row_lse) row_lse[i] = lse;
+  if (argmax_row) argmax_row[i] = A;
+}
+
 // ================================================================================================
 int sim_small(const void* p, const void* t, bool in_f32, int R, int C, int E, float alpha, float* S, cudaStream_t st) {
   if (E % 8) return set_error(-1, "similarity: E must be a multiple of 8");
@@ -384,6 +442,19 @@ int convert_f32_to_bf16(const float* in, long long n, void* out, cudaStream_t st
   f32_to_bf16_kernel<<<blocks, 256, 0, st>>>(in, n, reinterpret_cast<__nv_bfloat16*>(out));
   return check_launch("f32_to_bf16_kernel", st);
 }
+int sim_cols_combine(const float4* col_part, int nrb, int C, float* col_max, float* col_sum, int* col_argmax, cudaStream_t st) {
+  sim_cols_combine_kernel<<<(C + 255) / 256, 256, 0, st>>>(col_part, nrb, C, col_max, col_sum, col_argmax);
+  return check_launch("sim_cols_combine_kernel", st);
+}
+int sim_finish(const float4* row_part, int npart, int ld, const float* pos, const int* labels, int R, int C, float w_row,
+               float w_col, const float* col_max, const float* col_sum, float* col_lse, float* row_loss, float* row_lse,
+               int* argmax_row, cudaStream_t st) {
+  const int n = R > C ? R : C;
+  sim_finish_kernel<<<(n + 255) / 256, 256, 0, st>>>(row_part, npart, ld, pos, labels, R, C, w_row, w_col, col_max, col_sum,
+                                                     col_lse, row_loss, row_lse, argmax_row);
+  return check_launch("sim_finish_kernel", st);
+}
+
 int convert_bf16_to_f32(const void* in, long long n, float* out, cudaStream_t st) {
   const int blocks = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 8);
   bf16_to_f32_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in), n, out);

@@ -64,6 +64,10 @@ int ce_rows(float* S, const int* labels, int R, int C, float w_row, float w_col,
 int loss_mean(const float* row_loss, int R, float scale, float* loss, int accumulate, cudaStream_t st);
 int contract_small(const float* W, int ldw, bool transpose_w, const void* X, bool x_f32, int n_out, int n_red, int E,
                    float alpha, float* out, cudaStream_t st);
+int sim_cols_combine(const float4* col_part, int nrb, int C, float* col_max, float* col_sum, int* col_argmax, cudaStream_t st);
+int sim_finish(const float4* row_part, int npart, int ld, const float* pos, const int* labels, int R, int C, float w_row,
+               float w_col, const float* col_max, const float* col_sum, float* col_lse, float* row_loss, float* row_lse,
+               int* argmax_row, cudaStream_t st);
 int convert_f32_to_bf16(const float* in, long long n, void* out, cudaStream_t st);
 int convert_bf16_to_f32(const void* in, long long n, float* out, cudaStream_t st);
 
