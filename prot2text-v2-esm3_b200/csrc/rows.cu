@@ -61,16 +61,34 @@ __global__ void plan_count_kernel(const void* mask, int mask_bytes, int B, int L
 
 // grid B, block 256.  seq_off[B+1], chunk_off[B+1] (chunks of `rc` rows), n_rows[0] = total,
 // row_src[i] = flat source row (b*L + r) of packed row i.
-__global__ void plan_fill_kernel(const void* mask, int mask_bytes, int B, int L, const int* counts, int rc,
+template <bool COUNT_HERE>
+__global__ void plan_fill_kernel(const void* mask, int mask_bytes, int B, int L, int* counts, int rc,
                                  int* seq_off, int* chunk_off, int* n_rows, int* row_src, int* chunk_seq) {
   const int b = blockIdx.x;
   __shared__ int sh[2][8];
-  __shared__ int s_base, s_cbase;
+  __shared__ int s_base, s_cbase, s_cnt;
   int off = 0, coff = 0;
-  for (int i = threadIdx.x; i < b; i += blockDim.x) {
-    const int c = counts[i];
-    off += c;
-    coff += (c + rc - 1) / rc;
+  if constexpr (COUNT_HERE) {
+    // one launch instead of two (small batches): this block counts sequences 0..b itself, one warp per sequence
+    // (block b reads (b + 1) * L mask words: <= 256 KB at config 2, L2-resident after the first block touched them)
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    for (int i = w; i <= b; i += (int)(blockDim.x >> 5)) {
+      int c = 0;
+      for (int r = lane; r < L; r += 32) c += mask_at(mask, mask_bytes, (long long)i * L + r) ? 1 : 0;
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      if (lane == 0) {
+        if (i < b) { off += c; coff += (c + rc - 1) / rc; }
+        else { s_cnt = c; counts[b] = c; }
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < b; i += blockDim.x) {
+      const int c = counts[i];
+      off += c;
+      coff += (c + rc - 1) / rc;
+    }
   }
   for (int o = 16; o > 0; o >>= 1) {
     off += __shfl_xor_sync(0xffffffffu, off, o);
@@ -78,13 +96,14 @@ __global__ void plan_fill_kernel(const void* mask, int mask_bytes, int B, int L,
   }
   if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = off; sh[1][threadIdx.x >> 5] = coff; }
   __syncthreads();
+  const int cnt_b = COUNT_HERE ? s_cnt : counts[b];
   if (threadIdx.x == 0) {
     int t0 = 0, t1 = 0;
     for (int i = 0; i < 8; ++i) { t0 += sh[0][i]; t1 += sh[1][i]; }
     seq_off[b] = t0;
     chunk_off[b] = t1;
     if (b == B - 1) {
-      const int c = counts[b];
+      const int c = cnt_b;
       seq_off[B] = t0 + c;
       chunk_off[B] = t1 + (c + rc - 1) / rc;
       n_rows[0] = t0 + c;
@@ -94,7 +113,7 @@ __global__ void plan_fill_kernel(const void* mask, int mask_bytes, int B, int L,
   }
   __syncthreads();
   if (chunk_seq != nullptr) {  // one descriptor per pooling chunk: {first packed row, end row, sequence, 0}
-    const int cnt = counts[b];
+    const int cnt = cnt_b;
     const int nchunks = (cnt + rc - 1) / rc;
     int4* desc = reinterpret_cast<int4*>(chunk_seq);
     for (int j = threadIdx.x; j < nchunks; j += blockDim.x)
@@ -800,14 +819,17 @@ adapter_tail_bwd_kernel(const __half* __restrict__ a, const __half* __restrict__
 // adds parts y, y+32, ... of column 32*blockIdx.x + x, then the 32 rows are merged in shared memory (fixed order).
 constexpr int PARTS_Y = 32;
 __device__ __forceinline__ float sum_parts(const float* __restrict__ partial, int nparts, int D, int col) {
-  float s0 = 0.f, s1 = 0.f;
+  // four independent chains: the loads of a thread are latency-bound, not bandwidth-bound (fixed order: deterministic)
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   int k = threadIdx.y;
-  for (; k + PARTS_Y < nparts; k += 2 * PARTS_Y) {
+  for (; k + 3 * PARTS_Y < nparts; k += 4 * PARTS_Y) {
     s0 += partial[(long long)k * D + col];
     s1 += partial[(long long)(k + PARTS_Y) * D + col];
+    s2 += partial[(long long)(k + 2 * PARTS_Y) * D + col];
+    s3 += partial[(long long)(k + 3 * PARTS_Y) * D + col];
   }
-  if (k < nparts) s0 += partial[(long long)k * D + col];
-  return s0 + s1;
+  for (; k < nparts; k += PARTS_Y) s0 += partial[(long long)k * D + col];
+  return (s0 + s1) + (s2 + s3);
 }
 __global__ void __launch_bounds__(32 * PARTS_Y)
 parts_colsum_final_kernel(const float* __restrict__ partial, const int* __restrict__ chunk_off, int B,
@@ -1049,9 +1071,13 @@ __global__ void readout_last_kernel(const __nv_bfloat16* __restrict__ x, const i
 int rows_plan(const void* mask, int mask_bytes, int B, int L, int rc, int* counts, int* seq_off, int* chunk_off,
               int* n_rows, int* row_src, int* chunk_seq, cudaStream_t st) {
   if (B <= 0 || L <= 0) return set_error(-1, "rows_plan: empty batch");
+  if ((long long)B * L <= (1 << 17) && B <= 128) {  // small batch: count and fill in one launch
+    plan_fill_kernel<true><<<B, 256, 0, st>>>(mask, mask_bytes, B, L, counts, rc, seq_off, chunk_off, n_rows, row_src, chunk_seq);
+    return check_launch("plan_fill_kernel", st);
+  }
   plan_count_kernel<<<B, 256, 0, st>>>(mask, mask_bytes, B, L, counts);
   if (int rc_ = check_launch("plan_count_kernel", st)) return rc_;
-  plan_fill_kernel<<<B, 256, 0, st>>>(mask, mask_bytes, B, L, counts, rc, seq_off, chunk_off, n_rows, row_src, chunk_seq);
+  plan_fill_kernel<false><<<B, 256, 0, st>>>(mask, mask_bytes, B, L, counts, rc, seq_off, chunk_off, n_rows, row_src, chunk_seq);
   return check_launch("plan_fill_kernel", st);
 }
 
@@ -1059,7 +1085,7 @@ int rows_plan(const void* mask, int mask_bytes, int B, int L, int rc, int* count
 int rows_plan_counts(const int* counts, int B, int rc, int* seq_off, int* chunk_off, int* n_rows, int* chunk_seq,
                      cudaStream_t st) {
   if (B <= 0) return set_error(-1, "rows_plan_counts: empty batch");
-  plan_fill_kernel<<<B, 256, 0, st>>>(nullptr, 0, B, 0, counts, rc, seq_off, chunk_off, n_rows, nullptr, chunk_seq);
+  plan_fill_kernel<false><<<B, 256, 0, st>>>(nullptr, 0, B, 0, const_cast<int*>(counts), rc, seq_off, chunk_off, n_rows, nullptr, chunk_seq);
   return check_launch("plan_fill_kernel", st);
 }
 
