@@ -463,9 +463,10 @@ def main():
 
     # ------------------------------ per-kernel breakdown ------------------------------
     # One more eager pass with a CUDA event after EVERY library launch.  The text branch is kept on the main stream
-    # (one in-order stream: consecutive stamps bracket one kernel) and every step starts behind a ~2 ms device-side
-    # sleep, so the host has enqueued the whole step before its first kernel runs: the stamps then measure the GPU
-    # (kernel + the in-stream gap to its predecessor), not the Python launch rate.
+    # (one in-order stream) and every step starts behind a ~2 ms device-side sleep, so the host has enqueued the whole
+    # step before its first kernel runs.  Every kernel is bracketed by a "begin" stamp right before its launch and an
+    # end stamp right after: the difference is the kernel on the stream (plus one event record), not the Python launch
+    # rate and not the gap to its predecessor.
     stages = None
     if not args.no_stages and world == 1:
         os.environ["P2T_TEXT_STREAM"] = "0"
@@ -487,6 +488,9 @@ def main():
         for name, ms in stamps:
             if name == "mark":
                 seen, first_after_mark = {}, True
+                continue
+            if name == "begin":  # opens a bracket: the next stamp's time is the kernel alone
+                first_after_mark = False
                 continue
             k = seen[name] = seen.get(name, 0) + 1
             key = f"{name}#{k}"

@@ -18,6 +18,9 @@ int check_launch(const char* what, cudaStream_t st);
 // after each launch; consecutive stamps on an in-order stream bracket one kernel (plus its launch gap), and a
 // "mark" stamp (p2t_launch_timing_mark) opens each step.  Off by default; not for use under stream capture.
 void stamp_launch(const char* name, cudaStream_t st);
+// Optional "begin" stamp right before a launch: the kernel is then timed from it (one event, recorded when the
+// predecessor has finished) instead of from the previous kernel's end stamp, which would charge it the gap.
+inline void stamp_begin(cudaStream_t st) { stamp_launch("begin", st); }
 
 int sm_count();
 

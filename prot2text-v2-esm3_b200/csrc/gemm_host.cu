@@ -139,6 +139,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
       q.tma_store = 1;
     }
   }
+  stamp_begin(stream);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, td0, td1, q);
   if (timed) gemm_timing_record(stream, false);
   if (e != cudaSuccess) return set_error((int)e, "GEMM launch failed: %s", cudaGetErrorString(e));

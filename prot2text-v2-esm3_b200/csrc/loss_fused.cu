@@ -463,6 +463,7 @@ int loss_fused(const float* p, const float* t, void* const* peers, int world, in
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  stamp_begin(st);
   cudaError_t e = cudaLaunchKernelEx(&cfg, loss_fused_kernel, q);
   if (e != cudaSuccess) return set_error((int)e, "loss_fused_kernel: %s", cudaGetErrorString(e));
   count_launch();

@@ -28,6 +28,33 @@ __device__ __forceinline__ bool mask_at(const void* mask, int mask_bytes, long l
   }
 }
 
+// number of non-zero mask elements of one row, counted by a warp: 16-byte loads, four in flight per lane
+__device__ __forceinline__ int warp_count_row(const void* mask, int mask_bytes, long long first, int L, int lane) {
+  int c = 0;
+  const char* base = reinterpret_cast<const char*>(mask) + first * mask_bytes;
+  const long long bytes = (long long)L * mask_bytes;
+  if (((reinterpret_cast<uintptr_t>(base) | (uintptr_t)bytes) & 15) == 0) {
+    const uint4* vp = reinterpret_cast<const uint4*>(base);
+    const int nvec = (int)(bytes >> 4);
+    auto nz = [&](const uint4& u) {
+      if (mask_bytes == 8) return ((u.x | u.y) != 0) + ((u.z | u.w) != 0);
+      if (mask_bytes == 4) return (u.x != 0) + (u.y != 0) + (u.z != 0) + (u.w != 0);
+      return __popc(__vcmpne4(u.x, 0u) & 0x01010101u) + __popc(__vcmpne4(u.y, 0u) & 0x01010101u) +
+             __popc(__vcmpne4(u.z, 0u) & 0x01010101u) + __popc(__vcmpne4(u.w, 0u) & 0x01010101u);
+    };
+    int v = lane;
+    for (; v + 96 < nvec; v += 128) {
+      const uint4 a = __ldg(vp + v), b = __ldg(vp + v + 32), d = __ldg(vp + v + 64), e = __ldg(vp + v + 96);
+      c += nz(a) + nz(b) + nz(d) + nz(e);
+    }
+    for (; v < nvec; v += 32) c += nz(__ldg(vp + v));
+  } else {
+    for (int r = lane; r < L; r += 32) c += mask_at(mask, mask_bytes, first + r) ? 1 : 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  return c;
+}
+
 template <int THREADS>
 __device__ __forceinline__ float block_sum(float v, float* smem /*[THREADS/32]*/) {
   v = warp_sum(v);
@@ -75,9 +102,7 @@ __global__ void plan_fill_kernel(const void* mask, int mask_bytes, int B, int L,
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
     for (int i = w; i <= b; i += (int)(blockDim.x >> 5)) {
-      int c = 0;
-      for (int r = lane; r < L; r += 32) c += mask_at(mask, mask_bytes, (long long)i * L + r) ? 1 : 0;
-      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      const int c = warp_count_row(mask, mask_bytes, (long long)i * L, L, lane);
       if (lane == 0) {
         if (i < b) { off += c; coff += (c + rc - 1) / rc; }
         else { s_cnt = c; counts[b] = c; }
@@ -1072,6 +1097,7 @@ int rows_plan(const void* mask, int mask_bytes, int B, int L, int rc, int* count
               int* n_rows, int* row_src, int* chunk_seq, cudaStream_t st) {
   if (B <= 0 || L <= 0) return set_error(-1, "rows_plan: empty batch");
   if ((long long)B * L <= (1 << 17) && B <= 128) {  // small batch: count and fill in one launch
+    stamp_begin(st);
     plan_fill_kernel<true><<<B, 256, 0, st>>>(mask, mask_bytes, B, L, counts, rc, seq_off, chunk_off, n_rows, row_src, chunk_seq);
     return check_launch("plan_fill_kernel", st);
   }
@@ -1094,6 +1120,7 @@ int gather_rows(const void* src, long long ld_src, const int* row_src, const int
   if (D % 8) return set_error(-1, "gather_rows: D must be a multiple of 8");
   const long long total = (long long)cap * (D / 8);
   const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
+  stamp_begin(st);
   gather_rows_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), ld_src, row_src, n_rows, cap, D,
                                              reinterpret_cast<__nv_bfloat16*>(out));
   return check_launch("gather_rows_kernel", st);
@@ -1101,6 +1128,7 @@ int gather_rows(const void* src, long long ld_src, const int* row_src, const int
 
 int row_inv_norm(const float* rowsq, int nblk, const int* n_rows, int cap, float* inv_norm, cudaStream_t st) {
   const int blocks = std::min((cap + 31) / 32, sm_count() * 8);
+  stamp_begin(st);
   row_inv_norm_kernel<<<blocks, 256, 0, st>>>(rowsq, nblk, n_rows, cap, inv_norm);
   return check_launch("row_inv_norm_kernel", st);
 }
@@ -1127,6 +1155,7 @@ int pool_forward(const void* src, bool src_is_f16, long long ld_src, int src_row
     if (e1 != cudaSuccess || e2 != cudaSuccess) return set_error((int)(e1 != cudaSuccess ? e1 : e2), "pool_forward: cannot reserve %d bytes of shared memory", smem);
     configured = true;
   }
+  stamp_begin(st);
   int* seg_rows = reinterpret_cast<int*>(partial + (size_t)max_chunks * D);  // behind the partial records
   if (src_is_f16)
     pool_partial_kernel<true><<<grid, POOL_THREADS, smem, st>>>(tmap, sp, ld_src, row_src, inv_norm, chunk_off, desc, B, D, partial, seg_rows);
@@ -1146,6 +1175,7 @@ int pool_forward(const void* src, bool src_is_f16, long long ld_src, int src_row
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    stamp_begin(st);
     cudaError_t le = cudaLaunchKernelEx(&cfg, pool_finalize_normalize_kernel, (const float2*)partial, (const int*)seg_rows, seq_off,
                                         chunk_off, D, out, reinterpret_cast<__nv_bfloat16*>(norm_p_bf16), norm_p_f32, norm_out);
     if (le != cudaSuccess) return set_error((int)le, "pool_finalize_normalize_kernel: %s", cudaGetErrorString(le));
@@ -1201,6 +1231,7 @@ int adapter_tail_backward(const void* a, const void* g, const float* inv_norm, c
     grid = std::min(grid, ws_rows);
   }
   grid = std::max(1, std::min(grid, (cap + 2 * TAIL_R - 1) / (2 * TAIL_R)));
+  stamp_begin(st);
   if (threads == 256)
     adapter_tail_bwd_kernel<256><<<grid, 256, 0, st>>>(ap, gp, inv_norm, seq_off, B, c1, c2, n_rows, cap, D, op, colsum_partial, nparts_dev);
   else if (threads == 512)
@@ -1221,6 +1252,7 @@ int adapter_tail_backward(const void* a, const void* g, const float* inv_norm, c
 int bias_grads_final(const BiasJob& j0, const BiasJob& j1, cudaStream_t st) {
   const int blocks0 = j0.partial ? (j0.D + 31) / 32 : 0, blocks1 = j1.partial ? (j1.D + 31) / 32 : 0;
   if (blocks0 + blocks1 == 0) return 0;
+  stamp_begin(st);
   bias_grads_final_kernel<<<blocks0 + blocks1, dim3(32, PARTS_Y), 0, st>>>(j0, j1, blocks0);
   return check_launch("bias_grads_final_kernel", st);
 }
