@@ -1096,7 +1096,10 @@ __global__ void readout_last_kernel(const __nv_bfloat16* __restrict__ x, const i
 int rows_plan(const void* mask, int mask_bytes, int B, int L, int rc, int* counts, int* seq_off, int* chunk_off,
               int* n_rows, int* row_src, int* chunk_seq, cudaStream_t st) {
   if (B <= 0 || L <= 0) return set_error(-1, "rows_plan: empty batch");
-  if ((long long)B * L <= (1 << 17) && B <= 128) {  // small batch: count and fill in one launch
+  // (count-and-fill in one launch exists — plan_fill_kernel<true> — but measured SLOWER at config 2: block b has to
+  //  count b + 1 sequences behind one another, 26 us against 6 + 8 us for the two launches; it serves batches of a few
+  //  sequences only)
+  if (B <= 4 && (long long)B * L <= (1 << 14)) {
     stamp_begin(st);
     plan_fill_kernel<true><<<B, 256, 0, st>>>(mask, mask_bytes, B, L, counts, rc, seq_off, chunk_off, n_rows, row_src, chunk_seq);
     return check_launch("plan_fill_kernel", st);
