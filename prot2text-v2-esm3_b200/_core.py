@@ -91,6 +91,9 @@ def plan_rows(mask: torch.Tensor, want_row_src: bool = True, max_valid_rows: Opt
 def plan_packed(counts: torch.Tensor, total_rows: int) -> RowPlan:
     """Plan for rows that are already packed back to back: `counts` (B,) valid rows per sequence (any integer
     dtype, CPU or CUDA), `total_rows` = the packed buffer's row count (a host integer >= sum(counts))."""
+    if not counts.is_cuda:  # host-side lengths: check them here (device-side lengths are the caller's contract)
+        if int(counts.min()) < 0 or int(counts.sum()) > total_rows:
+            raise _lib.P2TError(f"packed rows: lengths must be >= 0 and sum to at most the buffer's {total_rows} rows")
     dev_counts = counts.to(device="cuda" if not counts.is_cuda else counts.device, dtype=torch.int32, non_blocking=True).contiguous()
     B = dev_counts.shape[0]
     dev = dev_counts.device

@@ -58,24 +58,27 @@ size_t gemm_streamk_workspace_bytes() {
 }
 
 int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
+  // per device: a process may drive more than one GPU (single-process multi-GPU tests, a changed current device)
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!n[dev]) cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+  return n[dev];
 }
 
 template <int CTA_GROUP, bool A_MN, bool B_MN, int EPI>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using S = GemmSmem<CTA_GROUP, EPI>;
   auto kern = gemm_bf16_tcgen05_kernel<CTA_GROUP, A_MN, B_MN, EPI>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};  // cudaFuncSetAttribute is a per-device setting
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  if (cur_dev < 0 || cur_dev >= 64) cur_dev = 0;
+  if (!configured[cur_dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(smem=%d): %s", S::TOTAL, cudaGetErrorString(e));
-    configured = true;
+    configured[cur_dev] = true;
   }
   const int tile_m = GEMM_BLOCK_M * CTA_GROUP;
   const long long tiles = (long long)((p.m + tile_m - 1) / tile_m) * ((p.n + GEMM_BLOCK_N - 1) / GEMM_BLOCK_N);

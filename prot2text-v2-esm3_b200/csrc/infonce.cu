@@ -228,10 +228,13 @@ ce_rows_kernel(float* __restrict__ S, const int* __restrict__ labels, int R, int
     s = sa + sb;
   }
   const float lse = m + __logf(s);
-  const int lab = labels[i];
+  const int lab_raw = labels[i];
+  const bool lab_ok = lab_raw >= 0 && lab_raw < C;  // a label outside the block poisons the loss, never reads out of bounds
+  const int lab = lab_ok ? lab_raw : 0;
   const float pos = row[lab];
   float loss = w_row * (lse - pos);
   if (w_col != 0.f) loss += w_col * (col_max[lab] + __logf(col_sum[lab]) - pos);
+  if (!lab_ok) loss = __int_as_float(0x7fc00000);
   if (lane == 0) {
     row_loss[i] = loss;
     if (row_lse) row_lse[i] = lse;

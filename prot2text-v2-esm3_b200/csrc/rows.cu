@@ -1151,7 +1151,11 @@ int pool_forward(const void* src, bool src_is_f16, long long ld_src, int src_row
   CUtensorMap tmap;
   if (int r = make_tmap_16bit(&tmap, src, D, src_rows, ld_src, POOL_BOX_COLS, POOL_BOX_ROWS, CU_TENSOR_MAP_SWIZZLE_NONE)) return r;
   const int smem = (int)sizeof(PoolSmem) + 1024;
-  static bool configured = false;
+  static bool configured_dev[64] = {false};  // per-device setting
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  if (cur_dev < 0 || cur_dev >= 64) cur_dev = 0;
+  bool& configured = configured_dev[cur_dev];
   if (!configured) {
     cudaError_t e1 = cudaFuncSetAttribute(pool_partial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaError_t e2 = cudaFuncSetAttribute(pool_partial_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

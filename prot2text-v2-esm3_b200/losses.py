@@ -15,18 +15,29 @@ def _as_bf16(t: torch.Tensor) -> torch.Tensor:
 class _InfoNCEFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, out1, out2, labels, temperature: float, w_row: float, w_col: float):
+        if out1.dim() != 2 or out2.dim() != 2 or out1.shape[1] != out2.shape[1] or out1.shape[1] % 8:
+            raise _core._lib.P2TError("InfoNCE inputs must be (rows, E) and (cols, E) with E a multiple of 8")
+        if labels.numel() != out1.shape[0]:
+            raise _core._lib.P2TError("one label per row of the first input")
         p_bf, t_bf = _as_bf16(out1), _as_bf16(out2)
+        # fp32 inputs keep their precision on the CUDA-core path (small / medium blocks): near-parallel embeddings make
+        # the bf16 rounding of p and t the dominant gradient error there
+        p_f32 = t_f32 = None
+        if out1.dtype == torch.float32 and out2.dtype == torch.float32:
+            p_f32, t_f32 = out1.detach().contiguous(), out2.detach().contiguous()
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        res = _core.infonce_forward(p_bf, t_bf, labels, temperature, w_row=w_row, w_col=w_col, need_grad=need)
+        res = _core.infonce_forward(p_bf, t_bf, labels, temperature, w_row=w_row, w_col=w_col, need_grad=need,
+                                    p_f32=p_f32, t_f32=t_f32)
         if need:
             ctx.res, ctx.p_bf, ctx.t_bf, ctx.tau = res, p_bf, t_bf, temperature
+            ctx.f32 = (p_f32, t_f32)
             ctx.dtypes = (out1.dtype, out2.dtype)
         return res.loss
 
     @staticmethod
     def backward(ctx, dloss):
         dp, dt = _core.infonce_backward(ctx.res, ctx.p_bf, ctx.t_bf, ctx.tau, need_dp=ctx.needs_input_grad[0],
-                                        need_dt=ctx.needs_input_grad[1])
+                                        need_dt=ctx.needs_input_grad[1], p_f32=ctx.f32[0], t_f32=ctx.f32[1])
         if dp is not None:
             dp = (dp * dloss).to(ctx.dtypes[0])
         if dt is not None:

@@ -74,7 +74,9 @@ class FusedAdamW(torch.optim.Optimizer):
             for k in ("exp_avg", "exp_avg_sq", "master"):
                 if k in s and (s[k].dtype != torch.float32 or s[k].device != dev or not s[k].is_contiguous()):
                     s[k] = s[k].to(device=dev, dtype=torch.float32).contiguous()
-        s0 = self.state[tensors[0]]
+        # the shared step counter lives with the group's FIRST parameter (whether or not it has a gradient this step),
+        # so the set of tensors with gradients may change between steps without moving the counter
+        s0 = self.state[self.param_groups[gi]["params"][0]]
         step = s0.get("step")
         if step is None:
             s0["step"] = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -132,6 +134,12 @@ class FusedAdamW(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         capturing = torch.cuda.is_current_stream_capturing() if torch.cuda.is_available() else False
+        mxn = self.max_grad_norm
+        if mxn is not None and not math.isinf(mxn) and sum(1 for g in self.param_groups if any(p.grad is not None for p in g["params"])) > 1:
+            # torch.nn.utils.clip_grad_norm_(model.parameters()) of the reference (scripts/train_contrast.py:456-463)
+            # clips by ONE norm over all parameters; the fused kernel forms the norm per launch, i.e. per group
+            raise _lib.P2TError("FusedAdamW clips by the norm of ONE parameter group: with max_grad_norm set, put all "
+                                "clipped parameters (the adapter's fc1/fc2) in a single group")
         for gi, group in enumerate(self.param_groups):
             tensors = [p for p in group["params"] if p.grad is not None]
             if not tensors:
