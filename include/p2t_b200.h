@@ -92,10 +92,12 @@ int p2t_rows_plan_counts(const int* counts, int B, int chunk_rows, int* seq_off,
 
 /* Host -> device staging of a padded host batch [B][L][row_bytes] (pinned memory) as PACKED rows: sequence b
  * contributes rows [starts[b], starts[b] + counts[b]) (HOST int arrays; contiguous valid ranges, i.e. right or
- * left padding), written back to back at dev_dst.  Only valid rows cross PCIe; one cudaMemcpyAsync per sequence
- * on `stream`.  Replaces `tensor.to(rank)` of the padded batch (scripts/train_contrast.py:329-330). */
+ * left padding), written back to back at dev_dst.  Only valid rows cross PCIe; one cudaMemcpyAsync per sequence,
+ * sequence b on streams[b % n_streams] (HOST array of cudaStream_t: several copy streams overlap one copy's DMA
+ * set-up with its neighbours' transfers; the caller joins the streams).  Replaces `tensor.to(rank)` of the padded
+ * batch (scripts/train_contrast.py:329-330). */
 int p2t_stage_rows_h2d(const void* host_src, long long seq_stride_bytes, long long row_bytes, const int* starts,
-                       const int* counts, int B, void* dev_dst, void* stream);
+                       const int* counts, int B, void* dev_dst, void* const* streams, int n_streams);
 
 /* out[i] = src[row_src[i]] (bf16 rows of D elements), zero rows from n_rows up to the next multiple
  * of 256 (<= rows_cap).  Packs the padded (B, L, D_in) residue states that

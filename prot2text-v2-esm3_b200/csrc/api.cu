@@ -103,10 +103,11 @@ int p2t_rows_plan_counts(const int* counts, int B, int chunk_rows, int* seq_off,
 }
 
 int p2t_stage_rows_h2d(const void* host_src, long long seq_stride_bytes, long long row_bytes, const int* starts,
-                       const int* counts, int B, void* dev_dst, void* stream) {
-  if (!host_src || !starts || !counts || !dev_dst) return set_error(-1, "p2t_stage_rows_h2d: null pointer");
-  if (row_bytes <= 0 || seq_stride_bytes < 0) return set_error(-1, "p2t_stage_rows_h2d: bad strides");
-  // one plain cudaMemcpyAsync per sequence (the batched-memcpy entry points are not used on purpose)
+                       const int* counts, int B, void* dev_dst, void* const* streams, int n_streams) {
+  if (!host_src || !starts || !counts || !dev_dst || !streams) return set_error(-1, "p2t_stage_rows_h2d: null pointer");
+  if (row_bytes <= 0 || seq_stride_bytes < 0 || n_streams < 1) return set_error(-1, "p2t_stage_rows_h2d: bad strides / stream count");
+  // one plain cudaMemcpyAsync per sequence (the batched-memcpy entry points are not used on purpose), dealt round-robin
+  // to the caller's copy streams so that the DMA set-up of one copy overlaps the transfer of its neighbours
   char* dst = reinterpret_cast<char*>(dev_dst);
   const char* src = reinterpret_cast<const char*>(host_src);
   for (int b = 0; b < B; ++b) {
@@ -114,7 +115,7 @@ int p2t_stage_rows_h2d(const void* host_src, long long seq_stride_bytes, long lo
     const size_t bytes = (size_t)counts[b] * (size_t)row_bytes;
     if (bytes) {
       cudaError_t e = cudaMemcpyAsync(dst, src + (size_t)b * seq_stride_bytes + (size_t)starts[b] * row_bytes, bytes,
-                                      cudaMemcpyHostToDevice, S(stream));
+                                      cudaMemcpyHostToDevice, S(streams[b % n_streams]));
       if (e != cudaSuccess) return set_error((int)e, "cudaMemcpyAsync: %s", cudaGetErrorString(e));
     }
     dst += bytes;
