@@ -202,10 +202,26 @@ int p2t_adapter_tail_bwd_dy(const void* a, const void* g2, const float* inv_norm
  * db2 != NULL, by [ceil(rows_cap/64)][d_out].
  * gemm_ws: optional split-K scratch for the two weight-gradient GEMMs (see p2t_gemm_bf16).
  * ------------------------------------------------------------------------------------------- */
+/* phases: which GEMMs this call enqueues (0 = all three).  The fused sharded training step issues DGRAD | DW2 first,
+ * finishes db2, and then DW1 with `overlap`: a gradient-mean channel (layout and meaning of p2t_peer_allreduce_mean,
+ * holding this rank's dW2 / db2 contribution) whose announce + reduce phases are serviced by `ctas` comm-role CTAs
+ * INSIDE the dW1 GEMM's launch — compute step and collective in one kernel over NVLink peer memory, with a fixed SM
+ * partition (ctas: a multiple of 2, e.g. 16; the GEMM runs on the other SMs).  The round is closed afterwards with
+ * p2t_peer_allreduce_mean(phases = 4).  Needs dw_is_f32 and cta_group 2.  (DDP overlaps its bucket all-reduces with
+ * the backward the same way, scripts/train_contrast.py:448 + :611-614.) */
+#define P2T_BWD_DGRAD 1
+#define P2T_BWD_DW2 2
+#define P2T_BWD_DW1 4
+typedef struct {
+  void* const* peers;      /* HOST array of `world` device pointers (see p2t_peer_allreduce_mean) */
+  int world, rank;
+  long long n_bytes, f32_from_byte;
+  int ctas;
+} p2t_overlap_reduce_t;
 int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, const void* h1, const void* g1, const void* dz2,
                     int d_in, int d_mid, int d_out, int rows_cap, const int* n_rows_dev, void* dz1, void* dw1,
                     void* db1, void* dw2, void* db2, void* dx, float* colsum_ws, void* gemm_ws, int accumulate,
-                    int dw_is_f32, int cta_group, void* stream);
+                    int dw_is_f32, int phases, const p2t_overlap_reduce_t* overlap, int cta_group, void* stream);
 /* Both bias gradients of the fused step in one launch, summed in a fixed order from the partial rows left by
  * p2t_adapter_bwd (db1_partial = its colsum_ws) and p2t_adapter_tail_bwd (db2_partial = its colsum_ws, nparts2_dev,
  * ws_rows2).  Outputs in fp32 (what the gradient all-reduce carries: ONE rounding to bf16, after the mean over ranks)

@@ -18,13 +18,13 @@ from .graph import GraphedContrastiveStep
 from .host_io import HostStager, StagedBatch
 from .step import StepAux, contrastive_step, segment_pooling_mask, text_embeddings
 from .optim import FusedAdamW
-from .peer import PeerAllGather, PeerBuffer, PeerGradAllReduce
+from .peer import OverlappedGradReduce, PeerAllGather, PeerBuffer, PeerGradAllReduce
 from .handoff import adapter_into_embeds, llm_hidden_states_at
 
 __all__ = [
     "ModalityAdapter", "ModalityAdapterConfig", "readout_embeddings", "BatchInfoNCELoss",
     "SegmentedBatchInfoNCELoss", "SymmetricInfoNCELoss", "contrastive_step", "text_embeddings", "segment_pooling_mask", "StepAux",
     "HostStager", "StagedBatch", "GraphedContrastiveStep",
-    "FusedAdamW", "PeerAllGather", "PeerBuffer", "PeerGradAllReduce", "adapter_into_embeds", "llm_hidden_states_at",
+    "FusedAdamW", "PeerAllGather", "PeerBuffer", "PeerGradAllReduce", "OverlappedGradReduce", "adapter_into_embeds", "llm_hidden_states_at",
     "P2TError",
 ]

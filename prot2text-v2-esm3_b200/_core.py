@@ -6,6 +6,7 @@ All functions enqueue on the CURRENT torch CUDA stream and never synchronise.
 """
 from __future__ import annotations
 
+import ctypes as C
 from dataclasses import dataclass
 from typing import Optional
 
@@ -202,13 +203,16 @@ def adapter_forward(x: torch.Tensor, x_rows: int, rows_cap: int, n_rows: torch.T
 def adapter_backward(acts: AdapterActs, dz2: torch.Tensor, w1, w2, need_dx: bool = False, need_db2: bool = True,
                      cta_group: Optional[int] = None, need_db1: bool = True, accumulate: bool = False,
                      dw1_out: Optional[torch.Tensor] = None, dw2_out: Optional[torch.Tensor] = None,
-                     dw_dtype=torch.bfloat16):
+                     dw_dtype=torch.bfloat16, mid_hook=None, overlap=None, overlap_ctas: int = 16):
     """Returns (dw1, db1, dw2, db2_or_None, dx_or_None) in bf16, nn.Linear layout.
 
     `need_db1=False`: db1 is returned as the fp32 partial column sums [ceil(rows_cap/32)][d_mid] the dgrad GEMM's
     epilogue left behind (finish them with `bias_grads`).  `dw1_out`/`dw2_out`: write (or, with `accumulate`, add)
     the weight gradients into the caller's tensors instead of fresh ones.  `dw_dtype=torch.float32`: the weight
-    gradients leave the GEMMs unrounded (what a gradient mean over ranks should carry)."""
+    gradients leave the GEMMs unrounded (what a gradient mean over ranks should carry).  `overlap`: a
+    peer.PeerGradAllReduce channel holding this rank's dW2 / db2 contribution — its announce + reduce phases are then
+    serviced by `overlap_ctas` comm-role CTAs inside the dW1 GEMM's launch; `mid_hook()` runs between the dW2 and the
+    dW1 GEMM (the caller finishes db2 there)."""
     d_mid, d_in = w1.shape
     d_out = w2.shape[0]
     dev = dz2.device
@@ -225,26 +229,49 @@ def adapter_backward(acts: AdapterActs, dz2: torch.Tensor, w1, w2, need_dx: bool
     dx = torch.empty(acts.rows_cap, d_in, dtype=bf, device=dev) if need_dx else None
     n32, n64 = (acts.rows_cap + 31) // 32, (acts.rows_cap + 63) // 64
     ws = torch.empty(n32 * d_mid + (n64 * d_out if need_db2 else 0), dtype=torch.float32, device=dev)
-    _lib.call("p2t_adapter_bwd", _ptr(acts.x), acts.x_rows, _ptr(w1), _ptr(w2), _ptr(acts.h1), _ptr(acts.g1),
-              _ptr(dz2), d_in, d_mid, d_out, acts.rows_cap, _ptr(acts.n_rows), _ptr(dz1), _ptr(dw1), _ptr(db1),
-              _ptr(dw2), _ptr(db2), _ptr(dx), _ptr(ws), _ptr(gemm_workspace(dev)), int(accumulate),
-              int(dw1.dtype == torch.float32), cta_group or default_cta_group(), _stream())
+    gws = gemm_workspace(dev)
+
+    def call(phases: int, ov):
+        _lib.call("p2t_adapter_bwd", _ptr(acts.x), acts.x_rows, _ptr(w1), _ptr(w2), _ptr(acts.h1), _ptr(acts.g1),
+                  _ptr(dz2), d_in, d_mid, d_out, acts.rows_cap, _ptr(acts.n_rows), _ptr(dz1), _ptr(dw1), _ptr(db1),
+                  _ptr(dw2), _ptr(db2), _ptr(dx), _ptr(ws), _ptr(gws), int(accumulate),
+                  int(dw1.dtype == torch.float32), phases, ov, cta_group or default_cta_group(), _stream())
+
+    if mid_hook is None and overlap is None:
+        call(0, None)
+    else:
+        # sharded training step: dgrad + dW2 first, then the caller finishes what the overlapped channel carries (db2),
+        # then dW1 with comm-role CTAs servicing that channel inside its launch
+        call(1 | 2, None)
+        if mid_hook is not None:
+            mid_hook()
+        ov = None
+        if overlap is not None:
+            ov = _lib.OverlapReduce(C.cast(overlap.buffer.table, C.POINTER(C.c_void_p)), overlap.world, overlap.rank, overlap.n_bytes, overlap.f32_from,
+                                    int(getattr(overlap, "comm_ctas", overlap_ctas)))
+        call(4, ov)
     return dw1, (db1 if need_db1 else ws), dw2, db2, dx
 
 
-def bias_grads(db1_partial: torch.Tensor, rows_cap: int, n_rows: torch.Tensor, d_mid: int, db2_partial: torch.Tensor,
-               nparts2: torch.Tensor, d_out: int, *, accumulate: bool = False,
+def bias_grads(db1_partial: Optional[torch.Tensor], rows_cap: int, n_rows: Optional[torch.Tensor], d_mid: int,
+               db2_partial: Optional[torch.Tensor], nparts2: Optional[torch.Tensor], d_out: int, *, accumulate: bool = False,
                out_f32: Optional[tuple] = None, out_bf16: Optional[tuple] = None):
     """(db1_bf16, db2_bf16, db1_f32, db2_f32) from the partial column sums of the dgrad GEMM's epilogue and of the
-    tail backward, one launch.  `out_f32` / `out_bf16`: (db1, db2) tensors to write into (fp32 is added to when
-    `accumulate`)."""
-    dev = db1_partial.device
-    f1, f2 = out_f32 if out_f32 is not None else (torch.empty(d_mid, dtype=torch.float32, device=dev),
-                                                  torch.empty(d_out, dtype=torch.float32, device=dev))
-    b1, b2 = out_bf16 if out_bf16 is not None else (torch.empty(d_mid, dtype=torch.bfloat16, device=dev),
-                                                    torch.empty(d_out, dtype=torch.bfloat16, device=dev))
+    tail backward, one launch.  Either job may be absent (partial None: its outputs come back None).  `out_f32` /
+    `out_bf16`: (db1, db2) tensors to write into (fp32 is added to when `accumulate`)."""
+    dev = (db1_partial if db1_partial is not None else db2_partial).device
+    of = out_f32 if out_f32 is not None else (None, None)
+    ob = out_bf16 if out_bf16 is not None else (None, None)
+    f1 = b1 = f2 = b2 = None
+    if db1_partial is not None:
+        f1 = of[0] if of[0] is not None else torch.empty(d_mid, dtype=torch.float32, device=dev)
+        b1 = ob[0] if ob[0] is not None else torch.empty(d_mid, dtype=torch.bfloat16, device=dev)
+    if db2_partial is not None:
+        f2 = of[1] if of[1] is not None else torch.empty(d_out, dtype=torch.float32, device=dev)
+        b2 = ob[1] if ob[1] is not None else torch.empty(d_out, dtype=torch.bfloat16, device=dev)
     _lib.call("p2t_bias_grads", _ptr(db1_partial), rows_cap, _ptr(n_rows), d_mid, _ptr(b1), _ptr(f1), _ptr(db2_partial),
-              _ptr(nparts2), db2_partial.shape[0], d_out, _ptr(b2), _ptr(f2), int(accumulate), _stream())
+              _ptr(nparts2), db2_partial.shape[0] if db2_partial is not None else 0, d_out, _ptr(b2), _ptr(f2),
+              int(accumulate), _stream())
     return b1, b2, f1, f2
 
 

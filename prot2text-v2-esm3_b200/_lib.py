@@ -13,6 +13,13 @@ LIB_PATH = os.path.join(_HERE, "libp2t_b200.so")
 
 _vp, _i, _ll, _f, _ull = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulonglong
 
+
+class OverlapReduce(C.Structure):
+    """p2t_overlap_reduce_t of include/p2t_b200.h"""
+    _fields_ = [("peers", C.POINTER(C.c_void_p)), ("world", C.c_int), ("rank", C.c_int), ("n_bytes", C.c_longlong),
+                ("f32_from_byte", C.c_longlong), ("ctas", C.c_int)]
+
+
 # name -> argument ctypes, in header order (include/p2t_b200.h)
 SIGNATURES = {
     "p2t_gemm_bf16": [_vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _vp],
@@ -32,7 +39,8 @@ SIGNATURES = {
     "p2t_readout_bwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "p2t_adapter_tail_bwd": [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp],
     "p2t_adapter_tail_bwd_dy": [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp],
-    "p2t_adapter_bwd": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "p2t_adapter_bwd": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
+                        C.POINTER(OverlapReduce), _i, _vp],
     "p2t_bias_grads": [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp],
     "p2t_loss_fused": [_vp, _vp, C.POINTER(_vp), _i, _i, _ll, _vp, _i, _i, _i, _i, _f, _f, _f, _f, _i, _i, _i,
                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],

@@ -230,15 +230,16 @@ int p2t_adapter_tail_bwd_dy(const void* a, const void* g2, const float* inv_norm
 int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, const void* h1, const void* g1, const void* dz2,
                     int d_in, int d_mid, int d_out, int rows_cap, const int* n_rows_dev, void* dz1, void* dw1,
                     void* db1, void* dw2, void* db2, void* dx, float* colsum_ws, void* gemm_ws, int accumulate,
-                    int dw_is_f32, int cta_group, void* stream) {
+                    int dw_is_f32, int phases, const p2t_overlap_reduce_t* overlap, int cta_group, void* stream) {
   if (!x || !w2 || !h1 || !g1 || !dz2 || !dz1 || !dw1 || !dw2 || !colsum_ws)
     return set_error(-1, "p2t_adapter_bwd: null pointer");
+  if (phases == 0) phases = P2T_BWD_DGRAD | P2T_BWD_DW2 | P2T_BWD_DW1;
   cudaStream_t st = S(stream);
   float* db1_partial = colsum_ws;                                               // [ceil(rows_cap/32)][d_mid]
   float* db2_ws = colsum_ws + (size_t)((rows_cap + 31) / 32) * (size_t)d_mid;   // [ceil(rows_cap/64)][d_out], only with db2
   // dz1 = (dz2 W2) * g1      A = dz2 [rows][d_out] (K-major), B[n][k] = W2[k][n] (MN-major, ld d_mid)
   // + per-32-row column sums of dz1 from the epilogue (db1 without a second pass over dz1)
-  {
+  if (phases & P2T_BWD_DGRAD) {
     GemmParams p = base_params(rows_cap, d_mid, d_out);
     p.dyn_m = n_rows_dev;
     p.d0 = dz1; p.ldd0 = d_mid;
@@ -247,15 +248,18 @@ int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, c
     if (int rc = launch_gemm(dz2, d_out, false, w2, d_mid, true, EPI_MUL_AUX, p, cta_group, st)) return rc;
   }
   // dW2 = dz2^T h1           both operands MN-major, K = residue rows
-  {
+  if (phases & P2T_BWD_DW2) {
     GemmParams p = base_params(d_out, d_mid, rows_cap);
     p.dyn_k = n_rows_dev;
     p.sk_ws = gemm_ws;
     p.d0 = dw2; p.ldd0 = d_mid;
     p.accumulate = accumulate;
     if (int rc = launch_gemm(dz2, d_out, true, h1, d_mid, true, dw_is_f32 ? EPI_STORE_F32 : EPI_STORE_BF16, p, cta_group, st)) return rc;
+    if (db2) if (int rc = colsum(dz2, n_rows_dev, rows_cap, d_out, db2_ws, db2, nullptr, st)) return rc;
   }
-  // dW1 = dz1^T x
+  if (!(phases & P2T_BWD_DW1)) return 0;
+  // dW1 = dz1^T x  — optionally with comm-role CTAs that service a gradient-mean channel behind it (the mean of
+  // dW2 / db2 over the ranks travels over NVLink while this GEMM runs: one launch, fixed SM partition)
   {
     GemmParams p = base_params(d_mid, d_in, rows_cap);
     p.dyn_k = n_rows_dev;
@@ -263,9 +267,26 @@ int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, c
     p.d0 = dw1; p.ldd0 = d_in;
     p.b_extent = x_rows;
     p.accumulate = accumulate;
-    if (int rc = launch_gemm(dz1, d_mid, true, x, d_in, true, dw_is_f32 ? EPI_STORE_F32 : EPI_STORE_BF16, p, cta_group, st)) return rc;
+    GemmCommReduce comm{};
+    const GemmCommReduce* cp = nullptr;
+    if (overlap != nullptr) {
+      if (!dw_is_f32 || cta_group != 2) return set_error(-1, "p2t_adapter_bwd: the overlapped reduce rides on the fp32 dW1 GEMM with cta_group 2");
+      if (!overlap->peers || overlap->world < 1 || overlap->world > kPeerMaxWorld || overlap->rank < 0 || overlap->rank >= overlap->world)
+        return set_error(-1, "p2t_adapter_bwd: bad overlap channel");
+      if (overlap->n_bytes <= 0 || overlap->n_bytes % 16 || overlap->f32_from_byte % 16)
+        return set_error(-1, "p2t_adapter_bwd: overlap channel sizes must be multiples of 16 bytes");
+      for (int r = 0; r < overlap->world; ++r) {
+        if (!overlap->peers[r]) return set_error(-1, "p2t_adapter_bwd: overlap peer %d not mapped", r);
+        comm.peers.base[r] = overlap->peers[r];
+      }
+      comm.world = overlap->world; comm.rank = overlap->rank; comm.ctas = overlap->ctas;
+      comm.n_vec = overlap->n_bytes / 16;
+      comm.f32_begin = (overlap->f32_from_byte < 0 || overlap->f32_from_byte > overlap->n_bytes ? overlap->n_bytes : overlap->f32_from_byte) / 16;
+      comm.scale = 1.f / (float)overlap->world;
+      cp = &comm;
+    }
+    if (int rc = launch_gemm(dz1, d_mid, true, x, d_in, true, dw_is_f32 ? EPI_STORE_F32 : EPI_STORE_BF16, p, cta_group, st, cp)) return rc;
   }
-  if (db2) if (int rc = colsum(dz2, n_rows_dev, rows_cap, d_out, db2_ws, db2, nullptr, st)) return rc;
   if (db1) {
     BiasJob j{}, none{};
     j.partial = db1_partial; j.D = d_mid; j.nparts_max = (rows_cap + 31) / 32; j.n_rows = n_rows_dev; j.n_static = rows_cap;

@@ -67,10 +67,14 @@ int sm_count() {
   return n[dev];
 }
 
-template <int CTA_GROUP, bool A_MN, bool B_MN, int EPI>
-static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+template <int CTA_GROUP, bool A_MN, bool B_MN, int EPI, bool COMM = false>
+static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream,
+                       const GemmCommReduce* comm = nullptr) {
   using S = GemmSmem<CTA_GROUP, EPI>;
-  auto kern = gemm_bf16_tcgen05_kernel<CTA_GROUP, A_MN, B_MN, EPI>;
+  auto kern = gemm_bf16_tcgen05_kernel<CTA_GROUP, A_MN, B_MN, EPI, COMM>;
+  const int comm_ctas = COMM ? comm->ctas : 0;
+  if (COMM && (comm_ctas < CTA_GROUP || comm_ctas % CTA_GROUP || comm_ctas > sm_count() / 2))
+    return set_error(-15, "GEMM with a comm role: %d comm CTAs (need a multiple of the cluster size, at most half the SMs)", comm_ctas);
   static bool configured[64] = {false};  // cudaFuncSetAttribute is a per-device setting
   int cur_dev = 0;
   cudaGetDevice(&cur_dev);
@@ -83,7 +87,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   const int tile_m = GEMM_BLOCK_M * CTA_GROUP;
   const long long tiles = (long long)((p.m + tile_m - 1) / tile_m) * ((p.n + GEMM_BLOCK_N - 1) / GEMM_BLOCK_N);
   if (tiles == 0) return 0;
-  const int all_workers = sm_count() / CTA_GROUP;
+  const int all_workers = (sm_count() - comm_ctas) / CTA_GROUP;  // comm-role CTAs take their SMs out of the GEMM's share
   int workers = all_workers;
   if (tiles < workers) workers = (int)tiles;
   GemmParams q = p;
@@ -113,7 +117,8 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     if (me != cudaSuccess) return set_error((int)me, "split-K flag reset failed: %s", cudaGetErrorString(me));
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(workers * CTA_GROUP);
+  if (COMM) workers = all_workers;  // fixed partition: the comm CTAs are the last comm_ctas of the grid
+  cfg.gridDim = dim3(workers * CTA_GROUP + comm_ctas);
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = S::TOTAL;
   cfg.stream = stream;
@@ -143,7 +148,9 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     }
   }
   stamp_begin(stream);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, td0, td1, q);
+  cudaError_t e;
+  if constexpr (COMM) e = cudaLaunchKernelEx(&cfg, kern, ta, tb, td0, td1, q, *comm);
+  else e = cudaLaunchKernelEx(&cfg, kern, ta, tb, td0, td1, q, 0);
   if (timed) gemm_timing_record(stream, false);
   if (e != cudaSuccess) return set_error((int)e, "GEMM launch failed: %s", cudaGetErrorString(e));
   count_launch();
@@ -177,8 +184,10 @@ static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, con
 // `a_rows_cap`/`b_rows_cap`: extent of the operand along its row (M/N resp. K for MN-major) axis that is
 // physically present, used for TMA bounds (zero fill beyond).
 int launch_gemm(const void* a, long long lda, bool a_mn, const void* b, long long ldb, bool b_mn, int epi,
-                GemmParams p, int cta_group, cudaStream_t stream) {
+                GemmParams p, int cta_group, cudaStream_t stream, const GemmCommReduce* comm) {
   if (p.m <= 0 || p.n <= 0 || p.k <= 0) return 0;
+  if (comm != nullptr && !(a_mn && b_mn && epi == EPI_STORE_F32 && cta_group == 2))
+    return set_error(-16, "the comm role rides on the fp32 weight-gradient GEMM (both operands MN-major, cta_group 2) only");
   CUtensorMap ta, tb;
   int rc;
   if (!a_mn) rc = make_tmap_bf16(&ta, a, p.k, p.a_extent > 0 ? p.a_extent : p.m, lda, GEMM_BLOCK_M);
@@ -189,6 +198,7 @@ int launch_gemm(const void* a, long long lda, bool a_mn, const void* b, long lon
   else rc = make_tmap_bf16(&tb, b, p.n, p.b_extent > 0 ? p.b_extent : p.k, ldb, GEMM_BLOCK_K);
   if (rc) return rc;
   if (p.rows_cap <= 0) p.rows_cap = p.m;
+  if (comm != nullptr) return launch_inst<2, true, true, EPI_STORE_F32, true>(ta, tb, p, stream, comm);
   if (cta_group == 2) {
     if (a_mn && b_mn) return launch_epi<2, true, true>(epi, ta, tb, p, stream);
     if (a_mn) return launch_epi<2, true, false>(epi, ta, tb, p, stream);

@@ -47,6 +47,7 @@
 #include <type_traits>
 #include "ptx.cuh"
 #include "mathfn.cuh"
+#include "peer_dev.cuh"
 
 namespace p2t {
 
@@ -490,11 +491,24 @@ __device__ __forceinline__ void epilogue_chunk_staged(const uint32_t (&v)[32], c
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int CTA_GROUP, bool A_MN, bool B_MN, int EPI>
+// COMM: the last `comm.ctas` CTAs of the grid do not compute tiles; they service one round of a peer-memory mean
+// all-reduce channel (announce, wait for all ranks, reduce this rank's slice, publish) WHILE the other CTAs run the
+// GEMM: the compute step and the collective that follows its predecessor are one launch with a fixed SM partition
+// (a separate communication kernel could not be told to leave the persistent GEMM's SMs alone).  Used for the dW1
+// GEMM of the sharded training step: the mean of dW2 / db2 over the ranks travels over NVLink behind it.
+template <int CTA_GROUP, bool A_MN, bool B_MN, int EPI, bool COMM = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_d0, const __grid_constant__ CUtensorMap tmap_d1,
-                         const GemmParams p) {
+                         const GemmParams p, const typename std::conditional<COMM, GemmCommReduce, int>::type comm) {
+  int grid_ctas = gridDim.x;
+  if constexpr (COMM) {
+    grid_ctas -= comm.ctas;
+    if ((int)blockIdx.x >= grid_ctas) {
+      comm_reduce_role(comm, (int)blockIdx.x - grid_ctas);
+      return;
+    }
+  }
   using S = GemmSmem<CTA_GROUP, EPI>;
   extern __shared__ uint8_t smem_raw[];
   // align inside the shared window with pointer arithmetic (keeps the address space known to the compiler)
@@ -525,7 +539,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int num_n_blk = (N + GEMM_BLOCK_N - 1) / GEMM_BLOCK_N;
   const int num_tiles = num_m_blk * num_n_blk;
   const int worker = blockIdx.x / CTA_GROUP;
-  const int num_workers = gridDim.x / CTA_GROUP;
+  const int num_workers = grid_ctas / CTA_GROUP;
   const int sk_splits = (p.sk_splits < 0) ? choose_sk_splits(num_tiles, num_kb, num_workers) : p.sk_splits;
 
   if (warp == 0 && lane == 0) {

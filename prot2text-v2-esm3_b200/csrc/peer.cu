@@ -24,30 +24,14 @@
 namespace p2t {
 namespace {
 
-// The CTA's stores are done (barrier), thread 0 fences them at system scope (cumulative over the barrier, the pattern
-// of a cooperative grid sync) and counts the CTA in; the last CTA of the grid to get here fences once more (acquire
-// of the other CTAs' counts + release of everything) and publishes `epoch` in slot `rank` of the flag row at byte
-// offset `flag_off` of every peer buffer with plain system-scope stores (and, optionally, advances the local epoch).
 __device__ __forceinline__ void publish_when_grid_done(const PeerTable& peers, int world, int rank, size_t flag_off,
                                                        unsigned epoch, unsigned* grid_counter, unsigned* epoch_word) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    const unsigned done = atomicAdd(grid_counter, 1u);
-    if (done == gridDim.x - 1) {
-      __threadfence_system();
-      if (flag_off != (size_t)-1)
-        for (int r = 0; r < world; ++r)
-          st_relaxed_sys(reinterpret_cast<unsigned*>(static_cast<char*>(peers.base[(rank + r) % world]) + flag_off) + rank, epoch);
-      *grid_counter = 0;
-      if (epoch_word) *epoch_word = epoch;
-    }
-  }
+  peer_publish_when_done(peers, world, rank, flag_off, epoch, grid_counter, gridDim.x, epoch_word);
 }
 
 constexpr size_t kCtrlBytes = kPeerCtrlBytes;
 __host__ __device__ constexpr size_t flag_row_off(int phase) { return peer_flag_row_off(phase); }
-constexpr unsigned kPoison = 0x7fffffffu;  // NaN as fp32 and as a pair of bf16
+constexpr unsigned kPoison = kPeerPoison;
 
 // ------------------------------------------------------------------------------------------------
 // all-gather, push half: slot (epoch parity, rank) of every peer's buffer := src
@@ -110,63 +94,13 @@ __global__ void peer_allreduce_ready_kernel(PeerTable peers, int world, int rank
 // trip is ~2 us); ranks are always added in rank order, so every rank computes bit-identical sums.
 // Vectors below `f32_begin` hold 8 bf16 values (mean stored as bf16), vectors from `f32_begin` on hold 4 fp32 values
 // (mean stored as fp32: the bias gradients travel unrounded and are rounded to bf16 once, after the mean).
-__device__ __forceinline__ void acc_vec(float (&acc)[8], const uint4& v, bool f32) {
-  if (f32) {
-    acc[0] += __uint_as_float(v.x); acc[1] += __uint_as_float(v.y); acc[2] += __uint_as_float(v.z); acc[3] += __uint_as_float(v.w);
-  } else {
-    const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
-    acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
-    acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
-  }
-}
 template <int RB, int U>
 __global__ void __launch_bounds__(256)
 peer_allreduce_reduce_kernel(PeerTable peers, int world, int rank, long long n_vec, long long f32_begin, float scale) {
   unsigned* ctrl = static_cast<unsigned*>(peers.base[rank]);
   const unsigned epoch = ctrl[0] + 1;
   const bool ok = wait_flags(reinterpret_cast<const unsigned*>(static_cast<char*>(peers.base[rank]) + flag_row_off(0)), world, epoch, ctrl + 4);
-  const long long per = (n_vec + world - 1) / world;
-  const long long lo = per * rank, hi = min(n_vec, lo + per);
-  const size_t in_off = kCtrlBytes, out_off = kCtrlBytes + (size_t)n_vec * sizeof(uint4);
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += U * stride) {
-    float acc[U][8];
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc[u][k] = 0.f;
-    for (int r0 = 0; r0 < world; r0 += RB) {
-      uint4 v[U][RB];
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int j = 0; j < RB; ++j)
-          if (r0 + j < world && i + u * stride < hi)
-            v[u][j] = ld_sys_v4(reinterpret_cast<const uint4*>(static_cast<char*>(peers.base[r0 + j]) + in_off) + i + u * stride);
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int j = 0; j < RB; ++j)
-          if (r0 + j < world && i + u * stride < hi) acc_vec(acc[u], v[u][j], i + u * stride >= f32_begin);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (i + u * stride >= hi) continue;
-      uint4 o;
-      if (!ok)
-        o = make_uint4(kPoison, kPoison, kPoison, kPoison);  // a contribution never arrived: NaN, not a partial mean
-      else if (i + u * stride >= f32_begin)
-        o = make_uint4(__float_as_uint(acc[u][0] * scale), __float_as_uint(acc[u][1] * scale), __float_as_uint(acc[u][2] * scale),
-                       __float_as_uint(acc[u][3] * scale));
-      else
-        o = make_uint4(pack_bf16x2(acc[u][0] * scale, acc[u][1] * scale), pack_bf16x2(acc[u][2] * scale, acc[u][3] * scale),
-                       pack_bf16x2(acc[u][4] * scale, acc[u][5] * scale), pack_bf16x2(acc[u][6] * scale, acc[u][7] * scale));
-      for (int r = 0; r < world; ++r) {
-        const int dst = (rank + r) % world;
-        reinterpret_cast<uint4*>(static_cast<char*>(peers.base[dst]) + out_off)[i + u * stride] = o;
-      }
-    }
-  }
+  peer_reduce_slice<RB, U>(peers, world, rank, n_vec, f32_begin, scale, ok, blockIdx.x, gridDim.x);
   publish_when_grid_done(peers, world, rank, flag_row_off(1), epoch, ctrl + 2, nullptr);
 }
 

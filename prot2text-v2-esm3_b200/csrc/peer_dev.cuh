@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "mathfn.cuh"
 
 namespace p2t {
 
@@ -64,6 +65,115 @@ __device__ __forceinline__ bool wait_flags(const unsigned* flags, int world, uns
   }
   __syncthreads();
   return s_timed_out == 0 && ld_relaxed_sys(status) == 0u;
+}
+
+constexpr unsigned kPeerPoison = 0x7fffffffu;  // NaN as fp32 and as a pair of bf16
+
+// `n_ctas` CTAs cooperate on a channel phase: the CTA's stores are done (barrier), thread 0 fences them at system scope
+// and counts the CTA in; the last of the `n_ctas` to get here fences once more and publishes `epoch` in slot `rank` of
+// the flag row at byte offset `flag_off` of every peer buffer (and, optionally, advances the local epoch).
+__device__ __forceinline__ void peer_publish_when_done(const PeerTable& peers, int world, int rank, size_t flag_off,
+                                                       unsigned epoch, unsigned* counter, unsigned n_ctas,
+                                                       unsigned* epoch_word) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned done = atomicAdd(counter, 1u);
+    if (done == n_ctas - 1) {
+      __threadfence_system();
+      if (flag_off != (size_t)-1)
+        for (int r = 0; r < world; ++r)
+          st_relaxed_sys(reinterpret_cast<unsigned*>(static_cast<char*>(peers.base[(rank + r) % world]) + flag_off) + rank, epoch);
+      *counter = 0;
+      if (epoch_word) *epoch_word = epoch;
+    }
+  }
+}
+
+// One rank's share of the two-shot mean all-reduce (see peer.cu): sum slice `rank` of every peer's contribution area in
+// fp32, in rank order (bit-identical on all ranks), and store the mean into every peer's result area.  Executed by
+// `n_ctas` CTAs (this one is `cta`); vectors below f32_begin hold 8 bf16 values, the others 4 fp32 values.
+template <int RB, int U>
+__device__ __forceinline__ void peer_reduce_slice(const PeerTable& peers, int world, int rank, long long n_vec,
+                                                  long long f32_begin, float scale, bool ok, int cta, int n_ctas) {
+  const long long per = (n_vec + world - 1) / world;
+  const long long lo = per * rank, hi = min(n_vec, lo + per);
+  const size_t in_off = kPeerCtrlBytes, out_off = kPeerCtrlBytes + (size_t)n_vec * sizeof(uint4);
+  const long long stride = (long long)n_ctas * blockDim.x;
+  for (long long i = lo + (long long)cta * blockDim.x + threadIdx.x; i < hi; i += U * stride) {
+    float acc[U][8];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[u][k] = 0.f;
+    for (int r0 = 0; r0 < world; r0 += RB) {
+      uint4 v[U][RB];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < RB; ++j)
+          if (r0 + j < world && i + u * stride < hi)
+            v[u][j] = ld_sys_v4(reinterpret_cast<const uint4*>(static_cast<char*>(peers.base[r0 + j]) + in_off) + i + u * stride);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < RB; ++j)
+          if (r0 + j < world && i + u * stride < hi) {
+            const uint4& q = v[u][j];
+            if (i + u * stride >= f32_begin) {
+              acc[u][0] += __uint_as_float(q.x); acc[u][1] += __uint_as_float(q.y);
+              acc[u][2] += __uint_as_float(q.z); acc[u][3] += __uint_as_float(q.w);
+            } else {
+              const float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
+              acc[u][0] += a.x; acc[u][1] += a.y; acc[u][2] += b.x; acc[u][3] += b.y;
+              acc[u][4] += c.x; acc[u][5] += c.y; acc[u][6] += d.x; acc[u][7] += d.y;
+            }
+          }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i + u * stride >= hi) continue;
+      uint4 o;
+      if (!ok)
+        o = make_uint4(kPeerPoison, kPeerPoison, kPeerPoison, kPeerPoison);  // a contribution never arrived: NaN, not a partial mean
+      else if (i + u * stride >= f32_begin)
+        o = make_uint4(__float_as_uint(acc[u][0] * scale), __float_as_uint(acc[u][1] * scale), __float_as_uint(acc[u][2] * scale),
+                       __float_as_uint(acc[u][3] * scale));
+      else
+        o = make_uint4(pack_bf16x2(acc[u][0] * scale, acc[u][1] * scale), pack_bf16x2(acc[u][2] * scale, acc[u][3] * scale),
+                       pack_bf16x2(acc[u][4] * scale, acc[u][5] * scale), pack_bf16x2(acc[u][6] * scale, acc[u][7] * scale));
+      for (int r = 0; r < world; ++r) {
+        const int dst = (rank + r) % world;
+        reinterpret_cast<uint4*>(static_cast<char*>(peers.base[dst]) + out_off)[i + u * stride] = o;
+      }
+    }
+  }
+}
+
+// The contribution phase + reduce phase of one channel round, run by `n_ctas` CTAs that are NOT a kernel of their own:
+// the comm-role CTAs at the end of a GEMM launch's grid (gemm_sm100.cuh).  This rank's contribution is complete before
+// the launch (stream order), so CTA 0 announces it right away; every CTA then waits for all ranks' announcements,
+// reduces its part of this rank's slice and the last one publishes the phase-1 flags.
+struct GemmCommReduce {
+  PeerTable peers;
+  int world, rank, ctas;     // ctas: CTAs of the grid that take the comm role (a multiple of the cluster size)
+  long long n_vec, f32_begin;
+  float scale;
+};
+__device__ __forceinline__ void comm_reduce_role(const GemmCommReduce& c, int cta) {
+  unsigned* ctrl = static_cast<unsigned*>(c.peers.base[c.rank]);
+  const unsigned epoch = ctrl[0] + 1;
+  if (cta == 0 && threadIdx.x == 0) {
+    __threadfence_system();
+    for (int r = 0; r < c.world; ++r)
+      st_relaxed_sys(reinterpret_cast<unsigned*>(static_cast<char*>(c.peers.base[(c.rank + r) % c.world]) + peer_flag_row_off(0)) + c.rank, epoch);
+  }
+  const bool ok = wait_flags(reinterpret_cast<const unsigned*>(static_cast<char*>(c.peers.base[c.rank]) + peer_flag_row_off(0)),
+                             c.world, epoch, ctrl + 4);
+  if (c.world <= 2) peer_reduce_slice<2, 8>(c.peers, c.world, c.rank, c.n_vec, c.f32_begin, c.scale, ok, cta, c.ctas);
+  else if (c.world <= 4) peer_reduce_slice<4, 4>(c.peers, c.world, c.rank, c.n_vec, c.f32_begin, c.scale, ok, cta, c.ctas);
+  else peer_reduce_slice<8, 2>(c.peers, c.world, c.rank, c.n_vec, c.f32_begin, c.scale, ok, cta, c.ctas);
+  peer_publish_when_done(c.peers, c.world, c.rank, peer_flag_row_off(1), epoch, ctrl + 2, (unsigned)c.ctas, nullptr);
 }
 
 }  // namespace p2t

@@ -71,8 +71,9 @@ int sim_finish(const float4* row_part, int npart, int ld, const float* pos, cons
 int convert_f32_to_bf16(const float* in, long long n, void* out, cudaStream_t st);
 int convert_bf16_to_f32(const void* in, long long n, float* out, cudaStream_t st);
 
+struct GemmCommReduce;
 int launch_gemm(const void* a, long long lda, bool a_mn, const void* b, long long ldb, bool b_mn, int epi,
-                GemmParams p, int cta_group, cudaStream_t stream);
+                GemmParams p, int cta_group, cudaStream_t stream, const GemmCommReduce* comm = nullptr);
 
 // peer.cu: exchange steps over NVLink peer memory
 size_t peer_ctrl_bytes();

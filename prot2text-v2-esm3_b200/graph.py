@@ -76,6 +76,7 @@ class GraphedContrastiveStep:
         d_out = adapter.fc2.weight.shape[0]
         bf, f32 = torch.bfloat16, torch.float32
         self._dw_f32 = grad_reducer is not None
+        self._overlapped = grad_reducer is not None and hasattr(grad_reducer, "late")
         if grad_reducer is not None:
             want = [((d_mid, d_in), f32), ((d_mid,), f32), ((d_out, d_mid), f32), ((d_out,), f32)]
             if [(s, d) for s, d in zip(grad_reducer.shapes, grad_reducer.dtypes)] != want:
@@ -121,11 +122,17 @@ class GraphedContrastiveStep:
                                                        temperature=self.kw["temperature"], symmetric=self.kw["symmetric"],
                                                        max_valid_rows=self.kw["max_valid_rows"])
         # on a boundary step without a reducer the bf16 bias gradients land directly in what param.grad is bound to
+        tail = last and with_tail
+        # boundary step with an OverlappedGradReduce: the mean of dW2 / db2 rides inside the dW1 GEMM's launch
+        ov = self.grad_reducer.late if (tail and self._overlapped) else None
         step_backward(state, None, accumulate=not first, dw_out=(self._dw1, self._dw2), dw_f32=self._dw_f32,
-                      db_f32_out=(self._db1_f32, self._db2_f32), db_bf16_out=(self._db1, self._db2))
-        if last and with_tail:
+                      db_f32_out=(self._db1_f32, self._db2_f32), db_bf16_out=(self._db1, self._db2), overlap_reduce=ov)
+        if tail:
             if self.grad_reducer is not None:
-                self.grad_reducer.exchange()
+                if self._overlapped:
+                    self.grad_reducer.finish()
+                else:
+                    self.grad_reducer.exchange()
                 for mean_f32, grad_bf16 in zip(self._reduced, self.grads):  # the one rounding: mean (fp32) -> param.grad (bf16)
                     _lib.call("p2t_f32_to_bf16", mean_f32.data_ptr(), mean_f32.numel(), grad_bf16.data_ptr(), _core._stream())
             if self.optimizer is not None:

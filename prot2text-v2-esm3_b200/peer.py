@@ -307,6 +307,10 @@ class PeerGradAllReduce:
         """Zero-copy form: the contribution is already in `views_in()`; after this call `views_out()` hold the mean."""
         self._phase(_READY | _REDUCE | _WAIT)
 
+    def wait_only(self) -> None:
+        """Close a round whose announce + reduce phases were serviced elsewhere (comm-role CTAs of a GEMM launch)."""
+        self._phase(_WAIT)
+
     def reduce_(self, grads: Sequence[torch.Tensor]) -> Sequence[torch.Tensor]:
         self.stage(grads)
         self.reduce()
@@ -316,3 +320,56 @@ class PeerGradAllReduce:
     def close(self) -> None:
         self._in = self._out = None
         self.buffer.close()
+
+
+class OverlappedGradReduce:
+    """The gradient mean of the sharded training step as TWO channels, so that most of it hides behind the backward:
+
+      late : [dW2, db2] (fp32) — complete after the dW2 GEMM; its announce + reduce phases are serviced by comm-role
+             CTAs INSIDE the dW1 GEMM's launch (one kernel: tcgen05 GEMM on most SMs, NVLink peer-memory reduce on
+             `comm_ctas` of them), DDP's bucket overlap (scripts/train_contrast.py:448 + :611-614) without a second
+             kernel fighting the persistent GEMM for SMs;
+      tail : [dW1, db1] (fp32) — reduced after the backward.
+
+    `views_in()` / `views_out()` are in parameter order [dW1, db1, dW2, db2]; pass the object as
+    `graph.GraphedContrastiveStep(grad_reducer=...)`."""
+
+    def __init__(self, adapter, group=None, comm_ctas: int = 16, _buffers: Optional[tuple] = None):
+        like = PeerGradAllReduce.adapter_like(adapter)
+        lb, tb = _buffers if _buffers is not None else (None, None)
+        self.late = PeerGradAllReduce([like[2], like[3]], group, _buffer=lb)
+        self.tail = PeerGradAllReduce([like[0], like[1]], group, _buffer=tb)
+        self.comm_ctas = int(comm_ctas)
+        self.late.comm_ctas = self.comm_ctas
+        self.rank, self.world = self.late.rank, self.late.world
+        self.shapes = [tuple(t.shape) for t in like]
+        self.dtypes = [t.dtype for t in like]
+
+    def views_in(self):
+        (w2, b2), (w1, b1) = self.late.views_in(), self.tail.views_in()
+        return [w1, b1, w2, b2]
+
+    def views_out(self):
+        (w2, b2), (w1, b1) = self.late.views_out(), self.tail.views_out()
+        return [w1, b1, w2, b2]
+
+    def finish(self) -> None:
+        """After the backward: close the overlapped round, then reduce the rest."""
+        self.late.wait_only()
+        self.tail.exchange()
+
+    class _Both:
+        def __init__(self, a, b):
+            self.a, self.b = a, b
+
+        def check(self):
+            self.a.check()
+            self.b.check()
+
+    @property
+    def buffer(self):
+        return OverlappedGradReduce._Both(self.late.buffer, self.tail.buffer)
+
+    def close(self) -> None:
+        self.late.close()
+        self.tail.close()

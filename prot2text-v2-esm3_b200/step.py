@@ -164,13 +164,17 @@ def step_forward(x, prot_mask, w1, b1, w2, b2, t_in, labels, cfg: dict, aux: Ste
 
 
 def step_backward(state, dloss: Optional[torch.Tensor], *, accumulate: bool = False, dw_out: Optional[tuple] = None,
-                  db_f32_out: Optional[tuple] = None, db_bf16_out: Optional[tuple] = None, dw_f32: bool = False):
+                  db_f32_out: Optional[tuple] = None, db_bf16_out: Optional[tuple] = None, dw_f32: bool = False,
+                  overlap_reduce=None):
     """Backward of the fused step: (dW1, db1, dW2, db2, db1_f32, db2_f32) — bf16 gradients in nn.Linear layout plus
     the bias gradients in fp32 (what a gradient all-reduce should carry) — for the upstream gradient `dloss` (device
     scalar; None = 1).  `dw_f32`: dW1/dW2 leave the GEMMs in fp32 instead (sharded training: the gradient mean over
     ranks then rounds once, after the mean).  `dw_out` = (dW1, dW2) / `db_f32_out` / `db_bf16_out`: write into the caller's tensors;
     `accumulate`: add to them (bf16 read-modify-write for the weights, fp32 for the biases) — the micro-batch
-    accumulation of scripts/train_contrast.py:448-465."""
+    accumulation of scripts/train_contrast.py:448-465.  `overlap_reduce`: a peer.PeerGradAllReduce channel over
+    [dW2, db2] whose contribution area `dw_out[1]` / `db_f32_out[1]` alias: db2 is finished right after the dW2 GEMM and
+    the channel's announce + reduce phases run on comm-role CTAs inside the dW1 GEMM's launch (DDP's bucket overlap,
+    scripts/train_contrast.py:448 + :611-614, as one fused GEMM + collective kernel)."""
     plan, acts, inv_norm, w1c, w2c, cfg, head = state
     used = cfg["rows_used"]
     d_out = w2c.shape[0]
@@ -201,11 +205,27 @@ def step_backward(state, dloss: Optional[torch.Tensor], *, accumulate: bool = Fa
             c1, c2 = _core.pool_backward_coef(de, stats, plan, d_out, "mix")
     dz2, (ws2, nparts2) = _core.adapter_tail_backward(acts, inv_norm, plan, c1, c2, finish_db2=False)
     dw1_out, dw2_out = dw_out if dw_out is not None else (None, None)
+    of = db_f32_out if db_f32_out is not None else (None, None)
+    ob = db_bf16_out if db_bf16_out is not None else (None, None)
+    if overlap_reduce is None:
+        dw1, ws1, dw2, _, _ = _core.adapter_backward(acts, dz2, w1c, w2c, need_db2=False, need_db1=False,
+                                                     accumulate=accumulate, dw1_out=dw1_out, dw2_out=dw2_out,
+                                                     dw_dtype=torch.float32 if dw_f32 else torch.bfloat16)
+        db1, db2, db1_f32, db2_f32 = _core.bias_grads(ws1, acts.rows_cap, acts.n_rows, d_mid, ws2, nparts2, d_out,
+                                                      accumulate=accumulate, out_f32=db_f32_out, out_bf16=db_bf16_out)
+        return dw1, db1, dw2, db2, db1_f32, db2_f32
+    late = {}
+
+    def finish_db2():  # between the dW2 and the dW1 GEMM: the overlapped channel's contribution must be complete
+        _, late["b"], _, late["f"] = _core.bias_grads(None, acts.rows_cap, None, d_mid, ws2, nparts2, d_out,
+                                                      accumulate=accumulate, out_f32=(None, of[1]), out_bf16=(None, ob[1]))
+
     dw1, ws1, dw2, _, _ = _core.adapter_backward(acts, dz2, w1c, w2c, need_db2=False, need_db1=False,
                                                  accumulate=accumulate, dw1_out=dw1_out, dw2_out=dw2_out,
-                                                 dw_dtype=torch.float32 if dw_f32 else torch.bfloat16)
-    db1, db2, db1_f32, db2_f32 = _core.bias_grads(ws1, acts.rows_cap, acts.n_rows, d_mid, ws2, nparts2, d_out,
-                                                  accumulate=accumulate, out_f32=db_f32_out, out_bf16=db_bf16_out)
+                                                 dw_dtype=torch.float32, mid_hook=finish_db2, overlap=overlap_reduce)
+    db1, _, db1_f32, _ = _core.bias_grads(ws1, acts.rows_cap, acts.n_rows, d_mid, None, None, d_out,
+                                          accumulate=accumulate, out_f32=(of[0], None), out_bf16=(ob[0], None))
+    db2, db2_f32 = late["b"], late["f"]
     return dw1, db1, dw2, db2, db1_f32, db2_f32
 
 

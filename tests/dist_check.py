@@ -48,13 +48,16 @@ def main():
     f32m = lambda n: torch.empty(n, dtype=torch.float32, device="meta")
     reducer_mixed = peer.PeerGradAllReduce([prms[0], f32m(prms[1].numel()), prms[2], f32m(prms[3].numel())])  # eager form
     dx, dpm, dtx, dtm = sb.x.to(dev), sb.prot_mask.to(dev), sb.text.to(dev), sb.text_mask.to(dev)
-    for sym, form in ((False, "nccl"), (True, "nccl"), (False, "peer"), (True, "peer"), (False, "peer+graph"), (True, "peer+graph")):
+    overlapped = peer.OverlappedGradReduce(ad)  # graph form with the dW2 / db2 mean inside the dW1 GEMM's launch
+    for sym, form in ((False, "nccl"), (True, "nccl"), (False, "peer"), (True, "peer"), (False, "peer+graph"), (True, "peer+graph"),
+                      (False, "peer+graph+overlap"), (True, "peer+graph+overlap")):
         ad.zero_grad(set_to_none=True)
         aux = pkg.StepAux()
         torch.cuda.synchronize()
         dist.barrier()  # rank 0 has finished the CPU oracle of the previous form: peer-memory waits give up after 20 s
-        if form == "peer+graph":
-            gstep = pkg.GraphedContrastiveStep(ad, dx, dpm, dtx, dtm, symmetric=sym, exchange=exchange, grad_reducer=reducer)
+        if form.startswith("peer+graph"):
+            gstep = pkg.GraphedContrastiveStep(ad, dx, dpm, dtx, dtm, symmetric=sym, exchange=exchange,
+                                               grad_reducer=overlapped if form.endswith("overlap") else reducer)
             for _ in range(3):
                 loss = gstep.replay()
             aux = gstep.aux
@@ -73,7 +76,7 @@ def main():
         lt = loss.detach().clone()
         dist.all_reduce(lt)
         grads = {}
-        if form == "peer+graph":
+        if form.startswith("peer+graph"):
             grads = {k: reduced[i] for i, k in enumerate(PARAMS)}
         elif form == "peer":
             # eager form of the same gradient mean: the mixed bf16 / fp32 reducer over NVLink peer memory (stage, reduce,
@@ -93,6 +96,7 @@ def main():
         exchange.check()
         reducer.buffer.check()
         reducer_mixed.buffer.check()
+        overlapped.buffer.check()
         am_row = [torch.empty_like(aux.argmax_row) for _ in range(world)]
         dist.all_gather(am_row, aux.argmax_row)
         if rank == 0:
@@ -155,6 +159,7 @@ def main():
     exchange.close()
     reducer.close()
     reducer_mixed.close()
+    overlapped.close()
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)
 
