@@ -675,13 +675,22 @@ def main():
         try:
             peer = importlib.import_module("p2t_b200.peer")
             opt2 = pkg.FusedAdamW(params, lr=1e-5, eps=1e-6, betas=(0.9, 0.999), max_grad_norm=1.0)
-            red2 = peer.PeerGradAllReduce.for_adapter(adapter) if world > 1 else None
             r0 = resident[0]
-            full = pkg.GraphedContrastiveStep(adapter, r0["x"], r0["pm"], r0["text"], r0["tm"], seed=4242, exchange=exchange,
-                                              grad_reducer=red2, optimizer=opt2, max_valid_rows=rows_bound)
-            plain = graphs[0]
+            variants = [("step_only", graphs[0], None)]
+            if world > 1:
+                red_plain = peer.PeerGradAllReduce.for_adapter(adapter)
+                red_fused = peer.OverlappedGradReduce(adapter)
+                variants.append(("step_reduce_optimizer_unfused", pkg.GraphedContrastiveStep(
+                    adapter, r0["x"], r0["pm"], r0["text"], r0["tm"], seed=4242, exchange=exchange, grad_reducer=red_plain,
+                    optimizer=opt2, max_valid_rows=rows_bound), red_plain))
+                variants.append(("step_reduce_optimizer", pkg.GraphedContrastiveStep(
+                    adapter, r0["x"], r0["pm"], r0["text"], r0["tm"], seed=4242, exchange=exchange, grad_reducer=red_fused,
+                    optimizer=opt2, max_valid_rows=rows_bound), red_fused))
+            else:
+                variants.append(("step_reduce_optimizer", pkg.GraphedContrastiveStep(
+                    adapter, r0["x"], r0["pm"], r0["text"], r0["tm"], seed=4242, optimizer=opt2, max_valid_rows=rows_bound), None))
             res_ms = {}
-            for name, g in (("step_only", plain), ("step_reduce_optimizer", full)):
+            for name, g, _ in variants:
                 for _ in range(3):
                     g.replay()
                 barrier()
@@ -692,13 +701,19 @@ def main():
                 t1e.record()
                 barrier()
                 res_ms[name] = max_over_ranks(t0e.elapsed_time(t1e)) / args.steps
+            full = variants[-1][1]
             train_leg = {"ms_per_step": res_ms["step_reduce_optimizer"], "step_only_ms": res_ms["step_only"],
                          "optimizer_side_ms": res_ms["step_reduce_optimizer"] - res_ms["step_only"],
                          "launches_per_replay": full.launches_per_replay,
-                         "includes": "fused step + " + ("fp32 gradient mean over ranks (peer memory, zero-copy) + " if world > 1 else "")
+                         "includes": "fused step + " + ("fp32 gradient mean over ranks — dW2/db2 by comm-role CTAs inside the dW1 GEMM's "
+                                                        "launch (fused tcgen05 GEMM + NVLink peer-memory reduce), dW1/db1 after it + "
+                                                        if world > 1 else "")
                                      + "clip_grad_norm_ + AdamW, one CUDA graph per step (same batch replayed)"}
-            if red2 is not None:
-                red2.buffer.check()
+            if world > 1:
+                train_leg["optimizer_side_ms_unfused"] = res_ms["step_reduce_optimizer_unfused"] - res_ms["step_only"]
+            for _, _, red in variants:
+                if red is not None:
+                    red.buffer.check()
         except Exception as exc:  # noqa: BLE001 - an extra leg must never cost the benchmark its line
             train_leg = {"error": f"{type(exc).__name__}: {exc}"}
 

