@@ -154,6 +154,8 @@ int p2t_pool_fwd(const void* src, int src_is_f16, long long ld_src, int src_rows
 
 /* readout_embeddings(..., "last") — :207-215 — out fp32 [B][D] from padded x [B][S][D] */
 int p2t_readout_last(const void* x, const int* counts, int B, int S, int D, float* out, void* stream);
+/* its backward: dx bf16 [B, S, D] = 0 except dx[b, counts[b] - 1] = dout[b] (bf16 [B, D]); writes every element of dx */
+int p2t_readout_last_bwd(const void* dout, const int* counts, int B, int S, int D, void* dx, void* stream);
 
 /* F.normalize(p=2, dim=-1) on pooled embeddings — scripts/train_contrast.py:354,365.
  * e fp32 [B][E] -> p (bf16 and/or fp32, either may be NULL), norm[B] (unclamped). */
@@ -207,7 +209,7 @@ int p2t_adapter_tail_bwd_dy(const void* a, const void* g2, const float* inv_norm
  * holding this rank's dW2 / db2 contribution) whose announce + reduce phases are serviced by `ctas` comm-role CTAs
  * INSIDE the dW1 GEMM's launch — compute step and collective in one kernel over NVLink peer memory, with a fixed SM
  * partition (ctas: a multiple of 2, e.g. 16; the GEMM runs on the other SMs).  The round is closed afterwards with
- * p2t_peer_allreduce_mean(phases = 4).  Needs dw_is_f32 and cta_group 2.  (DDP overlaps its bucket all-reduces with
+ * p2t_peer_allreduce_mean(phases = 4).  Needs dw_is_f32, cta_group 2 and an all-fp32 channel (f32_from_byte = 0).  (DDP overlaps its bucket all-reduces with
  * the backward the same way, scripts/train_contrast.py:448 + :611-614.) */
 #define P2T_BWD_DGRAD 1
 #define P2T_BWD_DW2 2
@@ -369,10 +371,13 @@ int p2t_peer_status(const void* channel_base, unsigned int* status_host);
  *   counter, incremented by the call.  max_norm <= 0 or inf: no clipping (|g| is still reported).
  *   g' = g * min(1, max_norm / (|g| + 1e-6));  p *= 1 - lr*wd;  m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2;
  *   p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).   zero_grad != 0 also clears the gradients.
+ *   grads_f32 (NULL, or NULL entries: none): fp32 sources of the gradients — the mean over ranks left by
+ *   p2t_peer_allreduce_mean — rounded to bf16 into grads[i] by the norm pass (the sharded step's ONE rounding; saves
+ *   the separate p2t_f32_to_bf16 launches), 16-byte aligned.
  * ------------------------------------------------------------------------------------------- */
 int p2t_adamw_workspace_floats(int count, const long long* numel);
-int p2t_adamw_step(int count, void* const* params, void* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
-                   float* const* master, const long long* numel, float* partial_ws, float* scal, const float* lr_dev,
+int p2t_adamw_step(int count, void* const* params, void* const* grads, const float* const* grads_f32, float* const* exp_avg,
+                   float* const* exp_avg_sq, float* const* master, const long long* numel, float* partial_ws, float* scal, const float* lr_dev,
                    long long* step_dev, float beta1, float beta2, float eps, float weight_decay, float max_norm,
                    int zero_grad, void* stream);
 

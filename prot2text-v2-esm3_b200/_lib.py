@@ -33,6 +33,7 @@ SIGNATURES = {
     "p2t_pool_fwd": [_vp, _i, _ll, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _ll, _vp, _vp, _vp, _vp],
     "p2t_loss_bwd_coef": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp],
     "p2t_readout_last": [_vp, _vp, _i, _i, _i, _vp, _vp],
+    "p2t_readout_last_bwd": [_vp, _vp, _i, _i, _i, _vp, _vp],
     "p2t_l2norm_fwd": [_vp, _i, _i, _vp, _vp, _vp, _vp],
     "p2t_l2norm_bwd": [_vp, _vp, _vp, _i, _i, _vp, _vp],
     "p2t_pool_bwd_coef": [_vp, _ll, _vp, _ll, _vp, _i, _i, _i, _vp, _vp, _vp],
@@ -65,7 +66,7 @@ SIGNATURES = {
     "p2t_peer_reset": [_vp, _vp],
     "p2t_copy_d2d": [_vp, _vp, _ull, _vp],
     "p2t_peer_status": [_vp, C.POINTER(C.c_uint)],
-    "p2t_adamw_step": [_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
+    "p2t_adamw_step": [_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
                        C.POINTER(_ll), _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _i, _vp],
     "p2t_launch_timing_mark": [_vp],
     "p2t_launch_timing_collect": [C.POINTER(C.c_double), _i, C.POINTER(C.c_int), C.c_char_p, _i],

@@ -181,6 +181,11 @@ int p2t_readout_last(const void* x, const int* counts, int B, int S_, int D, flo
   if (!x || !counts || !out) return set_error(-1, "p2t_readout_last: null pointer");
   return readout_last(x, counts, B, S_, D, out, S(stream));
 }
+int p2t_readout_last_bwd(const void* dout, const int* counts, int B, int S_, int D, void* dx, void* stream) {
+  if (!dout || !counts || !dx) return set_error(-1, "p2t_readout_last_bwd: null pointer");
+  if (B <= 0 || S_ <= 0 || D <= 0) return set_error(-1, "p2t_readout_last_bwd: empty shape");
+  return readout_last_bwd(dout, counts, B, S_, D, dx, S(stream));
+}
 
 int p2t_l2norm_fwd(const float* e, int B, int E, void* p_bf16, float* p_f32, float* norm, void* stream) {
   if (!e) return set_error(-1, "p2t_l2norm_fwd: null pointer");
@@ -275,13 +280,14 @@ int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, c
         return set_error(-1, "p2t_adapter_bwd: bad overlap channel");
       if (overlap->n_bytes <= 0 || overlap->n_bytes % 16 || overlap->f32_from_byte % 16)
         return set_error(-1, "p2t_adapter_bwd: overlap channel sizes must be multiples of 16 bytes");
+      if (overlap->f32_from_byte != 0) return set_error(-1, "p2t_adapter_bwd: the overlapped channel carries fp32 only (f32_from_byte = 0)");
+      if (overlap->ctas < 2 || overlap->ctas % 2) return set_error(-1, "p2t_adapter_bwd: overlap ctas must be a positive multiple of 2");
       for (int r = 0; r < overlap->world; ++r) {
         if (!overlap->peers[r]) return set_error(-1, "p2t_adapter_bwd: overlap peer %d not mapped", r);
         comm.peers.base[r] = overlap->peers[r];
       }
       comm.world = overlap->world; comm.rank = overlap->rank; comm.ctas = overlap->ctas;
       comm.n_vec = overlap->n_bytes / 16;
-      comm.f32_begin = (overlap->f32_from_byte < 0 || overlap->f32_from_byte > overlap->n_bytes ? overlap->n_bytes : overlap->f32_from_byte) / 16;
       comm.scale = 1.f / (float)overlap->world;
       cp = &comm;
     }
@@ -531,8 +537,8 @@ int p2t_adamw_workspace_floats(int count, const long long* numel) {
   for (int i = 0; i < count; ++i) blocks += adamw_blocks(numel[i]);
   return blocks;
 }
-int p2t_adamw_step(int count, void* const* params, void* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
-                   float* const* master, const long long* numel, float* partial_ws, float* scal, const float* lr_dev,
+int p2t_adamw_step(int count, void* const* params, void* const* grads, const float* const* grads_f32, float* const* exp_avg,
+                   float* const* exp_avg_sq, float* const* master, const long long* numel, float* partial_ws, float* scal, const float* lr_dev,
                    long long* step_dev, float beta1, float beta2, float eps, float weight_decay, float max_norm,
                    int zero_grad, void* stream) {
   if (!params || !grads || !exp_avg || !exp_avg_sq || !numel || !partial_ws || !scal || !lr_dev || !step_dev)
@@ -543,6 +549,7 @@ int p2t_adamw_step(int count, void* const* params, void* const* grads, float* co
   for (int i = 0; i < count; ++i) {
     t.param[i] = params[i]; t.grad[i] = grads[i]; t.exp_avg[i] = exp_avg[i]; t.exp_avg_sq[i] = exp_avg_sq[i];
     t.master[i] = master ? master[i] : nullptr;
+    t.grad_f32[i] = grads_f32 ? grads_f32[i] : nullptr;
     t.numel[i] = numel[i];
   }
   return adamw_step(t, partial_ws, scal, lr_dev, step_dev, beta1, beta2, eps, weight_decay, max_norm, zero_grad, S(stream));

@@ -37,13 +37,17 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* sh) {
   return r;  // valid in warp 0
 }
 
-// partial[block] = sum of squares of this block's chunk of gradient elements (fp32 accumulate, fixed order)
+// partial[block] = sum of squares of this block's chunk of gradient elements (fp32 accumulate, fixed order).
+// A tensor with an fp32 source (the mean over ranks left by the gradient all-reduce) is rounded to bf16 HERE — the
+// one rounding of the sharded step's gradients — into the bf16 gradient buffer the update kernel (and param.grad)
+// reads; the norm is that of the rounded values, i.e. what clip_grad_norm_ sees on the bf16 .grad.
 __global__ void __launch_bounds__(kOptThreads)
 grad_sqnorm_partial_kernel(AdamTable t, float* __restrict__ partial) {
   __shared__ float sh[kOptThreads / 32];
   int lb;
   const int ti = find_tensor(t, blockIdx.x, lb);
-  const __nv_bfloat16* g = static_cast<const __nv_bfloat16*>(t.grad[ti]);
+  __nv_bfloat16* g = static_cast<__nv_bfloat16*>(t.grad[ti]);
+  const float* src = t.grad_f32[ti];
   const long long n = t.numel[ti];
   const long long base = (long long)lb * kOptChunk;
   float s = 0.f;
@@ -51,11 +55,19 @@ grad_sqnorm_partial_kernel(AdamTable t, float* __restrict__ partial) {
   for (int k = 0; k < 4; ++k) {
     const long long e = base + ((long long)k * kOptThreads + threadIdx.x) * 8;
     if (e + 8 <= n) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(g + e));
+      uint4 u;
+      if (src != nullptr) {
+        const float4 lo = __ldg(reinterpret_cast<const float4*>(src + e)), hi = __ldg(reinterpret_cast<const float4*>(src + e + 4));
+        u = make_uint4(pack_bf16x2(lo.x, lo.y), pack_bf16x2(lo.z, lo.w), pack_bf16x2(hi.x, hi.y), pack_bf16x2(hi.z, hi.w));
+        *reinterpret_cast<uint4*>(g + e) = u;
+      } else {
+        u = __ldg(reinterpret_cast<const uint4*>(g + e));
+      }
       const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
       s += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
     } else {
       for (long long j = e; j < n; ++j) {
+        if (src != nullptr) g[j] = __float2bfloat16_rn(src[j]);
         const float x = __bfloat162float(g[j]);
         s += x * x;
       }
@@ -185,7 +197,7 @@ int adamw_step(AdamTable t, float* partial_ws, float* scal, const float* lr_dev,
       return set_error(-1, "p2t_adamw_step: tensor %d has a null pointer or no elements", i);
     if ((reinterpret_cast<uintptr_t>(t.param[i]) | reinterpret_cast<uintptr_t>(t.grad[i])) & 15 ||
         (reinterpret_cast<uintptr_t>(t.exp_avg[i]) | reinterpret_cast<uintptr_t>(t.exp_avg_sq[i]) |
-         reinterpret_cast<uintptr_t>(t.master[i])) & 15)
+         reinterpret_cast<uintptr_t>(t.master[i]) | reinterpret_cast<uintptr_t>(t.grad_f32[i])) & 15)
       return set_error(-1, "p2t_adamw_step: tensor %d is not 16-byte aligned", i);
     t.block_start[i] = blocks;
     blocks += adamw_blocks(t.numel[i]);

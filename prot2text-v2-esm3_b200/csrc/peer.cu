@@ -96,9 +96,15 @@ __global__ void peer_allreduce_ready_kernel(PeerTable peers, int world, int rank
 // (mean stored as fp32: the bias gradients travel unrounded and are rounded to bf16 once, after the mean).
 template <int RB, int U>
 __global__ void __launch_bounds__(256)
-peer_allreduce_reduce_kernel(PeerTable peers, int world, int rank, long long n_vec, long long f32_begin, float scale) {
+peer_allreduce_reduce_kernel(PeerTable peers, int world, int rank, long long n_vec, long long f32_begin, float scale, int announce) {
   unsigned* ctrl = static_cast<unsigned*>(peers.base[rank]);
   const unsigned epoch = ctrl[0] + 1;
+  if (announce && blockIdx.x == 0 && threadIdx.x == 0) {
+    // phase 0 folded into this launch: the contribution was complete before the launch (stream order)
+    __threadfence_system();
+    for (int r = 0; r < world; ++r)
+      st_relaxed_sys(reinterpret_cast<unsigned*>(static_cast<char*>(peers.base[(rank + r) % world]) + flag_row_off(0)) + rank, epoch);
+  }
   const bool ok = wait_flags(reinterpret_cast<const unsigned*>(static_cast<char*>(peers.base[rank]) + flag_row_off(0)), world, epoch, ctrl + 4);
   peer_reduce_slice<RB, U>(peers, world, rank, n_vec, f32_begin, scale, ok, blockIdx.x, gridDim.x);
   publish_when_grid_done(peers, world, rank, flag_row_off(1), epoch, ctrl + 2, nullptr);
@@ -227,7 +233,8 @@ int peer_allreduce_mean(void* const* peers, int world, int rank, long long n_byt
   if (f32_from_byte < 0 || f32_from_byte > n_bytes) f32_from_byte = n_bytes;
   if (f32_from_byte % 16) return set_error(-1, "p2t_peer_allreduce_mean: the fp32 part must start on a 16-byte boundary");
   const long long f32_begin = f32_from_byte / 16;
-  if (phases & 1) {
+  const int announce_in_reduce = (phases & 3) == 3;  // announce + reduce in one launch (CTA 0 raises the flags first)
+  if ((phases & 1) && !announce_in_reduce) {
     peer_allreduce_ready_kernel<<<1, 32, 0, st>>>(t, world, rank);
     if (int r = check_launch("peer_allreduce_ready_kernel", st)) return r;
   }
@@ -235,16 +242,17 @@ int peer_allreduce_mean(void* const* peers, int world, int rank, long long n_byt
     const float scale = 1.f / (float)world;
     const long long slice = (n_vec + world - 1) / world;
     if (world <= 2) {
-      peer_allreduce_reduce_kernel<2, 8><<<grid_for(slice / 8, 4), 256, 0, st>>>(t, world, rank, n_vec, f32_begin, scale);
+      peer_allreduce_reduce_kernel<2, 8><<<grid_for(slice / 8, 4), 256, 0, st>>>(t, world, rank, n_vec, f32_begin, scale, announce_in_reduce);
     } else if (world <= 4) {
-      peer_allreduce_reduce_kernel<4, 4><<<grid_for(slice / 4, 4), 256, 0, st>>>(t, world, rank, n_vec, f32_begin, scale);
+      peer_allreduce_reduce_kernel<4, 4><<<grid_for(slice / 4, 4), 256, 0, st>>>(t, world, rank, n_vec, f32_begin, scale, announce_in_reduce);
     } else {
-      peer_allreduce_reduce_kernel<8, 2><<<grid_for(slice / 2, 4), 256, 0, st>>>(t, world, rank, n_vec, f32_begin, scale);
+      peer_allreduce_reduce_kernel<8, 2><<<grid_for(slice / 2, 4), 256, 0, st>>>(t, world, rank, n_vec, f32_begin, scale, announce_in_reduce);
     }
     if (int r = check_launch("peer_allreduce_reduce_kernel", st)) return r;
   }
   if (phases & 4) {
-    peer_allreduce_wait_kernel<<<grid_for(n_vec, 4), 256, 0, st>>>(t, world, rank, n_vec, static_cast<uint4*>(dst));
+    // zero-copy callers (dst == NULL) only wait and close the round: one CTA (every CTA pays two system fences)
+    peer_allreduce_wait_kernel<<<dst ? grid_for(n_vec, 4) : 1, 256, 0, st>>>(t, world, rank, n_vec, static_cast<uint4*>(dst));
     if (int r = check_launch("peer_allreduce_wait_kernel", st)) return r;
   }
   return 0;

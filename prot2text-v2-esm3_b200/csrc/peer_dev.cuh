@@ -150,17 +150,60 @@ __device__ __forceinline__ void peer_reduce_slice(const PeerTable& peers, int wo
   }
 }
 
+// The same share for a channel that carries fp32 only (f32_begin == 0), light enough on registers to run inside a
+// kernel compiled for another job (the comm-role CTAs of a GEMM launch: 96 registers per thread there): RB * U = 8
+// 16-byte loads in flight per thread, 4 accumulators per vector.
+template <int RB, int U>
+__device__ __forceinline__ void peer_reduce_slice_f32(const PeerTable& peers, int world, int rank, long long n_vec, float scale,
+                                                      bool ok, int cta, int n_ctas) {
+  const long long per = (n_vec + world - 1) / world;
+  const long long lo = per * rank, hi = min(n_vec, lo + per);
+  const size_t in_off = kPeerCtrlBytes, out_off = kPeerCtrlBytes + (size_t)n_vec * sizeof(uint4);
+  const long long stride = (long long)n_ctas * blockDim.x;
+  for (long long i = lo + (long long)cta * blockDim.x + threadIdx.x; i < hi; i += U * stride) {
+    float4 acc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r0 = 0; r0 < world; r0 += RB) {
+      uint4 v[U][RB];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < RB; ++j)
+          if (r0 + j < world && i + u * stride < hi)
+            v[u][j] = ld_sys_v4(reinterpret_cast<const uint4*>(static_cast<char*>(peers.base[r0 + j]) + in_off) + i + u * stride);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < RB; ++j)
+          if (r0 + j < world && i + u * stride < hi) {
+            acc[u].x += __uint_as_float(v[u][j].x); acc[u].y += __uint_as_float(v[u][j].y);
+            acc[u].z += __uint_as_float(v[u][j].z); acc[u].w += __uint_as_float(v[u][j].w);
+          }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i + u * stride >= hi) continue;
+      const uint4 o = ok ? make_uint4(__float_as_uint(acc[u].x * scale), __float_as_uint(acc[u].y * scale),
+                                      __float_as_uint(acc[u].z * scale), __float_as_uint(acc[u].w * scale))
+                         : make_uint4(kPeerPoison, kPeerPoison, kPeerPoison, kPeerPoison);
+      for (int r = 0; r < world; ++r)
+        reinterpret_cast<uint4*>(static_cast<char*>(peers.base[(rank + r) % world]) + out_off)[i + u * stride] = o;
+    }
+  }
+}
+
 // The contribution phase + reduce phase of one channel round, run by `n_ctas` CTAs that are NOT a kernel of their own:
 // the comm-role CTAs at the end of a GEMM launch's grid (gemm_sm100.cuh).  This rank's contribution is complete before
 // the launch (stream order), so CTA 0 announces it right away; every CTA then waits for all ranks' announcements,
-// reduces its part of this rank's slice and the last one publishes the phase-1 flags.
+// reduces its part of this rank's slice and the last one publishes the phase-1 flags.  The channel carries fp32 only.
 struct GemmCommReduce {
   PeerTable peers;
   int world, rank, ctas;     // ctas: CTAs of the grid that take the comm role (a multiple of the cluster size)
-  long long n_vec, f32_begin;
+  long long n_vec;
   float scale;
 };
-__device__ __forceinline__ void comm_reduce_role(const GemmCommReduce& c, int cta) {
+static __device__ __noinline__ void comm_reduce_role(const GemmCommReduce& c, int cta) {
   unsigned* ctrl = static_cast<unsigned*>(c.peers.base[c.rank]);
   const unsigned epoch = ctrl[0] + 1;
   if (cta == 0 && threadIdx.x == 0) {
@@ -170,9 +213,9 @@ __device__ __forceinline__ void comm_reduce_role(const GemmCommReduce& c, int ct
   }
   const bool ok = wait_flags(reinterpret_cast<const unsigned*>(static_cast<char*>(c.peers.base[c.rank]) + peer_flag_row_off(0)),
                              c.world, epoch, ctrl + 4);
-  if (c.world <= 2) peer_reduce_slice<2, 8>(c.peers, c.world, c.rank, c.n_vec, c.f32_begin, c.scale, ok, cta, c.ctas);
-  else if (c.world <= 4) peer_reduce_slice<4, 4>(c.peers, c.world, c.rank, c.n_vec, c.f32_begin, c.scale, ok, cta, c.ctas);
-  else peer_reduce_slice<8, 2>(c.peers, c.world, c.rank, c.n_vec, c.f32_begin, c.scale, ok, cta, c.ctas);
+  if (c.world <= 2) peer_reduce_slice_f32<2, 4>(c.peers, c.world, c.rank, c.n_vec, c.scale, ok, cta, c.ctas);
+  else if (c.world <= 4) peer_reduce_slice_f32<4, 2>(c.peers, c.world, c.rank, c.n_vec, c.scale, ok, cta, c.ctas);
+  else peer_reduce_slice_f32<8, 1>(c.peers, c.world, c.rank, c.n_vec, c.scale, ok, cta, c.ctas);
   peer_publish_when_done(c.peers, c.world, c.rank, peer_flag_row_off(1), epoch, ctrl + 2, (unsigned)c.ctas, nullptr);
 }
 

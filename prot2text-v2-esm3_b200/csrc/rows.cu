@@ -1090,6 +1090,22 @@ __global__ void readout_last_kernel(const __nv_bfloat16* __restrict__ x, const i
   for (int i = threadIdx.x; i < D; i += blockDim.x) out[(long long)b * D + i] = __bfloat162float(row[i]);
 }
 
+// its backward: dx = 0 except dx[b, sum(mask[b]) - 1] = dout[b]; every element of dx is written here (no memset)
+__global__ void __launch_bounds__(256)
+readout_last_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const int* __restrict__ counts, int S, int D,
+                        __nv_bfloat16* __restrict__ dx) {
+  const int b = blockIdx.y;
+  int idx = counts[b] - 1;
+  if (idx < 0) idx += S;
+  const long long total = (long long)S * D;
+  __nv_bfloat16* base = dx + (long long)b * total;
+  const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(i / D);
+    base[i] = row == idx ? dout[(long long)b * D + (i - (long long)row * D)] : zero;
+  }
+}
+
 // ================================================================================================
 // host launchers
 // ================================================================================================
@@ -1319,6 +1335,14 @@ int colsum(const void* x, const int* n_rows, int n_static, int D, float* partial
 int readout_last(const void* x, const int* counts, int B, int S, int D, float* out, cudaStream_t st) {
   readout_last_kernel<<<B, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), counts, S, D, out);
   return check_launch("readout_last_kernel", st);
+}
+
+int readout_last_bwd(const void* dout, const int* counts, int B, int S, int D, void* dx, cudaStream_t st) {
+  const long long per = (long long)S * D;
+  const int gx = (int)std::min<long long>((per + 255) / 256, 64);
+  readout_last_bwd_kernel<<<dim3(gx, B), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dout), counts, S, D,
+                                                       reinterpret_cast<__nv_bfloat16*>(dx));
+  return check_launch("readout_last_bwd_kernel", st);
 }
 
 }  // namespace p2t

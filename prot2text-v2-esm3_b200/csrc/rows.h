@@ -53,6 +53,7 @@ int readout_backward(const void* x, const void* mask, int mask_bytes, int B, int
 int colsum(const void* x, const int* n_rows, int n_static, int D, float* partial, void* out_bf16, float* out_f32,
            cudaStream_t st);
 int readout_last(const void* x, const int* counts, int B, int S, int D, float* out, cudaStream_t st);
+int readout_last_bwd(const void* dout, const int* counts, int B, int S, int D, void* dx, cudaStream_t st);
 
 int sim_small(const void* p, const void* t, bool in_f32, int R, int C, int E, float alpha, float* S, cudaStream_t st);
 int col_stats(const float* S, int R, int C, float* col_max, float* col_sum, int* col_argmax, int row_index_base,
@@ -104,6 +105,7 @@ struct AdamTable {
   long long numel[kAdamMaxTensors];
   void* param[kAdamMaxTensors];       // bf16
   void* grad[kAdamMaxTensors];        // bf16
+  const float* grad_f32[kAdamMaxTensors];  // optional fp32 source of the gradient (rounded into `grad` by the norm pass)
   float* exp_avg[kAdamMaxTensors];
   float* exp_avg_sq[kAdamMaxTensors];
   float* master[kAdamMaxTensors];     // fp32 master weights or nullptr

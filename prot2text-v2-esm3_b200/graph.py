@@ -133,12 +133,20 @@ class GraphedContrastiveStep:
                     self.grad_reducer.finish()
                 else:
                     self.grad_reducer.exchange()
-                for mean_f32, grad_bf16 in zip(self._reduced, self.grads):  # the one rounding: mean (fp32) -> param.grad (bf16)
-                    _lib.call("p2t_f32_to_bf16", mean_f32.data_ptr(), mean_f32.numel(), grad_bf16.data_ptr(), _core._stream())
+                if self.optimizer is None or not hasattr(self.optimizer, "fp32_grad_sources"):
+                    for mean_f32, grad_bf16 in zip(self._reduced, self.grads):  # the one rounding: mean (fp32) -> param.grad (bf16)
+                        _lib.call("p2t_f32_to_bf16", mean_f32.data_ptr(), mean_f32.numel(), grad_bf16.data_ptr(), _core._stream())
             if self.optimizer is not None:
                 for p, g in zip(self.params, self.grads):
                     p.grad = g
-                self.optimizer.step()
+                fused_round = self.grad_reducer is not None and hasattr(self.optimizer, "fp32_grad_sources")
+                if fused_round:  # FusedAdamW's norm pass does that rounding itself (no separate conversion launches)
+                    self.optimizer.fp32_grad_sources = dict(zip(self.params, self._reduced))
+                try:
+                    self.optimizer.step()
+                finally:
+                    if fused_round:
+                        self.optimizer.fp32_grad_sources = {}
         return loss
 
     def _graph_for(self, first: bool, last: bool):

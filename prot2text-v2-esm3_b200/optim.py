@@ -42,6 +42,9 @@ class FusedAdamW(torch.optim.Optimizer):
         self.master_weights = master_weights
         self.zero_grad_in_step = zero_grad_in_step
         self._dev = {}      # per group index: device-side scalars and workspaces
+        # {parameter: fp32 tensor}: gradients whose fp32 source (the mean over ranks left by peer.PeerGradAllReduce)
+        # is rounded into the bf16 .grad by the norm pass of the next step() — set by graph.GraphedContrastiveStep
+        self.fp32_grad_sources: dict = {}
         self.grad_norm: Optional[torch.Tensor] = None
 
     # ------------------------------------------------------------------------------------------
@@ -160,10 +163,18 @@ class FusedAdamW(torch.optim.Optimizer):
                 st["lr"].fill_(lr)
                 st["lr_host"] = lr
             grads = (C.c_void_p * len(tensors))(*[p.grad.data_ptr() for p in tensors])
+            srcs = None
+            if self.fp32_grad_sources:
+                for p in tensors:
+                    f = self.fp32_grad_sources.get(p)
+                    if f is not None and (f.dtype != torch.float32 or f.numel() != p.numel() or not f.is_contiguous() or f.device != p.device):
+                        raise _lib.P2TError("FusedAdamW: an fp32 gradient source must be a contiguous fp32 tensor of the parameter's size")
+                srcs = (C.c_void_p * len(tensors))(*[(self.fp32_grad_sources[p].data_ptr() if p in self.fp32_grad_sources else None)
+                                                     for p in tensors])
             b1, b2 = group["betas"]
             mx = self.max_grad_norm
             mx = 0.0 if (mx is None or math.isinf(mx)) else float(mx)
-            _lib.call("p2t_adamw_step", len(tensors), st["params"], grads, st["m"], st["v"], st["w"], st["numel"],
+            _lib.call("p2t_adamw_step", len(tensors), st["params"], grads, srcs, st["m"], st["v"], st["w"], st["numel"],
                       st["partial"].data_ptr(), st["scal"].data_ptr(), st["lr"].data_ptr(), st["step"].data_ptr(),
                       float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), mx,
                       int(self.zero_grad_in_step), torch.cuda.current_stream().cuda_stream)

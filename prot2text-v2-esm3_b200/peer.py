@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -334,12 +335,12 @@ class OverlappedGradReduce:
     `views_in()` / `views_out()` are in parameter order [dW1, db1, dW2, db2]; pass the object as
     `graph.GraphedContrastiveStep(grad_reducer=...)`."""
 
-    def __init__(self, adapter, group=None, comm_ctas: int = 16, _buffers: Optional[tuple] = None):
+    def __init__(self, adapter, group=None, comm_ctas: int = 20, _buffers: Optional[tuple] = None):
         like = PeerGradAllReduce.adapter_like(adapter)
         lb, tb = _buffers if _buffers is not None else (None, None)
         self.late = PeerGradAllReduce([like[2], like[3]], group, _buffer=lb)
         self.tail = PeerGradAllReduce([like[0], like[1]], group, _buffer=tb)
-        self.comm_ctas = int(comm_ctas)
+        self.comm_ctas = int(os.environ.get("P2T_COMM_CTAS", comm_ctas))
         self.late.comm_ctas = self.comm_ctas
         self.rank, self.world = self.late.rank, self.late.world
         self.shapes = [tuple(t.shape) for t in like]

@@ -61,9 +61,9 @@ class _ReadoutLastFunction(torch.autograd.Function):
     def backward(ctx, dout):
         (counts,) = ctx.saved_tensors
         B, S, D = ctx.shape
-        dx = torch.zeros(B, S, D, dtype=dout.dtype, device=dout.device)
-        idx = (counts.long() - 1) % S
-        dx[torch.arange(B, device=dout.device), idx] = dout
+        dout = dout.contiguous()
+        dx = torch.empty(B, S, D, dtype=dout.dtype, device=dout.device)
+        _lib.call("p2t_readout_last_bwd", _core._ptr(dout), _core._ptr(counts), B, S, D, _core._ptr(dx), _core._stream())
         return dx, None
 
 

@@ -261,6 +261,36 @@ def test_fused_adamw_adapter_sized_against_the_oracle(p2t, mods, dev):
                 ref_p = [p.detach().float().cpu() for p in params]  # follow the bf16 trajectory like the kernel does
 
 
+def test_fused_adamw_rounds_fp32_gradient_sources_itself(p2t, mods, dev):
+    """With fp32 sources (the mean left by the gradient all-reduce) the norm pass does the rounding to bf16: same
+    .grad, norm, moments and weights, bit for bit, as converting first and stepping on the bf16 gradients."""
+    shapes = [(96, 160), (96,), (130, 96), (133,)]  # the last one has a ragged tail (133 % 8 != 0)
+    gen = torch.Generator().manual_seed(11)
+    p0 = [bf(torch.randn(s, generator=gen) * 0.02) for s in shapes]
+    pa = [torch.nn.Parameter(p.clone().to(dev)) for p in p0]
+    pb = [torch.nn.Parameter(p.clone().to(dev)) for p in p0]
+    oa = mods["optim"].FusedAdamW(pa, lr=1e-3, eps=1e-6, weight_decay=0.01, max_grad_norm=0.05)
+    ob = mods["optim"].FusedAdamW(pb, lr=1e-3, eps=1e-6, weight_decay=0.01, max_grad_norm=0.05)
+    for step in range(3):
+        f32 = [(torch.randn(s, generator=gen) * 0.01).to(dev) for s in shapes]
+        for p, g in zip(pa, f32):
+            p.grad = g.to(torch.bfloat16)
+        oa.step()
+        for p in pb:
+            p.grad = torch.full_like(p, float("nan"))  # must be overwritten by the norm pass
+        ob.fp32_grad_sources = dict(zip(pb, f32))
+        ob.step()
+        ob.fp32_grad_sources = {}
+        assert torch.equal(oa.grad_norm, ob.grad_norm)
+        for a, b in zip(pa, pb):
+            assert torch.equal(a.grad, b.grad) and torch.equal(a, b)
+            assert torch.equal(oa.state[a]["exp_avg_sq"], ob.state[b]["exp_avg_sq"])
+            assert torch.equal(oa.state[a]["master"], ob.state[b]["master"])
+    ob.fp32_grad_sources = {pb[0]: torch.zeros(3, device=dev)}
+    with pytest.raises(p2t.P2TError, match="fp32 gradient source"):
+        ob.step()
+
+
 def test_fused_adamw_is_capturable_and_follows_the_scheduler(p2t, mods, dev):
     w = torch.nn.Parameter(bf(torch.ones(64, 64)).to(dev))
     w.grad = bf(torch.full((64, 64), 0.5)).to(dev)

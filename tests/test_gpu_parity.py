@@ -328,6 +328,23 @@ def test_readout_matches_reference_golden(p2t, dev, golden_dir, mname, fn):
     assert bool((gemb.cpu()[g["mask_" + mname] == 0] == 0).all())  # padded positions get exactly zero
 
 
+def test_readout_last_backward_is_an_exact_scatter(p2t, dev):
+    """'last' backward (csrc/rows.cu readout_last_bwd_kernel): dx[b, len_b - 1] = dout[b], zero elsewhere, bit-exact;
+    an all-masked row indexes -1 like the reference's advanced indexing does (scripts/train_contrast.py:207-215)."""
+    gen = torch.Generator().manual_seed(3)
+    B, S, D = 5, 37, 72
+    emb = bf(torch.randn(B, S, D, generator=gen)).to(dev).requires_grad_()
+    lens = torch.tensor([37, 1, 20, 0, 9])
+    mask = (torch.arange(S)[None, :] < lens[:, None]).long().to(dev)
+    out = p2t.readout_embeddings(emb, mask, "last")
+    dout = bf(torch.randn(B, D, generator=gen)).to(dev)
+    (gx,) = torch.autograd.grad(out, emb, dout)
+    want = torch.zeros(B, S, D, dtype=torch.bfloat16, device=dev)
+    want[torch.arange(B), (lens - 1) % S] = dout
+    assert torch.equal(gx, want)
+    assert torch.equal(out, emb.detach()[torch.arange(B), (lens - 1) % S])
+
+
 def test_readout_degenerate_sequences_follow_the_reference(p2t, dev):
     """std of a constant / single-token sequence is 0 with a NaN gradient; an all-masked row is 0/0 = NaN."""
     emb = bf(torch.randn(3, 6, 16, generator=torch.Generator().manual_seed(1)))
