@@ -705,7 +705,7 @@ def main():
             train_leg = {"ms_per_step": res_ms["step_reduce_optimizer"], "step_only_ms": res_ms["step_only"],
                          "optimizer_side_ms": res_ms["step_reduce_optimizer"] - res_ms["step_only"],
                          "launches_per_replay": full.launches_per_replay,
-                         "includes": "fused step + " + ("fp32 gradient mean over ranks — dW2/db2 by comm-role CTAs inside the dW1 GEMM's "
+                         "includes": "fused step + " + ("fp32 gradient mean over ranks — dW2/db2 by the idle epilogue warps inside the dW1 GEMM's "
                                                         "launch (fused tcgen05 GEMM + NVLink peer-memory reduce), dW1/db1 after it + "
                                                         if world > 1 else "")
                                      + "clip_grad_norm_ + AdamW, one CUDA graph per step (same batch replayed)"}

@@ -206,11 +206,11 @@ int p2t_adapter_tail_bwd_dy(const void* a, const void* g2, const float* inv_norm
  * ------------------------------------------------------------------------------------------- */
 /* phases: which GEMMs this call enqueues (0 = all three).  The fused sharded training step issues DGRAD | DW2 first,
  * finishes db2, and then DW1 with `overlap`: a gradient-mean channel (layout and meaning of p2t_peer_allreduce_mean,
- * holding this rank's dW2 / db2 contribution) whose announce + reduce phases are serviced by `ctas` comm-role CTAs
- * INSIDE the dW1 GEMM's launch — compute step and collective in one kernel over NVLink peer memory, with a fixed SM
- * partition (ctas: a multiple of 2, e.g. 16; the GEMM runs on the other SMs).  The round is closed afterwards with
- * p2t_peer_allreduce_mean(phases = 4).  Needs dw_is_f32, cta_group 2 and an all-fp32 channel (f32_from_byte = 0).  (DDP overlaps its bucket all-reduces with
- * the backward the same way, scripts/train_contrast.py:448 + :611-614.) */
+ * holding this rank's dW2 / db2 contribution, all fp32: f32_from_byte = 0) whose announce + reduce phases are serviced
+ * INSIDE the dW1 GEMM's launch by the epilogue warps of every CTA while their first accumulator is being computed —
+ * compute step and collective in one kernel over NVLink peer memory, no SM taken from the GEMM.  The round is closed
+ * afterwards with p2t_peer_allreduce_mean(phases = 4).  Needs dw_is_f32 and cta_group 2.  (DDP overlaps its bucket
+ * all-reduces with the backward the same way, scripts/train_contrast.py:448 + :611-614.) */
 #define P2T_BWD_DGRAD 1
 #define P2T_BWD_DW2 2
 #define P2T_BWD_DW1 4
@@ -218,7 +218,6 @@ typedef struct {
   void* const* peers;      /* HOST array of `world` device pointers (see p2t_peer_allreduce_mean) */
   int world, rank;
   long long n_bytes, f32_from_byte;
-  int ctas;
 } p2t_overlap_reduce_t;
 int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, const void* h1, const void* g1, const void* dz2,
                     int d_in, int d_mid, int d_out, int rows_cap, const int* n_rows_dev, void* dz1, void* dw1,

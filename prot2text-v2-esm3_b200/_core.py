@@ -203,7 +203,7 @@ def adapter_forward(x: torch.Tensor, x_rows: int, rows_cap: int, n_rows: torch.T
 def adapter_backward(acts: AdapterActs, dz2: torch.Tensor, w1, w2, need_dx: bool = False, need_db2: bool = True,
                      cta_group: Optional[int] = None, need_db1: bool = True, accumulate: bool = False,
                      dw1_out: Optional[torch.Tensor] = None, dw2_out: Optional[torch.Tensor] = None,
-                     dw_dtype=torch.bfloat16, mid_hook=None, overlap=None, overlap_ctas: int = 16):
+                     dw_dtype=torch.bfloat16, mid_hook=None, overlap=None):
     """Returns (dw1, db1, dw2, db2_or_None, dx_or_None) in bf16, nn.Linear layout.
 
     `need_db1=False`: db1 is returned as the fp32 partial column sums [ceil(rows_cap/32)][d_mid] the dgrad GEMM's
@@ -211,7 +211,7 @@ def adapter_backward(acts: AdapterActs, dz2: torch.Tensor, w1, w2, need_dx: bool
     the weight gradients into the caller's tensors instead of fresh ones.  `dw_dtype=torch.float32`: the weight
     gradients leave the GEMMs unrounded (what a gradient mean over ranks should carry).  `overlap`: a
     peer.PeerGradAllReduce channel holding this rank's dW2 / db2 contribution — its announce + reduce phases are then
-    serviced by `overlap_ctas` comm-role CTAs inside the dW1 GEMM's launch; `mid_hook()` runs between the dW2 and the
+    serviced by the idle epilogue warps inside the dW1 GEMM's launch; `mid_hook()` runs between the dW2 and the
     dW1 GEMM (the caller finishes db2 there)."""
     d_mid, d_in = w1.shape
     d_out = w2.shape[0]
@@ -241,14 +241,13 @@ def adapter_backward(acts: AdapterActs, dz2: torch.Tensor, w1, w2, need_dx: bool
         call(0, None)
     else:
         # sharded training step: dgrad + dW2 first, then the caller finishes what the overlapped channel carries (db2),
-        # then dW1 with comm-role CTAs servicing that channel inside its launch
+        # then dW1, whose idle epilogue warps service that channel inside its launch
         call(1 | 2, None)
         if mid_hook is not None:
             mid_hook()
         ov = None
         if overlap is not None:
-            ov = _lib.OverlapReduce(C.cast(overlap.buffer.table, C.POINTER(C.c_void_p)), overlap.world, overlap.rank, overlap.n_bytes, overlap.f32_from,
-                                    int(getattr(overlap, "comm_ctas", overlap_ctas)))
+            ov = _lib.OverlapReduce(C.cast(overlap.buffer.table, C.POINTER(C.c_void_p)), overlap.world, overlap.rank, overlap.n_bytes, overlap.f32_from)
         call(4, ov)
     return dw1, (db1 if need_db1 else ws), dw2, db2, dx
 

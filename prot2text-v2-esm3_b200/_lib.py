@@ -17,7 +17,7 @@ _vp, _i, _ll, _f, _ull = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulong
 class OverlapReduce(C.Structure):
     """p2t_overlap_reduce_t of include/p2t_b200.h"""
     _fields_ = [("peers", C.POINTER(C.c_void_p)), ("world", C.c_int), ("rank", C.c_int), ("n_bytes", C.c_longlong),
-                ("f32_from_byte", C.c_longlong), ("ctas", C.c_int)]
+                ("f32_from_byte", C.c_longlong)]
 
 
 # name -> argument ctypes, in header order (include/p2t_b200.h)

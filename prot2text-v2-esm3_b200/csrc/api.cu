@@ -263,8 +263,8 @@ int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, c
     if (db2) if (int rc = colsum(dz2, n_rows_dev, rows_cap, d_out, db2_ws, db2, nullptr, st)) return rc;
   }
   if (!(phases & P2T_BWD_DW1)) return 0;
-  // dW1 = dz1^T x  — optionally with comm-role CTAs that service a gradient-mean channel behind it (the mean of
-  // dW2 / db2 over the ranks travels over NVLink while this GEMM runs: one launch, fixed SM partition)
+  // dW1 = dz1^T x  — optionally with its idle epilogue warps servicing a gradient-mean channel behind it (the mean of
+  // dW2 / db2 over the ranks travels over NVLink while this GEMM runs: one launch, no SM taken from the GEMM)
   {
     GemmParams p = base_params(d_mid, d_in, rows_cap);
     p.dyn_k = n_rows_dev;
@@ -281,12 +281,11 @@ int p2t_adapter_bwd(const void* x, int x_rows, const void* w1, const void* w2, c
       if (overlap->n_bytes <= 0 || overlap->n_bytes % 16 || overlap->f32_from_byte % 16)
         return set_error(-1, "p2t_adapter_bwd: overlap channel sizes must be multiples of 16 bytes");
       if (overlap->f32_from_byte != 0) return set_error(-1, "p2t_adapter_bwd: the overlapped channel carries fp32 only (f32_from_byte = 0)");
-      if (overlap->ctas < 2 || overlap->ctas % 2) return set_error(-1, "p2t_adapter_bwd: overlap ctas must be a positive multiple of 2");
       for (int r = 0; r < overlap->world; ++r) {
         if (!overlap->peers[r]) return set_error(-1, "p2t_adapter_bwd: overlap peer %d not mapped", r);
         comm.peers.base[r] = overlap->peers[r];
       }
-      comm.world = overlap->world; comm.rank = overlap->rank; comm.ctas = overlap->ctas;
+      comm.world = overlap->world; comm.rank = overlap->rank;
       comm.n_vec = overlap->n_bytes / 16;
       comm.scale = 1.f / (float)overlap->world;
       cp = &comm;

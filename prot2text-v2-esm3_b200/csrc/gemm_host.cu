@@ -72,9 +72,6 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
                        const GemmCommReduce* comm = nullptr) {
   using S = GemmSmem<CTA_GROUP, EPI>;
   auto kern = gemm_bf16_tcgen05_kernel<CTA_GROUP, A_MN, B_MN, EPI, COMM>;
-  const int comm_ctas = COMM ? comm->ctas : 0;
-  if (COMM && (comm_ctas < CTA_GROUP || comm_ctas % CTA_GROUP || comm_ctas > sm_count() / 2))
-    return set_error(-15, "GEMM with a comm role: %d comm CTAs (need a multiple of the cluster size, at most half the SMs)", comm_ctas);
   static bool configured[64] = {false};  // cudaFuncSetAttribute is a per-device setting
   int cur_dev = 0;
   cudaGetDevice(&cur_dev);
@@ -87,7 +84,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   const int tile_m = GEMM_BLOCK_M * CTA_GROUP;
   const long long tiles = (long long)((p.m + tile_m - 1) / tile_m) * ((p.n + GEMM_BLOCK_N - 1) / GEMM_BLOCK_N);
   if (tiles == 0) return 0;
-  const int all_workers = (sm_count() - comm_ctas) / CTA_GROUP;  // comm-role CTAs take their SMs out of the GEMM's share
+  const int all_workers = sm_count() / CTA_GROUP;
   int workers = all_workers;
   if (tiles < workers) workers = (int)tiles;
   GemmParams q = p;
@@ -117,8 +114,8 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     if (me != cudaSuccess) return set_error((int)me, "split-K flag reset failed: %s", cudaGetErrorString(me));
   }
   cudaLaunchConfig_t cfg{};
-  if (COMM) workers = all_workers;  // fixed partition: the comm CTAs are the last comm_ctas of the grid
-  cfg.gridDim = dim3(workers * CTA_GROUP + comm_ctas);
+  if (COMM) workers = all_workers;  // every CTA's epilogue warps take part in the channel round, tiles or not
+  cfg.gridDim = dim3(workers * CTA_GROUP);
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = S::TOTAL;
   cfg.stream = stream;

@@ -491,24 +491,18 @@ __device__ __forceinline__ void epilogue_chunk_staged(const uint32_t (&v)[32], c
 }
 
 // ------------------------------------------------------------------------------------------------
-// COMM: the last `comm.ctas` CTAs of the grid do not compute tiles; they service one round of a peer-memory mean
-// all-reduce channel (announce, wait for all ranks, reduce this rank's slice, publish) WHILE the other CTAs run the
-// GEMM: the compute step and the collective that follows its predecessor are one launch with a fixed SM partition
-// (a separate communication kernel could not be told to leave the persistent GEMM's SMs alone).  Used for the dW1
-// GEMM of the sharded training step: the mean of dW2 / db2 over the ranks travels over NVLink behind it.
+// COMM: the launch also services one round of a peer-memory mean all-reduce channel (announce, wait for all ranks,
+// reduce this rank's slice, publish).  The work is done by the epilogue warps of every CTA BEFORE their first
+// accumulator is ready: in a weight-gradient GEMM (K = all residue rows of the batch) they would otherwise sleep
+// on the TMEM barrier for ~100 us, so the collective costs the GEMM neither SMs nor issue slots it needs, and no
+// second kernel has to fight the persistent one for a place to run.  Used for the dW1 GEMM of the sharded training
+// step: the mean of dW2 / db2 over the ranks crosses NVLink behind it.
 template <int CTA_GROUP, bool A_MN, bool B_MN, int EPI, bool COMM = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_d0, const __grid_constant__ CUtensorMap tmap_d1,
                          const GemmParams p, const typename std::conditional<COMM, GemmCommReduce, int>::type comm) {
-  int grid_ctas = gridDim.x;
-  if constexpr (COMM) {
-    grid_ctas -= comm.ctas;
-    if ((int)blockIdx.x >= grid_ctas) {
-      comm_reduce_role(comm, (int)blockIdx.x - grid_ctas);
-      return;
-    }
-  }
+  const int grid_ctas = gridDim.x;
   using S = GemmSmem<CTA_GROUP, EPI>;
   extern __shared__ uint8_t smem_raw[];
   // align inside the shared window with pointer arithmetic (keeps the address space known to the compiler)
@@ -675,6 +669,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // load, generate the chunk's dropout bits (4 Philox blocks, independent of the data) while it is in
     // flight, then wait and run the math.  The chunk loop is NOT unrolled: the body is ~1000 instructions
     // and must stay inside the instruction cache.
+    if constexpr (COMM) comm_reduce_role(comm, (int)blockIdx.x, grid_ctas, (int)threadIdx.x - 64, 32 * GEMM_EPI_WARPS, 1);
     const int quarter = warp & 3;
     const int part = (warp - 2) >> 2;
     constexpr int COLS_PER_WARP = GEMM_BLOCK_N / (GEMM_EPI_WARPS / 4);

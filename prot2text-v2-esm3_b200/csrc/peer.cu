@@ -10,9 +10,11 @@
 // with cudaIpcOpenMemHandle; the handles travel through torch.distributed on the host side (peer.py).
 //
 // Flag protocol.  A channel owns, in its peer buffer, `world` arrival words per phase; a writer publishes with
-// data stores -> CTA barrier -> thread 0: __threadfence_system(), count the CTA in -> (last CTA) fence, flag := epoch;
-// a reader polls the flag with relaxed system-scope loads until flag - epoch >= 0, fences, and then reads the data
-// with L1-bypassing loads.  The epoch lives in device
+// data stores -> CTA barrier -> thread 0: fence.acq_rel.sys, count the CTA in -> (last CTA) fence, flag := epoch
+// (relaxed system-scope stores); a reader polls the flag with relaxed system-scope loads until flag - epoch >= 0,
+// re-reads it once with ld.acquire.sys (an L1 invalidate, no MEMBAR), and then reads the data with L1-bypassing
+// loads.  (The sequentially consistent __threadfence_system() this started with was most of the channel kernels'
+// time: profiles/r02_summary.md.)  The epoch lives in device
 // memory and is advanced by the channel's last kernel of a round, so graph replays need no host-side argument.
 // A reader that waits longer than `timeout_ns` gives up, records it in `status` and lets the stream drain (the host
 // raises on the next status check) instead of hanging the GPU.
@@ -101,7 +103,7 @@ peer_allreduce_reduce_kernel(PeerTable peers, int world, int rank, long long n_v
   const unsigned epoch = ctrl[0] + 1;
   if (announce && blockIdx.x == 0 && threadIdx.x == 0) {
     // phase 0 folded into this launch: the contribution was complete before the launch (stream order)
-    __threadfence_system();
+    fence_release_sys();
     for (int r = 0; r < world; ++r)
       st_relaxed_sys(reinterpret_cast<unsigned*>(static_cast<char*>(peers.base[(rank + r) % world]) + flag_row_off(0)) + rank, epoch);
   }

@@ -38,15 +38,24 @@ __device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
   asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {  // LDG.STRONG.SYS + CCTL.IVALL: no MEMBAR
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Release side of the flag protocol: acq_rel is all the pattern "data stores ; fence ; relaxed flag store" needs (the PTX
+// model's release pattern); __threadfence_system() is the sequentially consistent fence (MEMBAR.SC.SYS).
+__device__ __forceinline__ void fence_release_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ void st_relaxed_sys(unsigned* p, unsigned v) {
   asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Threads [0, world) of the CTA wait for flags[t] to reach `epoch` (relaxed polls, then one system fence = acquire);
-// the CTA barrier that follows extends the ordering to every thread of the CTA.  System-scope fences cost a few
-// microseconds each (they wait for the thread's outstanding NVLink traffic), so they are issued by the polling /
-// publishing threads only, never by all threads.  Returns false (to every thread of the CTA) when a wait gave up:
-// the caller must then POISON what it produces (NaN) instead of consuming a stale or partial block.
+// Threads [0, world) of the CTA wait for flags[t] to reach `epoch`: relaxed polls, then ONE acquire load of the flag
+// (it reads the releasing store or a later one; an acquire load costs an L1 invalidate, not a MEMBAR — ncu showed the
+// sequentially consistent system fence that used to stand here, and the two on the publishing side, as most of a
+// 56 us reduce launch); the CTA barrier that follows extends the ordering to every thread of the CTA.  Returns false
+// (to every thread of the CTA) when a wait gave up: the caller must then POISON what it produces (NaN) instead of
+// consuming a stale or partial block.
 __device__ __forceinline__ bool wait_flags(const unsigned* flags, int world, unsigned epoch, unsigned* status) {
   __shared__ int s_timed_out;
   if (threadIdx.x == 0) s_timed_out = 0;
@@ -61,7 +70,7 @@ __device__ __forceinline__ bool wait_flags(const unsigned* flags, int world, uns
       }
       __nanosleep(32);
     }
-    __threadfence_system();
+    (void)ld_acquire_sys(flags + threadIdx.x);
   }
   __syncthreads();
   return s_timed_out == 0 && ld_relaxed_sys(status) == 0u;
@@ -77,13 +86,17 @@ __device__ __forceinline__ void peer_publish_when_done(const PeerTable& peers, i
                                                        unsigned* epoch_word) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    const bool publish = flag_off != (size_t)-1;  // closing a round touches local words only: no system-scope ordering needed
+    if (publish) fence_release_sys(); else __threadfence();
     const unsigned done = atomicAdd(counter, 1u);
     if (done == n_ctas - 1) {
-      __threadfence_system();
-      if (flag_off != (size_t)-1)
+      if (publish) {
+        fence_release_sys();  // acquire of the other CTAs' counts + release of everything before the flags
         for (int r = 0; r < world; ++r)
           st_relaxed_sys(reinterpret_cast<unsigned*>(static_cast<char*>(peers.base[(rank + r) % world]) + flag_off) + rank, epoch);
+      } else {
+        __threadfence();
+      }
       *counter = 0;
       if (epoch_word) *epoch_word = epoch;
     }
@@ -150,17 +163,44 @@ __device__ __forceinline__ void peer_reduce_slice(const PeerTable& peers, int wo
   }
 }
 
-// The same share for a channel that carries fp32 only (f32_begin == 0), light enough on registers to run inside a
-// kernel compiled for another job (the comm-role CTAs of a GEMM launch: 96 registers per thread there): RB * U = 8
-// 16-byte loads in flight per thread, 4 accumulators per vector.
+// ---- the same protocol pieces for a GROUP of warps inside a CTA that is busy with something else ----
+// (the epilogue warps of a GEMM CTA while its first accumulator is being computed: gemm_sm100.cuh).  `tid` in
+// [0, nthr) is the thread's index in the group, `bar_id` a named barrier reserved for the group (nthr % 32 == 0).
+__device__ __forceinline__ void group_sync(int bar_id, int nthr) {
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthr) : "memory");
+}
+__device__ __forceinline__ bool wait_flags_group(const unsigned* flags, int world, unsigned epoch, unsigned* status, int tid,
+                                                 int nthr, int bar_id) {
+  __shared__ int s_group_timed_out;
+  if (tid == 0) s_group_timed_out = 0;
+  group_sync(bar_id, nthr);
+  if (tid < world) {
+    const unsigned long long t0 = global_ns();
+    while ((int)(ld_relaxed_sys(flags + tid) - epoch) < 0) {
+      if (global_ns() - t0 > kPeerTimeoutNs) {
+        atomicExch(status, 1u + tid);
+        s_group_timed_out = 1;
+        break;
+      }
+      __nanosleep(64);
+    }
+    (void)ld_acquire_sys(flags + tid);
+  }
+  group_sync(bar_id, nthr);
+  return s_group_timed_out == 0 && ld_relaxed_sys(status) == 0u;
+}
+
+// One rank's share of the two-shot mean all-reduce for a channel that carries fp32 only (f32_begin == 0), light enough
+// on registers to run inside a kernel compiled for another job (96 registers per thread in the GEMM): RB * U = 8
+// 16-byte loads in flight per thread, 4 accumulators per vector.  `part` of `n_parts` groups of `nthr` threads.
 template <int RB, int U>
 __device__ __forceinline__ void peer_reduce_slice_f32(const PeerTable& peers, int world, int rank, long long n_vec, float scale,
-                                                      bool ok, int cta, int n_ctas) {
+                                                      bool ok, int part, int n_parts, int tid, int nthr) {
   const long long per = (n_vec + world - 1) / world;
   const long long lo = per * rank, hi = min(n_vec, lo + per);
   const size_t in_off = kPeerCtrlBytes, out_off = kPeerCtrlBytes + (size_t)n_vec * sizeof(uint4);
-  const long long stride = (long long)n_ctas * blockDim.x;
-  for (long long i = lo + (long long)cta * blockDim.x + threadIdx.x; i < hi; i += U * stride) {
+  const long long stride = (long long)n_parts * nthr;
+  for (long long i = lo + (long long)part * nthr + tid; i < hi; i += U * stride) {
     float4 acc[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -193,30 +233,42 @@ __device__ __forceinline__ void peer_reduce_slice_f32(const PeerTable& peers, in
   }
 }
 
-// The contribution phase + reduce phase of one channel round, run by `n_ctas` CTAs that are NOT a kernel of their own:
-// the comm-role CTAs at the end of a GEMM launch's grid (gemm_sm100.cuh).  This rank's contribution is complete before
-// the launch (stream order), so CTA 0 announces it right away; every CTA then waits for all ranks' announcements,
-// reduces its part of this rank's slice and the last one publishes the phase-1 flags.  The channel carries fp32 only.
+// The contribution phase + reduce phase of one channel round, run by the otherwise idle epilogue warps of EVERY CTA of
+// a GEMM launch before their first accumulator is ready (gemm_sm100.cuh): no SM is taken from the GEMM and no second
+// kernel competes with the persistent one.  This rank's contribution is complete before the launch (stream order),
+// so CTA 0 announces it right away; every group then waits for all ranks' announcements, reduces its part of this
+// rank's slice, and the last group to finish publishes the phase-1 flags.  The channel carries fp32 only.
 struct GemmCommReduce {
   PeerTable peers;
-  int world, rank, ctas;     // ctas: CTAs of the grid that take the comm role (a multiple of the cluster size)
+  int world, rank;
   long long n_vec;
   float scale;
 };
-static __device__ __noinline__ void comm_reduce_role(const GemmCommReduce& c, int cta) {
+static __device__ __noinline__ void comm_reduce_role(const GemmCommReduce& c, int cta, int n_ctas, int tid, int nthr, int bar_id) {
   unsigned* ctrl = static_cast<unsigned*>(c.peers.base[c.rank]);
   const unsigned epoch = ctrl[0] + 1;
-  if (cta == 0 && threadIdx.x == 0) {
-    __threadfence_system();
+  if (cta == 0 && tid == 0) {
+    fence_release_sys();
     for (int r = 0; r < c.world; ++r)
       st_relaxed_sys(reinterpret_cast<unsigned*>(static_cast<char*>(c.peers.base[(c.rank + r) % c.world]) + peer_flag_row_off(0)) + c.rank, epoch);
   }
-  const bool ok = wait_flags(reinterpret_cast<const unsigned*>(static_cast<char*>(c.peers.base[c.rank]) + peer_flag_row_off(0)),
-                             c.world, epoch, ctrl + 4);
-  if (c.world <= 2) peer_reduce_slice_f32<2, 4>(c.peers, c.world, c.rank, c.n_vec, c.scale, ok, cta, c.ctas);
-  else if (c.world <= 4) peer_reduce_slice_f32<4, 2>(c.peers, c.world, c.rank, c.n_vec, c.scale, ok, cta, c.ctas);
-  else peer_reduce_slice_f32<8, 1>(c.peers, c.world, c.rank, c.n_vec, c.scale, ok, cta, c.ctas);
-  peer_publish_when_done(c.peers, c.world, c.rank, peer_flag_row_off(1), epoch, ctrl + 2, (unsigned)c.ctas, nullptr);
+  const bool ok = wait_flags_group(reinterpret_cast<const unsigned*>(static_cast<char*>(c.peers.base[c.rank]) + peer_flag_row_off(0)),
+                                   c.world, epoch, ctrl + 4, tid, nthr, bar_id);
+  if (c.world <= 2) peer_reduce_slice_f32<2, 4>(c.peers, c.world, c.rank, c.n_vec, c.scale, ok, cta, n_ctas, tid, nthr);
+  else if (c.world <= 4) peer_reduce_slice_f32<4, 2>(c.peers, c.world, c.rank, c.n_vec, c.scale, ok, cta, n_ctas, tid, nthr);
+  else peer_reduce_slice_f32<8, 1>(c.peers, c.world, c.rank, c.n_vec, c.scale, ok, cta, n_ctas, tid, nthr);
+  // this group's stores are done -> count the CTA in; the last one publishes phase 1 to every peer
+  group_sync(bar_id, nthr);
+  if (tid == 0) {
+    fence_release_sys();
+    const unsigned done = atomicAdd(ctrl + 2, 1u);
+    if (done == (unsigned)n_ctas - 1) {
+      fence_release_sys();
+      for (int r = 0; r < c.world; ++r)
+        st_relaxed_sys(reinterpret_cast<unsigned*>(static_cast<char*>(c.peers.base[(c.rank + r) % c.world]) + peer_flag_row_off(1)) + c.rank, epoch);
+      ctrl[2] = 0;
+    }
+  }
 }
 
 }  // namespace p2t

@@ -309,7 +309,7 @@ class PeerGradAllReduce:
         self._phase(_READY | _REDUCE | _WAIT)
 
     def wait_only(self) -> None:
-        """Close a round whose announce + reduce phases were serviced elsewhere (comm-role CTAs of a GEMM launch)."""
+        """Close a round whose announce + reduce phases were serviced elsewhere (inside a GEMM launch)."""
         self._phase(_WAIT)
 
     def reduce_(self, grads: Sequence[torch.Tensor]) -> Sequence[torch.Tensor]:
@@ -326,22 +326,20 @@ class PeerGradAllReduce:
 class OverlappedGradReduce:
     """The gradient mean of the sharded training step as TWO channels, so that most of it hides behind the backward:
 
-      late : [dW2, db2] (fp32) — complete after the dW2 GEMM; its announce + reduce phases are serviced by comm-role
-             CTAs INSIDE the dW1 GEMM's launch (one kernel: tcgen05 GEMM on most SMs, NVLink peer-memory reduce on
-             `comm_ctas` of them), DDP's bucket overlap (scripts/train_contrast.py:448 + :611-614) without a second
-             kernel fighting the persistent GEMM for SMs;
+      late : [dW2, db2] (fp32) — complete after the dW2 GEMM; its announce + reduce phases are serviced INSIDE the
+             dW1 GEMM's launch by the epilogue warps of every CTA while their first accumulator is being computed
+             (one kernel: tcgen05 GEMM + NVLink peer-memory reduce, no SM taken from the GEMM), DDP's bucket overlap
+             (scripts/train_contrast.py:448 + :611-614) without a second kernel fighting the persistent GEMM for SMs;
       tail : [dW1, db1] (fp32) — reduced after the backward.
 
     `views_in()` / `views_out()` are in parameter order [dW1, db1, dW2, db2]; pass the object as
     `graph.GraphedContrastiveStep(grad_reducer=...)`."""
 
-    def __init__(self, adapter, group=None, comm_ctas: int = 20, _buffers: Optional[tuple] = None):
+    def __init__(self, adapter, group=None, _buffers: Optional[tuple] = None):
         like = PeerGradAllReduce.adapter_like(adapter)
         lb, tb = _buffers if _buffers is not None else (None, None)
         self.late = PeerGradAllReduce([like[2], like[3]], group, _buffer=lb)
         self.tail = PeerGradAllReduce([like[0], like[1]], group, _buffer=tb)
-        self.comm_ctas = int(os.environ.get("P2T_COMM_CTAS", comm_ctas))
-        self.late.comm_ctas = self.comm_ctas
         self.rank, self.world = self.late.rank, self.late.world
         self.shapes = [tuple(t.shape) for t in like]
         self.dtypes = [t.dtype for t in like]

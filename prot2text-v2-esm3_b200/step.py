@@ -173,7 +173,7 @@ def step_backward(state, dloss: Optional[torch.Tensor], *, accumulate: bool = Fa
     `accumulate`: add to them (bf16 read-modify-write for the weights, fp32 for the biases) — the micro-batch
     accumulation of scripts/train_contrast.py:448-465.  `overlap_reduce`: a peer.PeerGradAllReduce channel over
     [dW2, db2] whose contribution area `dw_out[1]` / `db_f32_out[1]` alias: db2 is finished right after the dW2 GEMM and
-    the channel's announce + reduce phases run on comm-role CTAs inside the dW1 GEMM's launch (DDP's bucket overlap,
+    the channel's announce + reduce phases run on the idle epilogue warps inside the dW1 GEMM's launch (DDP's bucket overlap,
     scripts/train_contrast.py:448 + :611-614, as one fused GEMM + collective kernel)."""
     plan, acts, inv_norm, w1c, w2c, cfg, head = state
     used = cfg["rows_used"]

@@ -62,7 +62,7 @@ def test_sass_is_blackwell_native(built):
         assert mnemonic in sass, mnemonic
     assert "HMMA.16816" not in sass  # no legacy mma.sync path
     # the peer-memory exchange publishes / polls its flags at system scope (csrc/peer.cu)
-    for mnemonic in ("MEMBAR.SC.SYS", "STG.E.STRONG.SYS", "LDG.E.STRONG.SYS"):
+    for mnemonic in ("MEMBAR.ALL.SYS", "STG.E.STRONG.SYS", "LDG.E.STRONG.SYS"):
         assert mnemonic in sass, mnemonic
 
 

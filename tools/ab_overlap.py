@@ -2,11 +2,11 @@
 """A/B timing of the sharded TRAINING step's gradient-mean forms on N GPUs, interleaved inside one job.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-        tools/ab_overlap.py [--workload cfg2_esm2_3b_llama8b] [--reps 8] [--steps 20] [--comm-ctas 8,16,32]
+        tools/ab_overlap.py [--workload cfg2_esm2_3b_llama8b] [--reps 8] [--steps 20]
 
 Forms: the step alone; step + optimizer with the plain peer reducer (one channel after the backward); step + optimizer
-with the fused form (dW2 / db2 mean by comm-role CTAs inside the dW1 GEMM launch) for each --comm-ctas value.  Every
-form is one CUDA graph per step; times are device times, max over ranks.
+with the fused form (dW2 / db2 mean by the idle epilogue warps inside the dW1 GEMM launch).  Every form is one CUDA graph
+per step; times are device times, max over ranks, each taken right after a pass of the bare step (paired difference).
 """
 import argparse
 import importlib
@@ -23,7 +23,6 @@ def main():
     ap.add_argument("--workload", default="cfg2_esm2_3b_llama8b")
     ap.add_argument("--reps", type=int, default=8)
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--comm-ctas", default="8,16,32")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -60,11 +59,10 @@ def main():
     reducers.append(red)
     forms["plain reducer, no optimizer"] = graph(red, None)
     forms["plain reducer + optimizer"] = graph(red, opt)
-    for n in [int(v) for v in args.comm_ctas.split(",") if v]:
-        fr = peer.OverlappedGradReduce(ad, comm_ctas=n)
-        reducers.append(fr)
-        forms[f"fused, {n} comm CTAs, no optimizer"] = graph(fr, None)
-        forms[f"fused, {n} comm CTAs + optimizer"] = graph(fr, opt)
+    fr = peer.OverlappedGradReduce(ad)
+    reducers.append(fr)
+    forms["fused GEMM + reduce, no optimizer"] = graph(fr, None)
+    forms["fused GEMM + reduce + optimizer"] = graph(fr, opt)
     # per repetition every form is timed right after its own pass of the bare step, and the DIFFERENCE is what is
     # kept: power-cap drift between repetitions (several percent on a loaded box) then cancels to first order
     def timed(g):
