@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libp2t_b200.so")
+LIB_PATH = os.environ.get("P2T_LIB_PATH") or os.path.join(_HERE, "libp2t_b200.so")  # the override serves build-variant A/B runs
 
 _vp, _i, _ll, _f, _ull = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulonglong
 

@@ -116,7 +116,13 @@ struct GemmSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // (5 x 32 KB of operands in flight per SM is what keeps the MMA fed from L2: with 4 stages ncu showed the epilogue
   //  warps waiting for the accumulator 29 % of the time while the tensor pipe was 63 % active)
-  static constexpr int STAGES = TMA_STORE ? ((CTA_GROUP == 1) ? 3 : 5) : ((CTA_GROUP == 1) ? 4 : 6);
+#ifndef P2T_FC_STAGES
+#define P2T_FC_STAGES 5
+#endif
+#ifndef P2T_ST_STAGES
+#define P2T_ST_STAGES 6
+#endif
+  static constexpr int STAGES = TMA_STORE ? ((CTA_GROUP == 1) ? 3 : P2T_FC_STAGES) : ((CTA_GROUP == 1) ? 4 : P2T_ST_STAGES);
   static constexpr int BAR_BYTES = 1024;
   static constexpr int OUT_BOX_BYTES = 32 * 32 * 2;        // one staged output box
   static constexpr int OUT_BYTES = TMA_STORE ? GEMM_EPI_WARPS * 2 * OUT_BOX_BYTES : 0;

@@ -92,12 +92,12 @@ __global__ void peer_allreduce_ready_kernel(PeerTable peers, int world, int rank
 }
 
 // phase 1: reduce my slice out of every peer's `in`, store the mean into every peer's `out`.
-// RB ranks x U vectors = 16 independent 16-byte loads in flight per thread whatever the world size (an NVLink round
-// trip is ~2 us); ranks are always added in rank order, so every rank computes bit-identical sums.
+// RB ranks x U vectors = 8 independent 16-byte loads in flight per thread whatever the world size, two CTAs per SM
+// (an NVLink round trip is ~2 us); ranks are always added in rank order, so every rank computes bit-identical sums.
 // Vectors below `f32_begin` hold 8 bf16 values (mean stored as bf16), vectors from `f32_begin` on hold 4 fp32 values
 // (mean stored as fp32: the bias gradients travel unrounded and are rounded to bf16 once, after the mean).
 template <int RB, int U>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 peer_allreduce_reduce_kernel(PeerTable peers, int world, int rank, long long n_vec, long long f32_begin, float scale, int announce) {
   unsigned* ctrl = static_cast<unsigned*>(peers.base[rank]);
   const unsigned epoch = ctrl[0] + 1;
@@ -267,11 +267,11 @@ int peer_allreduce_mean(void* const* peers, int world, int rank, long long n_byt
       else if (world <= 4) peer_allreduce_reduce_f32_kernel<4, 4><<<grid_for(slice / 4, 4), 256, 0, st>>>(t, world, rank, n_vec, scale, announce_in_reduce);
       else peer_allreduce_reduce_f32_kernel<8, 2><<<grid_for(slice / 2, 4), 256, 0, st>>>(t, world, rank, n_vec, scale, announce_in_reduce);
     } else if (world <= 2) {
-      peer_allreduce_reduce_kernel<2, 8><<<grid_for(slice / 8, 4), 256, 0, st>>>(t, world, rank, n_vec, f32_begin, scale, announce_in_reduce);
+      peer_allreduce_reduce_kernel<2, 4><<<grid_for(slice / 4, 4), 256, 0, st>>>(t, world, rank, n_vec, f32_begin, scale, announce_in_reduce);
     } else if (world <= 4) {
-      peer_allreduce_reduce_kernel<4, 4><<<grid_for(slice / 4, 4), 256, 0, st>>>(t, world, rank, n_vec, f32_begin, scale, announce_in_reduce);
+      peer_allreduce_reduce_kernel<4, 2><<<grid_for(slice / 2, 4), 256, 0, st>>>(t, world, rank, n_vec, f32_begin, scale, announce_in_reduce);
     } else {
-      peer_allreduce_reduce_kernel<8, 2><<<grid_for(slice / 2, 4), 256, 0, st>>>(t, world, rank, n_vec, f32_begin, scale, announce_in_reduce);
+      peer_allreduce_reduce_kernel<8, 1><<<grid_for(slice, 4), 256, 0, st>>>(t, world, rank, n_vec, f32_begin, scale, announce_in_reduce);
     }
     if (int r = check_launch("peer_allreduce_reduce_kernel", st)) return r;
   }
