@@ -98,6 +98,14 @@ int p2t_rows_plan_counts(const int* counts, int B, int chunk_rows, int* seq_off,
  * batch (scripts/train_contrast.py:329-330). */
 int p2t_stage_rows_h2d(const void* host_src, long long seq_stride_bytes, long long row_bytes, const int* starts,
                        const int* counts, int B, void* dev_dst, void* const* streams, int n_streams);
+/* The same staging as ONE kernel that PULLS the valid rows out of pinned host memory (the pointer must be device-
+ * accessible: cudaHostAlloc / torch pin_memory under unified addressing) instead of one copy-engine transfer per
+ * sequence (~3.5 us of set-up each).  DEVICE arrays: table[3 * n_seg] int64 = {byte offset in the host batch, byte
+ * offset in dev_dst, byte length} per segment, all multiples of 16; piece_prefix[n_seg + 1] int32 = 32 KB pieces
+ * before each segment (last entry = total).  ctas: CTAs of the launch (0 = 32); they share the SMs with whatever else
+ * runs. */
+int p2t_stage_rows_pull(const void* host_mapped, const long long* table_dev, const int* piece_prefix_dev, int n_seg,
+                        void* dev_dst, int ctas, void* stream);
 
 /* out[i] = src[row_src[i]] (bf16 rows of D elements), zero rows from n_rows up to the next multiple
  * of 256 (<= rows_cap).  Packs the padded (B, L, D_in) residue states that

@@ -26,6 +26,7 @@ SIGNATURES = {
     "p2t_rows_plan": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "p2t_rows_plan_counts": [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "p2t_stage_rows_h2d": [_vp, _ll, _ll, _vp, _vp, _i, _vp, C.POINTER(_vp), _i],
+    "p2t_stage_rows_pull": [_vp, _vp, _vp, _i, _vp, _i, _vp],
     "p2t_row_inv_norm": [_vp, _i, _vp, _i, _vp, _vp],
     "p2t_gather_rows": [_vp, _ll, _vp, _vp, _i, _i, _vp, _vp],
     "p2t_adapter_fwd": [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _ull, _vp, _vp, _i, _vp],

@@ -123,6 +123,13 @@ int p2t_stage_rows_h2d(const void* host_src, long long seq_stride_bytes, long lo
   return 0;
 }
 
+int p2t_stage_rows_pull(const void* host_mapped, const long long* table_dev, const int* piece_prefix_dev, int n_seg,
+                        void* dev_dst, int ctas, void* stream) {
+  if (!host_mapped || !table_dev || !piece_prefix_dev || !dev_dst) return set_error(-1, "p2t_stage_rows_pull: null pointer");
+  if (n_seg < 0 || ctas < 0) return set_error(-1, "p2t_stage_rows_pull: bad segment / CTA count");
+  return stage_rows_pull(host_mapped, table_dev, piece_prefix_dev, n_seg, dev_dst, ctas, S(stream));
+}
+
 int p2t_gather_rows(const void* src, long long ld_src, const int* row_src, const int* n_rows_dev, int rows_cap,
                     int D, void* out, void* stream) {
   if (!src || !row_src || !n_rows_dev || !out) return set_error(-1, "p2t_gather_rows: null pointer");

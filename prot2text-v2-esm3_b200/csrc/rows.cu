@@ -1106,6 +1106,43 @@ readout_last_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const int* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// host -> device staging by PULL: a few CTAs read the valid rows of a padded batch straight out of pinned (mapped)
+// host memory and write them packed.  One launch for the whole batch: the copy-engine form pays ~3.5 us of set-up per
+// sequence (64 copies of 0.25-5 MB reach 49 GB/s where one packed copy reaches 54, tools/h2d_probe.py).
+//   table[3*s + 0..2] = byte offset of segment s in the host batch, in the packed destination, and its length
+//   (all multiples of 16); piece_prefix[s] = number of 32 KB pieces before segment s, piece_prefix[n_seg] = total.
+// Each CTA takes pieces round-robin; a piece is one sweep of 256 threads x 8 x 16 B = 32 KB, all loads of a thread
+// in flight before its first store (a PCIe read round trip is ~1.5 us).  Loads are system-scope (never a stale line).
+// ------------------------------------------------------------------------------------------------
+constexpr int kPullPieceBytes = 256 * 8 * 16;
+__global__ void __launch_bounds__(256)
+stage_rows_pull_kernel(const char* __restrict__ host_base, const long long* __restrict__ table,
+                       const int* __restrict__ piece_prefix, int n_seg, char* __restrict__ dst) {
+  const int n_pieces = piece_prefix[n_seg];
+  for (int piece = blockIdx.x; piece < n_pieces; piece += gridDim.x) {
+    const int s = find_segment(piece_prefix, n_seg, piece);
+    const long long off = (long long)(piece - piece_prefix[s]) * kPullPieceBytes;
+    const long long len = min((long long)kPullPieceBytes, table[3 * s + 2] - off);
+    const uint4* src = reinterpret_cast<const uint4*>(host_base + table[3 * s] + off);
+    uint4* out = reinterpret_cast<uint4*>(dst + table[3 * s + 1] + off);
+    const int n_vec = (int)(len >> 4);
+    uint4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = u * 256 + threadIdx.x;
+      if (i < n_vec)
+        asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(src + i) : "memory");
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = u * 256 + threadIdx.x;
+      if (i < n_vec) out[i] = v[u];
+    }
+  }
+}
+
 // ================================================================================================
 // host launchers
 // ================================================================================================
@@ -1335,6 +1372,15 @@ int colsum(const void* x, const int* n_rows, int n_static, int D, float* partial
 int readout_last(const void* x, const int* counts, int B, int S, int D, float* out, cudaStream_t st) {
   readout_last_kernel<<<B, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), counts, S, D, out);
   return check_launch("readout_last_kernel", st);
+}
+
+int stage_rows_pull(const void* host_base, const long long* table, const int* piece_prefix, int n_seg, void* dst, int ctas,
+                    cudaStream_t st) {
+  if (n_seg <= 0) return 0;
+  if (ctas <= 0) ctas = 32;
+  stage_rows_pull_kernel<<<ctas, 256, 0, st>>>(static_cast<const char*>(host_base), table, piece_prefix, n_seg,
+                                              static_cast<char*>(dst));
+  return check_launch("stage_rows_pull_kernel", st);
 }
 
 int readout_last_bwd(const void* dout, const int* counts, int B, int S, int D, void* dx, cudaStream_t st) {

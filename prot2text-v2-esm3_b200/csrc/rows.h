@@ -54,6 +54,8 @@ int colsum(const void* x, const int* n_rows, int n_static, int D, float* partial
            cudaStream_t st);
 int readout_last(const void* x, const int* counts, int B, int S, int D, float* out, cudaStream_t st);
 int readout_last_bwd(const void* dout, const int* counts, int B, int S, int D, void* dx, cudaStream_t st);
+int stage_rows_pull(const void* host_base, const long long* table, const int* piece_prefix, int n_seg, void* dst, int ctas,
+                    cudaStream_t st);
 
 int sim_small(const void* p, const void* t, bool in_f32, int R, int C, int E, float alpha, float* S, cudaStream_t st);
 int col_stats(const float* S, int R, int C, float* col_max, float* col_sum, int* col_argmax, int row_index_base,

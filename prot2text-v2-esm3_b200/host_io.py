@@ -9,6 +9,7 @@ pack (gather) kernel disappears.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -81,18 +82,27 @@ class HostStager:
                                 residue_lengths=batch.residue_lengths, text_lengths=batch.text_lengths)
     """
 
-    def __init__(self, device, residue_streams: int = 3):
+    def __init__(self, device, residue_streams: int = 3, mode: Optional[str] = None, pull_ctas: int = 32):
+        """`mode`: "copy" = one copy-engine transfer per sequence (default); "pull" = ONE kernel per side that reads the
+        valid rows out of the pinned host batch itself (no per-copy set-up; its `pull_ctas` CTAs share the SMs with
+        the step's kernels).  Env P2T_STAGE_MODE overrides the default."""
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.P2TError("HostStager needs a CUDA device: this package has no CPU path")
+        self.mode = mode or os.environ.get("P2T_STAGE_MODE", "copy")
+        if self.mode not in ("copy", "pull"):
+            raise _lib.P2TError(f"HostStager mode must be 'copy' or 'pull' (got {self.mode!r})")
+        self.pull_ctas = int(os.environ.get("P2T_STAGE_PULL_CTAS", pull_ctas))
         # several copy streams: the residue rows of a batch are ~32-64 separate 1-5 MB copies (one per sequence); on ONE
         # stream every copy pays its DMA set-up behind the previous one (~5 us x 64 = 0.3 ms of a 2.6 ms step).  The
         # sequences are dealt round-robin to `residue_streams` streams so that set-up and transfer of neighbouring
         # copies overlap; the text rows travel on their own stream.
-        self.nres = max(1, int(residue_streams))
-        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.nres)]
+        self.nres = max(1, int(os.environ.get("P2T_STAGE_STREAMS", residue_streams)))
+        # pull mode: high-priority streams, so that the staging kernels' few CTAs are placed as soon as an SM has room
+        prio = -1 if self.mode == "pull" else 0
+        self.streams = [torch.cuda.Stream(device=self.device, priority=prio) for _ in range(self.nres)]
         self.stream = self.streams[0]
-        self.stream2 = torch.cuda.Stream(device=self.device)
+        self.stream2 = torch.cuda.Stream(device=self.device, priority=prio)
         self._pending = []
 
     def _stage(self, src: torch.Tensor, mask: torch.Tensor, streams):
@@ -116,6 +126,27 @@ class HostStager:
         ready.record(lead)  # the destination buffer exists (its allocation is stream-ordered on `lead`)
         for st in streams[1:]:
             st.wait_event(ready)
+        if self.mode == "pull":
+            if not src.is_pinned():
+                raise _lib.P2TError("HostStager(mode='pull') reads the host batch from the device: it must be pinned")
+            cnt = counts.to(torch.int64)
+            seg_bytes = cnt * (D * 2)
+            keep = seg_bytes > 0
+            table = torch.stack([(torch.arange(B, dtype=torch.int64) * L + starts.to(torch.int64)) * (D * 2),
+                                 (torch.cumsum(seg_bytes, 0) - seg_bytes), seg_bytes], dim=1)[keep].contiguous()
+            piece = 256 * 8 * 16
+            pieces = (table[:, 2] + piece - 1) // piece
+            prefix = torch.zeros(table.shape[0] + 1, dtype=torch.int32)
+            prefix[1:] = torch.cumsum(pieces, 0).to(torch.int32)
+            if (D * 2) % 16:
+                raise _lib.P2TError("HostStager(mode='pull') needs rows of a multiple of 16 bytes")
+            with torch.cuda.stream(lead):
+                table_d = table.pin_memory().to(self.device, non_blocking=True)
+                prefix_d = prefix.pin_memory().to(self.device, non_blocking=True)
+                _lib.call("p2t_stage_rows_pull", src.data_ptr(), table_d.data_ptr(), prefix_d.data_ptr(), int(table.shape[0]),
+                          rows.data_ptr(), self.pull_ctas, lead.cuda_stream)
+            self._keep = getattr(self, "_keep", [])[-8:] + [(table_d, prefix_d, src)]  # alive until the kernel has run
+            return rows[:total] if total else rows[:0], lens, total * D * 2 + B * 4
         handles = (C.c_void_p * len(streams))(*[st.cuda_stream for st in streams])
         _lib.call("p2t_stage_rows_h2d", src.data_ptr(), L * D * 2, D * 2, starts.data_ptr(), counts.data_ptr(), B,
                   rows.data_ptr(), handles, len(streams))

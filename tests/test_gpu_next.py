@@ -207,6 +207,35 @@ def test_gradient_mean_inside_the_dw1_gemm_launch_equals_the_plain_step(p2t, mod
         red.close()
 
 
+def test_host_stager_pull_mode_equals_copy_mode(p2t, mods, dev):
+    """HostStager(mode="pull"): one kernel per side reads the valid rows out of the pinned host batch; same packed rows,
+    bit for bit, as the per-sequence copies — right and left padding, an empty sequence, a piece boundary inside a row."""
+    gen = torch.Generator().manual_seed(21)
+    B, L, D, T, H = 7, 300, 200, 40, 136
+    x = bf(torch.randn(B, L, D, generator=gen)).pin_memory()
+    text = bf(torch.randn(B, T, H, generator=gen)).pin_memory()
+    lens = torch.tensor([300, 1, 0, 157, 82, 299, 41])
+    tl = torch.tensor([40, 3, 17, 1, 40, 22, 9])
+    for left in (False, True):
+        ar, at = torch.arange(L)[None, :], torch.arange(T)[None, :]
+        pm = ((ar >= L - lens[:, None]) if left else (ar < lens[:, None])).long()
+        tm = ((at >= T - tl[:, None]) if left else (at < tl[:, None])).long()
+        got = {}
+        for mode in ("copy", "pull"):
+            st = p2t.HostStager(dev, mode=mode, pull_ctas=5)
+            st.submit(x, pm, text, tm)
+            b = st.take()
+            torch.cuda.synchronize()
+            got[mode] = (b.residue_rows.clone(), b.residue_lengths.clone(), b.text_rows.clone(), b.text_lengths.clone(), b.h2d_bytes)
+        for a, c in zip(got["copy"][:4], got["pull"][:4]):
+            assert torch.equal(a, c)
+        assert got["copy"][4] == got["pull"][4]
+        want = torch.cat([x[j][pm[j] != 0] for j in range(B)])
+        assert torch.equal(got["pull"][0].cpu(), want)
+    with pytest.raises(p2t.P2TError, match="pinned"):
+        p2t.HostStager(dev, mode="pull").submit(x.clone(), pm, text, tm)
+
+
 # --------------------------------------------------------------------------------------------------
 # clip_grad_norm_ + AdamW
 # --------------------------------------------------------------------------------------------------
