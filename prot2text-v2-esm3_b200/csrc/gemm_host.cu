@@ -134,7 +134,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   memset(&td1, 0, sizeof(td1));
   q.tma_store = 0;
   static const int tma_store_on = getenv("P2T_TMA_STORE") ? atoi(getenv("P2T_TMA_STORE")) : 1;  // 0: direct global stores (experiments)
-  if (S::TMA_STORE && !nostore && tma_store_on) {
+  if (S::TMA_STORE && nostore != 1 && tma_store_on) {
     const bool ok0 = !((reinterpret_cast<uintptr_t>(p.d0) & 15) || (p.ldd0 * 2) % 16);
     const bool ok1 = p.d1 == nullptr || !((reinterpret_cast<uintptr_t>(p.d1) & 15) || (p.ldd1 * 2) % 16);
     if (ok0 && ok1) {

@@ -102,7 +102,8 @@ struct GemmParams {
   int sk_splits;              // S, set by the launcher (1 = whole tiles only; -1 = chosen on the device from the actual
                               // tile count, for GEMMs whose M is a device scalar)
   int tma_store;              // FC epilogues: tmap_d0/tmap_d1 are valid, write outputs through shared memory + TMA
-  int debug_nostore;          // bring-up aid (P2T_DEBUG_NOSTORE=1): run the epilogue math, skip its global stores
+  int debug_nostore;          // timing aid (P2T_DEBUG_NOSTORE): 1 = run the epilogue math, skip its global stores; 2 / 3: see the
+                              // staged-store path (results are wrong in all three modes)
 };
 
 // The FC epilogues stage their two 16-bit outputs in shared memory (one 32-row x 32-column box per output and
@@ -690,7 +691,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     e.gscale = p.drop.threshold != 0 ? p.drop.scale : 1.f;
     const unsigned long long seed = p.drop.seed + (p.drop.seed_dev ? *p.drop.seed_dev : 0ull);
     e.key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
-    e.nostore = p.debug_nostore;
+    e.nostore = p.debug_nostore == 1;
     e.accumulate = p.accumulate;
     const int rows_cap = p.rows_cap;
     // the interior path moves 16-byte vectors: every row of every output/aux tensor must start 16-byte aligned
@@ -857,8 +858,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               epilogue_chunk_staged<EPI>(v, e, rnd, col, stage_addr, lane, row_valid, want_der, sumsq);
               fence_proxy_async_smem();
               __syncwarp();
-              if (lane == 0) {
-                const int row0 = row - lane;
+              if (lane == 0 && p.debug_nostore != 3) {   // (3: stage only, no TMA store — timing experiments)
+                // (2: every tile stores into the same 256 rows — the stores stay in L2, no DRAM write traffic)
+                const int row0 = p.debug_nostore == 2 ? ((row - lane) & 255) : row - lane;
                 tma_store_2d(&tmap_d0, out_stage, col, row0);
                 if (want_der) tma_store_2d(&tmap_d1, out_stage + S::OUT_BOX_BYTES, col, row0);
                 tma_store_commit();
