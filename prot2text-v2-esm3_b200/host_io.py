@@ -72,6 +72,23 @@ def _valid_ranges(mask: torch.Tensor):
     return starts.to(torch.int32).contiguous(), counts.to(torch.int32).contiguous()
 
 
+PULL_PIECE_BYTES = 256 * 8 * 16  # one sweep of the staging kernel's CTA (csrc/rows.cu: kPullPieceBytes)
+
+
+def pull_table(starts: torch.Tensor, counts: torch.Tensor, L: int, row_bytes: int):
+    """Segment table of `p2t_stage_rows_pull` for a padded host batch [B][L][row_bytes]: int64 [n_seg, 3] =
+    (byte offset in the host batch, byte offset in the packed destination, byte length) for every sequence with at
+    least one valid row, and int32 [n_seg + 1] = number of 32 KB pieces before each segment (last entry: total)."""
+    B = counts.shape[0]
+    seg_bytes = counts.to(torch.int64) * row_bytes
+    table = torch.stack([(torch.arange(B, dtype=torch.int64) * L + starts.to(torch.int64)) * row_bytes,
+                         torch.cumsum(seg_bytes, 0) - seg_bytes, seg_bytes], dim=1)[seg_bytes > 0].contiguous()
+    pieces = (table[:, 2] + PULL_PIECE_BYTES - 1) // PULL_PIECE_BYTES
+    prefix = torch.zeros(table.shape[0] + 1, dtype=torch.int32)
+    prefix[1:] = torch.cumsum(pieces, 0).to(torch.int32)
+    return table, prefix
+
+
 class HostStager:
     """Stages padded HOST batches (ideally pinned) as packed device rows on a private copy stream.
 
@@ -129,17 +146,9 @@ class HostStager:
         if self.mode == "pull":
             if not src.is_pinned():
                 raise _lib.P2TError("HostStager(mode='pull') reads the host batch from the device: it must be pinned")
-            cnt = counts.to(torch.int64)
-            seg_bytes = cnt * (D * 2)
-            keep = seg_bytes > 0
-            table = torch.stack([(torch.arange(B, dtype=torch.int64) * L + starts.to(torch.int64)) * (D * 2),
-                                 (torch.cumsum(seg_bytes, 0) - seg_bytes), seg_bytes], dim=1)[keep].contiguous()
-            piece = 256 * 8 * 16
-            pieces = (table[:, 2] + piece - 1) // piece
-            prefix = torch.zeros(table.shape[0] + 1, dtype=torch.int32)
-            prefix[1:] = torch.cumsum(pieces, 0).to(torch.int32)
             if (D * 2) % 16:
                 raise _lib.P2TError("HostStager(mode='pull') needs rows of a multiple of 16 bytes")
+            table, prefix = pull_table(starts, counts, L, D * 2)
             with torch.cuda.stream(lead):
                 table_d = table.pin_memory().to(self.device, non_blocking=True)
                 prefix_d = prefix.pin_memory().to(self.device, non_blocking=True)

@@ -104,3 +104,27 @@ def test_device_side_synthetic_batch_has_the_same_ragged_structure(p2t):
     assert not b.x[b.prot_mask == 0].any() and torch.equal(a.w1, b.w1)
     r0 = synth.make_config_batch("tiny", rank=0)
     assert sorted(a.prot_lens.tolist()) == sorted(r0.prot_lens.tolist())  # rank 0's multiset, permuted
+
+
+def test_pull_table_describes_the_valid_rows_of_a_padded_batch(p2t):
+    """host_io.pull_table (the segment table of the pull-mode staging kernel): replaying it on the CPU reproduces the
+    packed valid rows for right and left padding, skips empty sequences and counts the 32 KB pieces."""
+    import importlib
+    host_io = importlib.import_module("p2t_b200.host_io")
+    gen = torch.Generator().manual_seed(4)
+    B, L, D = 6, 90, 24
+    x = torch.randn(B, L, D, generator=gen).to(torch.bfloat16)
+    counts = torch.tensor([90, 0, 1, 57, 89, 13], dtype=torch.int32)
+    for starts in (torch.zeros(B, dtype=torch.int32), (L - counts).to(torch.int32)):
+        table, prefix = host_io.pull_table(starts, counts, L, D * 2)
+        assert table.shape == (5, 3) and prefix.shape == (6,) and prefix[0] == 0
+        raw = x.contiguous().view(torch.int16).reshape(-1)  # 2-byte elements
+        out = torch.zeros(int(counts.sum()) * D, dtype=torch.int16)
+        pieces = 0
+        for (src, dst, n), before in zip(table.tolist(), prefix.tolist()):
+            assert src % 16 == 0 and dst % 16 == 0 and n % 16 == 0 and before == pieces
+            out[dst // 2:(dst + n) // 2] = raw[src // 2:(src + n) // 2]
+            pieces += -(-n // host_io.PULL_PIECE_BYTES)
+        assert int(prefix[-1]) == pieces
+        want = torch.cat([x[b, int(starts[b]):int(starts[b]) + int(counts[b])] for b in range(B)])
+        assert torch.equal(out.view(torch.bfloat16).reshape(-1, D), want)
